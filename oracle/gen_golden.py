@@ -163,6 +163,18 @@ def gen_e2e(ref, arrays):
     cfg, tok = _setup(ref, case["meta_prompt"], hyper)
     cfg.thresholds = hyper["thresholds"]
     pipe = ref_loader.make_pipeline(ref, unet, tok)
+
+    class FixedTextEncoder:
+        """The reference's `_encode_prompt` cannot take `prompt_embeds` (`text_inputs` is unbound on that branch,
+        pipeline_guided_attention.py:105-199), so the synthetic embeddings enter through a stand-in text encoder:
+        the empty (negative) prompt maps to embeds[0], anything else to embeds[1]."""
+        dtype = torch.float32
+        config = types.SimpleNamespace()
+
+        def __call__(self, ids, attention_mask=None):
+            empty = bool(ids[0, 1] == tok.eos_token_id)
+            return (embeds[0:1] if empty else embeds[1:2],)
+    pipe.text_encoder = FixedTextEncoder()
     cfg.stable = pipe
     saved = []
     pipe.save_image = lambda latent, tag: saved.append(tag)      # PNG side effects off
@@ -179,7 +191,7 @@ def gen_e2e(ref, arrays):
         return orig_forward(*a, **k)
     pipe.forward = counting_forward
     out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=case["guidance_scale"],
-               generator=gen, latents=latents0.clone(), prompt_embeds=embeds[1:2], negative_prompt_embeds=embeds[0:1],
+               generator=gen, latents=latents0.clone(),
                num_inference_steps=case["steps"], max_iter_to_alter=25, run_standard_sd=False,
                thresholds=cfg.thresholds, scale_factor=20, scale_range=(1.0, 0.5), smooth_attentions=True, sigma=0.5,
                kernel_size=3, sd_2_1=False, output_type="latent_probe")
