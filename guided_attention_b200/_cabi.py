@@ -1,0 +1,93 @@
+"""ctypes binding of `include/guided_attn.h` (libguidedattn.so).
+
+The library is built in-tree by `__graft_entry__.build()` (or `python -m guided_attention_b200.build`).  Loading is
+lazy and failure is loud: there is no CPU / PyTorch fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libguidedattn.so")
+
+GA_OK = 0
+GA_F32, GA_F16, GA_BF16 = 0, 1, 2
+GA_IMPL_AUTO, GA_IMPL_SIMT, GA_IMPL_TCGEN05 = 0, 1, 2
+GA_TOKEN_COOR, GA_TOKEN_BOX, GA_TOKEN_KEYWORD = 0, 1, 2
+GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
+(GA_STAT_MAX, GA_STAT_SUM, GA_STAT_COL, GA_STAT_ROW, GA_STAT_INSIDE, GA_STAT_OUTSIDE, GA_STAT_SCALED,
+ GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER) = range(12)
+GA_STATS = 12
+GA_ABI_VERSION = 1
+
+
+class GaToken(C.Structure):
+    _fields_ = [("column", C.c_int32), ("kind", C.c_int32), ("box", C.c_int32), ("group", C.c_int32),
+                ("target_x", C.c_float), ("target_y", C.c_float), ("center_weight", C.c_float),
+                ("group_weight", C.c_float)]
+
+
+class GaTailParams(C.Structure):
+    _fields_ = [("res", C.c_int32), ("n_ctx", C.c_int32), ("first", C.c_int32), ("last", C.c_int32),
+                ("n_tokens", C.c_int32), ("n_groups", C.c_int32), ("strict", C.c_int32), ("smooth", C.c_int32),
+                ("w1d", C.c_float * 3), ("temperature", C.c_float), ("inv_count", C.c_float),
+                ("inside_scale", C.c_float), ("outside_scale", C.c_float), ("custom_total", C.c_float)]
+
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes); every symbol declared in include/guided_attn.h
+PROTOTYPES = {
+    "ga_version": (_i, []),
+    "ga_last_error": (C.c_char_p, []),
+    "ga_device_supported": (_i, [_i]),
+    "ga_cross_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_cross_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "ga_rasterize_boxes": (_i, [C.POINTER(C.c_double), _i, _i, C.c_double, _vp, _vp]),
+    "ga_guidance_tail_fwd": (_i, [C.POINTER(_vp), C.POINTER(C.c_int32), _i, C.POINTER(GaTailParams), C.POINTER(GaToken),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ga_guidance_tail_bwd": (_i, [C.POINTER(GaTailParams), C.POINTER(GaToken), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp]),
+    "ga_smooth_fwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
+    "ga_smooth_bwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
+    "ga_box_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "ga_box_loss_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class GuidedAttnLibraryError(RuntimeError):
+    pass
+
+
+def load(path: str = None) -> C.CDLL:
+    """dlopen libguidedattn.so and attach prototypes.  Raises if the library is missing: no fallback exists."""
+    global _lib
+    with _lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or os.environ.get("GA_LIB_PATH", LIB_PATH)
+        if not os.path.isfile(p):
+            raise GuidedAttnLibraryError(
+                f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  The guidance path has no CPU or PyTorch fallback.")
+        lib = C.CDLL(p)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)   # AttributeError if a declared symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.ga_version() != GA_ABI_VERSION:
+            raise GuidedAttnLibraryError(f"ABI mismatch: library {lib.ga_version()} vs binding {GA_ABI_VERSION}")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def check(rc: int, what: str):
+    if rc != GA_OK:
+        msg = load().ga_last_error().decode("utf-8", "replace")
+        raise GuidedAttnLibraryError(f"{what} failed ({rc}): {msg}")

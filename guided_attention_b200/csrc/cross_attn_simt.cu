@@ -1,0 +1,426 @@
+// K1 / K2, exact-fp32 SIMT variant: cross-attention against a short text context (T <= 128 keys) with the
+// attention-map accumulation fused in.  This is the variant for fp32 operands (the tensor cores would round to tf32,
+// outside the 1e-3 parity budget) and the on-device cross-check for the tcgen05 variant (cross_attn_tc.cu).
+//
+// Replaces reference utils/ptp_utils.py:77-85, 97-146 (QK^T -> softmax -> store -> PV) and its autograd.
+// Layout: q/o (B, N, H*d), k/v (B, T, H*d): head h of token n starts at ((b*N + n)*H + h)*d, d contiguous.
+//
+// One CTA = 64 query rows x `heads_per_cta` heads.  K, V of the head and the Q tile are staged in shared memory as
+// 32-bit words (1 float or 2 halves) with an odd row stride, so that lanes that own different keys read different
+// banks.  A warp owns 8 rows, processed 4 at a time: lanes are keys for S = QK^T and the softmax (row reductions are
+// warp shuffles), then lanes are channels for O = PV.  The head-sum of P for the AttentionStore accumulator stays in
+// registers across the head loop, so `acc` is written once, without atomics, in a fixed order (deterministic).
+#include "ga_common.cuh"
+
+namespace ga {
+namespace simt {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRowsPerCta = 64;
+constexpr int kRowsPerWarp = kRowsPerCta / kWarps;  // 8
+constexpr int kR = 4;                               // rows processed together by a warp
+constexpr int kGroups = kRowsPerWarp / kR;          // 2
+constexpr int kKPL = GA_MAX_CTX / 32;               // keys per lane (4)
+constexpr int kPStride = GA_MAX_CTX;                // per-row stride of the probability scratch
+constexpr int kMaxHeadDim = 256;
+
+template <typename T> struct Cfg {
+  static constexpr int E = Word<T>::E;
+  static constexpr int kWPL = kMaxHeadDim / E / 32;  // channel words per lane: 8 (fp32) or 4 (16-bit)
+};
+
+__device__ __forceinline__ int odd_stride(int words) { return words | 1; }
+
+// Cooperative copy of `rows` rows of `words` 32-bit words (row pitch `pitch_words` in global memory) into shared
+// memory with stride `stride`; rows >= valid_rows are zero-filled.  16-byte global loads.
+__device__ __forceinline__ void stage_rows(uint32_t* dst, const uint32_t* src, int rows, int valid_rows, int words,
+                                           int64_t pitch_words, int stride) {
+  const int vec_per_row = words >> 2;  // words % 4 == 0 is checked on the host (d % 8 == 0)
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+    const int r = i / vec_per_row, c = (i - r * vec_per_row) << 2;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < valid_rows) val = __ldg(reinterpret_cast<const uint4*>(src + r * pitch_words + c));
+    uint32_t* p = dst + r * stride + c;
+    p[0] = val.x; p[1] = val.y; p[2] = val.z; p[3] = val.w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void dot_step(float& s, float2 a, float2 b) {
+  s = fmaf(a.x, b.x, s);
+  if (Word<T>::E == 2) s = fmaf(a.y, b.y, s);
+}
+
+// ------------------------------------------------------------------------------------------------------ forward
+template <typename T, bool kProbsOnly>
+__global__ void __launch_bounds__(kThreads)
+cross_attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
+                      float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ probs, int H, int N, int Tctx,
+                      int d, float scale, int heads_per_cta) {
+  constexpr int E = Cfg<T>::E;
+  constexpr int kWPL = Cfg<T>::kWPL;
+  extern __shared__ uint32_t smem[];
+  const int words = d / E;
+  const int stride = odd_stride(words);
+  uint32_t* sK = smem;
+  uint32_t* sV = sK + Tctx * stride;
+  uint32_t* sQ = sV + Tctx * stride;
+  float* sP = reinterpret_cast<float*>(sQ + kRowsPerCta * stride);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int bh0 = blockIdx.y * heads_per_cta;
+  const int64_t pitch = (int64_t)H * words;  // words between consecutive tokens
+
+  float pacc[kGroups][kR][kKPL];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+    for (int r = 0; r < kR; ++r)
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) pacc[g][r][kk] = 0.f;
+
+  int jc[kKPL];
+#pragma unroll
+  for (int kk = 0; kk < kKPL; ++kk) jc[kk] = min(lane + 32 * kk, Tctx - 1);
+
+  for (int hh = 0; hh < heads_per_cta; ++hh) {
+    const int bh = bh0 + hh, b = bh / H, h = bh - b * H;
+    const uint32_t* gq = reinterpret_cast<const uint32_t*>(q) + ((int64_t)b * N + row0) * pitch + (int64_t)h * words;
+    const uint32_t* gk = reinterpret_cast<const uint32_t*>(k) + (int64_t)b * Tctx * pitch + (int64_t)h * words;
+    const uint32_t* gv = reinterpret_cast<const uint32_t*>(v) + (int64_t)b * Tctx * pitch + (int64_t)h * words;
+    __syncthreads();
+    stage_rows(sK, gk, Tctx, Tctx, words, pitch, stride);
+    if (!kProbsOnly) stage_rows(sV, gv, Tctx, Tctx, words, pitch, stride);
+    stage_rows(sQ, gq, kRowsPerCta, N - row0, words, pitch, stride);
+    __syncthreads();
+
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      const int rl = warp * kRowsPerWarp + g * kR;  // first local row of the group
+      float s[kR][kKPL];
+#pragma unroll
+      for (int r = 0; r < kR; ++r)
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) s[r][kk] = 0.f;
+      for (int kw = 0; kw < words; ++kw) {
+        float2 qv[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) qv[r] = Word<T>::unpack(sQ[(rl + r) * stride + kw]);
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          const float2 kv = Word<T>::unpack(sK[jc[kk] * stride + kw]);
+#pragma unroll
+          for (int r = 0; r < kR; ++r) dot_step<T>(s[r][kk], qv[r], kv);
+        }
+      }
+      float* pw = sP + (warp * kR) * kPStride;
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int row = row0 + rl + r;
+        float m = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          s[r][kk] *= scale;
+          if (lane + 32 * kk < Tctx) m = fmaxf(m, s[r][kk]);
+        }
+        m = warp_max(m);
+        float e[kKPL], sum = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          e[kk] = (lane + 32 * kk < Tctx) ? expf(s[r][kk] - m) : 0.f;
+          sum += e[kk];
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          const float p = e[kk] * inv;
+          const int j = lane + 32 * kk;
+          if (j < Tctx) {
+            if (kProbsOnly) {
+              if (row < N) probs[((int64_t)bh * N + row) * Tctx + j] = static_cast<T>(p);
+            } else {
+              pw[r * kPStride + j] = p;
+            }
+          }
+          pacc[g][r][kk] += p;
+        }
+        if (!kProbsOnly && lane == 0 && row < N) lse[(int64_t)bh * N + row] = m + logf(sum);
+      }
+      if (kProbsOnly) continue;
+      __syncwarp();
+
+      float oacc[kR][kWPL][E];
+#pragma unroll
+      for (int r = 0; r < kR; ++r)
+#pragma unroll
+        for (int m = 0; m < kWPL; ++m)
+#pragma unroll
+          for (int e2 = 0; e2 < E; ++e2) oacc[r][m][e2] = 0.f;
+      for (int j = 0; j < Tctx; ++j) {
+        float pj[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) pj[r] = pw[r * kPStride + j];
+#pragma unroll
+        for (int m = 0; m < kWPL; ++m) {
+          const int cw = lane + 32 * m;
+          if (cw < words) {
+            const float2 vv = Word<T>::unpack(sV[j * stride + cw]);
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+              oacc[r][m][0] = fmaf(pj[r], vv.x, oacc[r][m][0]);
+              if (E == 2) oacc[r][m][E - 1] = fmaf(pj[r], vv.y, oacc[r][m][E - 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int row = row0 + rl + r;
+        if (row >= N) continue;
+        uint32_t* go = reinterpret_cast<uint32_t*>(o) + ((int64_t)b * N + row) * pitch + (int64_t)h * words;
+#pragma unroll
+        for (int m = 0; m < kWPL; ++m) {
+          const int cw = lane + 32 * m;
+          if (cw < words) go[cw] = Word<T>::pack(oacc[r][m][0], oacc[r][m][E - 1]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (!kProbsOnly && acc != nullptr) {
+    const int b = bh0 / H;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int row = row0 + warp * kRowsPerWarp + g * kR + r;
+        if (row >= N) continue;
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          const int j = lane + 32 * kk;
+          if (j < Tctx) acc[((int64_t)b * N + row) * Tctx + j] = pacc[g][r][kk];
+        }
+      }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------- backward
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cross_attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                      const float* __restrict__ lse, const T* __restrict__ d_o, const float* __restrict__ d_acc,
+                      int64_t d_acc_bstride, T* __restrict__ d_q, float* __restrict__ d_k, float* __restrict__ d_v,
+                      int H, int N, int Tctx, int d, float scale) {
+  constexpr int E = Cfg<T>::E;
+  constexpr int kWPL = Cfg<T>::kWPL;
+  extern __shared__ uint32_t smem[];
+  const int words = d / E;
+  const int stride = odd_stride(words);
+  uint32_t* sK = smem;
+  uint32_t* sV = sK + Tctx * stride;
+  uint32_t* sQ = sV + Tctx * stride;
+  uint32_t* sG = sQ + kRowsPerCta * stride;  // dO tile
+  float* sDS = reinterpret_cast<float*>(sG + kRowsPerCta * stride);
+  float* sPP = sDS + kWarps * kR * kPStride;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int64_t pitch = (int64_t)H * words;
+  const int64_t tok_off = ((int64_t)b * N + row0) * pitch + (int64_t)h * words;
+  const int64_t ctx_off = (int64_t)b * Tctx * pitch + (int64_t)h * words;
+
+  stage_rows(sK, reinterpret_cast<const uint32_t*>(k) + ctx_off, Tctx, Tctx, words, pitch, stride);
+  stage_rows(sV, reinterpret_cast<const uint32_t*>(v) + ctx_off, Tctx, Tctx, words, pitch, stride);
+  stage_rows(sQ, reinterpret_cast<const uint32_t*>(q) + tok_off, kRowsPerCta, N - row0, words, pitch, stride);
+  stage_rows(sG, reinterpret_cast<const uint32_t*>(d_o) + tok_off, kRowsPerCta, N - row0, words, pitch, stride);
+  __syncthreads();
+
+  int jc[kKPL];
+#pragma unroll
+  for (int kk = 0; kk < kKPL; ++kk) jc[kk] = min(lane + 32 * kk, Tctx - 1);
+
+#pragma unroll 1
+  for (int g = 0; g < kGroups; ++g) {
+    const int rl = warp * kRowsPerWarp + g * kR;
+    float s[kR][kKPL], dp[kR][kKPL];
+#pragma unroll
+    for (int r = 0; r < kR; ++r)
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) s[r][kk] = dp[r][kk] = 0.f;
+    for (int kw = 0; kw < words; ++kw) {
+      float2 qv[kR], gv[kR];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        qv[r] = Word<T>::unpack(sQ[(rl + r) * stride + kw]);
+        gv[r] = Word<T>::unpack(sG[(rl + r) * stride + kw]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const float2 kv = Word<T>::unpack(sK[jc[kk] * stride + kw]);
+        const float2 vv = Word<T>::unpack(sV[jc[kk] * stride + kw]);
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          dot_step<T>(s[r][kk], qv[r], kv);
+          dot_step<T>(dp[r][kk], gv[r], vv);
+        }
+      }
+    }
+    float* dsw = sDS + (warp * kR) * kPStride;
+    float* ppw = sPP + (warp * kR) * kPStride;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int row = row0 + rl + r;
+      const bool live = row < N;
+      const float l = live ? lse[(int64_t)bh * N + row] : 0.f;
+      float p[kKPL], dsum = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        const bool ok = live && j < Tctx;
+        p[kk] = ok ? expf(s[r][kk] * scale - l) : 0.f;
+        if (ok && d_acc != nullptr) dp[r][kk] += d_acc[(int64_t)b * d_acc_bstride + (int64_t)row * Tctx + j];
+        dsum += p[kk] * dp[r][kk];
+      }
+      dsum = warp_sum(dsum);
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        if (j < Tctx) {
+          dsw[r * kPStride + j] = p[kk] * (dp[r][kk] - dsum) * scale;
+          ppw[r * kPStride + j] = p[kk];
+        }
+      }
+    }
+    __syncwarp();
+
+    // dQ = scale * dS K   (scale already folded into dsw)
+    float acc[kR][kWPL][E];
+#pragma unroll
+    for (int r = 0; r < kR; ++r)
+#pragma unroll
+      for (int m = 0; m < kWPL; ++m)
+#pragma unroll
+        for (int e2 = 0; e2 < E; ++e2) acc[r][m][e2] = 0.f;
+    for (int j = 0; j < Tctx; ++j) {
+      float dj[kR];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) dj[r] = dsw[r * kPStride + j];
+#pragma unroll
+      for (int m = 0; m < kWPL; ++m) {
+        const int cw = lane + 32 * m;
+        if (cw < words) {
+          const float2 kv = Word<T>::unpack(sK[j * stride + cw]);
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            acc[r][m][0] = fmaf(dj[r], kv.x, acc[r][m][0]);
+            if (E == 2) acc[r][m][E - 1] = fmaf(dj[r], kv.y, acc[r][m][E - 1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int row = row0 + rl + r;
+      if (row >= N) continue;
+      uint32_t* gq = reinterpret_cast<uint32_t*>(d_q) + ((int64_t)b * N + row) * pitch + (int64_t)h * words;
+#pragma unroll
+      for (int m = 0; m < kWPL; ++m) {
+        const int cw = lane + 32 * m;
+        if (cw < words) gq[cw] = Word<T>::pack(acc[r][m][0], acc[r][m][E - 1]);
+      }
+    }
+
+    // optional text-side gradients (never requested by the guidance path; used by the autograd tests)
+    if (d_k != nullptr || d_v != nullptr) {
+      for (int j = 0; j < Tctx; ++j) {
+        float dj[kR], pj[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          dj[r] = dsw[r * kPStride + j];
+          pj[r] = ppw[r * kPStride + j];
+        }
+#pragma unroll
+        for (int m = 0; m < kWPL; ++m) {
+          const int cw = lane + 32 * m;
+          if (cw >= words) continue;
+          float kx = 0.f, ky = 0.f, vx = 0.f, vy = 0.f;
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const float2 qv = Word<T>::unpack(sQ[(rl + r) * stride + cw]);
+            const float2 gv = Word<T>::unpack(sG[(rl + r) * stride + cw]);
+            kx = fmaf(dj[r], qv.x, kx); ky = fmaf(dj[r], qv.y, ky);
+            vx = fmaf(pj[r], gv.x, vx); vy = fmaf(pj[r], gv.y, vy);
+          }
+          const int64_t off = ((int64_t)b * Tctx + j) * (int64_t)H * d + (int64_t)h * d + (int64_t)cw * E;
+          if (d_k != nullptr) { atomicAdd(d_k + off, kx); if (E == 2) atomicAdd(d_k + off + 1, ky); }
+          if (d_v != nullptr) { atomicAdd(d_v + off, vx); if (E == 2) atomicAdd(d_v + off + 1, vy); }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------- launch
+template <typename T>
+int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, void* probs, int B, int H,
+               int N, int Tctx, int d, float scale, cudaStream_t st) {
+  const int words = d / Word<T>::E, stride = words | 1;
+  const bool probs_only = probs != nullptr;
+  size_t smem = (size_t)(2 * Tctx + kRowsPerCta) * stride * 4 + (size_t)kWarps * kR * kPStride * 4;
+  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention: head_dim %d needs %zu B smem", d, smem);
+  const int heads_per_cta = (acc != nullptr && !probs_only) ? H : 1;
+  dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H / heads_per_cta);
+  auto kern = probs_only ? cross_attn_fwd_kernel<T, true> : cross_attn_fwd_kernel<T, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  kern<<<grid, kThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, lse, acc, (T*)probs, H, N, Tctx, d,
+                                    scale, heads_per_cta);
+  return check_launch("cross_attn_fwd_simt");
+}
+
+template <typename T>
+int launch_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
+               int64_t bstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale,
+               cudaStream_t st) {
+  const int words = d / Word<T>::E, stride = words | 1;
+  size_t smem = (size_t)(2 * Tctx + 2 * kRowsPerCta) * stride * 4 + (size_t)2 * kWarps * kR * kPStride * 4;
+  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention bwd: head_dim %d needs %zu B smem", d, smem);
+  dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H);
+  auto kern = cross_attn_bwd_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  kern<<<grid, kThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, lse, (const T*)d_o, d_acc, bstride,
+                                    (T*)d_q, d_k, d_v, H, N, Tctx, d, scale);
+  return check_launch("cross_attn_bwd_simt");
+}
+
+int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, void* probs, int B, int H, int N,
+        int Tctx, int d, float scale, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case GA_F32: return launch_fwd<float>(q, k, v, o, lse, acc, probs, B, H, N, Tctx, d, scale, st);
+    case GA_F16: return launch_fwd<__half>(q, k, v, o, lse, acc, probs, B, H, N, Tctx, d, scale, st);
+    case GA_BF16: return launch_fwd<__nv_bfloat16>(q, k, v, o, lse, acc, probs, B, H, N, Tctx, d, scale, st);
+  }
+  return fail(GA_ERR_BAD_ARG, "unknown dtype %d", dtype);
+}
+
+int bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
+        int64_t bstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale, int dtype,
+        cudaStream_t st) {
+  switch (dtype) {
+    case GA_F32: return launch_bwd<float>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+    case GA_F16: return launch_bwd<__half>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+    case GA_BF16:
+      return launch_bwd<__nv_bfloat16>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+  }
+  return fail(GA_ERR_BAD_ARG, "unknown dtype %d", dtype);
+}
+
+}  // namespace simt
+}  // namespace ga

@@ -1,0 +1,608 @@
+// Guidance tail: everything between the per-layer attention-map accumulators and the scalar guidance loss, plus its
+// gradient back to the accumulators, plus the bit-exact box-mask rasteriser.
+//
+//   K5  rasterize_kernel      helpers.inside_box over a res x res grid          (reference utils/helpers.py:164-173)
+//   K3  phase R of tail_fwd   mean over layers/heads + x100 softmax over tokens (utils/ptp_utils.py:287-288,
+//                                                                                pipeline_guided_attention.py:217-219)
+//   K4  phase S of tail_fwd   3x3 separable Gaussian, reflect padding           (pipeline :251-254, gaussian_smoothing.py)
+//   K6  phase S of tail_fwd   max/argmax, normalise, centre of mass, box losses, loss assembly
+//                                                                               (pipeline :255-296, :390-451; helpers.py:215-277)
+//       tail_bwd_kernel       gradient of all of the above in ONE launch
+//
+// These are HBM/latency-bound integer-and-float streaming kernels (no contraction): the design rules are coalesced
+// rows (one warp per pixel, lanes over the 77 text tokens = one 308-byte row per slice), warp-shuffle reductions, no
+// atomics on data (summation order is fixed, results are run-to-run bit-stable), and ONE launch per direction: the
+// forward's per-token stage runs in the last CTA to finish the per-pixel stage (ticket counter), the backward needs no
+// second stage at all because every per-token scalar it needs was saved by the forward.
+#include "ga_common.cuh"
+
+namespace ga {
+namespace tail {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kKPL = GA_MAX_CTX / 32;  // text tokens per lane
+
+struct AccArgs {
+  const float* ptr[GA_MAX_ACC_SLICES];
+  int32_t slices[GA_MAX_ACC_SLICES];
+  int32_t n;
+};
+struct TokArgs {
+  ga_token_t t[GA_MAX_TOKENS];
+};
+struct BoxArgs {
+  double x[GA_MAX_BOXES], y[GA_MAX_BOXES], w[GA_MAX_BOXES], h[GA_MAX_BOXES];
+};
+
+__device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+// ------------------------------------------------------------------------------------------------ K5 rasteriser
+// float64, round-to-nearest intrinsics (no FMA contraction), the reference's operation order:
+//   ratio = float(res / 1);  x*ratio ...;  off = shrink * width;  x + off <= cx <= (x + width) - off   (inclusive)
+__global__ void rasterize_kernel(BoxArgs a, int n, int res, double shrink, uint8_t* __restrict__ masks) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npix = res * res;
+  if (idx >= n * npix) return;
+  const int i = idx / npix, pix = idx - i * npix, ii = pix / res, jj = pix - ii * res;
+  const double ratio = (double)res;
+  const double x = __dmul_rn(a.x[i], ratio), y = __dmul_rn(a.y[i], ratio);
+  const double w = __dmul_rn(a.w[i], ratio), h = __dmul_rn(a.h[i], ratio);
+  const double off_x = __dmul_rn(shrink, w), off_y = __dmul_rn(shrink, h);
+  const double cx = __dadd_rn((double)jj, 0.5), cy = __dadd_rn((double)ii, 0.5);
+  const bool in_x = cx >= __dadd_rn(x, off_x) && cx <= __dsub_rn(__dadd_rn(x, w), off_x);
+  const bool in_y = cy >= __dadd_rn(y, off_y) && cy <= __dsub_rn(__dadd_rn(y, h), off_y);
+  masks[idx] = (in_x && in_y) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------- smoothing helpers
+__device__ __forceinline__ float smooth_at(const float* img, int y, int x, int res, const float* w) {
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int yy = reflect(y + a - 1, res);
+    float rowacc = 0.f;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) rowacc = fmaf(w[b], img[yy * res + reflect(x + b - 1, res)], rowacc);
+    acc = fmaf(w[a], rowacc, acc);
+  }
+  return acc;
+}
+
+// adjoint tap of the 1-D reflect-padded filter: weight with which output position `src` reads input position `dst`
+__device__ __forceinline__ float adjoint_tap(int dst, int src, int n, const float* w) {
+  float m = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (reflect(src + a - 1, n) == dst) m += w[a];
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------ phase S (per token)
+// One warp per tracked token.  `img` is a per-warp shared-memory staging buffer of res*res floats.
+__device__ void token_stage(const ga_tail_params_t& p, const ga_token_t& tk, int t, const float* attn_text,
+                            const uint8_t* masks, const float* weights, float* img, float* smoothed, float* stats,
+                            int32_t* argmax) {
+  const int lane = threadIdx.x & 31;
+  const int res = p.res, npix = res * res, tp = p.last - p.first;
+  for (int pix = lane; pix < npix; pix += 32) img[pix] = __ldcg(attn_text + (int64_t)pix * tp + tk.column);
+  __syncwarp();
+  const bool is_box = tk.kind == GA_TOKEN_BOX && tk.box >= 0;
+  const uint8_t* mask = is_box ? masks + (int64_t)tk.box * npix : nullptr;
+  const float* wts = (is_box && p.strict && weights != nullptr) ? weights + (int64_t)tk.box * npix : nullptr;
+  float* sm = smoothed + (int64_t)t * npix;
+
+  float vmax = -INFINITY, sum = 0.f;
+  int imax = 0x7fffffff, nin = 0;
+  for (int pix = lane; pix < npix; pix += 32) {
+    const int y = pix / res, x = pix - y * res;
+    const float s = p.smooth ? smooth_at(img, y, x, res, p.w1d) : img[pix];
+    sm[pix] = s;
+    if (s > vmax) { vmax = s; imax = pix; }
+    sum += s;
+    if (is_box) nin += mask[pix];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+    if (ov > vmax || (ov == vmax && oi < imax)) { vmax = ov; imax = oi; }
+    nin += __shfl_xor_sync(0xffffffffu, nin, o);
+  }
+  sum = warp_sum(sum);
+
+  const float at_most = nin > 0 ? 1.f / (float)nin : 0.f;
+  float col = 0.f, row = 0.f, sin_ = 0.f, sout = 0.f, hin = 0.f, hout = 0.f;
+  for (int pix = lane; pix < npix; pix += 32) {
+    const int y = pix / res, x = pix - y * res;
+    const float pr = sm[pix] / sum;
+    col = fmaf((float)x + 0.5f, pr, col);
+    row = fmaf((float)y + 0.5f, pr, row);
+    if (is_box) {
+      const bool in = mask[pix] != 0;
+      if (p.strict) {
+        const float w = wts != nullptr ? wts[pix] : 1.f;
+        if (in) {
+          const float gap = at_most - pr;
+          if (gap > 0.f) { sin_ = fmaf(w * 2.f, gap, sin_); hin = fmaf(w, pr, hin); }
+        } else if (pr > 0.f) {
+          sout = fmaf(w, pr, sout);
+          hout = fmaf(w, pr, hout);
+        }
+      } else {
+        if (in) sin_ += pr; else sout += pr;
+      }
+    }
+  }
+  col = warp_sum(col); row = warp_sum(row); sin_ = warp_sum(sin_); sout = warp_sum(sout);
+  hin = warp_sum(hin); hout = warp_sum(hout);
+
+  if (lane == 0) {
+    const float inside = is_box ? (p.strict ? sin_ : 1.f - sin_) : 0.f;
+    const float outside = is_box ? sout : 0.f;
+    const float denom = (float)(res - 1);
+    const float center = fabsf(col - tk.target_x) / denom + 4.f * fabsf(row - tk.target_y) / denom;
+    float scaled = 0.f, unscaled = 0.f;
+    if (tk.kind == GA_TOKEN_COOR) {
+      scaled = unscaled = center;
+    } else if (tk.kind == GA_TOKEN_BOX) {
+      scaled = p.inside_scale * inside + p.outside_scale * outside;
+      if (tk.center_weight > 0.f) scaled += tk.center_weight * center;
+      unscaled = inside + outside;
+    }
+    float* st = stats + (int64_t)t * GA_STATS;
+    st[GA_STAT_MAX] = vmax; st[GA_STAT_SUM] = sum; st[GA_STAT_COL] = col; st[GA_STAT_ROW] = row;
+    st[GA_STAT_INSIDE] = inside; st[GA_STAT_OUTSIDE] = outside; st[GA_STAT_SCALED] = scaled;
+    st[GA_STAT_UNSCALED] = unscaled; st[GA_STAT_HINGE_IN] = hin; st[GA_STAT_HINGE_OUT] = hout;
+    st[GA_STAT_NINSIDE] = (float)nin; st[GA_STAT_CENTER] = center;
+    argmax[t] = imax;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------- forward
+// grid = ceil(res^2 / 8) CTAs x 256 threads.  Phase R: one warp per pixel.  The last CTA to finish runs phase S.
+__global__ void __launch_bounds__(kThreads)
+tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
+                const float* __restrict__ weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
+                float* total, unsigned int* ticket) {
+  extern __shared__ float simg[];  // kWarps * res*res floats (phase S only)
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npix = p.res * p.res, T = p.n_ctx, tp = p.last - p.first;
+  const int pix = blockIdx.x * kWarps + warp;
+  if (pix < npix) {
+    float v[kKPL];
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk) v[kk] = 0.f;
+    for (int a = 0; a < acc.n; ++a) {
+      const float* base = acc.ptr[a] + (int64_t)pix * T;
+      for (int s = 0; s < acc.slices[a]; ++s) {
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk) {
+          const int j = lane + 32 * kk;
+          if (j < T) v[kk] += __ldg(base + (int64_t)s * npix * T + j);
+        }
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int j = lane + 32 * kk;
+      v[kk] = (v[kk] * p.inv_count) * p.temperature;
+      if (j >= p.first && j < p.last) m = fmaxf(m, v[kk]);
+    }
+    m = warp_max(m);
+    float e[kKPL], sum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int j = lane + 32 * kk;
+      e[kk] = (j >= p.first && j < p.last) ? expf(v[kk] - m) : 0.f;
+      sum += e[kk];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int j = lane + 32 * kk;
+      if (j >= p.first && j < p.last) attn_text[(int64_t)pix * tp + (j - p.first)] = e[kk] / sum;
+    }
+  }
+
+  // ---- hand-over to phase S: the last CTA to take a ticket sees every other CTA's attn_text
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tkt = atomicAdd(ticket, 1u);
+    is_last = (tkt == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  for (int t0 = 0; t0 < p.n_tokens; t0 += kWarps) {
+    const int t = t0 + warp;
+    if (t < p.n_tokens)
+      token_stage(p, toks.t[t], t, attn_text, masks, weights, simg + (size_t)warp * npix, smoothed, stats, argmax);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = p.custom_total;
+    for (int t = 0; t < p.n_tokens; ++t) tot += toks.t[t].group_weight * stats[(int64_t)t * GA_STATS + GA_STAT_SCALED];
+    total[0] = tot;
+    *ticket = 0u;  // leave the workspace zero for the next launch
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- backward
+// One launch, one warp per pixel.  Lane t (< n_tokens) owns tracked token t: it turns the upstream gradients and the
+// forward's saved per-token scalars into d loss / d smoothed-map at the 3x3 neighbourhood of this pixel, pulls it
+// through the adjoint of the reflect-padded filter, and hands the result to the lane that owns the token's column;
+// then the warp does the x100-softmax backward over the tokens of this pixel.
+struct TokenGrad {
+  float g_col, g_row, g_in, g_out, g_max, g_sum, dp_mean, inv_sum, at_most;
+  int argmax, box, strict_box;
+};
+
+__device__ __forceinline__ TokenGrad make_token_grad(const ga_tail_params_t& p, const ga_token_t& tk,
+                                                     const float* st, int amax, float g_total, const float* gs) {
+  TokenGrad g;
+  const float denom = (float)(p.res - 1);
+  const bool is_box = tk.kind == GA_TOKEN_BOX && tk.box >= 0;
+  const float g_scaled = g_total * tk.group_weight + (gs ? gs[GA_STAT_SCALED] : 0.f);
+  const float g_unscaled = gs ? gs[GA_STAT_UNSCALED] : 0.f;
+  float g_center = gs ? gs[GA_STAT_CENTER] : 0.f;
+  g.g_in = gs ? gs[GA_STAT_INSIDE] : 0.f;
+  g.g_out = gs ? gs[GA_STAT_OUTSIDE] : 0.f;
+  if (tk.kind == GA_TOKEN_COOR) {
+    g_center += g_scaled + g_unscaled;
+  } else if (tk.kind == GA_TOKEN_BOX) {
+    g.g_in += g_scaled * p.inside_scale + g_unscaled;
+    g.g_out += g_scaled * p.outside_scale + g_unscaled;
+    if (tk.center_weight > 0.f) g_center += g_scaled * tk.center_weight;
+  }
+  if (!is_box) g.g_in = g.g_out = 0.f;
+  const float dc = st[GA_STAT_COL] - tk.target_x, dr = st[GA_STAT_ROW] - tk.target_y;
+  const float sgn_c = dc > 0.f ? 1.f : (dc < 0.f ? -1.f : 0.f);
+  const float sgn_r = dr > 0.f ? 1.f : (dr < 0.f ? -1.f : 0.f);
+  g.g_col = (gs ? gs[GA_STAT_COL] : 0.f) + g_center * sgn_c / denom;
+  g.g_row = (gs ? gs[GA_STAT_ROW] : 0.f) + g_center * 4.f * sgn_r / denom;
+  g.g_max = gs ? gs[GA_STAT_MAX] : 0.f;
+  g.g_sum = gs ? gs[GA_STAT_SUM] : 0.f;
+  g.inv_sum = 1.f / st[GA_STAT_SUM];
+  g.at_most = st[GA_STAT_NINSIDE] > 0.f ? 1.f / st[GA_STAT_NINSIDE] : 0.f;
+  g.argmax = amax;
+  g.box = is_box ? tk.box : -1;
+  g.strict_box = (is_box && p.strict) ? 1 : 0;
+  // sum over pixels of dp * p, in closed form from the saved statistics
+  g.dp_mean = g.g_col * st[GA_STAT_COL] + g.g_row * st[GA_STAT_ROW];
+  if (is_box) {
+    if (p.strict) g.dp_mean += -2.f * g.g_in * st[GA_STAT_HINGE_IN] + g.g_out * st[GA_STAT_HINGE_OUT];
+    else g.dp_mean += -g.g_in * (1.f - st[GA_STAT_INSIDE]) + g.g_out * st[GA_STAT_OUTSIDE];
+  }
+  return g;
+}
+
+// d loss / d smoothed[pix] for one token
+__device__ __forceinline__ float dsmoothed_at(const TokenGrad& g, int pix, int res, const uint8_t* masks,
+                                              const float* weights, const float* sm) {
+  const int npix = res * res;
+  const int y = pix / res, x = pix - y * res;
+  float dp = g.g_col * ((float)x + 0.5f) + g.g_row * ((float)y + 0.5f);
+  if (g.box >= 0) {
+    const bool in = masks[(int64_t)g.box * npix + pix] != 0;
+    if (g.strict_box) {
+      const float w = weights != nullptr ? weights[(int64_t)g.box * npix + pix] : 1.f;
+      const float pr = sm[pix] * g.inv_sum;
+      if (in) { if (g.at_most - pr > 0.f) dp -= 2.f * w * g.g_in; }
+      else if (pr > 0.f) dp += w * g.g_out;
+    } else {
+      dp += in ? -g.g_in : g.g_out;
+    }
+  }
+  float ds = (dp - g.dp_mean) * g.inv_sum + g.g_sum;
+  if (pix == g.argmax) ds += g.g_max;
+  return ds;
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks, const float* __restrict__ weights,
+                const float* __restrict__ attn_text, const float* __restrict__ smoothed,
+                const float* __restrict__ stats, const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
+                const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int res = p.res, npix = res * res, T = p.n_ctx, tp = p.last - p.first;
+  const int pix = blockIdx.x * kWarps + warp;
+  if (pix >= npix) return;
+  const int y = pix / res, x = pix - y * res;
+
+  // lane t: gradient of the loss w.r.t. the raw (pre-smoothing) map of token t at this pixel
+  float dimg = 0.f;
+  int my_col = -1;
+  if (lane < p.n_tokens) {
+    const ga_token_t& tk = toks.t[lane];
+    my_col = tk.column;
+    const float gt = g_total != nullptr ? g_total[0] : 0.f;
+    const TokenGrad g = make_token_grad(p, tk, stats + (int64_t)lane * GA_STATS, argmax[lane], gt,
+                                        g_stats != nullptr ? g_stats + (int64_t)lane * GA_STATS : nullptr);
+    const float* sm = smoothed + (int64_t)lane * npix;
+    if (p.smooth) {
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= res) continue;
+        const float my = adjoint_tap(y, yy, res, p.w1d);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= res) continue;
+          const float mx = adjoint_tap(x, xx, res, p.w1d);
+          dimg = fmaf(my * mx, dsmoothed_at(g, yy * res + xx, res, masks, weights, sm), dimg);
+        }
+      }
+    } else {
+      dimg = dsmoothed_at(g, pix, res, masks, weights, sm);
+    }
+  }
+  // tokens beyond 32 lanes: GA_MAX_TOKENS (24) < 32, so one pass is enough
+
+  // softmax backward over the text tokens of this pixel
+  float a[kKPL], da[kKPL], dot = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < kKPL; ++kk) {
+    const int j = lane + 32 * kk;
+    const bool live = j >= p.first && j < p.last;
+    a[kk] = live ? attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+    da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+  }
+  for (int t = 0; t < p.n_tokens; ++t) {
+    const float gv = __shfl_sync(0xffffffffu, dimg, t);
+    const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk)
+      if (j == lane + 32 * kk) da[kk] += gv;
+  }
+#pragma unroll
+  for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
+  dot = warp_sum(dot);
+  const float k = p.temperature * p.inv_count;
+#pragma unroll
+  for (int kk = 0; kk < kKPL; ++kk) {
+    const int j = lane + 32 * kk;
+    if (j < T) d_abar[(int64_t)pix * T + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
+  }
+}
+
+// --------------------------------------------------------------------------------------- stand-alone stages
+__global__ void smooth_fwd_kernel(const float* __restrict__ maps, float* __restrict__ out, int n, int res, float w0,
+                                  float w1, float w2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x, npix = res * res;
+  if (idx >= n * npix) return;
+  const int i = idx / npix, pix = idx - i * npix, y = pix / res, x = pix - y * res;
+  const float w[3] = {w0, w1, w2};
+  out[idx] = smooth_at(maps + (int64_t)i * npix, y, x, res, w);
+}
+
+__global__ void smooth_bwd_kernel(const float* __restrict__ g_out, float* __restrict__ g_maps, int n, int res, float w0,
+                                  float w1, float w2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x, npix = res * res;
+  if (idx >= n * npix) return;
+  const int i = idx / npix, pix = idx - i * npix, y = pix / res, x = pix - y * res;
+  const float w[3] = {w0, w1, w2};
+  const float* g = g_out + (int64_t)i * npix;
+  float acc = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= res) continue;
+    const float my = adjoint_tap(y, yy, res, w);
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= res) continue;
+      acc = fmaf(my * adjoint_tap(x, xx, res, w), g[yy * res + xx], acc);
+    }
+  }
+  g_maps[idx] = acc;
+}
+
+// one CTA; out2 = (inside, outside)
+__global__ void box_loss_fwd_kernel(const float* __restrict__ pmap, const uint8_t* __restrict__ mask,
+                                    const float* __restrict__ weights, int res, int strict, float* out2) {
+  __shared__ float red[3][kWarps];
+  const int npix = res * res, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float nin = 0.f;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) nin += mask[pix];
+  nin = warp_sum(nin);
+  if (lane == 0) red[0][warp] = nin;
+  __syncthreads();
+  nin = 0.f;
+  for (int w = 0; w < kWarps; ++w) nin += red[0][w];
+  const float at_most = nin > 0.f ? 1.f / nin : 0.f;
+  float sin_ = 0.f, sout = 0.f;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    const float pr = pmap[pix];
+    const bool in = mask[pix] != 0;
+    if (strict) {
+      const float w = weights != nullptr ? weights[pix] : 1.f;
+      if (in) { const float gap = at_most - pr; if (gap > 0.f) sin_ = fmaf(2.f * w, gap, sin_); }
+      else if (pr > 0.f) sout = fmaf(w, pr, sout);
+    } else {
+      if (in) sin_ += pr; else sout += pr;
+    }
+  }
+  sin_ = warp_sum(sin_); sout = warp_sum(sout);
+  if (lane == 0) { red[1][warp] = sin_; red[2][warp] = sout; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < kWarps; ++w) { a += red[1][w]; b += red[2][w]; }
+    out2[0] = strict ? a : 1.f - a;
+    out2[1] = b;
+  }
+}
+
+__global__ void box_loss_bwd_kernel(const float* __restrict__ pmap, const uint8_t* __restrict__ mask,
+                                    const float* __restrict__ weights, int res, int strict,
+                                    const float* __restrict__ g_out2, float* __restrict__ g_p) {
+  __shared__ float red[kWarps];
+  const int npix = res * res, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float nin = 0.f;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) nin += mask[pix];
+  nin = warp_sum(nin);
+  if (lane == 0) red[warp] = nin;
+  __syncthreads();
+  nin = 0.f;
+  for (int w = 0; w < kWarps; ++w) nin += red[w];
+  const float at_most = nin > 0.f ? 1.f / nin : 0.f;
+  const float gi = g_out2[0], go = g_out2[1];
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    const bool in = mask[pix] != 0;
+    float g = 0.f;
+    if (strict) {
+      const float w = weights != nullptr ? weights[pix] : 1.f;
+      const float pr = pmap[pix];
+      if (in) { if (at_most - pr > 0.f) g = -2.f * w * gi; }
+      else if (pr > 0.f) g = w * go;
+    } else {
+      g = in ? -gi : go;
+    }
+    g_p[pix] = g;
+  }
+}
+
+}  // namespace tail
+}  // namespace ga
+
+// =============================================================================================== C ABI wrappers
+using namespace ga;
+
+static int check_tail_params(const ga_tail_params_t* p, const ga_token_t* toks) {
+  GA_CHECK_ARG(p != nullptr, "params_host is NULL");
+  GA_CHECK_ARG(p->res >= 2 && p->res <= 256, "res %d out of range [2, 256]", p->res);
+  GA_CHECK_ARG(p->n_ctx >= 1 && p->n_ctx <= GA_MAX_CTX, "n_ctx %d out of range [1, %d]", p->n_ctx, GA_MAX_CTX);
+  GA_CHECK_ARG(p->first >= 0 && p->first < p->last && p->last <= p->n_ctx, "bad token window [%d, %d) for n_ctx %d",
+               p->first, p->last, p->n_ctx);
+  GA_CHECK_ARG(p->n_tokens >= 0 && p->n_tokens <= GA_MAX_TOKENS, "n_tokens %d out of range [0, %d]", p->n_tokens,
+               GA_MAX_TOKENS);
+  GA_CHECK_ARG(p->n_tokens == 0 || toks != nullptr, "tokens_host is NULL");
+  for (int t = 0; t < p->n_tokens; ++t) {
+    GA_CHECK_ARG(toks[t].column >= 0 && toks[t].column < p->last - p->first,
+                 "token %d: column %d outside the renormalised window of %d tokens", t, toks[t].column,
+                 p->last - p->first);
+    GA_CHECK_ARG(toks[t].kind >= GA_TOKEN_COOR && toks[t].kind <= GA_TOKEN_KEYWORD, "token %d: bad kind %d", t,
+                 toks[t].kind);
+  }
+  return GA_OK;
+}
+
+extern "C" int ga_rasterize_boxes(const double* boxes_host, int n_boxes, int res, double shrink, uint8_t* masks,
+                                  ga_stream_t stream) {
+  GA_CHECK_ARG(n_boxes >= 0 && res >= 1 && res <= 4096, "bad n_boxes %d / res %d", n_boxes, res);
+  if (n_boxes == 0) return GA_OK;
+  GA_CHECK_ARG(boxes_host != nullptr && masks != nullptr, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int b0 = 0; b0 < n_boxes; b0 += GA_MAX_BOXES) {
+    const int n = n_boxes - b0 < GA_MAX_BOXES ? n_boxes - b0 : GA_MAX_BOXES;
+    tail::BoxArgs a;
+    for (int i = 0; i < n; ++i) {
+      a.x[i] = boxes_host[4 * (b0 + i) + 0]; a.y[i] = boxes_host[4 * (b0 + i) + 1];
+      a.w[i] = boxes_host[4 * (b0 + i) + 2]; a.h[i] = boxes_host[4 * (b0 + i) + 3];
+    }
+    const int total = n * res * res;
+    tail::rasterize_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, n, res, shrink, masks + (size_t)b0 * res * res);
+    int rc = check_launch("rasterize_boxes");
+    if (rc != GA_OK) return rc;
+  }
+  return GA_OK;
+}
+
+extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t* slices_host, int n_acc,
+                                    const ga_tail_params_t* params_host, const ga_token_t* tokens_host,
+                                    const uint8_t* masks, const float* weights, float* attn_text, float* smoothed,
+                                    float* stats, int32_t* argmax, float* total, uint32_t* ticket,
+                                    ga_stream_t stream) {
+  int rc = check_tail_params(params_host, tokens_host);
+  if (rc != GA_OK) return rc;
+  GA_CHECK_ARG(n_acc >= 1 && n_acc <= GA_MAX_ACC_SLICES, "n_acc %d out of range [1, %d]", n_acc, GA_MAX_ACC_SLICES);
+  GA_CHECK_ARG(acc_host != nullptr && slices_host != nullptr && attn_text != nullptr && total != nullptr,
+               "NULL pointer");
+  const ga_tail_params_t& p = *params_host;
+  GA_CHECK_ARG(p.n_tokens == 0 || (smoothed != nullptr && stats != nullptr && argmax != nullptr), "NULL output");
+  tail::AccArgs acc;
+  acc.n = n_acc;
+  for (int i = 0; i < n_acc; ++i) {
+    GA_CHECK_ARG(acc_host[i] != nullptr && slices_host[i] >= 1, "accumulator %d is NULL or empty", i);
+    acc.ptr[i] = acc_host[i];
+    acc.slices[i] = slices_host[i];
+  }
+  tail::TokArgs toks;
+  for (int t = 0; t < p.n_tokens; ++t) {
+    toks.t[t] = tokens_host[t];
+    GA_CHECK_ARG(toks.t[t].kind != GA_TOKEN_BOX || toks.t[t].box < 0 || masks != nullptr, "BOX token without masks");
+  }
+  GA_CHECK_ARG(ticket != nullptr, "ticket workspace is NULL");
+  const int npix = p.res * p.res;
+  const size_t smem = (size_t)tail::kWarps * npix * sizeof(float);
+  if (smem > 200 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d too large for the fused tail", p.res);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  const int grid = (npix + tail::kWarps - 1) / tail::kWarps;
+  tail::tail_fwd_kernel<<<grid, tail::kThreads, smem, st>>>(acc, p, toks, masks, weights, attn_text, smoothed, stats,
+                                                            argmax, total, reinterpret_cast<unsigned int*>(ticket));
+  return check_launch("guidance_tail_fwd");
+}
+
+extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* tokens_host,
+                                    const uint8_t* masks, const float* weights, const float* attn_text,
+                                    const float* smoothed, const float* stats, const int32_t* argmax,
+                                    const float* g_total, const float* g_stats, const float* g_attn_text,
+                                    float* d_abar, ga_stream_t stream) {
+  int rc = check_tail_params(params_host, tokens_host);
+  if (rc != GA_OK) return rc;
+  const ga_tail_params_t& p = *params_host;
+  GA_CHECK_ARG(attn_text != nullptr && d_abar != nullptr, "NULL pointer");
+  GA_CHECK_ARG(p.n_tokens == 0 || (smoothed != nullptr && stats != nullptr && argmax != nullptr), "NULL saved tensor");
+  tail::TokArgs toks;
+  for (int t = 0; t < p.n_tokens; ++t) toks.t[t] = tokens_host[t];
+  const int npix = p.res * p.res;
+  const int grid = (npix + tail::kWarps - 1) / tail::kWarps;
+  tail::tail_bwd_kernel<<<grid, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar);
+  return check_launch("guidance_tail_bwd");
+}
+
+extern "C" int ga_smooth_fwd(const float* maps, float* out, int n_maps, int res, const float* w1d_host,
+                             ga_stream_t stream) {
+  GA_CHECK_ARG(maps && out && w1d_host && n_maps >= 0 && res >= 2, "bad argument");
+  const int total = n_maps * res * res;
+  if (total == 0) return GA_OK;
+  tail::smooth_fwd_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      maps, out, n_maps, res, w1d_host[0], w1d_host[1], w1d_host[2]);
+  return check_launch("smooth_fwd");
+}
+
+extern "C" int ga_smooth_bwd(const float* g_out, float* g_maps, int n_maps, int res, const float* w1d_host,
+                             ga_stream_t stream) {
+  GA_CHECK_ARG(g_out && g_maps && w1d_host && n_maps >= 0 && res >= 2, "bad argument");
+  const int total = n_maps * res * res;
+  if (total == 0) return GA_OK;
+  tail::smooth_bwd_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g_out, g_maps, n_maps, res, w1d_host[0], w1d_host[1], w1d_host[2]);
+  return check_launch("smooth_bwd");
+}
+
+extern "C" int ga_box_loss_fwd(const float* p, const uint8_t* mask, const float* weights, int res, int strict,
+                               float* out2, ga_stream_t stream) {
+  GA_CHECK_ARG(p && mask && out2 && res >= 1, "bad argument");
+  tail::box_loss_fwd_kernel<<<1, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, mask, weights, res, strict,
+                                                                                        out2);
+  return check_launch("box_loss_fwd");
+}
+
+extern "C" int ga_box_loss_bwd(const float* p, const uint8_t* mask, const float* weights, int res, int strict,
+                               const float* g_out2, float* g_p, ga_stream_t stream) {
+  GA_CHECK_ARG(p && mask && g_out2 && g_p && res >= 1, "bad argument");
+  tail::box_loss_bwd_kernel<<<1, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, mask, weights, res, strict,
+                                                                                        g_out2, g_p);
+  return check_launch("box_loss_bwd");
+}

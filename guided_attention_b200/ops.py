@@ -1,0 +1,405 @@
+"""PyTorch-facing operators over the C ABI (`include/guided_attn.h`): `torch.autograd.Function` wrappers whose forward and
+backward are single launches of the hand-written sm_100a kernels.  PyTorch is plumbing here (device memory, streams,
+autograd graph); no op in this file has a PyTorch or CPU implementation -- a missing library or a CPU tensor is an
+error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi as abi
+
+# Every launch made through this module is counted (bench.py reports it as `gpu_launches`).
+launch_counts = {}
+
+
+def _count(name, n=1):
+    launch_counts[name] = launch_counts.get(name, 0) + n
+
+
+def total_launches() -> int:
+    return sum(launch_counts.values())
+
+
+def reset_launch_counts():
+    launch_counts.clear()
+
+
+class LaunchProfiler:
+    """Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline leg).  Off by default."""
+
+    def __init__(self):
+        self.records = []   # (kernel, shape key, algorithmic bytes, start event, end event)
+
+    class _Span:
+        def __init__(self, prof, name, key, nbytes, device):
+            self.prof, self.name, self.key, self.nbytes, self.device = prof, name, key, nbytes, device
+
+        def __enter__(self):
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+            return self
+
+        def __exit__(self, *exc):
+            self.end.record(torch.cuda.current_stream(self.device))
+            self.prof.records.append((self.name, self.key, self.nbytes, self.start, self.end))
+            return False
+
+    def span(self, name, key, nbytes, device):
+        return LaunchProfiler._Span(self, name, key, nbytes, device)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, key, nbytes, s, e in self.records:
+            d = out.setdefault((name, key), {"launches": 0, "ms": 0.0, "bytes_per_launch": nbytes})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+        return out
+
+
+class _NoSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+profiler: Optional[LaunchProfiler] = None
+_NOSPAN = _NoSpan()
+
+
+def _span(name, key, nbytes, device):
+    return profiler.span(name, key, nbytes, device) if profiler is not None else _NOSPAN
+
+
+def attn_fwd_bytes(B, H, N, T, d, esize, with_acc):
+    """Algorithmic HBM bytes of one K1 launch: read Q, K, V, write O, row LSE, optional accumulator."""
+    D = H * d
+    return 2 * B * N * D * esize + 2 * B * T * D * esize + B * H * N * 4 + (B * N * T * 4 if with_acc else 0)
+
+
+def attn_bwd_bytes(B, H, N, T, d, esize, with_dacc):
+    """One K2 launch: read Q, dO, K, V, LSE (+ the (N, T) map gradient), write dQ."""
+    D = H * d
+    return 3 * B * N * D * esize + 2 * B * T * D * esize + B * H * N * 4 + (N * T * 4 if with_dacc else 0)
+
+
+_DTYPES = {torch.float32: abi.GA_F32, torch.float16: abi.GA_F16, torch.bfloat16: abi.GA_BF16}
+default_impl = abi.GA_IMPL_AUTO
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise abi.GuidedAttnLibraryError(
+                "guided_attention_b200 ops run on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# ======================================================================================== K1 / K2 cross-attention
+class _CrossAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, want_acc: bool, impl: int):
+        _need_cuda(q, k, v)
+        lib = abi.load()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        B, N, Cdim = q.shape
+        T = k.shape[1]
+        d = Cdim // heads
+        if k.shape[0] != B or k.shape[2] != Cdim or v.shape != k.shape:
+            raise ValueError(f"shape mismatch q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
+        o = torch.empty_like(q)
+        lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+        acc = torch.empty((B, N, T), dtype=torch.float32, device=q.device) if want_acc else None
+        nbytes = attn_fwd_bytes(B, heads, N, T, d, q.element_size(), want_acc)
+        with torch.cuda.device(q.device), _span("cross_attn_fwd", (B, heads, N, T, d, str(q.dtype), want_acc), nbytes,
+                                                q.device):
+            abi.check(lib.ga_cross_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(acc), B, heads, N, T, d,
+                                            float(scale), _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_fwd")
+        _count("cross_attn_fwd")
+        ctx.save_for_backward(q, k, v, lse)
+        ctx.meta = (heads, float(scale), impl)
+        if acc is None:
+            return o, None
+        return o, acc
+
+    @staticmethod
+    def backward(ctx, d_o, d_acc):
+        q, k, v, lse = ctx.saved_tensors
+        heads, scale, impl = ctx.meta
+        lib = abi.load()
+        B, N, Cdim = q.shape
+        T = k.shape[1]
+        d = Cdim // heads
+        d_o = torch.zeros_like(q) if d_o is None else d_o.contiguous()
+        bstride = 0
+        if d_acc is not None:
+            if d_acc.dtype != torch.float32:
+                d_acc = d_acc.float()
+            if d_acc.dim() == 3 and d_acc.stride(0) == 0 and d_acc.stride(1) == T and d_acc.stride(2) == 1:
+                bstride = 0                      # one (N, T) slice broadcast over the batch (what the tail returns)
+            else:
+                d_acc = d_acc.contiguous()
+                bstride = N * T
+        d_q = torch.empty_like(q)
+        need_k, need_v = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_k = torch.zeros(k.shape, dtype=torch.float32, device=q.device) if need_k else None
+        d_v = torch.zeros(v.shape, dtype=torch.float32, device=q.device) if need_v else None
+        nbytes = attn_bwd_bytes(B, heads, N, T, d, q.element_size(), d_acc is not None)
+        with torch.cuda.device(q.device), _span("cross_attn_bwd", (B, heads, N, T, d, str(q.dtype), d_acc is not None),
+                                                nbytes, q.device):
+            abi.check(lib.ga_cross_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(lse), _ptr(d_o), _ptr(d_acc), bstride,
+                                            _ptr(d_q), _ptr(d_k), _ptr(d_v), B, heads, N, T, d, scale,
+                                            _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_bwd")
+        _count("cross_attn_bwd")
+        return (d_q, d_k.to(k.dtype) if need_k else None, d_v.to(v.dtype) if need_v else None, None, None, None, None)
+
+
+def cross_attention(q, k, v, heads: int, scale: float, want_acc: bool = False, impl: Optional[int] = None):
+    """O = softmax(scale Q K^T) V per head, q (B, N, H*d), k/v (B, T, H*d).  Returns (o, acc) with
+    acc (B, N, T) fp32 = sum over heads of the probabilities (None unless `want_acc`).  Differentiable in q (and k, v
+    when they require grad) through BOTH outputs."""
+    return _CrossAttnFn.apply(q, k, v, heads, scale, want_acc, default_impl if impl is None else impl)
+
+
+def attention_probs(q, k, heads: int, scale: float):
+    """Materialised P (B*H, N, T), rows ordered b*H + h like the reference's stored maps.  Not differentiable; exists for
+    API compatibility (`AttentionStore.get_average_attention`) and for tests."""
+    _need_cuda(q, k)
+    lib = abi.load()
+    q, k = q.contiguous(), k.contiguous()
+    B, N, Cdim = q.shape
+    T = k.shape[1]
+    p = torch.empty((B * heads, N, T), dtype=q.dtype, device=q.device)
+    with torch.cuda.device(q.device):
+        abi.check(lib.ga_attn_probs(_ptr(q), _ptr(k), _ptr(p), B, heads, N, T, Cdim // heads, float(scale),
+                                    _DTYPES[q.dtype], _stream(q)), "ga_attn_probs")
+    _count("attn_probs")
+    return p
+
+
+# ============================================================================================== K5 rasteriser
+def rasterize_boxes(boxes: Sequence[Sequence[float]], res: int, shrink: float, device) -> torch.Tensor:
+    """(n, res, res) uint8 masks of `helpers.inside_box` for unit-square boxes (x, y, w, h); bit-exact vs the host."""
+    lib = abi.load()
+    n = len(boxes)
+    masks = torch.empty((n, res, res), dtype=torch.uint8, device=device)
+    _need_cuda(masks)
+    if n == 0:
+        return masks
+    arr = (C.c_double * (4 * n))(*[float(c) for b in boxes for c in b])
+    with torch.cuda.device(masks.device):
+        abi.check(lib.ga_rasterize_boxes(arr, n, res, float(shrink), _ptr(masks), _stream(masks)), "ga_rasterize_boxes")
+    _count("rasterize_boxes", (n + abi.GA_MAX_BOXES - 1) // abi.GA_MAX_BOXES)
+    return masks
+
+
+# ================================================================================================ guidance tail
+def gaussian_taps(kernel_size: int = 3, sigma: float = 0.5) -> List[float]:
+    """Separable taps equivalent to the reference's normalised 2-D kernel (utils/gaussian_smoothing.py:37-43): the 2-D
+    kernel is outer(g, g) / sum, i.e. outer(w, w) with w = g / sum(g); g uses the reference's exponent
+    exp(-((k - mean) / (2 sigma))^2) evaluated in fp32 like the reference."""
+    if kernel_size != 3:
+        raise NotImplementedError("the reference pads by one pixel (pipeline_guided_attention.py:253): only "
+                                  "kernel_size=3 keeps the map size")
+    ax = torch.arange(kernel_size, dtype=torch.float32)
+    mean = (kernel_size - 1) / 2
+    g = 1 / (sigma * math.sqrt(2 * math.pi)) * torch.exp(-((ax - mean) / (2 * sigma)) ** 2)
+    w = g.double() / g.double().sum()
+    return [float(x) for x in w]
+
+
+@dataclass
+class TailSpec:
+    """Everything the tail kernels need besides the accumulators: built once per (prompt, res) on the host."""
+    res: int
+    n_ctx: int
+    first: int
+    last: int
+    token_indices: List[int]
+    kinds: List[int]
+    groups: List[object]                 # sub-prompt of each token
+    tokens: object = None                # (GaToken * n)
+    params: abi.GaTailParams = None
+    masks: Optional[torch.Tensor] = None   # (n_boxes, res, res) uint8, device
+    weights: Optional[torch.Tensor] = None  # (n_boxes, res, res) fp32, device (strict only)
+    n_inside: List[int] = field(default_factory=list)
+
+
+_tickets = {}
+
+
+def _ticket(device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _tickets:
+        _tickets[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _tickets[key]
+
+
+class _GuidanceTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: TailSpec, n_maps: int, *accs):
+        _need_cuda(*accs)
+        lib = abi.load()
+        n = len(accs)
+        if n == 0:
+            raise ValueError("no attention accumulators to aggregate")   # reference: torch.cat([]) error
+        accs = [a.contiguous() for a in accs]
+        dev = accs[0].device
+        npix, T = spec.res * spec.res, spec.n_ctx
+        ptrs = (C.c_void_p * n)()
+        slices = (C.c_int32 * n)()
+        for i, a in enumerate(accs):
+            if a.dtype != torch.float32 or a.dim() != 3 or a.shape[1] != npix or a.shape[2] != T:
+                raise ValueError(f"accumulator {i}: expected (*, {npix}, {T}) fp32, got {tuple(a.shape)} {a.dtype}")
+            ptrs[i] = a.data_ptr()
+            slices[i] = a.shape[0]
+        p = abi.GaTailParams.from_buffer_copy(spec.params)
+        p.inv_count = 1.0 / float(n_maps)
+        nt, tp = p.n_tokens, spec.last - spec.first
+        attn_text = torch.empty((spec.res, spec.res, tp), dtype=torch.float32, device=dev)
+        smoothed = torch.empty((nt, spec.res, spec.res), dtype=torch.float32, device=dev)
+        stats = torch.empty((nt, abi.GA_STATS), dtype=torch.float32, device=dev)
+        argmax = torch.empty((nt,), dtype=torch.int32, device=dev)
+        total = torch.empty((1,), dtype=torch.float32, device=dev)
+        nbytes = (sum(a.numel() for a in accs) + attn_text.numel() + smoothed.numel()) * 4 + nt * npix
+        with torch.cuda.device(dev), _span("guidance_tail_fwd", (spec.res, T, n, nt), nbytes, dev):
+            abi.check(lib.ga_guidance_tail_fwd(ptrs, slices, n, C.byref(p), spec.tokens, _ptr(spec.masks),
+                                               _ptr(spec.weights), _ptr(attn_text), _ptr(smoothed), _ptr(stats),
+                                               _ptr(argmax), _ptr(total), _ptr(_ticket(dev)), _stream(attn_text)),
+                      "ga_guidance_tail_fwd")
+        _count("guidance_tail_fwd")
+        ctx.save_for_backward(attn_text, smoothed, stats, argmax)
+        ctx.spec, ctx.params, ctx.batches = spec, p, [a.shape[0] for a in accs]
+        ctx.mark_non_differentiable(smoothed, argmax)
+        return attn_text, smoothed, stats, argmax, total
+
+    @staticmethod
+    def backward(ctx, g_attn_text, g_smoothed, g_stats, g_argmax, g_total):
+        attn_text, smoothed, stats, argmax = ctx.saved_tensors
+        spec, p = ctx.spec, ctx.params
+        lib = abi.load()
+        dev = attn_text.device
+        npix, T = spec.res * spec.res, spec.n_ctx
+
+        def prep(g):
+            return None if g is None else g.contiguous().float()
+        g_attn_text, g_stats, g_total = prep(g_attn_text), prep(g_stats), prep(g_total)
+        d_abar = torch.empty((npix, T), dtype=torch.float32, device=dev)
+        nbytes = (attn_text.numel() + d_abar.numel()) * 4
+        with torch.cuda.device(dev), _span("guidance_tail_bwd", (spec.res, T, p.n_tokens), nbytes, dev):
+            abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, _ptr(spec.masks), _ptr(spec.weights),
+                                               _ptr(attn_text), _ptr(smoothed), _ptr(stats), _ptr(argmax),
+                                               _ptr(g_total), _ptr(g_stats), _ptr(g_attn_text), _ptr(d_abar),
+                                               _stream(d_abar)), "ga_guidance_tail_bwd")
+        _count("guidance_tail_bwd")
+        # every accumulator slice receives the same gradient: hand out stride-0 views, K2 reads them as a broadcast
+        return (None, None) + tuple(d_abar.unsqueeze(0).expand(b, npix, T) for b in ctx.batches)
+
+
+def guidance_tail(spec: TailSpec, accs: Sequence[torch.Tensor], n_maps: int):
+    """(attn_text (res,res,T'), smoothed (n,res,res), stats (n, GA_STATS), argmax (n), total (1)) -- one launch.
+    `accs`: K1 accumulators (B_l, res^2, T), each slice a sum over that layer's heads; `n_maps` = total number of
+    head-maps they hold (sum over layers of B_l * heads_l), the divisor of the reference's mean
+    (utils/ptp_utils.py:288)."""
+    return _GuidanceTailFn.apply(spec, int(n_maps), *accs)
+
+
+# ===================================================================================== stand-alone stage operators
+class _SmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, taps):
+        _need_cuda(maps)
+        lib = abi.load()
+        x = maps.contiguous().float()
+        n, res = x.shape[0], x.shape[-1]
+        out = torch.empty_like(x)
+        w = (C.c_float * 3)(*taps)
+        with torch.cuda.device(x.device):
+            abi.check(lib.ga_smooth_fwd(_ptr(x), _ptr(out), n, res, w, _stream(x)), "ga_smooth_fwd")
+        _count("smooth_fwd")
+        ctx.taps = taps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = abi.load()
+        g = g.contiguous().float()
+        n, res = g.shape[0], g.shape[-1]
+        out = torch.empty_like(g)
+        w = (C.c_float * 3)(*ctx.taps)
+        with torch.cuda.device(g.device):
+            abi.check(lib.ga_smooth_bwd(_ptr(g), _ptr(out), n, res, w, _stream(g)), "ga_smooth_bwd")
+        _count("smooth_bwd")
+        return out, None
+
+
+def smooth(maps: torch.Tensor, kernel_size: int = 3, sigma: float = 0.5) -> torch.Tensor:
+    """reflect-pad + 3x3 Gaussian on (n, res, res) maps (reference pipeline :253-254 + GaussianSmoothing.forward)."""
+    squeeze = maps.dim() == 2
+    x = maps[None] if squeeze else maps
+    out = _SmoothFn.apply(x, tuple(gaussian_taps(kernel_size, sigma)))
+    out = out.to(maps.dtype)
+    return out[0] if squeeze else out
+
+
+class _BoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, mask, weights, strict):
+        _need_cuda(p, mask)
+        lib = abi.load()
+        x = p.contiguous().float()
+        res = x.shape[-1]
+        out = torch.empty(2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            abi.check(lib.ga_box_loss_fwd(_ptr(x), _ptr(mask), _ptr(weights), res, int(strict), _ptr(out), _stream(x)),
+                      "ga_box_loss_fwd")
+        _count("box_loss_fwd")
+        ctx.save_for_backward(x, mask, weights if weights is not None else torch.empty(0, device=x.device))
+        ctx.strict, ctx.has_w = int(strict), weights is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mask, weights = ctx.saved_tensors
+        lib = abi.load()
+        g = g.contiguous().float()
+        gp = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            abi.check(lib.ga_box_loss_bwd(_ptr(x), _ptr(mask), _ptr(weights if ctx.has_w else None), x.shape[-1],
+                                          ctx.strict, _ptr(g), _ptr(gp), _stream(x)), "ga_box_loss_bwd")
+        _count("box_loss_bwd")
+        return gp, None, None, None
+
+
+def box_losses(image_softmax: torch.Tensor, rect, shrink: float, strict: bool):
+    """(loss_inside, loss_outside) as 1-element tensors; `rect` is a helpers.Rect already scaled to the map size."""
+    from . import helpers
+    res = image_softmax.shape[-1]
+    unit = (rect.x / rect.size, rect.y / rect.size, rect.width / rect.size, rect.height / rect.size)
+    # the rect arrives pre-scaled (reference call site pipeline :279): rasterise it as a size-`res` box on the host
+    # grid -- one multiplication by 1.0 keeps the doubles bit-identical
+    mask_np = helpers.box_mask_host(rect, res)
+    if int(mask_np.sum()) == 0:
+        raise ZeroDivisionError("float division by zero")   # reference: at_most = 1.0 / num_inside
+    dev = image_softmax.device
+    mask = torch.from_numpy(mask_np).to(dev)
+    weights = torch.from_numpy(helpers.strict_weights_host(rect, res)).to(dev) if strict else None
+    out = _BoxLossFn.apply(image_softmax, mask, weights, strict)
+    return out[0:1].to(image_softmax.dtype), out[1:2].to(image_softmax.dtype)

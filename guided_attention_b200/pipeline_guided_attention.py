@@ -1,0 +1,489 @@
+"""Guided-attention pipeline -- drop-in mirror of the reference's `pipeline_guided_attention.py` for the per-step guidance
+path (same class name, method names, argument meaning and return shapes), with the loss evaluation and its gradient
+running as fused sm_100a launches instead of ~30k tiny ATen ops:
+
+  reference                                              here
+  -----------------------------------------------------  ---------------------------------------------------------------
+  aggregate_attention (ptp_utils.py:273-289)              }
+  _compute_max_attention_per_index (:201-296)             }  ONE launch: ops.guidance_tail  (csrc/guidance_tail.cu)
+  helpers.calculate_bounding_box_losses (helpers:215-277) }
+  _compute_loss (:398-451)                                }
+  autograd of all of the above (~11k backward ops)           ONE launch: its backward
+  18 `.item()` syncs + PNG writes per evaluation             one small D2H read, only on steps that test a threshold
+
+The UNet, scheduler and prompt encoding are out of scope: they come from
+`guided_attention_b200.substrate` (or any object with the same duck interface, e.g. a diffusers UNet).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi as abi
+from . import helpers, ops
+from . import shared_state as state
+from .ptp_utils import AttentionStore, HeadSummedMaps, aggregate_attention, select_maps
+from .substrate import DDIMScheduler, StableDiffusionPipelineBase, StableDiffusionPipelineOutput
+
+AT = helpers.AnnotationType
+_KIND = {AT.COOR: abi.GA_TOKEN_COOR, AT.BOX: abi.GA_TOKEN_BOX, AT.KEYWORD: abi.GA_TOKEN_KEYWORD}
+
+
+class GuidedAttention(StableDiffusionPipelineBase):
+    """Pipeline for text-to-image generation with cross-attention guidance (boxes, crosshairs, keyword losses)."""
+
+    _optional_components = ["safety_checker", "feature_extractor"]
+    inside_iterative_refinement = False
+    optim = None
+
+    # ------------------------------------------------------------------------------------------ prompt encoding
+    def _encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
+                       prompt_embeds: Optional[torch.Tensor] = None,
+                       negative_prompt_embeds: Optional[torch.Tensor] = None):
+        """Returns (text_inputs, cat([negative, positive])) like the reference (:64-199).  No CLIP weights exist offline:
+        `prompt_embeds` (and `negative_prompt_embeds` for CFG) must be supplied unless a text encoder was attached."""
+        text_inputs = None
+        if prompt_embeds is None:
+            if not callable(getattr(self, "text_encoder", None)):
+                raise ValueError("no text encoder is available offline: pass `prompt_embeds` / `negative_prompt_embeds`")
+            text_inputs = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                         truncation=True, return_tensors="pt")
+            prompt_embeds = self.text_encoder(text_inputs.input_ids.to(device), attention_mask=None)[0]
+        elif prompt is not None:
+            text_inputs = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                         truncation=True, return_tensors="pt")
+        dtype = self.unet.dtype
+        prompt_embeds = prompt_embeds.to(dtype=dtype, device=device)
+        bs, seq, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
+        if do_classifier_free_guidance:
+            if negative_prompt_embeds is None:
+                if not callable(getattr(self, "text_encoder", None)):
+                    raise ValueError("classifier-free guidance needs `negative_prompt_embeds` (no text encoder offline)")
+                tokens = [negative_prompt or ""] * bs if not isinstance(negative_prompt, list) else negative_prompt
+                uncond = self.tokenizer(tokens, padding="max_length", max_length=seq, truncation=True,
+                                        return_tensors="pt")
+                negative_prompt_embeds = self.text_encoder(uncond.input_ids.to(device), attention_mask=None)[0]
+            negative_prompt_embeds = negative_prompt_embeds.to(dtype=dtype, device=device)
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(
+                bs * num_images_per_prompt, negative_prompt_embeds.shape[1], -1)
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds])
+        return text_inputs, prompt_embeds
+
+    # ------------------------------------------------------------------------------------------ tail specification
+    def _tail_spec(self, attention_res: int, n_ctx: int, smooth_attentions: bool, sigma: float, kernel_size: int,
+                   normalize_eot: bool, device) -> ops.TailSpec:
+        """Host-side, once per (prompt, hyper-parameters, resolution): token table, rasterised masks, strict weights.
+        Mirrors what the reference re-derives inside every loss evaluation (pipeline :209-228, :277-279;
+        helpers.py:216-246; :405-430)."""
+        cfg, hp = state.config, state.curHyperParams
+        last_idx = n_ctx - 1
+        if normalize_eot:
+            prompt = self.prompt[0] if isinstance(self.prompt, list) else self.prompt
+            last_idx = len(self.tokenizer(prompt)['input_ids']) - 1
+        token_dict = cfg.token_dict
+        key = (id(token_dict), tuple(token_dict.keys()), attention_res, n_ctx, last_idx, bool(smooth_attentions),
+               float(sigma), int(kernel_size), bool(hp["strict"]), float(hp["shrink_factor"]),
+               float(hp["inside_loss_scale"]), float(hp["outside_loss_scale"]), float(hp.get("bb_center_weight", .05)),
+               bool(getattr(cfg, "sub_prompt_avg_within", False)), str(device))
+        cached = getattr(self, "_tail_spec_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+
+        res = attention_res
+        indices = list(token_dict.keys())
+        if len(indices) > abi.GA_MAX_TOKENS:
+            raise ValueError(f"at most {abi.GA_MAX_TOKENS} tracked tokens are supported, got {len(indices)}")
+        subprompts = [token_dict[i]['subprompt'] for i in indices]
+        group_ids = {s: g for g, s in enumerate(dict.fromkeys(subprompts))}
+        # `_compute_loss` only emits a loss for COOR and BOX tokens; the sub-prompt mean divides by those (:376-379)
+        emitting = [token_dict[i]['loss_type'] in (AT.COOR, AT.BOX) for i in indices]
+        per_group = {s: sum(1 for s2, e in zip(subprompts, emitting) if e and s2 == s) for s in group_ids}
+        avg_within = bool(getattr(cfg, "sub_prompt_avg_within", False))
+        center_w = float(hp.get("bb_center_weight", .05))
+
+        boxes, box_of_token = [], {}
+        for i in indices:
+            info = token_dict[i]
+            if info['loss_type'] == AT.BOX:
+                r = info['loss']
+                box_of_token[i] = len(boxes)
+                boxes.append((r.x / r.size, r.y / r.size, r.width / r.size, r.height / r.size)
+                             if r.size != 1 else (r.x, r.y, r.width, r.height))
+        masks = ops.rasterize_boxes(boxes, res, float(hp["shrink_factor"]), device) if boxes else None
+        n_inside, weights = [], None
+        if boxes:
+            n_inside = [int(v) for v in masks.reshape(len(boxes), -1).sum(1).tolist()]   # one sync per prompt
+            if any(n == 0 for n in n_inside):
+                raise ZeroDivisionError("float division by zero")   # reference: at_most = 1.0 / num_inside
+            if hp["strict"]:
+                scaled = [token_dict[i]['loss'].of_size(float(res)) for i in indices if i in box_of_token]
+                saved = state.curHyperParams
+                weights = torch.from_numpy(np.stack([helpers.strict_weights_host(r, res) for r in scaled])).to(device)
+                state.curHyperParams = saved
+
+        toks = (abi.GaToken * max(len(indices), 1))()
+        for n, i in enumerate(indices):
+            info = token_dict[i]
+            kind = info['loss_type']
+            t = toks[n]
+            t.column, t.kind, t.box = i - 1, _KIND[kind], box_of_token.get(i, -1)
+            t.group = group_ids[info['subprompt']]
+            t.group_weight = (1.0 / per_group[info['subprompt']]) if (avg_within and emitting[n]) else 1.0
+            if kind == AT.BOX:
+                cx, cy = info['loss'].center()
+                t.center_weight = center_w
+            elif kind == AT.COOR:
+                cx, cy = info['loss']
+                t.center_weight = 1.0
+            else:
+                cx, cy, t.center_weight = 0.0, 0.0, 0.0
+            # reference: `col - center[0]*16` with a float32 tensor -> the python double is rounded to float32
+            t.target_x, t.target_y = float(np.float32(cx * res)), float(np.float32(cy * res))
+        p = abi.GaTailParams()
+        p.res, p.n_ctx, p.first, p.last = res, n_ctx, 1, last_idx
+        p.n_tokens, p.n_groups = len(indices), len(group_ids)
+        p.strict, p.smooth = int(bool(hp["strict"])), int(bool(smooth_attentions))
+        taps = ops.gaussian_taps(kernel_size, sigma) if smooth_attentions else [0.0, 1.0, 0.0]
+        for a in range(3):
+            p.w1d[a] = taps[a]
+        p.temperature, p.inv_count = 100.0, 1.0
+        p.inside_scale = float(hp["inside_loss_scale"])
+        p.outside_scale = float(hp["outside_loss_scale"] * 3)
+        p.custom_total = 0.0
+        spec = ops.TailSpec(res=res, n_ctx=n_ctx, first=1, last=last_idx, token_indices=indices,
+                            kinds=[_KIND[token_dict[i]['loss_type']] for i in indices], groups=subprompts, tokens=toks,
+                            params=p, masks=masks, weights=weights, n_inside=n_inside)
+        self._tail_spec_cache = (key, spec)
+        return spec
+
+    # ------------------------------------------------------------------------------------------- loss evaluation
+    def _compute_max_attention_per_index(self, attention_maps, smooth_attentions: bool = False, sigma: float = 0.5,
+                                         kernel_size: int = 3, normalize_eot: bool = False):
+        """Reference signature (:201-206) takes the aggregated (res, res, T) map.  Accepts either that tensor (it is then
+        treated as a single accumulator holding one map) or a list of `HeadSummedMaps`; returns the reference's
+        `losses_dict` (lists of 1-element tensors, token order = `config.token_dict` order) plus the fused extras."""
+        if isinstance(attention_maps, torch.Tensor):
+            res, T = attention_maps.shape[0], attention_maps.shape[-1]
+            accs, n_maps = [attention_maps.reshape(1, res * res, T).float()], 1
+        else:
+            accs = [m.acc for m in attention_maps]
+            n_maps = sum(m.n_maps for m in attention_maps)
+            res, T = int(round(accs[0].shape[1] ** 0.5)), accs[0].shape[2]
+        spec = self._tail_spec(res, T, smooth_attentions, sigma, kernel_size, normalize_eot, accs[0].device)
+        attn_text, smoothed, stats, argmax, total = ops.guidance_tail(spec, accs, n_maps)
+
+        n = len(spec.token_indices)
+        is_box = [k == abi.GA_TOKEN_BOX for k in spec.kinds]
+        losses_dict = {
+            "max_loss": [stats[i, abi.GA_STAT_MAX] for i in range(n)],
+            "col": [stats[i, abi.GA_STAT_COL:abi.GA_STAT_COL + 1] for i in range(n)],
+            "row": [stats[i, abi.GA_STAT_ROW:abi.GA_STAT_ROW + 1] for i in range(n)],
+            "inside_loss": [stats[i, abi.GA_STAT_INSIDE:abi.GA_STAT_INSIDE + 1] if is_box[i] else 0 for i in range(n)],
+            "outside_loss": [stats[i, abi.GA_STAT_OUTSIDE:abi.GA_STAT_OUTSIDE + 1] if is_box[i] else 0
+                             for i in range(n)],
+            # fused extras (not in the reference dict)
+            "_stats": stats, "_total": total, "_argmax": argmax, "_smoothed": smoothed, "_spec": spec,
+            "attention_for_text": attn_text,
+        }
+        if hasattr(state.config, "custom_loss"):
+            custom = torch.zeros(1, dtype=torch.float32, device=stats.device)
+            for _, (loss_obj, args) in state.config.custom_loss.items():
+                custom = custom + loss_obj.calc_loss(attn_text, args)
+            losses_dict["custom_loss"] = custom
+        if state.config.diagnostic_level > 0 or state.config.save_all_maps:
+            self._log_maps(losses_dict)
+        return losses_dict
+
+    def _aggregate_and_get_max_attention_per_token(self, attention_store: AttentionStore, attention_res: int = 16,
+                                                   smooth_attentions: bool = False, sigma: float = 0.5,
+                                                   kernel_size: int = 3, normalize_eot: bool = False):
+        """Aggregation + per-token statistics (reference :298-354): the per-layer accumulators go straight into the
+        tail kernel, the (res, res, 77) mean is never materialised."""
+        from_where = ("up", "down", "mid")
+        picked = select_maps(attention_store, attention_res, from_where, True)
+        if len(picked) == 0:
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")   # reference ptp_utils.py:287
+        return self._compute_max_attention_per_index(picked, smooth_attentions=smooth_attentions, sigma=sigma,
+                                                     kernel_size=kernel_size, normalize_eot=normalize_eot)
+
+    def _log_maps(self, losses_dict):
+        """Opt-in diagnostics (the reference does this unconditionally inside the loss, :243-246, :273-274)."""
+        stats = losses_dict["_stats"].detach().cpu()
+        for n, idx in enumerate(losses_dict["_spec"].token_indices):
+            helpers.log(f"{self.get_token(idx)}: weighted center col: {stats[n, abi.GA_STAT_COL].item()} "
+                        f"row: {stats[n, abi.GA_STAT_ROW].item()}")
+
+    @staticmethod
+    def group_losses_by_sumprompt(losses):
+        """(total, {sub-prompt: sum or mean}) -- reference :358-387."""
+        groups: Dict[Any, list] = {}
+        for idx, val in losses:
+            sub = None if idx is None else state.config.token_dict[idx]['subprompt']
+            groups.setdefault(sub, []).append(val)
+        total, final = 0., {}
+        for sub, vals in groups.items():
+            tot = 0.
+            for v in vals:
+                tot = tot + (v / len(vals) if state.config.sub_prompt_avg_within else v)
+            final[sub] = tot
+            total = total + tot
+        return total, final
+
+    @staticmethod
+    def get_centering_loss(center, losses_dict, i):
+        """reference :390-395 with 16 -> res, 15 -> res - 1."""
+        res = losses_dict["_spec"].res if "_spec" in losses_dict else 16
+        part1 = 1. * (losses_dict["col"][i] - center[0] * res).abs() / (res - 1.)
+        part2 = 4. * (losses_dict["row"][i] - center[1] * res).abs() / (res - 1.)
+        return part1 + part2
+
+    @staticmethod
+    def _compute_loss(losses_dict: dict, return_losses: bool = False):
+        """(loss, losses, unscaled_losses) -- reference :398-451.  The per-token terms and their weighted sum were
+        already produced by the tail kernel; this only packages them in the reference's list-of-tuples form."""
+        stats, spec = losses_dict["_stats"], losses_dict["_spec"]
+        losses, unscaled = [], []
+        for n, idx in enumerate(spec.token_indices):
+            if spec.kinds[n] == abi.GA_TOKEN_KEYWORD:
+                continue
+            losses.append((idx, stats[n, abi.GA_STAT_SCALED:abi.GA_STAT_SCALED + 1]))
+            unscaled.append((idx, stats[n, abi.GA_STAT_UNSCALED:abi.GA_STAT_UNSCALED + 1]))
+        loss = losses_dict["_total"]
+        if "custom_loss" in losses_dict:
+            losses.append((None, losses_dict["custom_loss"]))
+            unscaled.append((None, losses_dict["custom_loss"]))
+            loss = loss + losses_dict["custom_loss"]
+        return loss, losses, unscaled
+
+    @staticmethod
+    def _update_latent(latents: torch.Tensor, loss: torch.Tensor, step_size: float) -> torch.Tensor:
+        """latents - step_size * d loss / d latents (reference :455-470); the backward runs K2 in every cross layer and
+        the tail backward kernel once."""
+        grad_cond = torch.autograd.grad(loss.requires_grad_(True), [latents], retain_graph=True)[0]
+        return latents - step_size * grad_cond
+
+    # --------------------------------------------------------------------------------------- threshold (host side)
+    def meets_threshold(self, i, thresholds, losses):
+        """True when every sub-prompt's summed unscaled loss is <= the threshold (reference :1074-1088).  This is the one
+        place the loss values are read back to the host, and only on steps that own a threshold."""
+        if (i not in thresholds and i != -1) or len(thresholds) == 0:
+            return True
+        thresh = list(thresholds.values())[-1] if i == -1 else thresholds[i]
+        _, per_sub = GuidedAttention.group_losses_by_sumprompt(
+            [(idx, float(v)) if not isinstance(v, float) else (idx, v) for idx, v in self._host_values(losses)])
+        return all(not (v > thresh) for v in per_sub.values())
+
+    @staticmethod
+    def _host_values(losses):
+        """One D2H copy for the whole list."""
+        tensors = [v for _, v in losses if torch.is_tensor(v)]
+        if not tensors:
+            return list(losses)
+        flat = torch.cat([t.detach().reshape(-1)[:1].float() for t in tensors]).cpu().tolist()
+        it = iter(flat)
+        return [(idx, next(it) if torch.is_tensor(v) else float(v)) for idx, v in losses]
+
+    # -------------------------------------------------------------------------------------- iterative refinement
+    def _perform_iterative_refinement_step(self, latents: torch.Tensor, loss: torch.Tensor, threshold: float,
+                                           text_embeddings: torch.Tensor, text_input, attention_store: AttentionStore,
+                                           step_size: float, t: int, attention_res: int = 16,
+                                           smooth_attentions: bool = True, sigma: float = 0.5, kernel_size: int = 3,
+                                           max_refinement_steps: int = 5, normalize_eot: bool = False):
+        """Repeat [UNet forward (grad) -> loss -> latent update] until every sub-prompt meets the step's threshold or
+        `max_refinement_steps` is hit, then one more forward for the loss at the refined latent (reference :475-581)."""
+        self.inside_iterative_refinement = True
+        use_optimizer = state.curHyperParams.get("use_optimizer", False)
+        if use_optimizer:
+            self.optim = torch.optim.SGD([latents], lr=step_size / 2.5, momentum=0.8)
+        iteration = 0
+        state.sub_iteration = iteration
+        losses = unscaled_losses = None
+        kw = dict(attention_store=attention_store, attention_res=attention_res, smooth_attentions=smooth_attentions,
+                  sigma=sigma, kernel_size=kernel_size, normalize_eot=normalize_eot)
+        while losses is None or not self.meets_threshold(state.cur_time_step_iter, state.config.thresholds,
+                                                         unscaled_losses):
+            helpers.log(f"subiteration: {iteration}")
+            if use_optimizer:
+                self.optim.zero_grad()
+            iteration += 1
+            state.sub_iteration = iteration
+            if not use_optimizer:
+                latents = latents.clone().detach().requires_grad_(True)
+            self.unet(latents, t, encoder_hidden_states=text_embeddings[1].unsqueeze(0))
+            losses_dict = self._aggregate_and_get_max_attention_per_token(**kw)
+            loss, losses, unscaled_losses = self._compute_loss(losses_dict, return_losses=True)
+            if use_optimizer:
+                loss.backward()
+                self.optim.step()
+            elif self._nonzero(loss):
+                latents = self._update_latent(latents, loss, step_size)
+            if iteration >= max_refinement_steps:
+                helpers.log(f'\t Exceeded max number of iterations ({max_refinement_steps})! ', True)
+                break
+        latents = latents.clone().detach().requires_grad_(True)
+        self.unet(latents, t, encoder_hidden_states=text_embeddings[1].unsqueeze(0))
+        max_attention_per_index = self._aggregate_and_get_max_attention_per_token(**kw)
+        loss, losses, unscaled_losses = self._compute_loss(max_attention_per_index, return_losses=True)
+        helpers.log(f"\t Finished with loss iter: {iteration}", True)
+        state.sub_iteration = 0
+        self.inside_iterative_refinement = False
+        return loss, latents, max_attention_per_index
+
+    @staticmethod
+    def _nonzero(loss) -> bool:
+        """`loss != 0` of the reference (:552, :1002).  With at least one BOX/COOR token the loss is a sum of
+        non-negative terms that is zero only in degenerate cases; the exact test costs a host sync, so it is only
+        evaluated when no token can contribute."""
+        spec_tokens = state.config.token_dict
+        if any(v['loss_type'] in (AT.COOR, AT.BOX) for v in spec_tokens.values()):
+            return True
+        return bool(loss != 0)
+
+    # ---------------------------------------------------------------------------------------------------- call
+    @torch.no_grad()
+    def __call__(self, prompt: Union[str, List[str]], attention_store: AttentionStore, attention_res: int = 16,
+                 height: Optional[int] = None, width: Optional[int] = None, num_inference_steps: int = 50,
+                 guidance_scale: float = 7.5, negative_prompt: Optional[Union[str, List[str]]] = None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0,
+                 generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback: Optional[Callable[[int, int, torch.Tensor], None]] = None,
+                 callback_steps: Optional[int] = 1, cross_attention_kwargs: Optional[Dict[str, Any]] = None,
+                 max_iter_to_alter: Optional[int] = 25, run_standard_sd: bool = False,
+                 thresholds: Optional[dict] = {0: 0.05, 10: 0.5, 20: 0.8}, scale_factor: int = 20,
+                 scale_range: Tuple[float, float] = (1., 0.5), smooth_attentions: bool = True, sigma: float = 0.5,
+                 kernel_size: int = 3, sd_2_1: bool = False):
+        """Same arguments as the reference `__call__` (:746-777).  `output_type="latent"` returns the final latents
+        tensor in `.images` (no VAE exists offline; "pil"/"np" go through the placeholder decode)."""
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        self.check_inputs(prompt, height, width, callback_steps, negative_prompt, prompt_embeds, negative_prompt_embeds)
+
+        self.prompt = prompt
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self._execution_device
+        do_classifier_free_guidance = guidance_scale > 1.0
+        text_inputs, prompt_embeds = self._encode_prompt(prompt, device, num_images_per_prompt,
+                                                         do_classifier_free_guidance, negative_prompt,
+                                                         prompt_embeds=prompt_embeds,
+                                                         negative_prompt_embeds=negative_prompt_embeds)
+        state.always_save_iter = [0, 1, 2]
+        self.scheduler = DDIMScheduler.from_config(self.scheduler.config)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        state.sigmas = np.array(((1 - self.scheduler.alphas_cumprod) / self.scheduler.alphas_cumprod) ** 0.5)
+        timesteps = self.scheduler.timesteps
+        state.timesteps = timesteps
+
+        latents = self.prepare_latents(batch_size * num_images_per_prompt, self.unet.in_channels, height, width,
+                                       prompt_embeds.dtype, device, generator, latents)
+        extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
+        scale_range = np.linspace(scale_range[0], scale_range[1], len(self.scheduler.timesteps))
+        if max_iter_to_alter is None:
+            max_iter_to_alter = len(self.scheduler.timesteps) + 1
+
+        recurse_steps = max(state.curHyperParams.get("recurse_steps", 1), 1)
+        recurse_until = state.curHyperParams.get("recurse_until", 20)
+        if len(thresholds) == 0:
+            thresholds = {0: float("inf")}
+        renoise_gen = None
+        if recurse_steps > 1:
+            seed = generator.initial_seed() if generator is not None else 0
+            renoise_gen = torch.Generator("cpu").manual_seed(seed)   # CPU stream: reproducible on every device
+
+        loss_kw = dict(attention_store=attention_store, attention_res=attention_res,
+                       smooth_attentions=smooth_attentions, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
+        num_warmup_steps = len(timesteps) - num_inference_steps * self.scheduler.order
+        with self.progress_bar(total=num_inference_steps) as progress_bar:
+            for i, t in enumerate(timesteps):
+                t = int(t)
+                for recurse_step in range(0, recurse_steps):
+                    did_we_update = False
+                    state.cur_time_step_iter = i
+                    helpers.log(f"iteration {i}", True)
+                    with torch.enable_grad():
+                        latents = latents.clone().detach().requires_grad_(True)
+                        # text-conditioned forward with the autograd graph: fills the attention accumulators
+                        self.unet(latents, t, encoder_hidden_states=prompt_embeds[1].unsqueeze(0),
+                                  cross_attention_kwargs=cross_attention_kwargs)
+                        max_attention_per_index = self._aggregate_and_get_max_attention_per_token(**loss_kw)
+                        if not run_standard_sd:
+                            loss, losses, unscaled_losses = self._compute_loss(losses_dict=max_attention_per_index)
+                            if not self.meets_threshold(i, thresholds, unscaled_losses):
+                                did_we_update = True
+                                loss, latents, max_attention_per_index = self._perform_iterative_refinement_step(
+                                    latents=latents, loss=loss, threshold=thresholds[i], text_embeddings=prompt_embeds,
+                                    text_input=text_inputs, attention_store=attention_store,
+                                    step_size=scale_factor * np.sqrt(scale_range[i]), t=t,
+                                    attention_res=attention_res, smooth_attentions=smooth_attentions,
+                                    max_refinement_steps=10, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
+                            if (not state.config.only_update_on_threshold_steps and i < max_iter_to_alter) or \
+                                    (i in state.config.thresholds):
+                                # NB: like the reference (:1001) this tests the PRE-refinement unscaled losses
+                                if not self.meets_threshold(-1, state.config.thresholds, unscaled_losses):
+                                    did_we_update = True
+                                    loss, losses, unscaled_losses = self._compute_loss(
+                                        losses_dict=max_attention_per_index)
+                                    if self._nonzero(loss):
+                                        latents = self._update_latent(latents=latents, loss=loss,
+                                                                      step_size=scale_factor * np.sqrt(scale_range[i]))
+                    latent_model_input = torch.cat([latents] * 2) if do_classifier_free_guidance else latents
+                    latent_model_input = self.scheduler.scale_model_input(latent_model_input, t)
+                    noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=prompt_embeds,
+                                           cross_attention_kwargs=cross_attention_kwargs).sample
+                    if do_classifier_free_guidance:
+                        noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
+                        noise_pred = noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)
+                    ddim_output = self.scheduler.step(noise_pred, t, latents, **extra_step_kwargs)
+                    latents = ddim_output.prev_sample
+                    if state.config.diagnostic_level > 0:
+                        self.save_image(ddim_output.pred_original_sample, "pred")
+                    if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
+                        progress_bar.update()
+                        if callback is not None and i % callback_steps == 0:
+                            callback(i, t, latents)
+                    if i > recurse_until or not did_we_update:
+                        break
+                    if recurse_step != (recurse_steps - 1):
+                        prev_timestep = t - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
+                        if prev_timestep > 0:
+                            Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_timestep])
+                            noise = torch.randn(latents.shape, generator=renoise_gen, dtype=torch.float32)
+                            latents = (Bt ** 0.5) * latents + ((1 - Bt) ** 0.5) * noise.to(latents.device, latents.dtype)
+
+        latents = latents.detach()
+        has_nsfw_concept = False
+        if output_type == "latent":
+            image = latents
+        else:
+            image = self.decode_latents(latents)
+            if output_type == "pil":
+                image = self.numpy_to_pil(image)
+        if not return_dict:
+            return (image, has_nsfw_concept)
+        return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=has_nsfw_concept)
+
+    # ------------------------------------------------------------------------------------------------ diagnostics
+    def get_innermost_folder(self):
+        return str(state.cur_seed)
+
+    def get_token(self, index):
+        return self.tokenizer.decode(self.tokenizer(state.config.prompt)['input_ids'][index])
+
+    def save_image(self, latent, tag):
+        image = self.numpy_to_pil(self.decode_latents(latent.detach()))
+        fname = helpers.get_meta_prompt_clean() + state.get_name() + "_" + tag
+        for ch in "[]:.":
+            fname = fname.replace(ch, "_")
+        out = state.config.output_path / helpers.get_inner_folder_name() / self.get_innermost_folder()
+        out.mkdir(exist_ok=True, parents=True)
+        image[0].save(out / (fname + ".png"))

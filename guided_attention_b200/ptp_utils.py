@@ -1,0 +1,265 @@
+"""Attention hooks -- drop-in mirror of the reference's `utils/ptp_utils.py:59-289`.
+
+Same public names, signatures and bookkeeping (`register_attention_control`, `AttendExciteCrossAttnProcessor`,
+`AttentionControl`, `EmptyControl`, `AttentionStore`, `aggregate_attention`), different machinery underneath:
+
+  * for cross-attention layers the processor calls ONE fused sm_100a kernel (K1, `ops.cross_attention`) that computes
+    softmax(scale QK^T)V against the 77-token context and, for layers the store keeps (N <= 32^2), writes the head-sum of
+    the probabilities straight into that layer's fp32 accumulator.  The (B*H, N, 77) probability tensor the reference
+    materialises and retains for autograd (`utils/ptp_utils.py:82-85`) never exists; the backward (K2) recomputes it
+    from the saved row log-sum-exp and injects the map gradient.
+  * what the controller receives for a cross layer is therefore a `HeadSummedMaps` handle instead of a probability
+    tensor.  It has the `.shape` the reference tensor would have, so `AttentionStore.forward`'s size test is unchanged,
+    and `.probs()` materialises the per-head maps on demand (API compatibility, off the hot path).
+  * self-attention layers are off the guidance path; they run the same explicit math as the reference in PyTorch and
+    their maps are only stored when `AttentionStore(save_self_attention=True)` (the reference stores them
+    unconditionally although nothing reads them: `pipeline_guided_attention.py:309` hard-wires the reader off).
+"""
+from __future__ import annotations
+
+import abc
+from typing import List
+
+import torch
+
+from . import ops
+from . import shared_state as state
+
+
+class HeadSummedMaps:
+    """Handle to one cross-attention layer's maps for one UNet forward.
+
+    acc   (B, N, T) fp32, acc[b] = sum_h P[b, h]; autograd-connected to the layer's queries through K1/K2.
+    shape (B*H, N, T): the shape of the probability tensor the reference hands to the controller.
+    """
+
+    def __init__(self, acc: torch.Tensor, heads: int, q: torch.Tensor, k: torch.Tensor, scale: float):
+        self.acc, self.heads, self.scale = acc, heads, scale
+        self._q, self._k = q, k
+        self.shape = torch.Size((acc.shape[0] * heads, acc.shape[1], acc.shape[2]))
+        self.dtype, self.device = q.dtype, acc.device
+
+    @property
+    def n_maps(self) -> int:
+        return self.shape[0]
+
+    def probs(self) -> torch.Tensor:
+        """Per-head probabilities (B*H, N, T), recomputed by `ga_attn_probs`; detached."""
+        return ops.attention_probs(self._q.detach(), self._k.detach(), self.heads, self.scale)
+
+    def mean_map(self) -> torch.Tensor:
+        """(N, T) mean over batch x heads, differentiable."""
+        return self.acc.sum(0) / self.n_maps
+
+    def detach(self):
+        return HeadSummedMaps(self.acc.detach(), self.heads, self._q.detach(), self._k.detach(), self.scale)
+
+
+class AttendExciteCrossAttnProcessor:
+    """Same call contract as the reference processor (utils/ptp_utils.py:59-93)."""
+
+    def __init__(self, attnstore, place_in_unet):
+        super().__init__()
+        self.attnstore = attnstore
+        self.place_in_unet = place_in_unet
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
+        batch_size, sequence_length, _ = hidden_states.shape
+        attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length)
+        is_cross = encoder_hidden_states is not None
+        query = attn.to_q(hidden_states)
+
+        if is_cross:
+            if attention_mask is not None:
+                raise NotImplementedError("fused cross-attention takes no attention_mask (the guided pipeline never "
+                                          "passes one, reference pipeline_guided_attention.py:946-947)")
+            stop = state.curHyperParams.get("paint_with_words_stop", 0) if state.curHyperParams else 0
+            if stop and state.cur_time_step_iter is not None and state.cur_time_step_iter < stop:
+                raise NotImplementedError("paint-with-words score bias (reference utils/ptp_utils.py:113-138) is not "
+                                          "implemented in the fused kernel yet (off by default in the reference)")
+            key = attn.to_k(encoder_hidden_states)
+            value = attn.to_v(encoder_hidden_states)
+            keep = self.attnstore.wants_maps(sequence_length) if hasattr(self.attnstore, "wants_maps") \
+                else sequence_length <= 32 ** 2
+            out, acc = ops.cross_attention(query, key, value, attn.heads, attn.scale, want_acc=keep)
+            if keep:
+                maps = HeadSummedMaps(acc, attn.heads, query, key, attn.scale)
+            else:
+                maps = _ShapeOnly(batch_size * attn.heads, sequence_length, key.shape[1])
+            self.attnstore(maps, True, self.place_in_unet)
+            hidden_states = out
+        else:
+            # self-attention: off the guidance path, same explicit math as the reference (utils/ptp_utils.py:77-85)
+            key = attn.to_k(hidden_states)
+            value = attn.to_v(hidden_states)
+            query = attn.head_to_batch_dim(query)
+            key = attn.head_to_batch_dim(key)
+            value = attn.head_to_batch_dim(value)
+            attention_probs = attn.get_attention_scores(query, key, attention_mask)
+            self.attnstore(attention_probs, False, self.place_in_unet)
+            hidden_states = attn.batch_to_head_dim(torch.bmm(attention_probs, value))
+
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        return hidden_states
+
+
+class _ShapeOnly:
+    """Stand-in handed to the controller for layers whose maps are not kept (N > 32^2): only `.shape` is meaningful."""
+
+    def __init__(self, *shape):
+        self.shape = torch.Size(shape)
+
+
+def register_attention_control(model, controller):
+    """Installs the processor on every attention layer (self and cross) and sets `controller.num_att_layers`
+    (reference utils/ptp_utils.py:149-175; 32 for an SD-1.x UNet)."""
+    attn_procs = {}
+    count = 0
+    for name in model.unet.attn_processors.keys():
+        if name.startswith("mid_block"):
+            place = "mid"
+        elif name.startswith("up_blocks"):
+            place = "up"
+        elif name.startswith("down_blocks"):
+            place = "down"
+        else:
+            continue
+        count += 1
+        attn_procs[name] = AttendExciteCrossAttnProcessor(attnstore=controller, place_in_unet=place)
+    model.unet.set_attn_processor(attn_procs)
+    controller.num_att_layers = count
+
+
+class AttentionControl(abc.ABC):
+    """Per-forward layer counter; `between_steps` fires after `num_att_layers` calls (utils/ptp_utils.py:178-210)."""
+
+    def step_callback(self, x_t):
+        return x_t
+
+    def between_steps(self):
+        return
+
+    @property
+    def num_uncond_att_layers(self):
+        return 0
+
+    @abc.abstractmethod
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        raise NotImplementedError
+
+    def __call__(self, attn, is_cross: bool, place_in_unet: str):
+        if self.cur_att_layer >= self.num_uncond_att_layers:
+            self.forward(attn, is_cross, place_in_unet)
+        self.cur_att_layer += 1
+        if self.cur_att_layer == self.num_att_layers + self.num_uncond_att_layers:
+            self.cur_att_layer = 0
+            self.cur_step += 1
+            self.between_steps()
+
+    def reset(self):
+        self.cur_step = 0
+        self.cur_att_layer = 0
+
+    def __init__(self):
+        self.cur_step = 0
+        self.num_att_layers = -1
+        self.cur_att_layer = 0
+
+
+class EmptyControl(AttentionControl):
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        return attn
+
+
+class AttentionStore(AttentionControl):
+    """Keeps, per UNet forward, one `HeadSummedMaps` per cross layer with N <= 32^2 under the reference's six keys
+    (utils/ptp_utils.py:219-270)."""
+
+    @staticmethod
+    def get_empty_store():
+        return {"down_cross": [], "mid_cross": [], "up_cross": [],
+                "down_self": [], "mid_self": [], "up_self": []}
+
+    def wants_maps(self, n_query: int) -> bool:
+        save_all = bool(getattr(state.config, "save_individual_CA_maps", False)) if state.config is not None else False
+        return save_all or n_query <= 32 ** 2
+
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        key = f"{place_in_unet}_{'cross' if is_cross else 'self'}"
+        if not is_cross and not self.save_self_attention:
+            return attn
+        if self.wants_maps(attn.shape[1]) and not isinstance(attn, _ShapeOnly):
+            self.step_store[key].append(attn)
+        return attn
+
+    def between_steps(self):
+        self.attention_store = self.step_store
+        if self.save_global_store:
+            with torch.no_grad():
+                if len(self.global_store) == 0:
+                    self.global_store = {k: [self._as_sum(i) for i in v] for k, v in self.step_store.items()}
+                else:
+                    for key in self.global_store:
+                        for i in range(len(self.global_store[key])):
+                            self.global_store[key][i] += self._as_sum(self.step_store[key][i])
+        self.step_store = self.get_empty_store()
+
+    @staticmethod
+    def _as_sum(item):
+        return item.acc.detach().clone() if isinstance(item, HeadSummedMaps) else item.detach().clone()
+
+    def get_average_attention(self):
+        return self.attention_store
+
+    def get_average_global_attention(self):
+        return {key: [item / self.cur_step for item in self.global_store[key]] for key in self.attention_store}
+
+    def reset(self):
+        super(AttentionStore, self).reset()
+        self.step_store = self.get_empty_store()
+        self.attention_store = {}
+        self.global_store = {}
+
+    def __init__(self, save_global_store=False, save_self_attention=False):
+        super(AttentionStore, self).__init__()
+        self.save_global_store = save_global_store
+        self.save_self_attention = save_self_attention
+        self.step_store = self.get_empty_store()
+        self.attention_store = {}
+        self.global_store = {}
+        self.curr_step_index = 0
+
+
+def select_maps(attention_store: AttentionStore, res: int, from_where: List[str], is_cross: bool):
+    """The stored items with N == res^2 from the requested places, in the reference's order
+    (utils/ptp_utils.py:282-286)."""
+    picked = []
+    maps = attention_store.get_average_attention()
+    for location in from_where:
+        for item in maps[f"{location}_{'cross' if is_cross else 'self'}"]:
+            if item.shape[1] == res ** 2:
+                picked.append(item)
+    return picked
+
+
+def aggregate_attention(attention_store: AttentionStore, res: int, from_where: List[str], is_cross: bool,
+                        select: int) -> torch.Tensor:
+    """Mean over layers and heads at one resolution -> (res, res, T), differentiable (reference
+    utils/ptp_utils.py:273-289).  The guided pipeline does not call this on the hot path: the tail kernel consumes the
+    per-layer accumulators directly (`ops.guidance_tail`); this is the general-purpose view for other callers."""
+    if select != 0:
+        raise IndexError("index %d is out of bounds for dimension 0 with size 1" % select)
+    picked = select_maps(attention_store, res, from_where, is_cross)
+    if len(picked) == 0:
+        raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")
+    total, n = None, 0
+    for item in picked:
+        if isinstance(item, HeadSummedMaps):
+            part, cnt = item.acc.sum(0), item.n_maps
+        else:
+            part, cnt = item.float().sum(0), item.shape[0]
+        total = part if total is None else total + part
+        n += cnt
+    out = total / n
+    return out.reshape(res, res, out.shape[-1])

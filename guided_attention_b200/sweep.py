@@ -1,0 +1,73 @@
+"""Multi-GPU seed sweep (BASELINE config 5): seeds are independent units (reference run.py:97 loops them sequentially on
+one GPU), so they shard one process per GPU with NO collective on the hot path; the only communication is one gather of
+the final latents at the end (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def dist_env():
+    """(rank, world_size, local_rank) from the torchrun environment; (0, 1, 0) when not launched by torchrun."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0)))
+
+
+def init_distributed(backend: Optional[str] = None):
+    rank, world, local_rank = dist_env()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local_rank
+
+
+def shard_seeds(seeds: Sequence[int], rank: int, world: int) -> List[int]:
+    """Static round-robin: seed index i goes to rank i % world."""
+    return [s for i, s in enumerate(seeds) if i % world == rank]
+
+
+def gather_results(local: torch.Tensor, n_total: int, rank: int, world: int) -> Optional[torch.Tensor]:
+    """All ranks pass (n_local, ...) results for `shard_seeds` order; every rank gets (n_total, ...) back in seed order.
+    One all_gather on equal-sized, zero-padded chunks."""
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    chunks = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(chunks, pad)
+    out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        idx = list(range(r, n_total, world))
+        out[idx] = chunks[r][: len(idx)]
+    return out
+
+
+def run_seed_sweep(generate: Callable[[int], torch.Tensor], seeds: Sequence[int], rank: int, world: int,
+                   gather: bool = True):
+    """`generate(seed) -> (C, H, W) tensor`.  Returns (all results in seed order or None, this rank's results, failures).
+    A failing seed is reported and skipped (zeros in its slot); the other seeds continue."""
+    mine = shard_seeds(seeds, rank, world)
+    results, failures = [], []
+    for s in mine:
+        try:
+            results.append(generate(s))
+        except Exception as e:  # per-seed failure isolation
+            failures.append((s, repr(e)))
+            results.append(None)
+    template = next((r for r in results if r is not None), None)
+    if template is None:
+        return None, [], failures
+    local = torch.stack([r if r is not None else torch.zeros_like(template) for r in results])
+    full = gather_results(local, len(seeds), rank, world) if gather else None
+    return full, local, failures

@@ -1,0 +1,168 @@
+/* guided_attn.h -- C ABI of libguidedattn.so: the B200 (sm_100a) kernels of the cross-attention guidance path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one reference op sequence (paths relative to the
+ * jackBonadies/Guided-Attention tree) and is what a maintainer's FFI stub (ctypes) binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All `*_dev` / unqualified data pointers are DEVICE pointers owned
+ *     by the caller (PyTorch); the library never allocates, frees or synchronises.  `*_host` pointers are small HOST
+ *     arrays that are copied into kernel parameters at launch (no H2D memcpy, no staging buffer).
+ *   - every kernel is enqueued on the caller-supplied stream (`cudaStream_t` passed as void*).
+ *   - return value: GA_OK or a negative error code; `ga_last_error()` gives a thread-local message.  No C++ exception
+ *     crosses the boundary.
+ *   - tensors are dense row-major; attention operands use the projection layout (batch, tokens, heads*head_dim), i.e.
+ *     exactly what `attn.to_q/to_k/to_v` produce -- the `head_to_batch_dim` permutes of the reference
+ *     (utils/ptp_utils.py:77-79) are folded into the kernels' indexing.
+ */
+#ifndef GUIDED_ATTN_H_
+#define GUIDED_ATTN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GA_ABI_VERSION 1
+
+typedef void* ga_stream_t; /* cudaStream_t */
+
+enum ga_status { GA_OK = 0, GA_ERR_BAD_ARG = -1, GA_ERR_UNSUPPORTED = -2, GA_ERR_ALIGNMENT = -3, GA_ERR_CUDA = -4 };
+enum ga_dtype { GA_F32 = 0, GA_F16 = 1, GA_BF16 = 2 };
+/* kernel variant: AUTO picks TCGEN05 for 16-bit operands it supports, SIMT otherwise (fp32 is SIMT-only: exact fp32) */
+enum ga_impl { GA_IMPL_AUTO = 0, GA_IMPL_SIMT = 1, GA_IMPL_TCGEN05 = 2 };
+/* reference utils/helpers.py:10-13 (AnnotationType) */
+enum ga_token_kind { GA_TOKEN_COOR = 0, GA_TOKEN_BOX = 1, GA_TOKEN_KEYWORD = 2 };
+
+#define GA_MAX_ACC_SLICES 32 /* per-layer accumulators one tail launch can reduce */
+#define GA_MAX_TOKENS 24     /* tracked tokens per launch */
+#define GA_MAX_BOXES 32      /* boxes per rasteriser launch */
+#define GA_MAX_CTX 128       /* text-context length the attention kernels accept (SD: 77) */
+
+/* per-token outputs of the guidance tail, `stats[token][GA_STATS]` */
+enum ga_stat {
+  GA_STAT_MAX = 0,      /* max of the smoothed map          (reference pipeline_guided_attention.py:255)            */
+  GA_STAT_SUM = 1,      /* sum of the smoothed map          (:263)                                                  */
+  GA_STAT_COL = 2,      /* sum (jj+.5) p                    (:264-268)                                              */
+  GA_STAT_ROW = 3,      /* sum (ii+.5) p                                                                             */
+  GA_STAT_INSIDE = 4,   /* inside-box loss                  (utils/helpers.py:247-277)                              */
+  GA_STAT_OUTSIDE = 5,  /* outside-box loss                                                                          */
+  GA_STAT_SCALED = 6,   /* token's term of the total loss   (pipeline_guided_attention.py:405-438)                  */
+  GA_STAT_UNSCALED = 7, /* token's threshold quantity       (:424, :411)                                            */
+  GA_STAT_HINGE_IN = 8, /* strict mode only: sum_in  w [p < 1/n_in] p   (saved for the backward)                    */
+  GA_STAT_HINGE_OUT = 9,/* strict mode only: sum_out w [p > 0] p                                                    */
+  GA_STAT_NINSIDE = 10, /* number of inside pixels                                                                  */
+  GA_STAT_CENTER = 11,  /* centring loss |col-cx*res|/(res-1) + 4|row-cy*res|/(res-1)   (:390-395)                  */
+  GA_STATS = 12
+};
+
+/* One tracked text token = one entry of the reference's `config.token_dict` (run.py:81-91). */
+typedef struct ga_token {
+  int32_t column;      /* token index - first: column of the renormalised map (pipeline_guided_attention.py:228)    */
+  int32_t kind;        /* ga_token_kind                                                                              */
+  int32_t box;         /* index into masks / weights for BOX tokens, -1 otherwise                                    */
+  int32_t group;       /* sub-prompt id (threshold grouping, :358-387)                                               */
+  float target_x;      /* float32(cx * res): box centre or crosshair x at map resolution (:392)                      */
+  float target_y;      /* float32(cy * res)                                                                          */
+  float center_weight; /* weight of the centring term in the scaled loss: bb_center_weight (BOX) or 1 (COOR)         */
+  float group_weight;  /* 1, or 1/len(sub-prompt) when sub_prompt_avg_within (:376-379)                              */
+} ga_token_t;
+
+typedef struct ga_tail_params {
+  int32_t res;          /* map side: res*res == n_query of the accumulators                                          */
+  int32_t n_ctx;        /* text-context length T (77)                                                                */
+  int32_t first, last;  /* tokens [first, last) enter the renormalisation softmax; reference: 1 and T-1 (or n_ids-1) */
+  int32_t n_tokens;     /* <= GA_MAX_TOKENS                                                                          */
+  int32_t n_groups;
+  int32_t strict;       /* curHyperParams["strict"] (utils/helpers.py:250)                                           */
+  int32_t smooth;       /* smooth_attentions (pipeline_guided_attention.py:251)                                      */
+  float w1d[3];         /* separable smoothing taps, normalised to sum 1 (utils/gaussian_smoothing.py:37-43)         */
+  float temperature;    /* 100 (:218)                                                                                */
+  float inv_count;      /* 1 / (number of (n_query, n_ctx) head-maps summed into the accumulators)                   */
+  float inside_scale;   /* curHyperParams["inside_loss_scale"]                                                       */
+  float outside_scale;  /* curHyperParams["outside_loss_scale"] * 3 (:426)                                           */
+  float custom_total;   /* reserved (0)                                                                              */
+} ga_tail_params_t;
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+int ga_version(void);               /* GA_ABI_VERSION */
+const char* ga_last_error(void);    /* thread-local, never NULL */
+int ga_device_supported(int device); /* 1 if `device` is compute capability 10.x, 0 otherwise, <0 on error */
+
+/* ---- K1: fused cross-attention forward ------------------------------------------------------------------------------
+ * Replaces AttendExciteCrossAttnProcessor.__call__'s  baddbmm -> softmax -> controller(P) -> bmm  sequence
+ * (utils/ptp_utils.py:77-85, 97-146) together with AttentionStore.forward (:226-230) and the per-layer part of
+ * aggregate_attention (:273-289): P is never written to HBM.
+ *   q (B, N, H*d)   k, v (B, T, H*d)   o (B, N, H*d)   all `dtype`
+ *   lse (B, H, N) fp32: row log-sum-exp of scale*q.k, saved for the backward
+ *   acc (B, N, T) fp32 or NULL: acc[b] = sum over heads of P[b, h]  (deterministic, no atomics)
+ * T <= GA_MAX_CTX, d % 8 == 0, d <= 256. */
+int ga_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, int batch,
+                      int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl,
+                      ga_stream_t stream);
+
+/* ---- K2: fused cross-attention backward ------------------------------------------------------------------------------
+ * autograd of K1 with the attention-map gradient injected:
+ *   dP = dO V^T + d_acc[b]      dS = P o (dP - rowsum(P o dP))      dQ = scale dS K
+ *   d_o (B, N, H*d) `dtype`;  d_acc fp32 (N, T) slices with batch stride `d_acc_batch_stride` elements
+ *   (0 = one slice broadcast over the batch), or NULL;  d_q (B, N, H*d) `dtype`.
+ *   d_k, d_v: fp32 (B, T, H*d), ACCUMULATED with atomics (caller zero-fills), or NULL (the reference only
+ *   differentiates w.r.t. the latents, pipeline_guided_attention.py:466). */
+int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
+                      const float* d_acc, int64_t d_acc_batch_stride, void* d_q, float* d_k, float* d_v, int batch,
+                      int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl,
+                      ga_stream_t stream);
+
+/* Materialise P (B*H, N, T) in `dtype`, batch-major rows b*H+h, for API compatibility with code that reads the
+ * reference's per-head maps (AttentionStore.get_average_attention, utils/ptp_utils.py:245-247).  Off the hot path. */
+int ga_attn_probs(const void* q, const void* k, void* probs, int batch, int heads, int n_query, int n_ctx,
+                  int head_dim, float scale, int dtype, ga_stream_t stream);
+
+/* ---- K5: box-mask rasteriser ------------------------------------------------------------------------------------------
+ * masks[i, ii, jj] = inside_box(jj, ii, Rect(box_i, size 1).of_size(res))   (utils/helpers.py:164-173, 28-30)
+ * float64, no FMA contraction, the reference's operation order: bit-exact.  boxes_host: n x (x, y, w, h). */
+int ga_rasterize_boxes(const double* boxes_host, int n_boxes, int res, double shrink, uint8_t* masks,
+                       ga_stream_t stream);
+
+/* ---- K3+K4+K6: guidance tail -------------------------------------------------------------------------------------------
+ * Replaces aggregate_attention's mean (utils/ptp_utils.py:287-288), _compute_max_attention_per_index
+ * (pipeline_guided_attention.py:201-296), helpers.calculate_bounding_box_losses (utils/helpers.py:215-277) and
+ * _compute_loss (:398-451):
+ *   Abar = inv_count * sum of accumulator slices;  A = softmax(temperature * Abar[:, first:last]);
+ *   per token: 3x3 separable Gaussian with reflect padding, max/argmax, normalise, centre of mass, box losses, loss.
+ * acc_host[i] points to slices_host[i] consecutive (res*res, n_ctx) fp32 slices (one K1 `acc` tensor).
+ * Outputs: attn_text (res*res, last-first) fp32;  smoothed (n_tokens, res*res) fp32;  stats (n_tokens, GA_STATS) fp32;
+ *          argmax (n_tokens) int32 first-occurrence row-major;  total (1) fp32 = sum group_weight * scaled.
+ * masks (n_boxes, res, res) u8 and weights (n_boxes, res, res) fp32 (strict mode only, may be NULL otherwise).
+ * ticket: 4-byte device workspace that hands the per-pixel stage over to the per-token stage inside the single
+ *         launch; zero it once, every launch leaves it zero; launches sharing a ticket must be stream-ordered. */
+int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t* slices_host, int n_acc,
+                         const ga_tail_params_t* params_host, const ga_token_t* tokens_host, const uint8_t* masks,
+                         const float* weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
+                         float* total, uint32_t* ticket, ga_stream_t stream);
+
+/* Backward of the tail, one launch:  d_abar (res*res, n_ctx) fp32 = d loss / d (each accumulator slice), i.e. already
+ * multiplied by inv_count.  Upstream gradients (all DEVICE, any may be NULL = zero): g_total (1), g_stats
+ * (n_tokens, GA_STATS; only MAX/COL/ROW/INSIDE/OUTSIDE are differentiable outputs), g_attn_text (res*res, last-first). */
+int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* tokens_host, const uint8_t* masks,
+                         const float* weights, const float* attn_text, const float* smoothed, const float* stats,
+                         const int32_t* argmax, const float* g_total, const float* g_stats, const float* g_attn_text,
+                         float* d_abar, ga_stream_t stream);
+
+/* ---- stand-alone stages (same device code as the tail), for the module-level API -----------------------------------
+ * GaussianSmoothing.forward on reflect-padded maps (utils/gaussian_smoothing.py:63-71 + pipeline :253):
+ *   maps (n, res, res) fp32 -> out (n, res, res) */
+int ga_smooth_fwd(const float* maps, float* out, int n_maps, int res, const float* w1d_host, ga_stream_t stream);
+int ga_smooth_bwd(const float* g_out, float* g_maps, int n_maps, int res, const float* w1d_host, ga_stream_t stream);
+
+/* helpers.calculate_bounding_box_losses (utils/helpers.py:215-277) on one normalised map p (res, res):
+ *   out2 = (loss_inside, loss_outside);  bwd: g_p = g_out2[0] d inside/dp + g_out2[1] d outside/dp */
+int ga_box_loss_fwd(const float* p, const uint8_t* mask, const float* weights, int res, int strict, float* out2,
+                    ga_stream_t stream);
+int ga_box_loss_bwd(const float* p, const uint8_t* mask, const float* weights, int res, int strict,
+                    const float* g_out2, float* g_p, ga_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUIDED_ATTN_H_ */

@@ -1,0 +1,151 @@
+"""CPU: host-side mirror of the reference API (parser, token table, geometry, store bookkeeping, thresholds) against the
+golden fixtures from the unmodified reference, and the C-ABI library's exported surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from guided_attention_b200 import _cabi, helpers, shared_state as S
+from guided_attention_b200 import run as R
+from guided_attention_b200.helpers import AnnotationType as AT
+from tests.gpu_harness import setup_prompt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _meta_json(meta_info):
+    out = []
+    for sub, kind, payload in meta_info:
+        if kind == AT.BOX:
+            payload = [payload.x, payload.y, payload.width, payload.height]
+        elif kind == AT.COOR:
+            payload = list(payload)
+        out.append([sub, kind.name, payload])
+    return out
+
+
+def test_parse_and_token_dict_bit_exact(kat):
+    for rec in kat["parse"]:
+        if "error" in rec:
+            with pytest.raises(Exception) as ei:
+                setup_prompt(rec["meta_prompt"])
+            assert type(ei.value).__name__ == rec["error"], rec["meta_prompt"]
+            continue
+        cfg = setup_prompt(rec["meta_prompt"])
+        assert cfg.prompt == rec["prompt"], rec["meta_prompt"]
+        assert _meta_json(cfg.meta_info) == rec["meta_info"]
+        assert {k: v[1] for k, v in cfg.custom_loss.items()} == rec["custom"]
+        td = {str(k): {"word": v["word"], "kind": v["loss_type"].name, "subprompt": v["subprompt"]}
+              for k, v in cfg.token_dict.items()}
+        assert td == rec["token_dict"]
+        assert list(td.keys()) == list(rec["token_dict"].keys())   # insertion order = output order
+
+
+def test_shipped_hyperparameters():
+    """effective thresholds and hyper-parameters after overrideConfig."""
+    cfg = setup_prompt()
+    assert cfg.thresholds == {0: 1.0}
+    assert S.curHyperParams == {"strict": False, "inside_loss_scale": .2, "outside_loss_scale": .2,
+                                "shrink_factor": .15, "thresholds": {0: 1.}, "use_optimizer": False,
+                                "recurse_until": 14, "recurse_steps": 3}
+
+
+def test_host_masks_and_rect_bit_exact(kat):
+    for rec in kat["masks"]:
+        S.curHyperParams = {"shrink_factor": rec["shrink"]}
+        r = helpers.Rect(*rec["box"], 1).of_size(float(rec["res"]) if rec["res"] == 16 else rec["res"])
+        assert [r.x, r.y, r.width, r.height] == rec["rect_at_res"]
+        m = helpers.box_mask_host(r, rec["res"])
+        assert ["".join(map(str, row)) for row in m.tolist()] == rec["mask_rows"]
+
+
+def test_gaussian_taps_match_reference_kernel(kat):
+    from guided_attention_b200 import ops
+    for rec in kat["gaussian"]:
+        w = np.array(ops.gaussian_taps(rec["kernel_size"], rec["sigma"]))
+        np.testing.assert_allclose(np.outer(w, w), np.array(rec["weight"]), rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        ops.gaussian_taps(5, 0.5)
+
+
+def test_find_matching_bracket():
+    assert helpers.findMatchingBracket("robot:.1,.2]") == 11
+    assert helpers.findMatchingBracket("a [b] c] d") == 7
+    assert helpers.findMatchingBracket("no close") == -1
+
+
+def test_store_bookkeeping_matches_reference_counts():
+    """Layer counter / between_steps / key layout (reference utils/ptp_utils.py:194-243) with shape-only stand-ins."""
+    from guided_attention_b200.ptp_utils import AttentionStore, _ShapeOnly, HeadSummedMaps
+    setup_prompt()
+    store = AttentionStore()
+    store.num_att_layers = 4
+    acc = torch.zeros(1, 256, 77)
+    q = torch.zeros(1, 256, 16)
+    k = torch.zeros(1, 77, 16)
+    m = HeadSummedMaps(acc, 8, q, k, 0.25)
+    assert tuple(m.shape) == (8, 256, 77) and m.n_maps == 8
+    store(m, True, "down")
+    store(_ShapeOnly(8, 4096, 77), True, "up")          # too large: not kept
+    store(torch.zeros(8, 256, 256), False, "down")      # self maps are not kept by default
+    assert store.cur_step == 0 and store.attention_store == {}
+    store(m, True, "mid")
+    assert store.cur_step == 1 and store.cur_att_layer == 0
+    got = {k2: len(v) for k2, v in store.get_average_attention().items()}
+    assert got == {"down_cross": 1, "mid_cross": 1, "up_cross": 0, "down_self": 0, "mid_self": 0, "up_self": 0}
+    assert store.step_store == AttentionStore.get_empty_store()
+
+
+def test_register_attention_control_counts_32_layers():
+    from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control, \
+        AttendExciteCrossAttnProcessor
+    from guided_attention_b200.substrate import UNetConfig, build_unet
+    import types
+    unet = build_unet(UNetConfig.tiny())
+    store = AttentionStore()
+    register_attention_control(types.SimpleNamespace(unet=unet), store)
+    assert store.num_att_layers == 32
+    procs = unet.attn_processors
+    assert all(isinstance(p, AttendExciteCrossAttnProcessor) for p in procs.values())
+    places = {n.split(".")[0]: p.place_in_unet for n, p in procs.items()}
+    assert places == {"down_blocks": "down", "mid_block": "mid", "up_blocks": "up"}
+
+
+def test_meets_threshold_truth_table(kat):
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    pipe = GuidedAttention(unet=None)
+    for rec in kat["loss"]:
+        case_prompt = next(c for c in __import__("oracle.cases", fromlist=["LOSS_CASES"]).LOSS_CASES
+                           if c["name"] == rec["name"])
+        setup_prompt(case_prompt["meta_prompt"], case_prompt.get("hyper"), case_prompt.get("cfg"))
+        unscaled = [(k, v) for k, v in rec["unscaled"]]
+        thr = {int(k): v for k, v in rec["thresholds"].items()}
+        for i, want in rec["meets"].items():
+            assert pipe.meets_threshold(int(i), thr, unscaled) == want, (rec["name"], i)
+
+
+def test_library_exports_every_declared_symbol():
+    """No compute calls here (no GPU): the library loads and exports exactly what include/guided_attn.h declares."""
+    header = open(os.path.join(ROOT, "include", "guided_attn.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(ga_\w+)\(", header, flags=re.M))
+    assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
+    lib = _cabi.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ga_version() == _cabi.GA_ABI_VERSION
+    assert ctypes.sizeof(_cabi.GaToken) == 32 and ctypes.sizeof(_cabi.GaTailParams) == 64
+
+
+def test_ops_refuse_cpu_tensors():
+    from guided_attention_b200 import ops
+    q = torch.zeros(1, 64, 16)
+    with pytest.raises(_cabi.GuidedAttnLibraryError):
+        ops.cross_attention(q, torch.zeros(1, 77, 16), torch.zeros(1, 77, 16), 2, 0.3)
+
+
+def test_missing_library_is_loud(tmp_path):
+    with pytest.raises(_cabi.GuidedAttnLibraryError):
+        _cabi.load(str(tmp_path / "nope.so"))
