@@ -1,15 +1,446 @@
-// K1 / K2, tcgen05 variant (placeholder until the tensor-core kernels land).
+// K1, tcgen05 variant: fused cross-attention forward against the short text context on the 5th-gen tensor cores.
+//
+//   one CTA  = 128 query rows x (heads_per_cta heads, looped)            one cluster = all heads of a row tile
+//   TMA      : Q tile, K, V of the head -> shared memory, 128-byte swizzle (cp.async.bulk.tensor.4d + mbarrier)
+//   MMA 1    : S[128 x 80]  = Q[128 x d] . K^T          tcgen05.mma kind::f16, A/B K-major from smem, D in TMEM
+//   softmax  : one thread per row (TMEM lane), tcgen05.ld, exp2, fp32; P normalised before the second GEMM
+//   MMA 2    : O[128 x d]   = P[128 x 80] . V[80 x d]    A = P written back to TMEM as packed 16-bit, B = V MN-major
+//   epilogue : tcgen05.ld O -> 16-bit -> global;  row log-sum-exp -> global
+//   maps     : every thread keeps its row of head-summed probabilities in registers; the heads of one row tile form a
+//              thread-block cluster and the per-head tiles are reduced over distributed shared memory in a fixed order
+//              -> the AttentionStore accumulator `acc[b]` is written once, coalesced, without atomics (deterministic).
+//
+// Replaces reference utils/ptp_utils.py:77-85, 97-146, 226-230 (+ the per-layer part of :273-289) for 16-bit operands.
+// The probability tensor never reaches HBM.  This kernel is HBM/latency-bound (77 keys: 60-76 FLOP/B): the
+// tensor cores are used because the contraction is dense, not because it is the bottleneck.
+#include <cuda.h>
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "ga_common.cuh"
+
+namespace cg = cooperative_groups;
+
 namespace ga {
 namespace tc {
-bool supports_fwd(int, int, int, int, bool) { return false; }
-bool supports_bwd(int, int, int, int, bool) { return false; }
-int fwd(const void*, const void*, const void*, void*, float*, float*, int, int, int, int, int, float, int, cudaStream_t) {
-  return fail(GA_ERR_UNSUPPORTED, "tcgen05 forward not built");
+
+constexpr int kM = 128;         // query rows per tile = UMMA M
+constexpr int kTpad = 80;       // keys padded to a multiple of 16 (UMMA N granularity at M = 128)
+constexpr int kBlockCols = 64;  // 16-bit elements per 128-byte swizzle row
+constexpr int kThreads = 128;
+constexpr int kQBlockBytes = kM * 128;      // one 64-column block of the Q tile
+constexpr int kKVBlockBytes = kTpad * 128;  // one 64-column block of K or V
+constexpr int kAccStride = kTpad + 1;       // padded row stride (floats) of the cluster-reduction staging tile
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// TMEM column map (fp32 columns).  P (packed 16-bit, 40 columns) overwrites the head of S once every thread has read
+// its row of S; O follows.  Everything fits 256 columns up to d = 160, so two CTAs share an SM's 512 columns.
+constexpr int kColS = 0;
+constexpr int kColP = 0;
+constexpr int kColO = 96;
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) -------------------------------------------------
+// shared-memory matrix descriptor, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1
+// [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32 [4,6)=1 | A fmt [7,10) | B fmt [10,13) | A major bit15 | B major bit16 | N>>3 [17,23)
+// | M>>4 [24,29)      (fmt: 0 = f16, 1 = bf16; major: 0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int b_mn_major, int n, int m) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct FwdParams {
+  void* o;
+  float* lse;
+  float* acc;
+  int B, H, N, T, d;
+  int nblk;           // 64-column blocks of the head dimension
+  int npv;            // UMMA N of the second GEMM: d rounded up to 16
+  int heads_per_cta;
+  int tmem_cols;
+  int bf16;
+  float scale;
+};
+
+// ------------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads)
+cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                         const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y, b = blockIdx.z;
+  const int head0 = blockIdx.x * p.heads_per_cta;
+  const int row0 = tile * kM;
+
+  // 1024-byte aligned carve-up (the 128-byte swizzle pattern repeats every 8 rows = 1024 bytes)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + p.nblk * kQBlockBytes;
+  const uint32_t sV = sK + p.nblk * kKVBlockBytes;
+  float* sAcc = reinterpret_cast<float*>(base_ptr + p.nblk * (kQBlockBytes + 2 * kKVBlockBytes));
+  const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_k);
+    prefetch_tmap(&map_v);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's quarter of the 128 TMEM lanes
+
+  const int fmt = p.bf16 ? 1 : 0;
+  const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
+  const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+  const uint32_t tx_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
+  const float sc = p.scale * 1.4426950408889634f;
+  const int ksteps = (p.d + 15) >> 4;
+
+  float pacc[kTpad];
+#pragma unroll
+  for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+
+  uint32_t ph_load = 0, ph_mma = 0;   // mbarrier phase parities: bar_load flips once per head, bar_mma twice
+  for (int hh = 0; hh < p.heads_per_cta; ++hh) {
+    const int h = head0 + hh;
+    // ---- TMA: Q tile + K + V of this head; MMA 1 -----------------------------------------------------------
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, tx_bytes);
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
+        tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
+        tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+      }
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after();
+      // S = Q K^T: K-major operands; a k-step of 16 elements is 32 bytes inside the 128-byte swizzled row
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t off = (uint32_t)(ks >> 2) , in = (uint32_t)(ks & 3) * 32u;
+        const uint64_t da = smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024);
+        const uint64_t db = smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024);
+        mma_ss(tmem + kColS, da, db, idesc_qk, ks > 0 ? 1u : 0u);
+      }
+      tc_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+
+    // ---- softmax over the keys of this thread's row ----------------------------------------------------------
+    float s[kTpad];
+#pragma unroll
+    for (int c = 0; c < kTpad / 16; ++c) tmem_ld16(lane_addr + kColS + c * 16, s + c * 16);
+    tmem_ld_wait();
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kTpad; ++j)
+      if (j < p.T) m = fmaxf(m, s[j]);
+    const float mo = m * sc;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTpad; ++j) {
+      const float e = (j < p.T) ? exp2f(fmaf(s[j], sc, -mo)) : 0.f;
+      s[j] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    uint32_t packed[kTpad / 2];
+#pragma unroll
+    for (int j = 0; j < kTpad; j += 2) {
+      const float p0 = s[j] * inv, p1 = s[j + 1] * inv;
+      pacc[j] += p0;
+      pacc[j + 1] += p1;
+      packed[j >> 1] = pack16(p0, p1, p.bf16 != 0);
+    }
+    const int row = row0 + tid;
+    if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(sum);
+    // P -> TMEM (A operand of the second GEMM), over the columns S occupied
+#pragma unroll
+    for (int c = 0; c < kTpad / 16; ++c) tmem_st8(lane_addr + kColP + c * 8, packed + c * 8);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- MMA 2: O = P V  (V is MN-major: rows = keys, 128-byte rows of 64 channels) -------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < kTpad / 16; ++ks) {
+        // 16 keys = two 8-row swizzle atoms (SBO = 1024 B apart); channel blocks are LBO = one K/V block apart
+        const uint64_t db = smem_desc_sw128(sV + ks * 2048u, kKVBlockBytes, 1024);
+        mma_ts(tmem + kColO, tmem + kColP + ks * 8, db, idesc_pv, ks > 0 ? 1u : 0u);
+      }
+      tc_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue: O row -> 16-bit -> global -----------------------------------------------------------------
+    {
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+      for (int c = 0; c < p.npv / 16; ++c) {
+        float ov[16];
+        tmem_ld16(lane_addr + kColO + c * 16, ov);
+        tmem_ld_wait();
+        if (row < p.N) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], p.bf16 != 0);
+          const int col = c * 16;
+          if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+    }
+    // all TMEM reads of this head are done before the next head's MMA overwrites S / O, and before smem is reloaded
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    ph_load ^= 1;
+  }
+
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+
+  // ---- head reduction of the probability rows across the cluster (DSMEM), fixed order -----------------------
+  if (p.acc != nullptr) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+#pragma unroll
+    for (int j = 0; j < kTpad; ++j) sAcc[tid * kAccStride + j] = pacc[j];
+    cluster.sync();
+    for (int i = (int)crank + (int)csize * warp; i < kM; i += (int)csize * (kThreads / 32)) {
+      const int r = row0 + i;
+      if (r >= p.N) continue;
+      float v[3] = {0.f, 0.f, 0.f};
+      for (unsigned c = 0; c < csize; ++c) {
+        const float* remote = cluster.map_shared_rank(sAcc, c) + i * kAccStride;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int j = lane + 32 * kk;
+          if (j < p.T) v[kk] += remote[j];
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        const int j = lane + 32 * kk;
+        if (j < p.T) p.acc[((int64_t)b * p.N + r) * p.T + j] = v[kk];
+      }
+    }
+    cluster.sync();   // nobody leaves while a peer may still read its staging tile
+  }
+}
+
+// --------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// (d, H, rows, B) view of a (B, rows, H*d) tensor; box = 64 channels x 1 head x box_rows rows; 128-byte swizzle;
+// out-of-range channels / rows are filled with zeros.
+static int make_map(CUtensorMap* map, const void* ptr, int dtype, int B, int rows, int H, int d, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)H, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)H * d * 2, (cuuint64_t)rows * H * d * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockCols, 1u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, dtype == GA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GA_OK;
+}
+
+static int heads_per_cta_for(int H) {
+  for (int hpc = 1; hpc <= H; ++hpc)
+    if (H % hpc == 0 && H / hpc <= 8) return hpc;
+  return H;
+}
+
+// GA_DISABLE_TCGEN05=1 makes AUTO pick the SIMT variant everywhere (debugging aid: A/B the two variants)
+static bool tc_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GA_DISABLE_TCGEN05");
+    on = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc) {
+  (void)heads; (void)with_acc;
+  return tc_enabled() && (dtype == GA_F16 || dtype == GA_BF16) && n_ctx >= 1 && n_ctx <= kTpad && head_dim % 8 == 0 &&
+         head_dim >= 8 && head_dim <= 256;
+}
+bool supports_bwd(int, int, int, int, bool) { return false; }
+
+int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, int B, int H, int N, int T, int d,
+        float scale, int dtype, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+  if ((rc = make_map(&mk, k, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
+  if ((rc = make_map(&mv, v, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
+
+  FwdParams p;
+  p.o = o; p.lse = lse; p.acc = acc;
+  p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
+  p.nblk = (d + kBlockCols - 1) / kBlockCols;
+  p.npv = (d + 15) & ~15;
+  p.heads_per_cta = acc != nullptr ? heads_per_cta_for(H) : 1;
+  const int need_cols = kColO + p.npv;
+  p.tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
+  p.bf16 = dtype == GA_BF16;
+  p.scale = scale;
+
+  size_t smem = 1024 + (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
+  if (acc != nullptr) smem += (size_t)kM * kAccStride * sizeof(float);
+  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention: %zu B of shared memory", smem);
+  cudaError_t e = cudaFuncSetAttribute(cross_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H / p.heads_per_cta, (N + kM - 1) / kM, B);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = acc != nullptr ? H / p.heads_per_cta : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, cross_attn_fwd_tc_kernel, mq, mk, mv, p);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cross_attn_fwd_tc launch: %s", cudaGetErrorString(e));
+  return check_launch("cross_attn_fwd_tc");
+}
+
 int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, void*, int, int, int,
         int, int, float, int, cudaStream_t) {
   return fail(GA_ERR_UNSUPPORTED, "tcgen05 backward not built");
 }
+
 }  // namespace tc
 }  // namespace ga

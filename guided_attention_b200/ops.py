@@ -94,7 +94,8 @@ def attn_bwd_bytes(B, H, N, T, d, esize, with_dacc):
 
 
 _DTYPES = {torch.float32: abi.GA_F32, torch.float16: abi.GA_F16, torch.bfloat16: abi.GA_BF16}
-default_impl = abi.GA_IMPL_AUTO
+default_impl = abi.GA_IMPL_AUTO       # forward kernel variant (tests force SIMT / TCGEN05 through `impl=`)
+default_bwd_impl = abi.GA_IMPL_AUTO   # backward kernel variant
 
 
 def _stream(t: torch.Tensor):
@@ -142,7 +143,8 @@ class _CrossAttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_o, d_acc):
         q, k, v, lse = ctx.saved_tensors
-        heads, scale, impl = ctx.meta
+        heads, scale, _ = ctx.meta
+        impl = default_bwd_impl
         lib = abi.load()
         B, N, Cdim = q.shape
         T = k.shape[1]

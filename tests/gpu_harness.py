@@ -119,9 +119,9 @@ def run_microcase(res=16, heads=8, head_dim=40, layers=5, batch=1, dtype=torch.f
     grads = torch.autograd.grad(loss, qs)
     torch.cuda.synchronize()
     info = {
-        "loss": float(loss), "oracle_loss": float(r.loss),
-        "loss_rel_err": abs(float(loss) - float(r.loss)) / abs(float(r.loss)),
-        "out_rel_err": max(rel_err(o.float().cpu().numpy(), oo_.detach().numpy()) for o, oo_ in zip(outs, oo)),
+        "loss": float(loss.detach()), "oracle_loss": float(r.loss.detach()),
+        "loss_rel_err": abs(float(loss.detach()) - float(r.loss.detach())) / abs(float(r.loss.detach())),
+        "out_rel_err": max(rel_err(o.detach().float().cpu().numpy(), oo_.detach().numpy()) for o, oo_ in zip(outs, oo)),
         "grad_rel_err": max(rel_err(g.float().cpu().numpy(), og_.numpy()) for g, og_ in zip(grads, og)),
         "argmax_equal": [int(a) for a in ld["_argmax"].cpu().tolist()] == r.argmax,
     }

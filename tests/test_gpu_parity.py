@@ -89,6 +89,52 @@ def test_cross_attention_forward(shape, dtype, rtol):
     assert none is None and torch.equal(o2, o)      # same result with and without the accumulator, bit for bit
 
 
+@pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("with_acc", [False, True])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, with_acc):
+    """The tcgen05/TMA/TMEM variant explicitly (impl = GA_IMPL_TCGEN05), against the oracle and the SIMT variant."""
+    from guided_attention_b200 import ops, _cabi as abi
+    H, d, N, T, B = shape
+    if T > 80:
+        with pytest.raises(abi.GuidedAttnLibraryError):
+            q, k, v = _attn_case(H, d, N, T, B, dtype)
+            ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, d ** -0.5, want_acc=with_acc,
+                                impl=abi.GA_IMPL_TCGEN05)
+        return
+    q, k, v = _attn_case(H, d, N, T, B, dtype, seed=5)
+    scale = d ** -0.5
+    P, Oo = O.cross_attention(O.head_to_batch(q.float(), H), O.head_to_batch(k.float(), H),
+                              O.head_to_batch(v.float(), H), scale)
+    o, acc = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=with_acc,
+                                 impl=abi.GA_IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(o.float().cpu().numpy(), O.batch_to_head(Oo, H).numpy()) < rtol
+    o_s, acc_s = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=with_acc,
+                                     impl=abi.GA_IMPL_SIMT)
+    assert rel_err(o.float().cpu().numpy(), o_s.float().cpu().numpy()) < rtol
+    if with_acc:
+        assert rel_err(acc.cpu().numpy(), P.reshape(B, H, N, T).sum(1).numpy()) < 1e-3
+        assert rel_err(acc.cpu().numpy(), acc_s.cpu().numpy()) < 1e-3
+        o2, acc2 = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=True,
+                                       impl=abi.GA_IMPL_TCGEN05)
+        assert torch.equal(acc2, acc) and torch.equal(o2, o)        # deterministic cluster reduction
+
+
+def test_tcgen05_lse_matches_simt():
+    from guided_attention_b200 import ops, _cabi as abi
+    H, d, N, T, B = 8, 80, 1024, 77, 2
+    q, k, v = _attn_case(H, d, N, T, B, torch.float16, seed=9)
+    qd = q.to(DEV).requires_grad_(True)
+    g = torch.randn(B, N, H * d, generator=torch.Generator("cpu").manual_seed(1)).half().to(DEV)
+    outs = []
+    for impl in (abi.GA_IMPL_TCGEN05, abi.GA_IMPL_SIMT):
+        o, _ = ops.cross_attention(qd, k.to(DEV), v.to(DEV), H, d ** -0.5, want_acc=False, impl=impl)
+        (dq,) = torch.autograd.grad(o, qd, g)      # the backward consumes the saved LSE of each variant
+        outs.append(dq.float().cpu().numpy())
+    assert rel_err(outs[0], outs[1]) < FP16_RTOL
+
+
 # -------------------------------------------------------------------------------------------------- K2 backward
 @pytest.mark.parametrize("dtype,rtol", [(torch.float32, FP32_RTOL), (torch.float16, FP16_RTOL)])
 @pytest.mark.parametrize("shape", [(8, 40, 1024, 77, 1), (8, 160, 256, 77, 2), (5, 64, 576, 77, 1),
@@ -343,6 +389,8 @@ def _psnr(a, b):
 
 
 def test_pipeline_matches_reference_call_on_tiny_unet(e2e_golden):
+    torch.backends.cudnn.allow_tf32 = False      # fp32 parity run: keep cuDNN/cuBLAS in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     """The product pipeline (CUDA kernels, fp32) against the final latents of the reference's own `__call__`
     (tests/golden/reference_e2e.npz): same number of UNet forwards, PSNR > 60 dB, cosine > 0.99999."""
     from guided_attention_b200 import run as R, shared_state as S
