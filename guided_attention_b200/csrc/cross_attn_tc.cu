@@ -339,6 +339,151 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   }
 }
 
+
+// ============================================================================================== K2 (backward)
+//   S  = Q K^T, dP = dO V^T                two K-major GEMMs into two TMEM regions
+//   P  = exp(scale S - lse);  dP += d_acc[row]  (the attention-map gradient injected by the guidance tail)
+//   dS = P o (dP - rowsum(P o dP)) * scale   -> packed 16-bit back into TMEM (A operand)
+//   dQ = dS K                               K is the MN-major B operand (same tile the first GEMM read K-major)
+// autograd of reference utils/ptp_utils.py:77-85 restricted to the latent path (dK / dV: SIMT variant).
+constexpr int kColDP = 80;   // dP, later overwritten by dQ (dP is dead once it is in registers)
+
+struct BwdParams {
+  void* d_q;
+  const float* lse;
+  const float* d_acc;
+  int64_t d_acc_bstride;
+  int B, H, N, T, d;
+  int nblk, npv, tmem_cols, bf16;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kThreads)
+cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                         const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                         const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, tile = blockIdx.y, b = blockIdx.z;
+  const int row0 = tile * kM, row = row0 + tid;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sG = sQ + p.nblk * kQBlockBytes;          // dO tile
+  const uint32_t sK = sG + p.nblk * kQBlockBytes;
+  const uint32_t sV = sK + p.nblk * kKVBlockBytes;
+  const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+
+  const int fmt = p.bf16 ? 1 : 0;
+  const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
+  const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+  const int ksteps = (p.d + 15) >> 4;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_load, (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes));
+    for (int blk = 0; blk < p.nblk; ++blk) {
+      tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
+      tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
+      tma_load_4d(sG + blk * kQBlockBytes, &map_do, bar_load, blk * kBlockCols, h, row0, b);
+      tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+    }
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+      mma_ss(tmem + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
+             smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+    }
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+      mma_ss(tmem + kColDP, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
+             smem_desc_sw128(sV + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+    }
+    tc_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  float s[kTpad], dp[kTpad];
+#pragma unroll
+  for (int c = 0; c < kTpad / 16; ++c) {
+    tmem_ld16(lane_addr + kColS + c * 16, s + c * 16);
+    tmem_ld16(lane_addr + kColDP + c * 16, dp + c * 16);
+  }
+  tmem_ld_wait();
+  const bool live = row < p.N;
+  const float sc = p.scale * 1.4426950408889634f;
+  const float l2 = live ? p.lse[((int64_t)b * p.H + h) * p.N + row] * 1.4426950408889634f : 0.f;
+  const float* dacc = (p.d_acc != nullptr && live) ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.T
+                                                   : nullptr;
+  float dsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTpad; ++j) {
+    const bool ok = live && j < p.T;
+    const float pr = ok ? exp2f(fmaf(s[j], sc, -l2)) : 0.f;
+    float g = ok ? dp[j] : 0.f;
+    if (dacc != nullptr && j < p.T) g += __ldg(dacc + j);
+    s[j] = pr;
+    dp[j] = g;
+    dsum = fmaf(pr, g, dsum);
+  }
+  uint32_t packed[kTpad / 2];
+#pragma unroll
+  for (int j = 0; j < kTpad; j += 2)
+    packed[j >> 1] = pack16(s[j] * (dp[j] - dsum) * p.scale, s[j + 1] * (dp[j + 1] - dsum) * p.scale, p.bf16 != 0);
+#pragma unroll
+  for (int c = 0; c < kTpad / 16; ++c) tmem_st8(lane_addr + kColP + c * 8, packed + c * 8);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    for (int ks = 0; ks < kTpad / 16; ++ks)
+      mma_ts(tmem + kColDP, tmem + kColP + ks * 8, smem_desc_sw128(sK + ks * 2048u, kKVBlockBytes, 1024), idesc_dq,
+             ks > 0 ? 1u : 0u);
+    tc_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+
+  uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+  for (int c = 0; c < p.npv / 16; ++c) {
+    float ov[16];
+    tmem_ld16(lane_addr + kColDP + c * 16, ov);
+    tmem_ld_wait();
+    if (live) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], p.bf16 != 0);
+      const int col = c * 16;
+      if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
 // --------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -393,7 +538,9 @@ bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc) 
   return tc_enabled() && (dtype == GA_F16 || dtype == GA_BF16) && n_ctx >= 1 && n_ctx <= kTpad && head_dim % 8 == 0 &&
          head_dim >= 8 && head_dim <= 256;
 }
-bool supports_bwd(int, int, int, int, bool) { return false; }
+bool supports_bwd(int dtype, int n_ctx, int head_dim, int heads, bool with_dkv) {
+  return !with_dkv && supports_fwd(dtype, n_ctx, head_dim, heads, false);
+}
 
 int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, int B, int H, int N, int T, int d,
         float scale, int dtype, cudaStream_t st) {
@@ -437,9 +584,29 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
   return check_launch("cross_attn_fwd_tc");
 }
 
-int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, void*, int, int, int,
-        int, int, float, int, cudaStream_t) {
-  return fail(GA_ERR_UNSUPPORTED, "tcgen05 backward not built");
+int bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
+        int64_t d_acc_bstride, void* d_q, int B, int H, int N, int T, int d, float scale, int dtype, cudaStream_t st) {
+  CUtensorMap mq, mg, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+  if ((rc = make_map(&mg, d_o, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+  if ((rc = make_map(&mk, k, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
+  if ((rc = make_map(&mv, v, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
+  BwdParams p;
+  p.d_q = d_q; p.lse = lse; p.d_acc = d_acc; p.d_acc_bstride = d_acc_bstride;
+  p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
+  p.nblk = (d + kBlockCols - 1) / kBlockCols;
+  p.npv = (d + 15) & ~15;
+  p.tmem_cols = (kColDP + p.npv) <= 256 ? 256 : 512;
+  p.bf16 = dtype == GA_BF16;
+  p.scale = scale;
+  const size_t smem = 1024 + (size_t)p.nblk * 2 * (kQBlockBytes + kKVBlockBytes);
+  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention bwd: %zu B of shared memory", smem);
+  cudaError_t e = cudaFuncSetAttribute(cross_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 grid(H, (N + kM - 1) / kM, B);
+  cross_attn_bwd_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mg, mk, mv, p);
+  return check_launch("cross_attn_bwd_tc");
 }
 
 }  // namespace tc

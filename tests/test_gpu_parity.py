@@ -169,6 +169,45 @@ def test_cross_attention_backward(shape, dtype, rtol, broadcast):
     assert torch.equal(dq2, dq)
 
 
+@pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("shape", [(8, 40, 4096, 77, 1), (8, 80, 1024, 77, 2), (8, 160, 256, 77, 2), (8, 160, 64, 77, 1),
+                                   (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 13, 2)])
+@pytest.mark.parametrize("with_dacc", [False, True])
+def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc):
+    """K2 on the tensor cores (impl = GA_IMPL_TCGEN05) against the oracle's autograd and the SIMT variant."""
+    from guided_attention_b200 import ops, _cabi as abi
+    H, d, N, T, B = shape
+    q, k, v = _attn_case(H, d, N, T, B, dtype, seed=11)
+    scale = d ** -0.5
+    g = torch.Generator("cpu").manual_seed(12)
+    d_o = torch.randn(B, N, H * d, generator=g).to(dtype)
+    d_acc = 3.0 * torch.randn(1, N, T, generator=g)
+    qo = q.float().requires_grad_(True)
+    P, Oo = O.cross_attention(O.head_to_batch(qo, H), O.head_to_batch(k.float(), H), O.head_to_batch(v.float(), H),
+                              scale)
+    obj = (O.batch_to_head(Oo, H) * d_o.float()).sum()
+    if with_dacc:
+        obj = obj + (P.reshape(B, H, N, T).sum(1) * d_acc).sum()
+    (gq,) = torch.autograd.grad(obj, qo)
+    res = {}
+    for impl in (abi.GA_IMPL_TCGEN05, abi.GA_IMPL_SIMT):
+        ops.default_bwd_impl = impl
+        try:
+            qd = q.to(DEV).requires_grad_(True)
+            o, acc = ops.cross_attention(qd, k.to(DEV), v.to(DEV), H, scale, want_acc=True, impl=impl)
+            outs, gs = [o], [d_o.to(DEV)]
+            if with_dacc:
+                outs.append(acc)
+                gs.append(d_acc.to(DEV).expand(B, N, T))
+            (dq,) = torch.autograd.grad(outs, (qd,), gs)
+            torch.cuda.synchronize()
+            res[impl] = dq.float().cpu().numpy()
+        finally:
+            ops.default_bwd_impl = abi.GA_IMPL_AUTO
+    assert rel_err(res[abi.GA_IMPL_TCGEN05], gq.numpy()) < rtol
+    assert rel_err(res[abi.GA_IMPL_TCGEN05], res[abi.GA_IMPL_SIMT]) < rtol
+
+
 # ------------------------------------------------------------------------------------------------ guidance tail
 def _tail_inputs_from_case(case, kat):
     cfg = setup_prompt(case["meta_prompt"], case.get("hyper"), case.get("cfg"))
