@@ -179,6 +179,7 @@ def workload_config(args, dtype):
                         f"(batch 2), {dtype}, thresholds {HYPER['thresholds']} (guidance on early steps), "
                         "recurse_steps 3, attention_res 16" + ("" if args.unet == "sd14" else " [TINY UNET: NOT THE BASELINE CONFIG]"),
             "unet": args.unet, "denoise_steps": args.denoise_steps, "images_per_step_per_gpu": 1,
+            "cuda_graphs": not getattr(args, "no_graphs", False),
             "l2_policy": "inputs larger than L2: every UNet pass streams 1.7 GB of fp16 weights (L2 is 126 MB)",
             "parallelism": f"seed-sharded, {args.gpus} process(es), no hot-path collective"}
 
@@ -204,6 +205,7 @@ def run_ours(args):
     unet = build_unet(ucfg, seed=0, dtype=torch.float16, device=dev)
     pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=WhitespaceTokenizer())
     cfg.stable = pipe
+    pipe.use_cuda_graphs = not args.no_graphs
     R.register_custom_loss("toLeftOf", R.ToLeftOf())
     R.overrideConfig(cfg)
     R.parseMetaPrompt(cfg)
@@ -287,10 +289,13 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # (3) roofline: one more image with per-launch CUDA events on the launching stream
+    # (CUDA events cannot be recorded inside a graph replay: this pass runs the eager loop, same kernels)
+    pipe.use_cuda_graphs = False
     ops.profiler = ops.LaunchProfiler()
     image(seed_of(1, 0), embeds_dev, dev_lat[0])
     prof = ops.profiler.summary()
     ops.profiler = None
+    pipe.use_cuda_graphs = not args.no_graphs
     roofline, kernel_table = roofline_from(prof)
 
     # parity self-check of this very process (tiny, oracle as the checker)
@@ -355,6 +360,7 @@ def main():
     ap.add_argument("--unet", default="sd14", choices=["sd14", "tiny"], help="tiny is for plumbing checks only")
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

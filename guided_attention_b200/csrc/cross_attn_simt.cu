@@ -367,6 +367,21 @@ cross_attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 }
 
 // ------------------------------------------------------------------------------------------------------- launch
+// Raise the opt-in dynamic shared-memory limit once per (device, kernel instantiation): no attribute calls afterwards,
+// which keeps steady-state launches cheap and CUDA-graph capture clean.
+template <typename T>
+static cudaError_t ensure_smem(const void* kernel, int slot) {
+  static bool done[64][3] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (done[dev][slot]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) done[dev][slot] = true;
+  return e;
+}
+
 template <typename T>
 int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, void* probs, int B, int H,
                int N, int Tctx, int d, float scale, cudaStream_t st) {
@@ -377,7 +392,7 @@ int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
   const int heads_per_cta = (acc != nullptr && !probs_only) ? H : 1;
   dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H / heads_per_cta);
   auto kern = probs_only ? cross_attn_fwd_kernel<T, true> : cross_attn_fwd_kernel<T, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem<T>(reinterpret_cast<const void*>(kern), probs_only ? 1 : 0);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<grid, kThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, lse, acc, (T*)probs, H, N, Tctx, d,
                                     scale, heads_per_cta);
@@ -393,7 +408,7 @@ int launch_bwd(const void* q, const void* k, const void* v, const float* lse, co
   if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention bwd: head_dim %d needs %zu B smem", d, smem);
   dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H);
   auto kern = cross_attn_bwd_kernel<T>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem<T>(reinterpret_cast<const void*>(kern), 2);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<grid, kThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, lse, (const T*)d_o, d_acc, bstride,
                                     (T*)d_q, d_k, d_v, H, N, Tctx, d, scale);

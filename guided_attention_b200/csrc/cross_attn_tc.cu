@@ -513,8 +513,30 @@ static int make_map(CUtensorMap* map, const void* ptr, int dtype, int B, int row
   CUresult r = fn(map, dtype == GA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // first call on a thread that has no current context yet (e.g. a fresh autograd worker): let the runtime bind the
+    // primary context of the current device, then retry
+    cudaFree(nullptr);
+    r = fn(map, dtype == GA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return GA_OK;
+}
+
+// The opt-in dynamic shared-memory limit is raised once per (device, kernel) to the largest size the kernel can ask
+// for, so steady-state launches (and CUDA-graph captures) make no attribute call at all.
+static cudaError_t ensure_smem(const void* kernel, int slot, size_t) {
+  static bool done[64][2] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (done[dev][slot]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) done[dev][slot] = true;
+  return e;
 }
 
 static int heads_per_cta_for(int H) {
@@ -564,7 +586,7 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
   size_t smem = 1024 + (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   if (acc != nullptr) smem += (size_t)kM * kAccStride * sizeof(float);
   if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention: %zu B of shared memory", smem);
-  cudaError_t e = cudaFuncSetAttribute(cross_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_kernel), 0, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 
   cudaLaunchConfig_t cfg = {};
@@ -602,7 +624,7 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
   p.scale = scale;
   const size_t smem = 1024 + (size_t)p.nblk * 2 * (kQBlockBytes + kKVBlockBytes);
   if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention bwd: %zu B of shared memory", smem);
-  cudaError_t e = cudaFuncSetAttribute(cross_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_kernel), 1, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   dim3 grid(H, (N + kM - 1) / kM, B);
   cross_attn_bwd_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mg, mk, mv, p);

@@ -542,7 +542,7 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
   const size_t smem = (size_t)tail::kWarps * npix * sizeof(float);
   if (smem > 200 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d too large for the fused tail", p.res);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (smem > 48 * 1024) {
+  if (smem > 48 * 1024) {   // res > 39: not a size the AttentionStore keeps; set per call
     cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }

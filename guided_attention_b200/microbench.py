@@ -1,0 +1,134 @@
+"""Kernel-only timing of the guidance-path kernels (BASELINE config 3 and its batch sweep).
+
+Each measurement replays a CUDA graph holding `reps` back-to-back launches of ONE kernel on rotating buffer sets, between
+two CUDA events on the launching stream: no host launch overhead inside the timed region, and the working set
+(`sets` x bytes-per-launch) is sized past the 126 MB L2 unless `l2_resident=True` is asked for explicitly.
+`python -m guided_attention_b200.microbench` prints the sweep as JSON lines (used for profiles/ and by bench.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import sys
+
+import torch
+
+from . import _cabi as abi
+from . import ops
+
+L2_BYTES = 126 * 1024 * 1024
+
+
+def _time_graph(launch, n_sets, reps=20, replays=5):
+    """launch(i) enqueues one kernel using buffer set i % n_sets.  Returns microseconds per launch."""
+    for i in range(min(n_sets, 3)):
+        launch(i)                      # warm-up (lazy attributes, module load)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            launch(i % n_sets)
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(replays):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e3 / (reps * replays)
+
+
+def time_cross_attn(B, H, N, T, d, dtype=torch.float16, with_acc=True, direction="fwd", impl=abi.GA_IMPL_AUTO,
+                    l2_resident=False, device="cuda:0"):
+    """One K1 (or K2) launch on (B, N, H*d) operands.  Returns dict(us, bytes, gbs)."""
+    lib = abi.load()
+    es = torch.empty((), dtype=dtype).element_size()
+    nbytes = (ops.attn_fwd_bytes if direction == "fwd" else ops.attn_bwd_bytes)(B, H, N, T, d, es, with_acc)
+    n_sets = 1 if l2_resident else max(2, min(64, (2 * L2_BYTES) // max(nbytes, 1) + 1))
+    sets = []
+    g = torch.Generator(device=device).manual_seed(0)
+    for _ in range(n_sets):
+        q = torch.randn(B, N, H * d, device=device, dtype=dtype, generator=g)
+        k = torch.randn(B, T, H * d, device=device, dtype=dtype, generator=g)
+        v = torch.randn(B, T, H * d, device=device, dtype=dtype, generator=g)
+        o = torch.empty_like(q)
+        lse = torch.empty(B, H, N, device=device, dtype=torch.float32)
+        acc = torch.empty(B, N, T, device=device, dtype=torch.float32) if with_acc else None
+        do = torch.randn_like(q)
+        dq = torch.empty_like(q)
+        sets.append((q, k, v, o, lse, acc, do, dq))
+    dacc = torch.randn(N, T, device=device, dtype=torch.float32) if with_acc else None
+    dt = ops._DTYPES[dtype]
+    scale = d ** -0.5
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)   # noqa: E731
+
+    def fwd(i):
+        q, k, v, o, lse, acc, do, dq = sets[i]
+        abi.check(lib.ga_cross_attn_fwd(ops._ptr(q), ops._ptr(k), ops._ptr(v), ops._ptr(o), ops._ptr(lse), ops._ptr(acc),
+                                        B, H, N, T, d, scale, dt, impl, st()), "ga_cross_attn_fwd")
+
+    def bwd(i):
+        q, k, v, o, lse, acc, do, dq = sets[i]
+        abi.check(lib.ga_cross_attn_bwd(ops._ptr(q), ops._ptr(k), ops._ptr(v), ops._ptr(lse), ops._ptr(do),
+                                        ops._ptr(dacc), 0, ops._ptr(dq), None, None, B, H, N, T, d, scale, dt, impl,
+                                        st()), "ga_cross_attn_bwd")
+    if direction == "bwd":
+        for i in range(n_sets):
+            fwd(i)                      # valid LSE for the backward
+    us = _time_graph(fwd if direction == "fwd" else bwd, n_sets)
+    return {"kernel": f"cross_attn_{direction}", "B": B, "H": H, "N": N, "T": T, "d": d, "dtype": str(dtype),
+            "with_maps": with_acc, "impl": impl, "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3,
+            "buffer_sets": n_sets}
+
+
+def time_tail(res, n_layers, n_samples_per_layer, T=77, direction="fwd", device="cuda:0"):
+    """One guidance-tail launch (forward or backward) on `n_layers` accumulators of `n_samples_per_layer` slices."""
+    from tests.gpu_harness import setup_prompt   # prompt/config fixture shared with the tests
+    from .pipeline_guided_attention import GuidedAttention
+    cfg = setup_prompt()
+    pipe = GuidedAttention(unet=None, tokenizer=cfg.stable.tokenizer)
+    pipe.prompt = cfg.prompt
+    npix = res * res
+    accs = [torch.rand(n_samples_per_layer, npix, T, device=device).softmax(-1) for _ in range(n_layers)]
+    spec = pipe._tail_spec(res, T, True, 0.5, 3, False, torch.device(device))
+    n_maps = n_layers * n_samples_per_layer
+    outs = ops.guidance_tail(spec, [a.requires_grad_(True) for a in accs], n_maps)
+    total = outs[4]
+    nt = spec.params.n_tokens
+    if direction == "fwd":
+        nbytes = (n_maps * npix * T + npix * (spec.last - spec.first) + nt * npix) * 4 + nt * npix
+
+        def launch(i):
+            ops.guidance_tail(spec, accs, n_maps)
+    else:
+        nbytes = (npix * (spec.last - spec.first) + npix * T) * 4
+
+        def launch(i):
+            torch.autograd.grad(total, accs[0], retain_graph=True)
+    with torch.no_grad() if direction == "fwd" else torch.enable_grad():
+        us = _time_graph(launch, 1)
+    return {"kernel": f"guidance_tail_{direction}", "res": res, "layers": n_layers, "slices": n_samples_per_layer,
+            "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3}
+
+
+def sweep(device="cuda:0"):
+    """BASELINE config 3: H=8, T=77, res 16 (d=160) and 32 (d=80), batch 2, plus the batch sweep and the 64^2 level."""
+    rows = []
+    for (N, d) in ((256, 160), (1024, 80), (4096, 40)):
+        for B in (1, 2, 8, 32, 128, 512):
+            if B * N * 8 * d * 2 * 8 > 8e9:      # keep the rotating buffer sets within a few GB
+                continue
+            for direction in ("fwd", "bwd"):
+                rows.append(time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=N <= 1024, direction=direction,
+                                            device=device))
+    for res in (16, 32):
+        for direction in ("fwd", "bwd"):
+            rows.append(time_tail(res, 5, 2, direction=direction, device=device))
+    return rows
+
+
+if __name__ == "__main__":
+    for r in sweep():
+        print(json.dumps(r))
+        sys.stdout.flush()

@@ -32,6 +32,105 @@ AT = helpers.AnnotationType
 _KIND = {AT.COOR: abi.GA_TOKEN_COOR, AT.BOX: abi.GA_TOKEN_BOX, AT.KEYWORD: abi.GA_TOKEN_KEYWORD}
 
 
+
+class _StepGraphs:
+    """CUDA-graph execution of the three device programs the guided loop keeps re-issuing (DESIGN.md "CUDA graphs"):
+
+      eval    text-conditioned UNet forward (hooks -> K1 accumulators) + guidance tail          -> per-token stats, loss
+      update  the same forward with the autograd graph + tail + backward (tail bwd, K2, UNet bwd)
+              + latents <- latents - step * grad                                               -> stats, new latents
+      cfg     CFG UNet forward (batch 2) + guidance combine + DDIM step                        -> next latents
+
+    The reference re-launches ~10^3 kernels from Python for each of these; a replay is one graph launch.  Inputs are
+    copied into static buffers (latents, timestep, step size, DDIM coefficients, text embeddings); control flow
+    (thresholds, refinement loop) stays on the host and reads only the small `stats` tensor."""
+
+    def __init__(self, pipe, store, loss_kw, prompt_embeds, guidance_scale, latents_like):
+        self.pipe, self.store, self.loss_kw, self.gs = pipe, store, loss_kw, float(guidance_scale)
+        dev, dt = latents_like.device, latents_like.dtype
+        self.lat = torch.zeros_like(latents_like)
+        self.lat_out = torch.zeros_like(latents_like)
+        self.t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step = torch.zeros((), dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.embeds = prompt_embeds.detach().clone()
+        self.graphs, self.outputs, self.launches, self.replays = {}, {}, {}, {}
+        self.pool = None
+
+    # -- the three programs ---------------------------------------------------------------------------------------
+    def _prog_eval(self):
+        with torch.no_grad():
+            self.pipe.unet(self.lat, self.t, encoder_hidden_states=self.embeds[1:2])
+            ld = self.pipe._aggregate_and_get_max_attention_per_token(**self.loss_kw)
+            loss, losses, unscaled = self.pipe._compute_loss(ld)
+        return {"loss": loss, "losses": losses, "unscaled": unscaled, "stats": ld["_stats"]}
+
+    def _prog_update(self):
+        with torch.enable_grad():
+            lat = self.lat.detach().clone().requires_grad_(True)
+            self.pipe.unet(lat, self.t, encoder_hidden_states=self.embeds[1:2])
+            ld = self.pipe._aggregate_and_get_max_attention_per_token(**self.loss_kw)
+            loss, losses, unscaled = self.pipe._compute_loss(ld)
+            (g,) = torch.autograd.grad(loss, [lat])
+        with torch.no_grad():
+            self.lat_out.copy_((lat.detach().float() - self.step * g.float()).to(lat.dtype))
+        return {"loss": loss.detach(), "losses": [(i, v.detach()) for i, v in losses],
+                "unscaled": [(i, v.detach()) for i, v in unscaled], "stats": ld["_stats"].detach()}
+
+    def _prog_cfg(self):
+        with torch.no_grad():
+            x2 = torch.cat([self.lat] * 2)
+            noise = self.pipe.unet(x2, self.t, encoder_hidden_states=self.embeds).sample
+            n_u, n_t = noise.chunk(2)
+            noise = n_u + self.gs * (n_t - n_u)
+            out = self.pipe.scheduler.step(noise, None, self.lat, coeffs=(self.coef[0], self.coef[1], self.coef[2],
+                                                                          self.coef[3]))
+            self.lat_out.copy_(out.prev_sample)
+        return {}
+
+    def _graph(self, name):
+        if name in self.graphs:
+            return self.graphs[name]
+        prog = getattr(self, "_prog_" + name)
+        # warm-up on a side stream (allocator, cuDNN heuristics, lazy kernel attributes), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                prog()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        snap = dict(ops.launch_counts)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            self.outputs[name] = prog()
+        if self.pool is None:
+            self.pool = g.pool()
+        # launches recorded by the capture pass = launches every replay performs; the capture itself ran nothing
+        self.launches[name] = {k: v - snap.get(k, 0) for k, v in ops.launch_counts.items() if v - snap.get(k, 0) > 0}
+        for k, v in self.launches[name].items():
+            ops.launch_counts[k] -= v
+        self.graphs[name] = g
+        return g
+
+    def run(self, name, latents, t, step_size=None, coeffs=None):
+        """Copies the inputs into the static buffers and replays `name`; returns (static outputs, new latents | None).
+        The static outputs are overwritten by the next replay of the same program."""
+        g = self._graph(name)
+        self.lat.copy_(latents)
+        self.t.fill_(int(t))
+        if step_size is not None:
+            self.step.fill_(float(step_size))
+        if coeffs is not None:
+            for n, c in enumerate(coeffs):
+                self.coef[n].fill_(float(c))
+        g.replay()
+        self.replays[name] = self.replays.get(name, 0) + 1
+        for k, v in self.launches[name].items():
+            ops._count(k, v)
+        return self.outputs[name], (self.lat_out.clone() if name != "eval" else None)
+
+
 class GuidedAttention(StableDiffusionPipelineBase):
     """Pipeline for text-to-image generation with cross-attention guidance (boxes, crosshairs, keyword losses)."""
 
@@ -264,7 +363,8 @@ class GuidedAttention(StableDiffusionPipelineBase):
         """latents - step_size * d loss / d latents (reference :455-470); the backward runs K2 in every cross layer and
         the tail backward kernel once."""
         grad_cond = torch.autograd.grad(loss.requires_grad_(True), [latents], retain_graph=True)[0]
-        return latents - step_size * grad_cond
+        # fp32 arithmetic, one rounding: identical whether `step_size` is a python float or a device scalar (graphs)
+        return (latents.float() - step_size * grad_cond.float()).to(latents.dtype)
 
     # --------------------------------------------------------------------------------------- threshold (host side)
     def meets_threshold(self, i, thresholds, losses):
@@ -343,6 +443,89 @@ class GuidedAttention(StableDiffusionPipelineBase):
             return True
         return bool(loss != 0)
 
+    # ------------------------------------------------------------------------------------- CUDA-graph execution
+    use_cuda_graphs = False   # opt-in: `pipe.use_cuda_graphs = True` (bench.py and run.py turn it on)
+
+    def _step_graphs(self, attention_store, loss_kw, prompt_embeds, guidance_scale, latents) -> "_StepGraphs":
+        """Graphs are cached on the pipeline and reused across calls (seeds) while everything baked into them is
+        unchanged: UNet, shapes, dtype, tracked tokens, boxes and hyper-parameters, guidance scale, number of steps."""
+        hp, cfg = state.curHyperParams, state.config
+        key = (id(self.unet), id(attention_store), tuple(prompt_embeds.shape), prompt_embeds.dtype, tuple(latents.shape),
+               float(guidance_scale), (loss_kw["attention_res"], loss_kw["smooth_attentions"], loss_kw["sigma"],
+                                       loss_kw["kernel_size"], loss_kw["normalize_eot"]),
+               tuple((i, v['loss_type'], v['subprompt'],
+                      v['loss'].as_tuple() if hasattr(v['loss'], 'as_tuple') else v['loss'])
+                     for i, v in cfg.token_dict.items()),
+               tuple(sorted((k, str(v)) for k, v in hp.items())), bool(cfg.sub_prompt_avg_within),
+               tuple(getattr(cfg, "custom_loss", {}).keys()), self.scheduler.num_inference_steps, str(latents.device))
+        cached = getattr(self, "_graphs_cache", None)
+        if cached is None or cached[0] != key:
+            self._graphs_cache = (key, _StepGraphs(self, attention_store, loss_kw, prompt_embeds, guidance_scale,
+                                                   latents))
+        G = self._graphs_cache[1]
+        G.embeds.copy_(prompt_embeds)
+        return G
+
+    def _denoise_graphed(self, G, latents, timesteps, thresholds, scale_range, scale_factor, recurse_steps,
+                         recurse_until, max_iter_to_alter, run_standard_sd, renoise_gen, callback, callback_steps):
+        """The guided loop of `__call__` (reference :925-1053) with every device program replayed from a CUDA graph.
+        Host control flow, thresholds and random streams are exactly those of the eager loop below."""
+        cfg = state.config
+        for i, t in enumerate(timesteps):
+            t = int(t)
+            for recurse_step in range(0, recurse_steps):
+                did_we_update = False
+                state.cur_time_step_iter = i
+                step_size = scale_factor * np.sqrt(scale_range[i])
+                out, _ = G.run("eval", latents, t)
+                if not run_standard_sd:
+                    update_cond = (not cfg.only_update_on_threshold_steps and i < max_iter_to_alter) or \
+                        (i in cfg.thresholds)
+                    met, do_update = True, False
+                    if i in thresholds or update_cond:
+                        u0 = self._host_values(out["unscaled"])          # the one D2H read of this evaluation
+                        met = self.meets_threshold(i, thresholds, u0)
+                        do_update = update_cond and not self.meets_threshold(-1, cfg.thresholds, u0)
+                    if not met:
+                        did_we_update = True
+                        iteration, u = 0, None
+                        state.sub_iteration = 0
+                        while u is None or not self.meets_threshold(i, cfg.thresholds, u):
+                            iteration += 1
+                            state.sub_iteration = iteration
+                            o, latents = G.run("update", latents, t, step_size=step_size)
+                            u = self._host_values(o["unscaled"])
+                            if iteration >= 10:
+                                helpers.log('\t Exceeded max number of iterations (10)! ', True)
+                                break
+                        state.sub_iteration = 0
+                        # final evaluation at the refined latents; on a threshold step it carries the update of :1003
+                        if do_update:
+                            _, latents = G.run("update", latents, t, step_size=step_size)
+                        else:
+                            G.run("eval", latents, t)
+                    elif do_update:
+                        _, latents = G.run("update", latents, t, step_size=step_size)
+                    did_we_update = did_we_update or do_update
+                _, latents = G.run("cfg", latents, t, coeffs=self.scheduler.coefficients(t))
+                if callback is not None and i % callback_steps == 0:
+                    callback(i, t, latents)
+                if i > recurse_until or not did_we_update:
+                    break
+                if recurse_step != (recurse_steps - 1):
+                    latents = self._renoise(latents, t, renoise_gen)
+        return latents
+
+    def _renoise(self, latents, t, renoise_gen):
+        """Back to the previous noise level before a recursion (reference :1046-1050)."""
+        prev_timestep = t - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
+        if prev_timestep > 0:
+            Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_timestep])
+            noise = torch.randn(latents.shape, generator=renoise_gen, dtype=torch.float32)
+            latents = ((Bt ** 0.5) * latents.float()
+                       + ((1 - Bt) ** 0.5) * noise.to(latents.device)).to(latents.dtype)
+        return latents
+
     # ---------------------------------------------------------------------------------------------------- call
     @torch.no_grad()
     def __call__(self, prompt: Union[str, List[str]], attention_store: AttentionStore, attention_res: int = 16,
@@ -403,6 +586,15 @@ class GuidedAttention(StableDiffusionPipelineBase):
         loss_kw = dict(attention_store=attention_store, attention_res=attention_res,
                        smooth_attentions=smooth_attentions, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
         num_warmup_steps = len(timesteps) - num_inference_steps * self.scheduler.order
+        graphed = (self.use_cuda_graphs and latents.is_cuda and state.config.diagnostic_level == 0
+                   and do_classifier_free_guidance and latents.shape[0] == 1
+                   and not state.curHyperParams.get("use_optimizer", False) and cross_attention_kwargs is None)
+        if graphed:
+            G = self._step_graphs(attention_store, loss_kw, prompt_embeds, guidance_scale, latents)
+            latents = self._denoise_graphed(G, latents, timesteps, thresholds, scale_range, scale_factor,
+                                            recurse_steps, recurse_until, max_iter_to_alter, run_standard_sd,
+                                            renoise_gen, callback, callback_steps)
+            timesteps = []      # the eager loop below has nothing left to do
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 t = int(t)
@@ -454,11 +646,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                     if i > recurse_until or not did_we_update:
                         break
                     if recurse_step != (recurse_steps - 1):
-                        prev_timestep = t - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
-                        if prev_timestep > 0:
-                            Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_timestep])
-                            noise = torch.randn(latents.shape, generator=renoise_gen, dtype=torch.float32)
-                            latents = (Bt ** 0.5) * latents + ((1 - Bt) ** 0.5) * noise.to(latents.device, latents.dtype)
+                        latents = self._renoise(latents, t, renoise_gen)
 
         latents = latents.detach()
         has_nsfw_concept = False

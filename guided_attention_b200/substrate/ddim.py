@@ -54,15 +54,22 @@ class DDIMScheduler:
     def scale_model_input(self, sample, timestep=None):
         return sample
 
-    def step(self, model_output, timestep, sample, eta=0.0, generator=None, **_):
+    def coefficients(self, timestep):
+        """(sqrt(1 - a_t), sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev)) as python floats for this step."""
         t = int(timestep)
         prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
-        # python-float coefficients: no device sync, identical values on the CPU oracle and the CUDA path
         a_t = float(self.alphas_cumprod[t])
         a_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else float(self.final_alpha_cumprod)
-        pred_x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        return ((1 - a_t) ** 0.5, a_t ** 0.5, a_prev ** 0.5, (1 - a_prev) ** 0.5)
+
+    def step(self, model_output, timestep, sample, eta=0.0, generator=None, coeffs=None, **_):
+        """eta = 0 DDIM update.  The arithmetic runs in fp32 and is rounded to the sample dtype once; `coeffs` may be
+        python floats (eager, no device sync) or four fp32 device scalars (CUDA-graph replay: same kernels, the step's
+        coefficients are data instead of baked-in constants) -- both give bit-identical results."""
+        c = self.coefficients(timestep) if coeffs is None else coeffs
+        x, eps = sample.float(), model_output.float()
+        pred_x0 = (x - c[0] * eps) / c[1]
         if self.config.clip_sample:
             pred_x0 = pred_x0.clamp(-1, 1)
-        # eta = 0: no variance term
-        prev = a_prev ** 0.5 * pred_x0 + (1 - a_prev) ** 0.5 * model_output
+        prev = c[2] * pred_x0 + c[3] * eps
         return DDIMOutput(prev_sample=prev.to(sample.dtype), pred_original_sample=pred_x0.to(sample.dtype))

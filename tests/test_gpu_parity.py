@@ -166,7 +166,10 @@ def test_cross_attention_backward(shape, dtype, rtol, broadcast):
     qd2 = q.to(DEV).requires_grad_(True)
     o2, acc2 = ops.cross_attention(qd2, k.to(DEV), v.to(DEV), H, scale, want_acc=True)
     (dq2,) = torch.autograd.grad([o2, acc2], (qd2,), [d_o.to(DEV), da])
-    assert torch.equal(dq2, dq)
+    if dtype == torch.float32:
+        assert torch.equal(dq2, dq)          # same SIMT kernel with and without the dK/dV outputs
+    else:                                    # 16-bit: this path runs the tcgen05 variant, the one above the SIMT one
+        assert rel_err(dq2.float().cpu().numpy(), dq.float().cpu().numpy()) < rtol
 
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
@@ -462,6 +465,50 @@ def test_pipeline_matches_reference_call_on_tiny_unet(e2e_golden):
     cos = float((got * gold).sum() / (np.linalg.norm(got) * np.linalg.norm(gold)))
     assert cos > 0.99999, cos
     assert _psnr(got, gold) > 60, _psnr(got, gold)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_cuda_graph_execution_equals_eager(dtype):
+    """`pipe.use_cuda_graphs = True` replays the same kernels: final latents equal the eager loop's (same seeds,
+    refinement, recursion and re-noising), and a second image reuses the captured graphs."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
+    from guided_attention_b200.substrate import DDIMScheduler
+    from guided_attention_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    case = E2E_CASE
+    unet, embeds, latents, _ = make_e2e_inputs(case)
+    cfg = setup_prompt(case["meta_prompt"], case["hyper"])
+    cfg.thresholds = case["hyper"]["thresholds"]
+    unet = unet.to(DEV, dtype)
+    pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=cfg.stable.tokenizer)
+    cfg.stable = pipe
+    store = AttentionStore()
+    register_attention_control(pipe, store)
+
+    def run(seed):
+        gen = torch.Generator("cpu").manual_seed(seed)
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(seed))
+        ops.reset_launch_counts()
+        out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5, generator=gen,
+                   latents=lat, prompt_embeds=embeds[1:2], negative_prompt_embeds=embeds[0:1],
+                   num_inference_steps=case["steps"], thresholds=cfg.thresholds, output_type="latent")
+        return out.images.float().cpu().numpy(), dict(ops.launch_counts)
+    pipe.use_cuda_graphs = False
+    eager28, n_eager = run(28)
+    eager29, _ = run(29)
+    pipe.use_cuda_graphs = True
+    graph28, n_graph = run(28)
+    graph29, _ = run(29)          # replays only: the graphs captured for seed 28 are reused
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert np.abs(graph28 - eager28).max() <= tol * max(1.0, np.abs(eager28).max())
+    assert np.abs(graph29 - eager29).max() <= tol * max(1.0, np.abs(eager29).max())
+    assert not np.allclose(graph28, graph29)
+    # same kernels, counted per replay (the graphed loop may re-run one evaluation where the eager loop reuses a graph)
+    assert set(n_graph) == set(n_eager)
+    for k in n_eager:
+        assert abs(n_graph[k] - n_eager[k]) <= 0.05 * n_eager[k] + 16, (k, n_graph, n_eager)
 
 
 def test_full_size_sd14_guidance_step_fp16():
