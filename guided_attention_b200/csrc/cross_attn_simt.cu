@@ -377,7 +377,11 @@ static cudaError_t ensure_smem(const void* kernel, int slot) {
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (done[dev][slot]) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int optin = 0;
+  cudaFuncAttributes fa;
+  if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
   if (e == cudaSuccess) done[dev][slot] = true;
   return e;
 }
@@ -388,7 +392,7 @@ int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
   const int words = d / Word<T>::E, stride = words | 1;
   const bool probs_only = probs != nullptr;
   size_t smem = (size_t)(2 * Tctx + kRowsPerCta) * stride * 4 + (size_t)kWarps * kR * kPStride * 4;
-  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention: head_dim %d needs %zu B smem", d, smem);
+  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention: head_dim %d needs %zu B smem", d, smem);
   const int heads_per_cta = (acc != nullptr && !probs_only) ? H : 1;
   dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H / heads_per_cta);
   auto kern = probs_only ? cross_attn_fwd_kernel<T, true> : cross_attn_fwd_kernel<T, false>;
@@ -405,7 +409,7 @@ int launch_bwd(const void* q, const void* k, const void* v, const float* lse, co
                cudaStream_t st) {
   const int words = d / Word<T>::E, stride = words | 1;
   size_t smem = (size_t)(2 * Tctx + 2 * kRowsPerCta) * stride * 4 + (size_t)2 * kWarps * kR * kPStride * 4;
-  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention bwd: head_dim %d needs %zu B smem", d, smem);
+  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "SIMT cross-attention bwd: head_dim %d needs %zu B smem", d, smem);
   dim3 grid((N + kRowsPerCta - 1) / kRowsPerCta, B * H);
   auto kern = cross_attn_bwd_kernel<T>;
   cudaError_t e = ensure_smem<T>(reinterpret_cast<const void*>(kern), 2);

@@ -534,7 +534,11 @@ static cudaError_t ensure_smem(const void* kernel, int slot, size_t) {
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (done[dev][slot]) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int optin = 0;
+  cudaFuncAttributes fa;
+  if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
   if (e == cudaSuccess) done[dev][slot] = true;
   return e;
 }
@@ -585,7 +589,7 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
 
   size_t smem = 1024 + (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   if (acc != nullptr) smem += (size_t)kM * kAccStride * sizeof(float);
-  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention: %zu B of shared memory", smem);
+  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention: %zu B of shared memory", smem);
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_kernel), 0, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 
@@ -623,7 +627,7 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
   p.bf16 = dtype == GA_BF16;
   p.scale = scale;
   const size_t smem = 1024 + (size_t)p.nblk * 2 * (kQBlockBytes + kKVBlockBytes);
-  if (smem > 227 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention bwd: %zu B of shared memory", smem);
+  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention bwd: %zu B of shared memory", smem);
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_kernel), 1, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   dim3 grid(H, (N + kM - 1) / kM, B);
