@@ -265,11 +265,12 @@ def run_ours(args):
     # (1) device-resident inputs: `value`
     dev_lat = [host_latents(seed_of(1, i)).to(dev) for i in range(args.steps)]
     ops.reset_launch_counts()
-    unet_calls["n"] = 0
+    cfg_before = pipe.pass_counts["cfg"]
     ms_value, _ = timed(lambda i: image(seed_of(1, i), embeds_dev, dev_lat[i]), args.steps)
     launches = ops.total_launches()
     counts = dict(ops.launch_counts)
-    unet_passes = unet_calls["n"]
+    cfg_passes = pipe.pass_counts["cfg"] - cfg_before
+    unet_passes = counts.get("guidance_tail_fwd", 0) + cfg_passes
     # (2) end to end: host buffers in, host buffer out, inside the timed region; final NCCL gather of the latents
     host_lat = [host_latents(seed_of(1, i)) for i in range(args.steps)]
     out_host = torch.empty(args.steps, 4, 64, 64, dtype=torch.float16).pin_memory()
@@ -316,7 +317,7 @@ def run_ours(args):
         per_image = {"grad_fwd": counts.get("guidance_tail_fwd", 0) / args.steps,
                      "loss_eval": counts.get("guidance_tail_fwd", 0) / args.steps,
                      "bwd": counts.get("guidance_tail_bwd", 0) / args.steps,
-                     "cfg_fwd": (unet_passes - counts.get("guidance_tail_fwd", 0)) / args.steps}
+                     "cfg_fwd": cfg_passes / args.steps}
         line["cpu_baseline"] = {
             "value": cpu_images_per_s(times, per_image), "unit": "img/s", "cores": threads, "kind": "port",
             "sample": "1 grad-enabled B=1 UNet forward with explicit-softmax hooks + 1 loss evaluation + 1 backward to "

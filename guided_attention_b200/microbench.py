@@ -103,10 +103,20 @@ def time_tail(res, n_layers, n_samples_per_layer, T=77, direction="fwd", device=
             ops.guidance_tail(spec, accs, n_maps)
     else:
         nbytes = (npix * (spec.last - spec.first) + npix * T) * 4
+        lib = abi.load()
+        attn_text, smoothed, stats, argmax = (o.detach() for o in outs[:4])
+        g_total = torch.ones(1, device=device)
+        d_abar = torch.empty(npix, T, device=device)
+        p = abi.GaTailParams.from_buffer_copy(spec.params)
+        p.inv_count = 1.0 / n_maps
 
-        def launch(i):
-            torch.autograd.grad(total, accs[0], retain_graph=True)
-    with torch.no_grad() if direction == "fwd" else torch.enable_grad():
+        def launch(i):   # the C ABI directly: an autograd backward of a graph built outside the capture cannot be captured
+            abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, ops._ptr(spec.masks), ops._ptr(spec.weights),
+                                               ops._ptr(attn_text), ops._ptr(smoothed), ops._ptr(stats),
+                                               ops._ptr(argmax), ops._ptr(g_total), None, None, ops._ptr(d_abar),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                      "ga_guidance_tail_bwd")
+    with torch.no_grad():
         us = _time_graph(launch, 1)
     return {"kernel": f"guidance_tail_{direction}", "res": res, "layers": n_layers, "slices": n_samples_per_layer,
             "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3}
@@ -114,18 +124,16 @@ def time_tail(res, n_layers, n_samples_per_layer, T=77, direction="fwd", device=
 
 def sweep(device="cuda:0"):
     """BASELINE config 3: H=8, T=77, res 16 (d=160) and 32 (d=80), batch 2, plus the batch sweep and the 64^2 level."""
-    rows = []
     for (N, d) in ((256, 160), (1024, 80), (4096, 40)):
         for B in (1, 2, 8, 32, 128, 512):
             if B * N * 8 * d * 2 * 8 > 8e9:      # keep the rotating buffer sets within a few GB
                 continue
             for direction in ("fwd", "bwd"):
-                rows.append(time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=N <= 1024, direction=direction,
-                                            device=device))
+                yield time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=N <= 1024, direction=direction,
+                                      device=device)
     for res in (16, 32):
         for direction in ("fwd", "bwd"):
-            rows.append(time_tail(res, 5, 2, direction=direction, device=device))
-    return rows
+            yield time_tail(res, 5, 2, direction=direction, device=device)
 
 
 if __name__ == "__main__":

@@ -126,6 +126,7 @@ class _StepGraphs:
                 self.coef[n].fill_(float(c))
         g.replay()
         self.replays[name] = self.replays.get(name, 0) + 1
+        self.pipe._count_pass(name)
         for k, v in self.launches[name].items():
             ops._count(k, v)
         return self.outputs[name], (self.lat_out.clone() if name != "eval" else None)
@@ -135,6 +136,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
     """Pipeline for text-to-image generation with cross-attention guidance (boxes, crosshairs, keyword losses)."""
 
     _optional_components = ["safety_checker", "feature_extractor"]
+    update_calls = 0          # number of eager `_update_latent` backward passes (class-level: the method is static)
     inside_iterative_refinement = False
     optim = None
 
@@ -363,6 +365,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         """latents - step_size * d loss / d latents (reference :455-470); the backward runs K2 in every cross layer and
         the tail backward kernel once."""
         grad_cond = torch.autograd.grad(loss.requires_grad_(True), [latents], retain_graph=True)[0]
+        GuidedAttention.update_calls += 1
         # fp32 arithmetic, one rounding: identical whether `step_size` is a python float or a device scalar (graphs)
         return (latents.float() - step_size * grad_cond.float()).to(latents.dtype)
 
@@ -414,6 +417,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
             if not use_optimizer:
                 latents = latents.clone().detach().requires_grad_(True)
             self.unet(latents, t, encoder_hidden_states=text_embeddings[1].unsqueeze(0))
+            self._count_pass("eval")
             losses_dict = self._aggregate_and_get_max_attention_per_token(**kw)
             loss, losses, unscaled_losses = self._compute_loss(losses_dict, return_losses=True)
             if use_optimizer:
@@ -426,6 +430,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                 break
         latents = latents.clone().detach().requires_grad_(True)
         self.unet(latents, t, encoder_hidden_states=text_embeddings[1].unsqueeze(0))
+        self._count_pass("eval")
         max_attention_per_index = self._aggregate_and_get_max_attention_per_token(**kw)
         loss, losses, unscaled_losses = self._compute_loss(max_attention_per_index, return_losses=True)
         helpers.log(f"\t Finished with loss iter: {iteration}", True)
@@ -442,6 +447,13 @@ class GuidedAttention(StableDiffusionPipelineBase):
         if any(v['loss_type'] in (AT.COOR, AT.BOX) for v in spec_tokens.values()):
             return True
         return bool(loss != 0)
+
+    # UNet-pass bookkeeping (both execution modes): eval = text-cond forward + loss; update = the backward to the
+    # latents (+ its forward when replayed from a graph); cfg = the CFG forward + scheduler step
+    def _count_pass(self, name, n=1):
+        if not hasattr(self, "pass_counts"):
+            self.pass_counts = {"eval": 0, "update": 0, "cfg": 0}
+        self.pass_counts[name] += n
 
     # ------------------------------------------------------------------------------------- CUDA-graph execution
     use_cuda_graphs = False   # opt-in: `pipe.use_cuda_graphs = True` (bench.py and run.py turn it on)
@@ -607,6 +619,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                         # text-conditioned forward with the autograd graph: fills the attention accumulators
                         self.unet(latents, t, encoder_hidden_states=prompt_embeds[1].unsqueeze(0),
                                   cross_attention_kwargs=cross_attention_kwargs)
+                        self._count_pass("eval")
                         max_attention_per_index = self._aggregate_and_get_max_attention_per_token(**loss_kw)
                         if not run_standard_sd:
                             loss, losses, unscaled_losses = self._compute_loss(losses_dict=max_attention_per_index)
@@ -632,6 +645,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                     latent_model_input = self.scheduler.scale_model_input(latent_model_input, t)
                     noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=prompt_embeds,
                                            cross_attention_kwargs=cross_attention_kwargs).sample
+                    self._count_pass("cfg")
                     if do_classifier_free_guidance:
                         noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
                         noise_pred = noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)
