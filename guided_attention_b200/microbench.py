@@ -136,7 +136,17 @@ def sweep(device="cuda:0"):
             yield time_tail(res, 5, 2, direction=direction, device=device)
 
 
+def single(argv):
+    """`--single fwd|bwd B N d [maps]`: a handful of plain (non-graph) launches of one configuration, for ncu."""
+    direction, B, N, d = argv[0], int(argv[1]), int(argv[2]), int(argv[3])
+    with_maps = len(argv) > 4 and argv[4] == "maps"
+    print(json.dumps(time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=with_maps, direction=direction)))
+
+
 if __name__ == "__main__":
-    for r in sweep():
-        print(json.dumps(r))
-        sys.stdout.flush()
+    if len(sys.argv) > 1 and sys.argv[1] == "--single":
+        single(sys.argv[2:])
+    else:
+        for r in sweep():
+            print(json.dumps(r))
+            sys.stdout.flush()

@@ -549,6 +549,8 @@ def test_cuda_graph_image_matches_eager_image():
         cos = float((g * e).sum() / (np.linalg.norm(g) * np.linalg.norm(e)))
         assert cos > 0.99999 and _psnr(g, e) > 55, (cos, _psnr(g, e))
     assert not np.allclose(graph28, graph29)
+    n_eager.pop("rasterize_boxes", None)       # one-off prompt set-up, issued by whichever run comes first
+    n_graph.pop("rasterize_boxes", None)
     assert set(n_graph) == set(n_eager)
     for k in n_eager:   # same kernels, counted per replay (a graphed update re-runs its forward)
         assert abs(n_graph[k] - n_eager[k]) <= 0.1 * n_eager[k] + 16, (k, n_graph, n_eager)
