@@ -265,6 +265,7 @@ def run_ours(args):
     # (1) device-resident inputs: `value`
     dev_lat = [host_latents(seed_of(1, i)).to(dev) for i in range(args.steps)]
     ops.reset_launch_counts()
+    pipe._count_pass("cfg", 0)
     cfg_before = pipe.pass_counts["cfg"]
     ms_value, _ = timed(lambda i: image(seed_of(1, i), embeds_dev, dev_lat[i]), args.steps)
     launches = ops.total_launches()
