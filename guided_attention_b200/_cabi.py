@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libguidedattn.so")
 
 GA_OK = 0
 GA_F32, GA_F16, GA_BF16 = 0, 1, 2
-GA_IMPL_AUTO, GA_IMPL_SIMT, GA_IMPL_TCGEN05 = 0, 1, 2
+GA_IMPL_AUTO, GA_IMPL_SIMT, GA_IMPL_TCGEN05, GA_IMPL_TCGEN05_SINGLE, GA_IMPL_TCGEN05_PIPE = 0, 1, 2, 3, 4
 GA_TOKEN_COOR, GA_TOKEN_BOX, GA_TOKEN_KEYWORD = 0, 1, 2
 GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
 (GA_STAT_MAX, GA_STAT_SUM, GA_STAT_COL, GA_STAT_ROW, GA_STAT_INSIDE, GA_STAT_OUTSIDE, GA_STAT_SCALED,

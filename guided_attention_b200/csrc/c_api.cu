@@ -29,7 +29,7 @@ int bwd(const void*, const void*, const void*, const float*, const void*, const 
 namespace tc {
 bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc);
 bool supports_bwd(int dtype, int n_ctx, int head_dim, int heads, bool with_dkv);
-int fwd(const void*, const void*, const void*, void*, float*, float*, int, int, int, int, int, float, int,
+int fwd(const void*, const void*, const void*, void*, float*, float*, int, int, int, int, int, float, int, int,
         cudaStream_t);
 int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, void*, int, int, int,
         int, int, float, int, cudaStream_t);
@@ -72,11 +72,14 @@ extern "C" int ga_cross_attn_fwd(const void* q, const void* k, const void* v, vo
   GA_CHECK_ALIGN(o, 16, "o");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc_ok = tc::supports_fwd(dtype, n_ctx, head_dim, heads, acc != nullptr);
-  if (impl == GA_IMPL_TCGEN05 && !tc_ok)
+  const bool want_tc = impl == GA_IMPL_TCGEN05 || impl == GA_IMPL_TCGEN05_SINGLE || impl == GA_IMPL_TCGEN05_PIPE;
+  if (want_tc && !tc_ok)
     return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention does not support dtype %d / n_ctx %d / head_dim %d", dtype,
                 n_ctx, head_dim);
-  if (impl == GA_IMPL_TCGEN05 || (impl == GA_IMPL_AUTO && tc_ok))
-    return tc::fwd(q, k, v, o, lse, acc, batch, heads, n_query, n_ctx, head_dim, scale, dtype, st);
+  if (want_tc || (impl == GA_IMPL_AUTO && tc_ok)) {
+    const int force = impl == GA_IMPL_TCGEN05_SINGLE ? 0 : (impl == GA_IMPL_TCGEN05_PIPE ? 1 : -1);
+    return tc::fwd(q, k, v, o, lse, acc, batch, heads, n_query, n_ctx, head_dim, scale, dtype, force, st);
+  }
   return simt::fwd(q, k, v, o, lse, acc, nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, st);
 }
 
@@ -93,9 +96,10 @@ extern "C" int ga_cross_attn_bwd(const void* q, const void* k, const void* v, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool want_dkv = d_k != nullptr || d_v != nullptr;
   const bool tc_ok = tc::supports_bwd(dtype, n_ctx, head_dim, heads, want_dkv);
-  if (impl == GA_IMPL_TCGEN05 && !tc_ok)
+  const bool want_tc = impl == GA_IMPL_TCGEN05 || impl == GA_IMPL_TCGEN05_SINGLE || impl == GA_IMPL_TCGEN05_PIPE;
+  if (want_tc && !tc_ok)
     return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention backward does not support this configuration");
-  if (impl == GA_IMPL_TCGEN05 || (impl == GA_IMPL_AUTO && tc_ok))
+  if (want_tc || (impl == GA_IMPL_AUTO && tc_ok))
     return tc::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_q, batch, heads, n_query, n_ctx, head_dim, scale,
                    dtype, st);
   return simt::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_q, d_k, d_v, batch, heads, n_query, n_ctx, head_dim,

@@ -340,6 +340,266 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 }
 
 
+// ============================================================================= K1, persistent pipelined variant
+// The single-shot kernel above is latency-bound per CTA (TMA -> MMA -> softmax -> MMA -> epilogue in sequence, two CTAs
+// per SM).  For launches with enough work per SM this variant keeps ONE persistent CTA per SM and overlaps the stages
+// of consecutive work items with warp specialisation:
+//
+//   warp 0          TMA producer     runs up to `smem_stages` items ahead (full / smem_free mbarriers)
+//   warp 1          MMA issuer       MMA1(k) is issued before MMA2(k-1): the softmax of item k-1 overlaps the loads
+//                                    and the first GEMM of item k
+//   warps 4-7       compute group 0  items 0, 2, 4, ...   TMEM stage 0 (columns   0-255: S/P at +0, O at +96)
+//   warps 8-11      compute group 1  items 1, 3, 5, ...   TMEM stage 1 (columns 256-511)
+//
+// Work items: flat (b, h, tile) when no maps are kept; with maps a CTA takes whole (b, tile) groups and streams the H
+// heads through the pipeline, so the head-sum of P stays in the two groups' registers and is combined once per group
+// through one shared staging tile, in a fixed order, then written coalesced: deterministic, no atomics, no cluster.
+constexpr int kPipeThreads = 384;
+constexpr int kStageCols = 256;
+constexpr int kGroupThreads = 128;
+
+struct PipeParams {
+  void* o;
+  float* lse;
+  float* acc;
+  int B, H, N, T, d;
+  int nblk, npv, bf16;
+  int tiles;        // row tiles per (b, h)
+  int units;        // work units: B*tiles (grouped) or B*H*tiles (flat)
+  int grouped;      // 1: a unit is a (b, tile) group of H items
+  int smem_stages;  // 1 or 2
+  float scale;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int kRegs> __device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs> __device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
+struct ItemCoord { int b, h, tile; };
+__device__ __forceinline__ ItemCoord item_coord(const PipeParams& p, int k) {
+  ItemCoord c;
+  if (p.grouped) {
+    const int unit = blockIdx.x + (k / p.H) * gridDim.x;
+    c.h = k % p.H;
+    c.b = unit / p.tiles;
+    c.tile = unit - c.b * p.tiles;
+  } else {
+    const int unit = blockIdx.x + k * gridDim.x;
+    c.tile = unit % p.tiles;
+    const int bh = unit / p.tiles;
+    c.b = bh / p.H;
+    c.h = bh - c.b * p.H;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                              const __grid_constant__ CUtensorMap map_v, const PipeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // full[2], smem_free[2], s_ready[2], p_ready[2], o_ready[2], tmem_free[2]
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stage_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
+  float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)p.smem_stages * stage_bytes);
+  auto bar = [&](int which, int s) { return smem_u32(&bars[which * 2 + s]); };
+  enum { FULL = 0, SMEM_FREE = 1, S_READY = 2, P_READY = 3, O_READY = 4, TMEM_FREE = 5 };
+
+  // number of items this CTA owns
+  int my_units = 0;
+  for (int u = blockIdx.x; u < p.units; u += gridDim.x) ++my_units;
+  const int n_items = p.grouped ? my_units * p.H : my_units;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(FULL, s), 1);
+      mbar_init(bar(SMEM_FREE, s), 1);
+      mbar_init(bar(S_READY, s), 1);
+      mbar_init(bar(P_READY, s), kGroupThreads);
+      mbar_init(bar(O_READY, s), 1);
+      mbar_init(bar(TMEM_FREE, s), kGroupThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const int fmt = p.bf16 ? 1 : 0;
+  const int ksteps = (p.d + 15) >> 4;
+  const int S = p.smem_stages;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------------------------- TMA producer
+      for (int k = 0; k < n_items; ++k) {
+        const int ss = k % S;
+        if (k >= S) mbar_wait(bar(SMEM_FREE, ss), ((uint32_t)(k / S) & 1u) ^ 1u);
+        const ItemCoord c = item_coord(p, k);
+        const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
+        mbar_expect_tx(bar(FULL, ss), stage_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar(FULL, ss), blk * kBlockCols, c.h, c.tile * kM, c.b);
+          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar(FULL, ss), blk * kBlockCols, c.h, 0, c.b);
+          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar(FULL, ss), blk * kBlockCols, c.h, 0, c.b);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // -------------------------------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      auto mma1 = [&](int k) {
+        const int ss = k % S, ts = k & 1;
+        mbar_wait(bar(FULL, ss), (uint32_t)(k / S) & 1u);
+        if (k >= 2) mbar_wait(bar(TMEM_FREE, ts), ((uint32_t)(k >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + ts * kStageCols + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar(S_READY, ts));
+      };
+      auto mma2 = [&](int k) {
+        const int ss = k % S, ts = k & 1;
+        mbar_wait(bar(P_READY, ts), (uint32_t)(k >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t sV = base + ss * stage_bytes + p.nblk * (kQBlockBytes + kKVBlockBytes);
+        for (int ks = 0; ks < kTpad / 16; ++ks)
+          mma_ts(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP + ks * 8,
+                 smem_desc_sw128(sV + ks * 2048u, kKVBlockBytes, 1024), idesc_pv, ks > 0 ? 1u : 0u);
+        tc_commit(bar(O_READY, ts));
+        tc_commit(bar(SMEM_FREE, ss));
+      };
+      for (int k = 0; k < n_items; ++k) {
+        if (S == 1) {            // one smem stage: the loads of item k can only start once MMA2(k-1) has retired
+          if (k >= 1) mma2(k - 1);
+          mma1(k);
+        } else {
+          mma1(k);
+          if (k >= 1) mma2(k - 1);
+        }
+      }
+      if (n_items >= 1) mma2(n_items - 1);
+    }
+  } else {
+    reg_alloc<232>();
+    // ------------------------------------------------------------------------------------ compute groups
+    const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage
+    const int r = ((warp & 3) << 5) + lane;           // row of the tile = TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
+    const float sc = p.scale * 1.4426950408889634f;
+    float pacc[kTpad];
+#pragma unroll
+    for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+
+    for (int k = 0; k < n_items; ++k) {
+      const ItemCoord c = item_coord(p, k);
+      const int row = c.tile * kM + r;
+      if ((k & 1) == g) {
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        mbar_wait(bar(S_READY, g), ph);
+        tc_fence_after();
+        float s[kTpad];
+#pragma unroll
+        for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
+        tmem_ld_wait();
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j)
+          if (j < p.T) m = fmaxf(m, s[j]);
+        const float mo = m * sc;
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) {
+          const float e = (j < p.T) ? exp2f(fmaf(s[j], sc, -mo)) : 0.f;
+          s[j] = e;
+          sum += e;
+        }
+        const float inv = 1.f / sum;
+        uint32_t packed[kTpad / 2];
+#pragma unroll
+        for (int j = 0; j < kTpad; j += 2) {
+          const float p0 = s[j] * inv, p1 = s[j + 1] * inv;
+          if (p.grouped) { pacc[j] += p0; pacc[j + 1] += p1; }
+          packed[j >> 1] = pack16(p0, p1, p.bf16 != 0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar(P_READY, g));
+        if (row < p.N) p.lse[((int64_t)c.b * p.H + c.h) * p.N + row] = m * p.scale + logf(sum);
+
+        mbar_wait(bar(O_READY, g), ph);
+        tc_fence_after();
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)c.b * p.N + row) * p.H + c.h) * (int64_t)p.d * 2;
+        for (int cc = 0; cc < p.npv / 16; ++cc) {
+          float ov[16];
+          tmem_ld16(lane_addr + kColO + cc * 16, ov);
+          tmem_ld_wait();
+          if (row < p.N) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], p.bf16 != 0);
+            const int col = cc * 16;
+            if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar(TMEM_FREE, g));
+      }
+      // ---- end of a (b, tile) group: combine the two groups' head sums, write the accumulator rows coalesced
+      if (p.grouped && (k % p.H) == p.H - 1) {
+        if (g == 1) {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] = pacc[j];
+        }
+        named_bar_sync(1, 2 * kGroupThreads);
+        if (g == 0) {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] += pacc[j];
+        }
+        named_bar_sync(2, 2 * kGroupThreads);
+        const int cw = warp - 4;                         // 0..7: compute warp index
+        for (int i = cw; i < kM; i += 8) {
+          const int gr = c.tile * kM + i;
+          if (gr >= p.N) break;
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const int j = lane + 32 * kk;
+            if (j < p.T) p.acc[((int64_t)c.b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
+          }
+        }
+        named_bar_sync(3, 2 * kGroupThreads);
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // ============================================================================================== K2 (backward)
 //   S  = Q K^T, dP = dO V^T                two K-major GEMMs into two TMEM regions
 //   P  = exp(scale S - lse);  dP += d_acc[row]  (the attention-map gradient injected by the guidance tail)
@@ -528,7 +788,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int dtype, int B, int row
 // The opt-in dynamic shared-memory limit is raised once per (device, kernel) to the largest size the kernel can ask
 // for, so steady-state launches (and CUDA-graph captures) make no attribute call at all.
 static cudaError_t ensure_smem(const void* kernel, int slot, size_t) {
-  static bool done[64][2] = {};
+  static bool done[64][4] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -559,6 +819,46 @@ static bool tc_enabled() {
   return on == 1;
 }
 
+
+static int sm_count() {
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev] > 0 ? n[dev] : 148;
+}
+
+// GA_TC_PIPE=0/1 forces the single-shot / persistent variant (debugging and A/B measurements)
+static int pipe_override() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("GA_TC_PIPE");
+    v = (e == nullptr) ? -1 : (e[0] == '1' ? 1 : 0);
+  }
+  return v;
+}
+
+static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdParams& f,
+                    cudaStream_t st) {
+  PipeParams p;
+  p.o = f.o; p.lse = f.lse; p.acc = f.acc;
+  p.B = f.B; p.H = f.H; p.N = f.N; p.T = f.T; p.d = f.d;
+  p.nblk = f.nblk; p.npv = f.npv; p.bf16 = f.bf16; p.scale = f.scale;
+  p.tiles = (f.N + kM - 1) / kM;
+  p.grouped = f.acc != nullptr ? 1 : 0;
+  p.units = p.grouped ? f.B * p.tiles : f.B * f.H * p.tiles;
+  const size_t stage = (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
+  const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 0);
+  p.smem_stages = (2 * stage + extra <= 226 * 1024) ? 2 : 1;
+  const size_t smem = p.smem_stages * stage + extra;
+  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel), 2, smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = p.units < sm_count() ? p.units : sm_count();
+  cross_attn_fwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mk, mv, p);
+  return check_launch("cross_attn_fwd_tc_pipe");
+}
+
 bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc) {
   (void)heads; (void)with_acc;
   return tc_enabled() && (dtype == GA_F16 || dtype == GA_BF16) && n_ctx >= 1 && n_ctx <= kTpad && head_dim % 8 == 0 &&
@@ -569,7 +869,7 @@ bool supports_bwd(int dtype, int n_ctx, int head_dim, int heads, bool with_dkv) 
 }
 
 int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc, int B, int H, int N, int T, int d,
-        float scale, int dtype, cudaStream_t st) {
+        float scale, int dtype, int force_variant, cudaStream_t st) {
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
@@ -587,6 +887,20 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
   p.bf16 = dtype == GA_BF16;
   p.scale = scale;
 
+  // Variant choice: the persistent pipelined kernel needs enough work units to occupy the SMs (a unit is a (b, tile)
+  // group of H heads when maps are kept, a single (b, h, tile) otherwise) and d <= 160 (two 256-column TMEM stages).
+  {
+    const int tiles = (N + kM - 1) / kM;
+    const int units = acc != nullptr ? B * tiles : B * H * tiles;
+    bool use_pipe = d <= 160 && units >= (acc != nullptr ? sm_count() / 2 : 2 * sm_count());
+    if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
+    if (force_variant == 0) use_pipe = false;
+    if (force_variant == 1) {
+      if (d > 160) return fail(GA_ERR_UNSUPPORTED, "pipelined tcgen05 cross-attention needs head_dim <= 160");
+      use_pipe = true;
+    }
+    if (use_pipe) return fwd_pipe(mq, mk, mv, p, st);
+  }
   size_t smem = 1024 + (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   if (acc != nullptr) smem += (size_t)kM * kAccStride * sizeof(float);
   if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention: %zu B of shared memory", smem);

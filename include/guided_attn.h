@@ -29,8 +29,11 @@ typedef void* ga_stream_t; /* cudaStream_t */
 
 enum ga_status { GA_OK = 0, GA_ERR_BAD_ARG = -1, GA_ERR_UNSUPPORTED = -2, GA_ERR_ALIGNMENT = -3, GA_ERR_CUDA = -4 };
 enum ga_dtype { GA_F32 = 0, GA_F16 = 1, GA_BF16 = 2 };
-/* kernel variant: AUTO picks TCGEN05 for 16-bit operands it supports, SIMT otherwise (fp32 is SIMT-only: exact fp32) */
-enum ga_impl { GA_IMPL_AUTO = 0, GA_IMPL_SIMT = 1, GA_IMPL_TCGEN05 = 2 };
+/* kernel variant: AUTO picks TCGEN05 for 16-bit operands it supports, SIMT otherwise (fp32 is SIMT-only: exact fp32).
+ * TCGEN05 itself picks between the single-shot kernel (few work items: latency) and the persistent pipelined kernel
+ * (many work items: bandwidth); _SINGLE / _PIPE force one of the two (tests, A/B measurements). */
+enum ga_impl { GA_IMPL_AUTO = 0, GA_IMPL_SIMT = 1, GA_IMPL_TCGEN05 = 2, GA_IMPL_TCGEN05_SINGLE = 3,
+               GA_IMPL_TCGEN05_PIPE = 4 };
 /* reference utils/helpers.py:10-13 (AnnotationType) */
 enum ga_token_kind { GA_TOKEN_COOR = 0, GA_TOKEN_BOX = 1, GA_TOKEN_KEYWORD = 2 };
 

@@ -91,23 +91,26 @@ def test_cross_attention_forward(shape, dtype, rtol):
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
 @pytest.mark.parametrize("with_acc", [False, True])
-@pytest.mark.parametrize("shape", SHAPES)
-def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, with_acc):
-    """The tcgen05/TMA/TMEM variant explicitly (impl = GA_IMPL_TCGEN05), against the oracle and the SIMT variant."""
+@pytest.mark.parametrize("variant", ["single", "pipe"])
+@pytest.mark.parametrize("shape", SHAPES + [(8, 40, 4096, 77, 4), (8, 160, 256, 77, 40), (5, 64, 576, 77, 9)])
+def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, with_acc, variant):
+    """The tcgen05/TMA/TMEM kernels explicitly -- the single-shot one and the persistent pipelined one -- against the
+    oracle and the SIMT variant."""
     from guided_attention_b200 import ops, _cabi as abi
     H, d, N, T, B = shape
+    TC = abi.GA_IMPL_TCGEN05_SINGLE if variant == "single" else abi.GA_IMPL_TCGEN05_PIPE
     if T > 80:
         with pytest.raises(abi.GuidedAttnLibraryError):
             q, k, v = _attn_case(H, d, N, T, B, dtype)
             ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, d ** -0.5, want_acc=with_acc,
-                                impl=abi.GA_IMPL_TCGEN05)
+                                impl=TC)
         return
     q, k, v = _attn_case(H, d, N, T, B, dtype, seed=5)
     scale = d ** -0.5
     P, Oo = O.cross_attention(O.head_to_batch(q.float(), H), O.head_to_batch(k.float(), H),
                               O.head_to_batch(v.float(), H), scale)
     o, acc = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=with_acc,
-                                 impl=abi.GA_IMPL_TCGEN05)
+                                 impl=TC)
     torch.cuda.synchronize()
     assert rel_err(o.float().cpu().numpy(), O.batch_to_head(Oo, H).numpy()) < rtol
     o_s, acc_s = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=with_acc,
@@ -117,7 +120,7 @@ def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, 
         assert rel_err(acc.cpu().numpy(), P.reshape(B, H, N, T).sum(1).numpy()) < 1e-3
         assert rel_err(acc.cpu().numpy(), acc_s.cpu().numpy()) < 1e-3
         o2, acc2 = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=True,
-                                       impl=abi.GA_IMPL_TCGEN05)
+                                       impl=TC)
         assert torch.equal(acc2, acc) and torch.equal(o2, o)        # deterministic cluster reduction
 
 
