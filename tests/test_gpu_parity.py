@@ -543,11 +543,11 @@ def test_cuda_graph_image_matches_eager_image():
                    num_inference_steps=case["steps"], thresholds=cfg.thresholds, output_type="latent")
         return out.images.float().cpu().numpy(), dict(ops.launch_counts), dict(pipe.pass_counts)
     pipe.use_cuda_graphs = False
-    eager28, n_eager, _ = run(28)
-    eager29, _, _ = run(29)
+    eager28, _, _ = run(28)
+    eager29, n_eager, _ = run(29)
     pipe.use_cuda_graphs = True
-    graph28, n_graph, passes = run(28)
-    graph29, _, _ = run(29)          # replays only: the graphs captured for seed 28 are reused
+    graph28, _, _ = run(28)          # captures the three programs (warm-up launches included in its counts)
+    graph29, n_graph, passes = run(29)          # replays only: the graphs captured for seed 28 are reused
     for g, e in ((graph28, eager28), (graph29, eager29)):
         cos = float((g * e).sum() / (np.linalg.norm(g) * np.linalg.norm(e)))
         assert cos > 0.99999 and _psnr(g, e) > 55, (cos, _psnr(g, e))
