@@ -146,6 +146,39 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Row softmax over up to kTpad keys held by one thread, un-normalised: on return s[j] = exp(scale*(s[j] - max)) for
+// j < T and 0 beyond, packed[] holds the same values as 16-bit pairs (the A operand of the second GEMM), and the row sum
+// is returned through `sum` (the normalisation 1/sum is applied to the fp32 O accumulator and to the map accumulator,
+// not to the 16-bit operand).  Only the last 16 columns are predicated on T: the callers guarantee T > kTpad - 16.
+__device__ __forceinline__ void row_softmax(float* s, uint32_t* packed, int T, float sc, bool bf16, float& m, float& sum) {
+  m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kTpad - 16; ++j) m = fmaxf(m, s[j]);
+#pragma unroll
+  for (int j = kTpad - 16; j < kTpad; ++j)
+    if (j < T) m = fmaxf(m, s[j]);
+  const float mo = m * sc;
+  sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTpad - 16; ++j) {
+    s[j] = ex2_approx(fmaf(s[j], sc, -mo));
+    sum += s[j];
+  }
+#pragma unroll
+  for (int j = kTpad - 16; j < kTpad; ++j) {
+    s[j] = (j < T) ? ex2_approx(fmaf(s[j], sc, -mo)) : 0.f;
+    sum += s[j];
+  }
+#pragma unroll
+  for (int j = 0; j < kTpad; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
+}
+
 struct FwdParams {
   void* o;
   float* lse;
@@ -239,26 +272,13 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 #pragma unroll
     for (int c = 0; c < kTpad / 16; ++c) tmem_ld16(lane_addr + kColS + c * 16, s + c * 16);
     tmem_ld_wait();
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kTpad; ++j)
-      if (j < p.T) m = fmaxf(m, s[j]);
-    const float mo = m * sc;
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < kTpad; ++j) {
-      const float e = (j < p.T) ? exp2f(fmaf(s[j], sc, -mo)) : 0.f;
-      s[j] = e;
-      sum += e;
-    }
-    const float inv = 1.f / sum;
+    float m, sum;
     uint32_t packed[kTpad / 2];
+    row_softmax(s, packed, p.T, sc, p.bf16 != 0, m, sum);
+    const float inv = 1.f / sum;
+    if (p.acc != nullptr) {
 #pragma unroll
-    for (int j = 0; j < kTpad; j += 2) {
-      const float p0 = s[j] * inv, p1 = s[j + 1] * inv;
-      pacc[j] += p0;
-      pacc[j + 1] += p1;
-      packed[j >> 1] = pack16(p0, p1, p.bf16 != 0);
+      for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
     }
     const int row = row0 + tid;
     if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(sum);
@@ -294,7 +314,7 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         if (row < p.N) {
           uint32_t w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], p.bf16 != 0);
+          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, p.bf16 != 0);
           const int col = c * 16;
           if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
           if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -384,30 +404,12 @@ template <int kRegs> __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
-struct ItemCoord { int b, h, tile; };
-__device__ __forceinline__ ItemCoord item_coord(const PipeParams& p, int k) {
-  ItemCoord c;
-  if (p.grouped) {
-    const int unit = blockIdx.x + (k / p.H) * gridDim.x;
-    c.h = k % p.H;
-    c.b = unit / p.tiles;
-    c.tile = unit - c.b * p.tiles;
-  } else {
-    const int unit = blockIdx.x + k * gridDim.x;
-    c.tile = unit % p.tiles;
-    const int bh = unit / p.tiles;
-    c.b = bh / p.H;
-    c.h = bh - c.b * p.H;
-  }
-  return c;
-}
-
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                               const __grid_constant__ CUtensorMap map_v, const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // full[2], smem_free[2], s_ready[2], p_ready[2], o_ready[2], tmem_free[2]
-  __shared__ __align__(8) uint64_t bars[12];
+  // full[4], smem_free[4] (per shared-memory stage); s_ready[2], p_ready[2], o_ready[2], tmem_free[2] (per TMEM stage)
+  __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -415,23 +417,25 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)p.smem_stages * stage_bytes);
-  auto bar = [&](int which, int s) { return smem_u32(&bars[which * 2 + s]); };
-  enum { FULL = 0, SMEM_FREE = 1, S_READY = 2, P_READY = 3, O_READY = 4, TMEM_FREE = 5 };
+  auto FULL = [&](int s) { return smem_u32(&bars[s]); };
+  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[4 + s]); };
+  auto S_READY = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto P_READY = [&](int s) { return smem_u32(&bars[10 + s]); };
+  auto O_READY = [&](int s) { return smem_u32(&bars[12 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[14 + s]); };
 
-  // number of items this CTA owns
-  int my_units = 0;
-  for (int u = blockIdx.x; u < p.units; u += gridDim.x) ++my_units;
+  // number of work units / items this CTA owns (units are dealt round-robin over the grid)
+  const int my_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_items = p.grouped ? my_units * p.H : my_units;
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(FULL, s), 1);
-      mbar_init(bar(SMEM_FREE, s), 1);
-      mbar_init(bar(S_READY, s), 1);
-      mbar_init(bar(P_READY, s), kGroupThreads);
-      mbar_init(bar(O_READY, s), 1);
-      mbar_init(bar(TMEM_FREE, s), kGroupThreads);
+      mbar_init(S_READY(s), 1);
+      mbar_init(P_READY(s), kGroupThreads);
+      mbar_init(O_READY(s), 1);
+      mbar_init(TMEM_FREE(s), kGroupThreads);
     }
     fence_mbar_init();
   }
@@ -448,26 +452,33 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     reg_dealloc<40>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------------------------------- TMA producer
+      // coordinates advance incrementally (no divisions in the loop)
+      int unit = blockIdx.x, h = 0, ss = 0;
+      uint32_t par = 0;                                 // parity of the use of stage ss that is about to start
       for (int k = 0; k < n_items; ++k) {
-        const int ss = k % S;
-        if (k >= S) mbar_wait(bar(SMEM_FREE, ss), ((uint32_t)(k / S) & 1u) ^ 1u);
-        const ItemCoord c = item_coord(p, k);
+        int b, tile, hh;
+        if (p.grouped) { b = unit / p.tiles; tile = unit - b * p.tiles; hh = h; }
+        else { tile = unit % p.tiles; const int bh = unit / p.tiles; b = bh / p.H; hh = bh - b * p.H; }
+        if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
         const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
-        mbar_expect_tx(bar(FULL, ss), stage_bytes);
+        mbar_expect_tx(FULL(ss), stage_bytes);
         for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar(FULL, ss), blk * kBlockCols, c.h, c.tile * kM, c.b);
-          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar(FULL, ss), blk * kBlockCols, c.h, 0, c.b);
-          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar(FULL, ss), blk * kBlockCols, c.h, 0, c.b);
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, hh, tile * kM, b);
+          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, hh, 0, b);
+          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, hh, 0, b);
         }
+        if (p.grouped) { if (++h == p.H) { h = 0; unit += gridDim.x; } } else unit += gridDim.x;
+        if (++ss == S) { ss = 0; par ^= 1u; }
       }
     } else if (warp == 1 && lane == 0) {
       // -------------------------------------------------------------------------------------- MMA issuer
+      // tcgen05.mma instructions retire in issue order, so MMA1(k+2) -- which overwrites the S/P columns of its TMEM
+      // stage -- needs no wait on MMA2(k); only the O columns are handed back by the compute group (TMEM_FREE).
       const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
-      auto mma1 = [&](int k) {
-        const int ss = k % S, ts = k & 1;
-        mbar_wait(bar(FULL, ss), (uint32_t)(k / S) & 1u);
-        if (k >= 2) mbar_wait(bar(TMEM_FREE, ts), ((uint32_t)(k >> 1) & 1u) ^ 1u);
+      auto mma1 = [&](int k, int ss, uint32_t par) {
+        const int ts = k & 1;
+        mbar_wait(FULL(ss), par);
         tc_fence_after();
         const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -475,100 +486,109 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           mma_ss(tmem + ts * kStageCols + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
                  smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
         }
-        tc_commit(bar(S_READY, ts));
+        tc_commit(S_READY(ts));
       };
-      auto mma2 = [&](int k) {
-        const int ss = k % S, ts = k & 1;
-        mbar_wait(bar(P_READY, ts), (uint32_t)(k >> 1) & 1u);
+      auto mma2 = [&](int k, int ss) {
+        const int ts = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        mbar_wait(P_READY(ts), ph);
+        if (k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);      // the epilogue of item k-2 has drained the O columns
         tc_fence_after();
         const uint32_t sV = base + ss * stage_bytes + p.nblk * (kQBlockBytes + kKVBlockBytes);
         for (int ks = 0; ks < kTpad / 16; ++ks)
           mma_ts(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP + ks * 8,
                  smem_desc_sw128(sV + ks * 2048u, kKVBlockBytes, 1024), idesc_pv, ks > 0 ? 1u : 0u);
-        tc_commit(bar(O_READY, ts));
-        tc_commit(bar(SMEM_FREE, ss));
+        tc_commit(O_READY(ts));
+        tc_commit(SMEM_FREE(ss));
       };
+      int ss = 0, ss_prev = 0;
+      uint32_t par = 0;
       for (int k = 0; k < n_items; ++k) {
         if (S == 1) {            // one smem stage: the loads of item k can only start once MMA2(k-1) has retired
-          if (k >= 1) mma2(k - 1);
-          mma1(k);
+          if (k >= 1) mma2(k - 1, 0);
+          mma1(k, 0, (uint32_t)k & 1u);
         } else {
-          mma1(k);
-          if (k >= 1) mma2(k - 1);
+          mma1(k, ss, par);
+          if (k >= 1) mma2(k - 1, ss_prev);
+          ss_prev = ss;
+          if (++ss == S) { ss = 0; par ^= 1u; }
         }
       }
-      if (n_items >= 1) mma2(n_items - 1);
+      if (n_items >= 1) mma2(n_items - 1, S == 1 ? 0 : ss_prev);
     }
   } else {
     reg_alloc<232>();
     // ------------------------------------------------------------------------------------ compute groups
-    const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage
+    const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage; handles items k with k % 2 == g
     const int r = ((warp & 3) << 5) + lane;           // row of the tile = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
     const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
     float pacc[kTpad];
+    if (p.grouped) {
 #pragma unroll
-    for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+      for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+    }
 
-    for (int k = 0; k < n_items; ++k) {
-      const ItemCoord c = item_coord(p, k);
-      const int row = c.tile * kM + r;
-      if ((k & 1) == g) {
-        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        mbar_wait(bar(S_READY, g), ph);
-        tc_fence_after();
-        float s[kTpad];
+    auto process = [&](int k, int b, int h, int tile) {
+      const int row = tile * kM + r;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      mbar_wait(S_READY(g), ph);
+      tc_fence_after();
+      float s[kTpad];
 #pragma unroll
-        for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
-        tmem_ld_wait();
-        float m = -INFINITY;
+      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
+      tmem_ld_wait();
+      float m, sum;
+      uint32_t packed[kTpad / 2];
+      row_softmax(s, packed, p.T, sc, bf16, m, sum);
 #pragma unroll
-        for (int j = 0; j < kTpad; ++j)
-          if (j < p.T) m = fmaxf(m, s[j]);
-        const float mo = m * sc;
-        float sum = 0.f;
+      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(P_READY(g));
+      const float inv = 1.f / sum;
+      if (p.grouped) {
 #pragma unroll
-        for (int j = 0; j < kTpad; ++j) {
-          const float e = (j < p.T) ? exp2f(fmaf(s[j], sc, -mo)) : 0.f;
-          s[j] = e;
-          sum += e;
-        }
-        const float inv = 1.f / sum;
-        uint32_t packed[kTpad / 2];
-#pragma unroll
-        for (int j = 0; j < kTpad; j += 2) {
-          const float p0 = s[j] * inv, p1 = s[j + 1] * inv;
-          if (p.grouped) { pacc[j] += p0; pacc[j + 1] += p1; }
-          packed[j >> 1] = pack16(p0, p1, p.bf16 != 0);
-        }
-#pragma unroll
-        for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(bar(P_READY, g));
-        if (row < p.N) p.lse[((int64_t)c.b * p.H + c.h) * p.N + row] = m * p.scale + logf(sum);
-
-        mbar_wait(bar(O_READY, g), ph);
-        tc_fence_after();
-        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)c.b * p.N + row) * p.H + c.h) * (int64_t)p.d * 2;
-        for (int cc = 0; cc < p.npv / 16; ++cc) {
-          float ov[16];
-          tmem_ld16(lane_addr + kColO + cc * 16, ov);
-          tmem_ld_wait();
-          if (row < p.N) {
-            uint32_t w[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], p.bf16 != 0);
-            const int col = cc * 16;
-            if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(bar(TMEM_FREE, g));
+        for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
       }
-      // ---- end of a (b, tile) group: combine the two groups' head sums, write the accumulator rows coalesced
-      if (p.grouped && (k % p.H) == p.H - 1) {
+      if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(sum);
+
+      mbar_wait(O_READY(g), ph);
+      tc_fence_after();
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+      for (int cc = 0; cc < p.npv / 16; ++cc) {
+        float ov[16];
+        tmem_ld16(lane_addr + kColO + cc * 16, ov);
+        tmem_ld_wait();
+        if (row < p.N) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
+          const int col = cc * 16;
+          if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(g));
+    };
+
+    if (!p.grouped) {
+      // flat items: this group takes every second unit of the CTA
+      for (int k = g; k < n_items; k += 2) {
+        const int unit = blockIdx.x + k * gridDim.x;
+        const int tile = unit % p.tiles, bh = unit / p.tiles, b = bh / p.H;
+        process(k, b, bh - b * p.H, tile);
+      }
+    } else {
+      int k = 0;
+      for (int u = 0; u < my_units; ++u) {
+        const int unit = blockIdx.x + u * gridDim.x;
+        const int b = unit / p.tiles, tile = unit - b * p.tiles;
+        for (int h = 0; h < p.H; ++h, ++k)
+          if ((k & 1) == g) process(k, b, h, tile);
+        // ---- end of the (b, tile) group: combine the two groups' head sums, write the accumulator rows coalesced
         if (g == 1) {
 #pragma unroll
           for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] = pacc[j];
@@ -579,14 +599,13 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] += pacc[j];
         }
         named_bar_sync(2, 2 * kGroupThreads);
-        const int cw = warp - 4;                         // 0..7: compute warp index
-        for (int i = cw; i < kM; i += 8) {
-          const int gr = c.tile * kM + i;
+        for (int i = warp - 4; i < kM; i += 8) {
+          const int gr = tile * kM + i;
           if (gr >= p.N) break;
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
             const int j = lane + 32 * kk;
-            if (j < p.T) p.acc[((int64_t)c.b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
+            if (j < p.T) p.acc[((int64_t)b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
           }
         }
         named_bar_sync(3, 2 * kGroupThreads);
@@ -849,7 +868,9 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   p.units = p.grouped ? f.B * p.tiles : f.B * f.H * p.tiles;
   const size_t stage = (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 0);
-  p.smem_stages = (2 * stage + extra <= 226 * 1024) ? 2 : 1;
+  p.smem_stages = 1;
+  for (int n = 4; n >= 2; --n)
+    if (n * stage + extra <= 226 * 1024) { p.smem_stages = n; break; }
   const size_t smem = p.smem_stages * stage + extra;
   if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel), 2, smem);
@@ -861,8 +882,9 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
 
 bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc) {
   (void)heads; (void)with_acc;
-  return tc_enabled() && (dtype == GA_F16 || dtype == GA_BF16) && n_ctx >= 1 && n_ctx <= kTpad && head_dim % 8 == 0 &&
-         head_dim >= 8 && head_dim <= 256;
+  // the row softmax predicates only the last 16 of the 80 key columns on n_ctx: 65..80 keys (SD: 77)
+  return tc_enabled() && (dtype == GA_F16 || dtype == GA_BF16) && n_ctx > kTpad - 16 && n_ctx <= kTpad &&
+         head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 256;
 }
 bool supports_bwd(int dtype, int n_ctx, int head_dim, int heads, bool with_dkv) {
   return !with_dkv && supports_fwd(dtype, n_ctx, head_dim, heads, false);

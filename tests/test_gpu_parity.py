@@ -99,7 +99,7 @@ def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, 
     from guided_attention_b200 import ops, _cabi as abi
     H, d, N, T, B = shape
     TC = abi.GA_IMPL_TCGEN05_SINGLE if variant == "single" else abi.GA_IMPL_TCGEN05_PIPE
-    if T > 80:
+    if T > 80 or T <= 64:      # the tensor-core kernels take 65..80 keys (SD: 77); other sizes run the SIMT variant
         with pytest.raises(abi.GuidedAttnLibraryError):
             q, k, v = _attn_case(H, d, N, T, B, dtype)
             ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, d ** -0.5, want_acc=with_acc,
@@ -177,7 +177,7 @@ def test_cross_attention_backward(shape, dtype, rtol, broadcast):
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
 @pytest.mark.parametrize("shape", [(8, 40, 4096, 77, 1), (8, 80, 1024, 77, 2), (8, 160, 256, 77, 2), (8, 160, 64, 77, 1),
-                                   (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 13, 2)])
+                                   (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 70, 2)])
 @pytest.mark.parametrize("with_dacc", [False, True])
 def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc):
     """K2 on the tensor cores (impl = GA_IMPL_TCGEN05) against the oracle's autograd and the SIMT variant."""
