@@ -44,13 +44,14 @@ PROTOTYPES = {
     "ga_last_error": (C.c_char_p, []),
     "ga_device_supported": (_i, [_i]),
     "ga_cross_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
-    "ga_cross_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_cross_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i,
+                                _vp]),
     "ga_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_rasterize_boxes": (_i, [C.POINTER(C.c_double), _i, _i, C.c_double, _vp, _vp]),
     "ga_guidance_tail_fwd": (_i, [C.POINTER(_vp), C.POINTER(C.c_int32), _i, C.POINTER(GaTailParams), C.POINTER(GaToken),
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ga_guidance_tail_bwd": (_i, [C.POINTER(GaTailParams), C.POINTER(GaToken), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  _vp, _vp, _vp]),
+                                  _vp, _vp, _i, _vp]),
     "ga_smooth_fwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "ga_smooth_bwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "ga_box_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

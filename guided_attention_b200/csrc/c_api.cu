@@ -23,16 +23,16 @@ int fail(int code, const char* fmt, ...) {
 namespace simt {
 int fwd(const void*, const void*, const void*, void*, float*, float*, void*, int, int, int, int, int, float, int,
         cudaStream_t);
-int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, void*, float*, float*,
-        int, int, int, int, int, float, int, cudaStream_t);
+int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, int, void*, float*,
+        float*, int, int, int, int, int, float, int, cudaStream_t);
 }  // namespace simt
 namespace tc {
 bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc);
 bool supports_bwd(int dtype, int n_ctx, int head_dim, int heads, bool with_dkv);
 int fwd(const void*, const void*, const void*, void*, float*, float*, int, int, int, int, int, float, int, int,
         cudaStream_t);
-int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, void*, int, int, int,
-        int, int, float, int, cudaStream_t);
+int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, int, void*, int, int,
+        int, int, int, float, int, int, cudaStream_t);
 }  // namespace tc
 
 static int check_attn_args(const void* q, const void* k, int batch, int heads, int n_query, int n_ctx, int head_dim,
@@ -84,8 +84,8 @@ extern "C" int ga_cross_attn_fwd(const void* q, const void* k, const void* v, vo
 }
 
 extern "C" int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
-                                 const float* d_acc, int64_t d_acc_batch_stride, void* d_q, float* d_k, float* d_v,
-                                 int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
+                                 const float* d_acc, int64_t d_acc_batch_stride, int d_acc_row_stride, void* d_q,
+                                 float* d_k, float* d_v, int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
                                  int impl, ga_stream_t stream) {
   int rc = check_attn_args(q, k, batch, heads, n_query, n_ctx, head_dim, dtype);
   if (rc != GA_OK) return rc;
@@ -93,17 +93,21 @@ extern "C" int ga_cross_attn_bwd(const void* q, const void* k, const void* v, co
   GA_CHECK_ALIGN(v, 16, "v");
   GA_CHECK_ALIGN(d_o, 16, "d_o");
   GA_CHECK_ALIGN(d_q, 16, "d_q");
+  GA_CHECK_ARG(d_acc == nullptr || d_acc_row_stride >= n_ctx, "d_acc_row_stride %d < n_ctx %d", d_acc_row_stride, n_ctx);
+  if (d_acc != nullptr && (d_acc_row_stride & 3) == 0) GA_CHECK_ALIGN(d_acc, 16, "d_acc (16-byte rows)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool want_dkv = d_k != nullptr || d_v != nullptr;
   const bool tc_ok = tc::supports_bwd(dtype, n_ctx, head_dim, heads, want_dkv);
   const bool want_tc = impl == GA_IMPL_TCGEN05 || impl == GA_IMPL_TCGEN05_SINGLE || impl == GA_IMPL_TCGEN05_PIPE;
   if (want_tc && !tc_ok)
     return fail(GA_ERR_UNSUPPORTED, "tcgen05 cross-attention backward does not support this configuration");
-  if (want_tc || (impl == GA_IMPL_AUTO && tc_ok))
-    return tc::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_q, batch, heads, n_query, n_ctx, head_dim, scale,
-                   dtype, st);
-  return simt::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_q, d_k, d_v, batch, heads, n_query, n_ctx, head_dim,
-                   scale, dtype, st);
+  if (want_tc || (impl == GA_IMPL_AUTO && tc_ok)) {
+    const int force = impl == GA_IMPL_TCGEN05_SINGLE ? 0 : (impl == GA_IMPL_TCGEN05_PIPE ? 1 : -1);
+    return tc::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_acc_row_stride, d_q, batch, heads, n_query, n_ctx,
+                   head_dim, scale, dtype, force, st);
+  }
+  return simt::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_acc_row_stride, d_q, d_k, d_v, batch, heads, n_query,
+                   n_ctx, head_dim, scale, dtype, st);
 }
 
 extern "C" int ga_attn_probs(const void* q, const void* k, void* probs, int batch, int heads, int n_query, int n_ctx,

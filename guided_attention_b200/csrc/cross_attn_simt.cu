@@ -213,8 +213,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cross_attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                       const float* __restrict__ lse, const T* __restrict__ d_o, const float* __restrict__ d_acc,
-                      int64_t d_acc_bstride, T* __restrict__ d_q, float* __restrict__ d_k, float* __restrict__ d_v,
-                      int H, int N, int Tctx, int d, float scale) {
+                      int64_t d_acc_bstride, int d_acc_rstride, T* __restrict__ d_q, float* __restrict__ d_k,
+                      float* __restrict__ d_v, int H, int N, int Tctx, int d, float scale) {
   constexpr int E = Cfg<T>::E;
   constexpr int kWPL = Cfg<T>::kWPL;
   extern __shared__ uint32_t smem[];
@@ -283,7 +283,7 @@ cross_attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
         const int j = lane + 32 * kk;
         const bool ok = live && j < Tctx;
         p[kk] = ok ? expf(s[r][kk] * scale - l) : 0.f;
-        if (ok && d_acc != nullptr) dp[r][kk] += d_acc[(int64_t)b * d_acc_bstride + (int64_t)row * Tctx + j];
+        if (ok && d_acc != nullptr) dp[r][kk] += d_acc[(int64_t)b * d_acc_bstride + (int64_t)row * d_acc_rstride + j];
         dsum += p[kk] * dp[r][kk];
       }
       dsum = warp_sum(dsum);
@@ -405,7 +405,7 @@ int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
 
 template <typename T>
 int launch_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
-               int64_t bstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale,
+               int64_t bstride, int rstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale,
                cudaStream_t st) {
   const int words = d / Word<T>::E, stride = words | 1;
   size_t smem = (size_t)(2 * Tctx + 2 * kRowsPerCta) * stride * 4 + (size_t)2 * kWarps * kR * kPStride * 4;
@@ -415,7 +415,7 @@ int launch_bwd(const void* q, const void* k, const void* v, const float* lse, co
   cudaError_t e = ensure_smem<T>(reinterpret_cast<const void*>(kern), 2);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<grid, kThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, lse, (const T*)d_o, d_acc, bstride,
-                                    (T*)d_q, d_k, d_v, H, N, Tctx, d, scale);
+                                    rstride, (T*)d_q, d_k, d_v, H, N, Tctx, d, scale);
   return check_launch("cross_attn_bwd_simt");
 }
 
@@ -430,13 +430,13 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
 }
 
 int bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
-        int64_t bstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale, int dtype,
+        int64_t bstride, int rstride, void* d_q, float* d_k, float* d_v, int B, int H, int N, int Tctx, int d, float scale, int dtype,
         cudaStream_t st) {
   switch (dtype) {
-    case GA_F32: return launch_bwd<float>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
-    case GA_F16: return launch_bwd<__half>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+    case GA_F32: return launch_bwd<float>(q, k, v, lse, d_o, d_acc, bstride, rstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+    case GA_F16: return launch_bwd<__half>(q, k, v, lse, d_o, d_acc, bstride, rstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
     case GA_BF16:
-      return launch_bwd<__nv_bfloat16>(q, k, v, lse, d_o, d_acc, bstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
+      return launch_bwd<__nv_bfloat16>(q, k, v, lse, d_o, d_acc, bstride, rstride, d_q, d_k, d_v, B, H, N, Tctx, d, scale, st);
   }
   return fail(GA_ERR_BAD_ARG, "unknown dtype %d", dtype);
 }

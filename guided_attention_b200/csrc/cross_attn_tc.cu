@@ -632,6 +632,7 @@ struct BwdParams {
   const float* lse;
   const float* d_acc;
   int64_t d_acc_bstride;
+  int d_acc_rstride;   // elements between consecutive rows of the map gradient (>= T; 80 = 16-byte aligned rows)
   int B, H, N, T, d;
   int nblk, npv, tmem_cols, bf16;
   float scale;
@@ -710,13 +711,13 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const bool live = row < p.N;
   const float sc = p.scale * 1.4426950408889634f;
   const float l2 = live ? p.lse[((int64_t)b * p.H + h) * p.N + row] * 1.4426950408889634f : 0.f;
-  const float* dacc = (p.d_acc != nullptr && live) ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.T
-                                                   : nullptr;
+  const float* dacc = (p.d_acc != nullptr && live)
+                          ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.d_acc_rstride : nullptr;
   float dsum = 0.f;
 #pragma unroll
   for (int j = 0; j < kTpad; ++j) {
     const bool ok = live && j < p.T;
-    const float pr = ok ? exp2f(fmaf(s[j], sc, -l2)) : 0.f;
+    const float pr = ok ? ex2_approx(fmaf(s[j], sc, -l2)) : 0.f;
     float g = ok ? dp[j] : 0.f;
     if (dacc != nullptr && j < p.T) g += __ldg(dacc + j);
     s[j] = pr;
@@ -761,6 +762,227 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ============================================================================ K2, persistent pipelined variant
+// Same warp roles as the pipelined forward.  Per item: TMA brings Q, dO, K, V; the MMA warp issues S = QK^T and
+// dP = dO V^T back to back into two TMEM regions; a compute group turns them into dS (16-bit, written over S), the MMA
+// warp issues dQ = dS K (K as the MN-major B operand), the group converts and stores dQ.  dQ has its own TMEM columns
+// when they fit (d <= 80), so the next item's first two GEMMs never wait for an epilogue.
+struct BwdPipeParams {
+  void* d_q;
+  const float* lse;
+  const float* d_acc;
+  int64_t d_acc_bstride;
+  int d_acc_rstride;
+  int B, H, N, T, d;
+  int nblk, npv, bf16;
+  int tiles, units, smem_stages;
+  int col_dq;          // TMEM column of dQ inside a stage: 160 (own columns) or 80 (over dP)
+  float scale;
+};
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                              const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                              const BwdPipeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes);
+  auto FULL = [&](int s) { return smem_u32(&bars[s]); };
+  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[4 + s]); };
+  auto SD_READY = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto DS_READY = [&](int s) { return smem_u32(&bars[10 + s]); };
+  auto DQ_READY = [&](int s) { return smem_u32(&bars[12 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[14 + s]); };
+  const int n_items = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool dq_aliased = p.col_dq == kColDP;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(SD_READY(s), 1);
+      mbar_init(DS_READY(s), kGroupThreads);
+      mbar_init(DQ_READY(s), 1);
+      mbar_init(TMEM_FREE(s), kGroupThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const int fmt = p.bf16 ? 1 : 0;
+  const int ksteps = (p.d + 15) >> 4;
+  const int S = p.smem_stages;
+
+  auto coords = [&](int k, int& b, int& h, int& tile) {
+    const int unit = blockIdx.x + k * gridDim.x;
+    tile = unit % p.tiles;
+    const int bh = unit / p.tiles;
+    b = bh / p.H;
+    h = bh - b * p.H;
+  };
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0 && lane == 0) {
+      int ss = 0;
+      uint32_t par = 0;
+      for (int k = 0; k < n_items; ++k) {
+        int b, h, tile;
+        coords(k, b, h, tile);
+        if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
+        const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
+                       sV = sK + p.nblk * kKVBlockBytes;
+        mbar_expect_tx(FULL(ss), stage_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, h, tile * kM, b);
+          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, h, 0, b);
+          tma_load_4d(sG + blk * kQBlockBytes, &map_do, FULL(ss), blk * kBlockCols, h, tile * kM, b);
+          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, h, 0, b);
+        }
+        if (++ss == S) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
+      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      auto mma12 = [&](int k, int ss, uint32_t par) {
+        const int ts = k & 1;
+        mbar_wait(FULL(ss), par);
+        // dQ over dP: the epilogue of item k-2 must have drained those columns before dP(k) is written
+        if (dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), (((uint32_t)(k >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
+                       sV = sK + p.nblk * kKVBlockBytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + ts * kStageCols + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+        }
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + ts * kStageCols + kColDP, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sV + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(SD_READY(ts));
+      };
+      auto mma3 = [&](int k, int ss) {
+        const int ts = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        mbar_wait(DS_READY(ts), ph);
+        if (!dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
+        tc_fence_after();
+        const uint32_t sK = base + ss * stage_bytes + 2u * p.nblk * kQBlockBytes;
+        for (int ks = 0; ks < kTpad / 16; ++ks)
+          mma_ts(tmem + ts * kStageCols + p.col_dq, tmem + ts * kStageCols + kColP + ks * 8,
+                 smem_desc_sw128(sK + ks * 2048u, kKVBlockBytes, 1024), idesc_dq, ks > 0 ? 1u : 0u);
+        tc_commit(DQ_READY(ts));
+        tc_commit(SMEM_FREE(ss));
+      };
+      int ss = 0, ss_prev = 0;
+      uint32_t par = 0;
+      for (int k = 0; k < n_items; ++k) {
+        if (S == 1) {
+          if (k >= 1) mma3(k - 1, 0);
+          mma12(k, 0, (uint32_t)k & 1u);
+        } else {
+          mma12(k, ss, par);
+          if (k >= 1) mma3(k - 1, ss_prev);
+          ss_prev = ss;
+          if (++ss == S) { ss = 0; par ^= 1u; }
+        }
+      }
+      if (n_items >= 1) mma3(n_items - 1, S == 1 ? 0 : ss_prev);
+    }
+  } else {
+    reg_alloc<232>();
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
+    const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
+    for (int k = g; k < n_items; k += 2) {
+      int b, h, tile;
+      coords(k, b, h, tile);
+      const int row = tile * kM + r;
+      const bool live = row < p.N;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      // issue the row's LSE load before waiting for the GEMMs
+      const float l2 = live ? __ldg(p.lse + ((int64_t)b * p.H + h) * p.N + row) * 1.4426950408889634f : 0.f;
+      const float* dacc = (p.d_acc != nullptr && live)
+                              ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.d_acc_rstride : nullptr;
+      mbar_wait(SD_READY(g), ph);
+      tc_fence_after();
+      float s[kTpad], dp[kTpad];
+#pragma unroll
+      for (int cc = 0; cc < kTpad / 16; ++cc) {
+        tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
+        tmem_ld16(lane_addr + kColDP + cc * 16, dp + cc * 16);
+      }
+      tmem_ld_wait();
+      if (dacc != nullptr) {
+        if ((p.d_acc_rstride & 3) == 0) {          // 16-byte aligned rows (the tail kernel pads them to 80 floats)
+#pragma unroll
+          for (int j = 0; j < kTpad; j += 4) {
+            if (j + 3 < p.d_acc_rstride) {
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(dacc + j));
+              dp[j] += v4.x; dp[j + 1] += v4.y; dp[j + 2] += v4.z; dp[j + 3] += v4.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j)
+            if (j < p.T) dp[j] += __ldg(dacc + j);
+        }
+      }
+      float dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTpad; ++j) {
+        const bool ok = live && (j < kTpad - 16 || j < p.T);
+        const float pr = ok ? ex2_approx(fmaf(s[j], sc, -l2)) : 0.f;
+        s[j] = pr;
+        dsum = fmaf(pr, dp[j], dsum);
+      }
+      uint32_t packed[kTpad / 2];
+#pragma unroll
+      for (int j = 0; j < kTpad; j += 2)
+        packed[j >> 1] = pack16(s[j] * (dp[j] - dsum) * p.scale, s[j + 1] * (dp[j + 1] - dsum) * p.scale, bf16);
+#pragma unroll
+      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(DS_READY(g));
+
+      mbar_wait(DQ_READY(g), ph);
+      tc_fence_after();
+      uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+      for (int cc = 0; cc < p.npv / 16; ++cc) {
+        float ov[16];
+        tmem_ld16(lane_addr + p.col_dq + cc * 16, ov);
+        tmem_ld_wait();
+        if (live) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
+          const int col = cc * 16;
+          if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(g));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
 // --------------------------------------------------------------------------------------------------- host side
@@ -947,18 +1169,47 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
 }
 
 int bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o, const float* d_acc,
-        int64_t d_acc_bstride, void* d_q, int B, int H, int N, int T, int d, float scale, int dtype, cudaStream_t st) {
+        int64_t d_acc_bstride, int d_acc_rstride, void* d_q, int B, int H, int N, int T, int d, float scale, int dtype,
+        int force_variant, cudaStream_t st) {
   CUtensorMap mq, mg, mk, mv;
   int rc;
   if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
   if ((rc = make_map(&mg, d_o, dtype, B, N, H, d, kM)) != GA_OK) return rc;
   if ((rc = make_map(&mk, k, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
   if ((rc = make_map(&mv, v, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
+  const int nblk = (d + kBlockCols - 1) / kBlockCols, npv = (d + 15) & ~15;
+  const int tiles = (N + kM - 1) / kM, units = B * H * tiles;
+  bool use_pipe = d <= 160 && units >= 2 * sm_count();
+  if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
+  if (force_variant == 0) use_pipe = false;
+  if (force_variant == 1) {
+    if (d > 160) return fail(GA_ERR_UNSUPPORTED, "pipelined tcgen05 cross-attention needs head_dim <= 160");
+    use_pipe = true;
+  }
+  if (use_pipe) {
+    BwdPipeParams p;
+    p.d_q = d_q; p.lse = lse; p.d_acc = d_acc; p.d_acc_bstride = d_acc_bstride; p.d_acc_rstride = d_acc_rstride;
+    p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
+    p.nblk = nblk; p.npv = npv; p.bf16 = dtype == GA_BF16; p.scale = scale;
+    p.tiles = tiles; p.units = units;
+    p.col_dq = (2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP;
+    const size_t stage = (size_t)nblk * 2 * (kQBlockBytes + kKVBlockBytes);
+    p.smem_stages = 1;
+    for (int n = 4; n >= 2; --n)
+      if (n * stage + 1024 <= 226 * 1024) { p.smem_stages = n; break; }
+    const size_t smem = p.smem_stages * stage + 1024;
+    if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined bwd: %zu B of shared memory", smem);
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_pipe_kernel), 3, smem);
+    if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = units < sm_count() ? units : sm_count();
+    cross_attn_bwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mg, mk, mv, p);
+    return check_launch("cross_attn_bwd_tc_pipe");
+  }
   BwdParams p;
-  p.d_q = d_q; p.lse = lse; p.d_acc = d_acc; p.d_acc_bstride = d_acc_bstride;
+  p.d_q = d_q; p.lse = lse; p.d_acc = d_acc; p.d_acc_bstride = d_acc_bstride; p.d_acc_rstride = d_acc_rstride;
   p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
-  p.nblk = (d + kBlockCols - 1) / kBlockCols;
-  p.npv = (d + 15) & ~15;
+  p.nblk = nblk;
+  p.npv = npv;
   p.tmem_cols = (kColDP + p.npv) <= 256 ? 256 : 512;
   p.bf16 = dtype == GA_BF16;
   p.scale = scale;

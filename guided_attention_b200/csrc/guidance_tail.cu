@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(kThreads)
 tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks, const float* __restrict__ weights,
                 const float* __restrict__ attn_text, const float* __restrict__ smoothed,
                 const float* __restrict__ stats, const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
-                const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar) {
+                const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar,
+                int d_abar_rstride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int res = p.res, npix = res * res, T = p.n_ctx, tp = p.last - p.first;
   const int pix = blockIdx.x * kWarps + warp;
@@ -367,7 +368,8 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
 #pragma unroll
   for (int kk = 0; kk < kKPL; ++kk) {
     const int j = lane + 32 * kk;
-    if (j < T) d_abar[(int64_t)pix * T + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
+    if (j < d_abar_rstride)   // padding columns (>= n_ctx) are written as zeros too
+      d_abar[(int64_t)pix * d_abar_rstride + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
   }
 }
 
@@ -556,18 +558,21 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
                                     const uint8_t* masks, const float* weights, const float* attn_text,
                                     const float* smoothed, const float* stats, const int32_t* argmax,
                                     const float* g_total, const float* g_stats, const float* g_attn_text,
-                                    float* d_abar, ga_stream_t stream) {
+                                    float* d_abar, int d_abar_row_stride, ga_stream_t stream) {
   int rc = check_tail_params(params_host, tokens_host);
   if (rc != GA_OK) return rc;
   const ga_tail_params_t& p = *params_host;
   GA_CHECK_ARG(attn_text != nullptr && d_abar != nullptr, "NULL pointer");
+  GA_CHECK_ARG(d_abar_row_stride >= p.n_ctx && d_abar_row_stride <= GA_MAX_CTX, "d_abar_row_stride %d out of range",
+               d_abar_row_stride);
   GA_CHECK_ARG(p.n_tokens == 0 || (smoothed != nullptr && stats != nullptr && argmax != nullptr), "NULL saved tensor");
   tail::TokArgs toks;
   for (int t = 0; t < p.n_tokens; ++t) toks.t[t] = tokens_host[t];
   const int npix = p.res * p.res;
   const int grid = (npix + tail::kWarps - 1) / tail::kWarps;
   tail::tail_bwd_kernel<<<grid, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar);
+      p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar,
+      d_abar_row_stride);
   return check_launch("guidance_tail_bwd");
 }
 

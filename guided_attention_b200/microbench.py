@@ -58,7 +58,7 @@ def time_cross_attn(B, H, N, T, d, dtype=torch.float16, with_acc=True, direction
         do = torch.randn_like(q)
         dq = torch.empty_like(q)
         sets.append((q, k, v, o, lse, acc, do, dq))
-    dacc = torch.randn(N, T, device=device, dtype=torch.float32) if with_acc else None
+    dacc = torch.randn(N, (T + 3) // 4 * 4, device=device, dtype=torch.float32) if with_acc else None
     dt = ops._DTYPES[dtype]
     scale = d ** -0.5
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)   # noqa: E731
@@ -71,7 +71,7 @@ def time_cross_attn(B, H, N, T, d, dtype=torch.float16, with_acc=True, direction
     def bwd(i):
         q, k, v, o, lse, acc, do, dq = sets[i]
         abi.check(lib.ga_cross_attn_bwd(ops._ptr(q), ops._ptr(k), ops._ptr(v), ops._ptr(lse), ops._ptr(do),
-                                        ops._ptr(dacc), 0, ops._ptr(dq), None, None, B, H, N, T, d, scale, dt, impl,
+                                        ops._ptr(dacc), 0, dacc.shape[1] if dacc is not None else T, ops._ptr(dq), None, None, B, H, N, T, d, scale, dt, impl,
                                         st()), "ga_cross_attn_bwd")
     if direction == "bwd":
         for i in range(n_sets):
@@ -113,7 +113,7 @@ def time_tail(res, n_layers, n_samples_per_layer, T=77, direction="fwd", device=
         def launch(i):   # the C ABI directly: an autograd backward of a graph built outside the capture cannot be captured
             abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, ops._ptr(spec.masks), ops._ptr(spec.weights),
                                                ops._ptr(attn_text), ops._ptr(smoothed), ops._ptr(stats),
-                                               ops._ptr(argmax), ops._ptr(g_total), None, None, ops._ptr(d_abar),
+                                               ops._ptr(argmax), ops._ptr(g_total), None, None, ops._ptr(d_abar), T,
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                       "ga_guidance_tail_bwd")
     with torch.no_grad():

@@ -150,15 +150,16 @@ class _CrossAttnFn(torch.autograd.Function):
         T = k.shape[1]
         d = Cdim // heads
         d_o = torch.zeros_like(q) if d_o is None else d_o.contiguous()
-        bstride = 0
+        bstride, rstride = 0, T
         if d_acc is not None:
             if d_acc.dtype != torch.float32:
                 d_acc = d_acc.float()
-            if d_acc.dim() == 3 and d_acc.stride(0) == 0 and d_acc.stride(1) == T and d_acc.stride(2) == 1:
-                bstride = 0                      # one (N, T) slice broadcast over the batch (what the tail returns)
+            if d_acc.dim() == 3 and d_acc.stride(0) == 0 and d_acc.stride(1) >= T and d_acc.stride(2) == 1:
+                # one (N, T) slice broadcast over the batch, rows possibly padded (what the tail backward returns)
+                bstride, rstride = 0, d_acc.stride(1)
             else:
                 d_acc = d_acc.contiguous()
-                bstride = N * T
+                bstride, rstride = N * T, T
         d_q = torch.empty_like(q)
         need_k, need_v = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_k = torch.zeros(k.shape, dtype=torch.float32, device=q.device) if need_k else None
@@ -167,7 +168,7 @@ class _CrossAttnFn(torch.autograd.Function):
         with torch.cuda.device(q.device), _span("cross_attn_bwd", (B, heads, N, T, d, str(q.dtype), d_acc is not None),
                                                 nbytes, q.device):
             abi.check(lib.ga_cross_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(lse), _ptr(d_o), _ptr(d_acc), bstride,
-                                            _ptr(d_q), _ptr(d_k), _ptr(d_v), B, heads, N, T, d, scale,
+                                            rstride, _ptr(d_q), _ptr(d_k), _ptr(d_v), B, heads, N, T, d, scale,
                                             _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_bwd")
         _count("cross_attn_bwd")
         return (d_q, d_k.to(k.dtype) if need_k else None, d_v.to(v.dtype) if need_v else None, None, None, None, None)
@@ -303,16 +304,17 @@ class _GuidanceTailFn(torch.autograd.Function):
         def prep(g):
             return None if g is None else g.contiguous().float()
         g_attn_text, g_stats, g_total = prep(g_attn_text), prep(g_stats), prep(g_total)
-        d_abar = torch.empty((npix, T), dtype=torch.float32, device=dev)
+        pitch = (T + 3) // 4 * 4      # rows padded to 16 bytes: K2 reads them with 128-bit loads
+        d_abar = torch.empty((npix, pitch), dtype=torch.float32, device=dev)
         nbytes = (attn_text.numel() + d_abar.numel()) * 4
         with torch.cuda.device(dev), _span("guidance_tail_bwd", (spec.res, T, p.n_tokens), nbytes, dev):
             abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, _ptr(spec.masks), _ptr(spec.weights),
                                                _ptr(attn_text), _ptr(smoothed), _ptr(stats), _ptr(argmax),
-                                               _ptr(g_total), _ptr(g_stats), _ptr(g_attn_text), _ptr(d_abar),
+                                               _ptr(g_total), _ptr(g_stats), _ptr(g_attn_text), _ptr(d_abar), pitch,
                                                _stream(d_abar)), "ga_guidance_tail_bwd")
         _count("guidance_tail_bwd")
         # every accumulator slice receives the same gradient: hand out stride-0 views, K2 reads them as a broadcast
-        return (None, None) + tuple(d_abar.unsqueeze(0).expand(b, npix, T) for b in ctx.batches)
+        return (None, None) + tuple(d_abar[:, :T].unsqueeze(0).expand(b, npix, T) for b in ctx.batches)
 
 
 def guidance_tail(spec: TailSpec, accs: Sequence[torch.Tensor], n_maps: int):

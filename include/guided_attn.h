@@ -107,12 +107,14 @@ int ga_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, floa
 /* ---- K2: fused cross-attention backward ------------------------------------------------------------------------------
  * autograd of K1 with the attention-map gradient injected:
  *   dP = dO V^T + d_acc[b]      dS = P o (dP - rowsum(P o dP))      dQ = scale dS K
- *   d_o (B, N, H*d) `dtype`;  d_acc fp32 (N, T) slices with batch stride `d_acc_batch_stride` elements
- *   (0 = one slice broadcast over the batch), or NULL;  d_q (B, N, H*d) `dtype`.
+ *   d_o (B, N, H*d) `dtype`;  d_acc fp32 (N, T) slices, rows `d_acc_row_stride` elements apart (>= T; the tail kernel
+ *   pads rows to a multiple of 4 floats so they can be read with 16-byte loads), slices `d_acc_batch_stride` elements
+ *   apart (0 = one slice broadcast over the batch), or NULL;  d_q (B, N, H*d) `dtype`.
  *   d_k, d_v: fp32 (B, T, H*d), ACCUMULATED with atomics (caller zero-fills), or NULL (the reference only
  *   differentiates w.r.t. the latents, pipeline_guided_attention.py:466). */
 int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
-                      const float* d_acc, int64_t d_acc_batch_stride, void* d_q, float* d_k, float* d_v, int batch,
+                      const float* d_acc, int64_t d_acc_batch_stride, int d_acc_row_stride, void* d_q, float* d_k,
+                      float* d_v, int batch,
                       int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl,
                       ga_stream_t stream);
 
@@ -145,12 +147,12 @@ int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t* slices_hos
                          float* total, uint32_t* ticket, ga_stream_t stream);
 
 /* Backward of the tail, one launch:  d_abar (res*res, n_ctx) fp32 = d loss / d (each accumulator slice), i.e. already
- * multiplied by inv_count.  Upstream gradients (all DEVICE, any may be NULL = zero): g_total (1), g_stats
+ * multiplied by inv_count; rows are `d_abar_row_stride` (>= n_ctx) floats apart.  Upstream gradients (all DEVICE, any may be NULL = zero): g_total (1), g_stats
  * (n_tokens, GA_STATS; only MAX/COL/ROW/INSIDE/OUTSIDE are differentiable outputs), g_attn_text (res*res, last-first). */
 int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* tokens_host, const uint8_t* masks,
                          const float* weights, const float* attn_text, const float* smoothed, const float* stats,
                          const int32_t* argmax, const float* g_total, const float* g_stats, const float* g_attn_text,
-                         float* d_abar, ga_stream_t stream);
+                         float* d_abar, int d_abar_row_stride, ga_stream_t stream);
 
 /* ---- stand-alone stages (same device code as the tail), for the module-level API -----------------------------------
  * GaussianSmoothing.forward on reflect-padded maps (utils/gaussian_smoothing.py:63-71 + pipeline :253):

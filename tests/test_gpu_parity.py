@@ -179,9 +179,12 @@ def test_cross_attention_backward(shape, dtype, rtol, broadcast):
 @pytest.mark.parametrize("shape", [(8, 40, 4096, 77, 1), (8, 80, 1024, 77, 2), (8, 160, 256, 77, 2), (8, 160, 64, 77, 1),
                                    (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 70, 2)])
 @pytest.mark.parametrize("with_dacc", [False, True])
-def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc):
-    """K2 on the tensor cores (impl = GA_IMPL_TCGEN05) against the oracle's autograd and the SIMT variant."""
+@pytest.mark.parametrize("variant", ["single", "pipe"])
+def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc, variant):
+    """K2 on the tensor cores (single-shot and persistent pipelined kernels) against the oracle's autograd and the SIMT
+    variant; the map gradient comes in as a broadcast slice with padded (16-byte) rows like the tail kernel emits."""
     from guided_attention_b200 import ops, _cabi as abi
+    TCB = abi.GA_IMPL_TCGEN05_SINGLE if variant == "single" else abi.GA_IMPL_TCGEN05_PIPE
     H, d, N, T, B = shape
     q, k, v = _attn_case(H, d, N, T, B, dtype, seed=11)
     scale = d ** -0.5
@@ -196,7 +199,7 @@ def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc):
         obj = obj + (P.reshape(B, H, N, T).sum(1) * d_acc).sum()
     (gq,) = torch.autograd.grad(obj, qo)
     res = {}
-    for impl in (abi.GA_IMPL_TCGEN05, abi.GA_IMPL_SIMT):
+    for impl in (TCB, abi.GA_IMPL_SIMT):
         ops.default_bwd_impl = impl
         try:
             qd = q.to(DEV).requires_grad_(True)
@@ -204,14 +207,16 @@ def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc):
             outs, gs = [o], [d_o.to(DEV)]
             if with_dacc:
                 outs.append(acc)
-                gs.append(d_acc.to(DEV).expand(B, N, T))
+                padded = torch.zeros(1, N, 80, device=DEV)
+                padded[:, :, :T] = d_acc.to(DEV)
+                gs.append(padded[:, :, :T].expand(B, N, T))     # strides (0, 80, 1)
             (dq,) = torch.autograd.grad(outs, (qd,), gs)
             torch.cuda.synchronize()
             res[impl] = dq.float().cpu().numpy()
         finally:
             ops.default_bwd_impl = abi.GA_IMPL_AUTO
-    assert rel_err(res[abi.GA_IMPL_TCGEN05], gq.numpy()) < rtol
-    assert rel_err(res[abi.GA_IMPL_TCGEN05], res[abi.GA_IMPL_SIMT]) < rtol
+    assert rel_err(res[TCB], gq.numpy()) < rtol
+    assert rel_err(res[TCB], res[abi.GA_IMPL_SIMT]) < rtol
 
 
 # ------------------------------------------------------------------------------------------------ guidance tail
