@@ -33,7 +33,7 @@ class GaTailParams(C.Structure):
     _fields_ = [("res", C.c_int32), ("n_ctx", C.c_int32), ("first", C.c_int32), ("last", C.c_int32),
                 ("n_tokens", C.c_int32), ("n_groups", C.c_int32), ("strict", C.c_int32), ("smooth", C.c_int32),
                 ("w1d", C.c_float * 3), ("temperature", C.c_float), ("inv_count", C.c_float),
-                ("inside_scale", C.c_float), ("outside_scale", C.c_float), ("custom_total", C.c_float)]
+                ("inside_scale", C.c_float), ("outside_scale", C.c_float), ("n_samples", C.c_int32)]
 
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64

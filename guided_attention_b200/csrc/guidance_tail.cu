@@ -170,12 +170,19 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npix = p.res * p.res, T = p.n_ctx, tp = p.last - p.first;
   const int pix = blockIdx.x * kWarps + warp;
+  const int smp = blockIdx.y;                       // independent sample
+  attn_text += (int64_t)smp * npix * tp;
+  smoothed += (int64_t)smp * p.n_tokens * npix;
+  stats += (int64_t)smp * p.n_tokens * GA_STATS;
+  argmax += (int64_t)smp * p.n_tokens;
+  total += smp;
+  ticket += smp;
   if (pix < npix) {
     float v[kKPL];
 #pragma unroll
     for (int kk = 0; kk < kKPL; ++kk) v[kk] = 0.f;
     for (int a = 0; a < acc.n; ++a) {
-      const float* base = acc.ptr[a] + (int64_t)pix * T;
+      const float* base = acc.ptr[a] + ((int64_t)smp * acc.slices[a] * npix + pix) * T;
       for (int s = 0; s < acc.slices[a]; ++s) {
 #pragma unroll
         for (int kk = 0; kk < kKPL; ++kk) {
@@ -225,7 +232,7 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = p.custom_total;
+    float tot = 0.f;
     for (int t = 0; t < p.n_tokens; ++t) tot += toks.t[t].group_weight * stats[(int64_t)t * GA_STATS + GA_STAT_SCALED];
     total[0] = tot;
     *ticket = 0u;  // leave the workspace zero for the next launch
@@ -314,6 +321,15 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   const int pix = blockIdx.x * kWarps + warp;
   if (pix >= npix) return;
   const int y = pix / res, x = pix - y * res;
+  const int smp = blockIdx.y;
+  attn_text += (int64_t)smp * npix * tp;
+  smoothed += (int64_t)smp * p.n_tokens * npix;
+  stats += (int64_t)smp * p.n_tokens * GA_STATS;
+  argmax += (int64_t)smp * p.n_tokens;
+  if (g_total != nullptr) g_total += smp;
+  if (g_stats != nullptr) g_stats += (int64_t)smp * p.n_tokens * GA_STATS;
+  if (g_attn_text != nullptr) g_attn_text += (int64_t)smp * npix * tp;
+  d_abar += (int64_t)smp * npix * d_abar_rstride;
 
   // lane t: gradient of the loss w.r.t. the raw (pre-smoothing) map of token t at this pixel
   float dimg = 0.f;
@@ -484,6 +500,7 @@ static int check_tail_params(const ga_tail_params_t* p, const ga_token_t* toks) 
   GA_CHECK_ARG(p->n_tokens >= 0 && p->n_tokens <= GA_MAX_TOKENS, "n_tokens %d out of range [0, %d]", p->n_tokens,
                GA_MAX_TOKENS);
   GA_CHECK_ARG(p->n_tokens == 0 || toks != nullptr, "tokens_host is NULL");
+  GA_CHECK_ARG(p->n_samples >= 1 && p->n_samples <= 65535, "n_samples %d out of range [1, 65535]", p->n_samples);
   for (int t = 0; t < p->n_tokens; ++t) {
     GA_CHECK_ARG(toks[t].column >= 0 && toks[t].column < p->last - p->first,
                  "token %d: column %d outside the renormalised window of %d tokens", t, toks[t].column,
@@ -548,7 +565,7 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
     cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  const int grid = (npix + tail::kWarps - 1) / tail::kWarps;
+  const dim3 grid((npix + tail::kWarps - 1) / tail::kWarps, p.n_samples);
   tail::tail_fwd_kernel<<<grid, tail::kThreads, smem, st>>>(acc, p, toks, masks, weights, attn_text, smoothed, stats,
                                                             argmax, total, reinterpret_cast<unsigned int*>(ticket));
   return check_launch("guidance_tail_fwd");
@@ -569,7 +586,7 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   tail::TokArgs toks;
   for (int t = 0; t < p.n_tokens; ++t) toks.t[t] = tokens_host[t];
   const int npix = p.res * p.res;
-  const int grid = (npix + tail::kWarps - 1) / tail::kWarps;
+  const dim3 grid((npix + tail::kWarps - 1) / tail::kWarps, p.n_samples);
   tail::tail_bwd_kernel<<<grid, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar,
       d_abar_row_stride);

@@ -82,44 +82,48 @@ def time_cross_attn(B, H, N, T, d, dtype=torch.float16, with_acc=True, direction
             "buffer_sets": n_sets}
 
 
-def time_tail(res, n_layers, n_samples_per_layer, T=77, direction="fwd", device="cuda:0"):
-    """One guidance-tail launch (forward or backward) on `n_layers` accumulators of `n_samples_per_layer` slices."""
+def time_tail(res, n_layers, slices_per_layer, n_samples=1, T=77, direction="fwd", device="cuda:0"):
+    """One guidance-tail launch (forward or backward): `n_samples` independent evaluations, each over `n_layers`
+    accumulators of `slices_per_layer` (N, T) slices (the reference's shape is n_samples = 1, 5 layers, 1-2 slices)."""
     from tests.gpu_harness import setup_prompt   # prompt/config fixture shared with the tests
     from .pipeline_guided_attention import GuidedAttention
     cfg = setup_prompt()
     pipe = GuidedAttention(unet=None, tokenizer=cfg.stable.tokenizer)
     pipe.prompt = cfg.prompt
-    npix = res * res
-    accs = [torch.rand(n_samples_per_layer, npix, T, device=device).softmax(-1) for _ in range(n_layers)]
+    npix, S = res * res, n_samples
     spec = pipe._tail_spec(res, T, True, 0.5, 3, False, torch.device(device))
-    n_maps = n_layers * n_samples_per_layer
-    outs = ops.guidance_tail(spec, [a.requires_grad_(True) for a in accs], n_maps)
-    total = outs[4]
-    nt = spec.params.n_tokens
+    n_maps = n_layers * slices_per_layer
+    tp, nt = spec.last - spec.first, spec.params.n_tokens
+    fwd_bytes = S * ((n_maps * npix * T + npix * tp + nt * npix) * 4 + nt * npix)
+    bwd_bytes = S * (npix * tp + npix * T) * 4
+    nbytes = fwd_bytes if direction == "fwd" else bwd_bytes
+    n_sets = max(1, min(16, (2 * L2_BYTES) // max(fwd_bytes, 1) + 1)) if S > 1 else 1
+    sets = [[torch.rand(S * slices_per_layer, npix, T, device=device).softmax(-1) for _ in range(n_layers)]
+            for _ in range(n_sets)]
+    lib = abi.load()
+    p = abi.GaTailParams.from_buffer_copy(spec.params)
+    p.inv_count, p.n_samples = 1.0 / n_maps, S
     if direction == "fwd":
-        nbytes = (n_maps * npix * T + npix * (spec.last - spec.first) + nt * npix) * 4 + nt * npix
-
         def launch(i):
-            ops.guidance_tail(spec, accs, n_maps)
+            ops.guidance_tail(spec, sets[i], n_maps, S)
     else:
-        nbytes = (npix * (spec.last - spec.first) + npix * T) * 4
-        lib = abi.load()
-        attn_text, smoothed, stats, argmax = (o.detach() for o in outs[:4])
-        g_total = torch.ones(1, device=device)
-        d_abar = torch.empty(npix, T, device=device)
-        p = abi.GaTailParams.from_buffer_copy(spec.params)
-        p.inv_count = 1.0 / n_maps
+        saved = []
+        for accs in sets:
+            outs = ops.guidance_tail(spec, accs, n_maps, S)
+            saved.append(tuple(o.detach() for o in outs[:4]) + (torch.empty(S, npix, 80, device=device),))
+        g_total = torch.ones(S, device=device)
 
         def launch(i):   # the C ABI directly: an autograd backward of a graph built outside the capture cannot be captured
+            attn_text, smoothed, stats, argmax, d_abar = saved[i]
             abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, ops._ptr(spec.masks), ops._ptr(spec.weights),
                                                ops._ptr(attn_text), ops._ptr(smoothed), ops._ptr(stats),
-                                               ops._ptr(argmax), ops._ptr(g_total), None, None, ops._ptr(d_abar), T,
+                                               ops._ptr(argmax), ops._ptr(g_total), None, None, ops._ptr(d_abar), 80,
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                       "ga_guidance_tail_bwd")
     with torch.no_grad():
-        us = _time_graph(launch, 1)
-    return {"kernel": f"guidance_tail_{direction}", "res": res, "layers": n_layers, "slices": n_samples_per_layer,
-            "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3}
+        us = _time_graph(launch, n_sets)
+    return {"kernel": f"guidance_tail_{direction}", "res": res, "layers": n_layers, "slices": slices_per_layer,
+            "samples": S, "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3, "buffer_sets": n_sets}
 
 
 def sweep(device="cuda:0"):
@@ -132,8 +136,9 @@ def sweep(device="cuda:0"):
                 yield time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=N <= 1024, direction=direction,
                                       device=device)
     for res in (16, 32):
-        for direction in ("fwd", "bwd"):
-            yield time_tail(res, 5, 2, direction=direction, device=device)
+        for S in (1, 8, 64, 512, 2048):
+            for direction in ("fwd", "bwd"):
+                yield time_tail(res, 5, 2, n_samples=S, direction=direction, device=device)
 
 
 def single(argv):

@@ -248,16 +248,16 @@ class TailSpec:
 _tickets = {}
 
 
-def _ticket(device) -> torch.Tensor:
+def _ticket(device, n=1) -> torch.Tensor:
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    if key not in _tickets:
-        _tickets[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    if key not in _tickets or _tickets[key].numel() < n:
+        _tickets[key] = torch.zeros(max(n, 64), dtype=torch.int32, device=device)
     return _tickets[key]
 
 
 class _GuidanceTailFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec: TailSpec, n_maps: int, *accs):
+    def forward(ctx, spec: TailSpec, n_maps: int, n_samples: int, *accs):
         _need_cuda(*accs)
         lib = abi.load()
         n = len(accs)
@@ -265,27 +265,29 @@ class _GuidanceTailFn(torch.autograd.Function):
             raise ValueError("no attention accumulators to aggregate")   # reference: torch.cat([]) error
         accs = [a.contiguous() for a in accs]
         dev = accs[0].device
-        npix, T = spec.res * spec.res, spec.n_ctx
+        npix, T, S = spec.res * spec.res, spec.n_ctx, int(n_samples)
         ptrs = (C.c_void_p * n)()
         slices = (C.c_int32 * n)()
         for i, a in enumerate(accs):
-            if a.dtype != torch.float32 or a.dim() != 3 or a.shape[1] != npix or a.shape[2] != T:
-                raise ValueError(f"accumulator {i}: expected (*, {npix}, {T}) fp32, got {tuple(a.shape)} {a.dtype}")
+            if a.dtype != torch.float32 or a.dim() != 3 or a.shape[1] != npix or a.shape[2] != T or a.shape[0] % S:
+                raise ValueError(f"accumulator {i}: expected ({S}*k, {npix}, {T}) fp32, got {tuple(a.shape)} {a.dtype}")
             ptrs[i] = a.data_ptr()
-            slices[i] = a.shape[0]
+            slices[i] = a.shape[0] // S
         p = abi.GaTailParams.from_buffer_copy(spec.params)
         p.inv_count = 1.0 / float(n_maps)
+        p.n_samples = S
         nt, tp = p.n_tokens, spec.last - spec.first
-        attn_text = torch.empty((spec.res, spec.res, tp), dtype=torch.float32, device=dev)
-        smoothed = torch.empty((nt, spec.res, spec.res), dtype=torch.float32, device=dev)
-        stats = torch.empty((nt, abi.GA_STATS), dtype=torch.float32, device=dev)
-        argmax = torch.empty((nt,), dtype=torch.int32, device=dev)
-        total = torch.empty((1,), dtype=torch.float32, device=dev)
-        nbytes = (sum(a.numel() for a in accs) + attn_text.numel() + smoothed.numel()) * 4 + nt * npix
-        with torch.cuda.device(dev), _span("guidance_tail_fwd", (spec.res, T, n, nt), nbytes, dev):
+        lead = () if S == 1 else (S,)
+        attn_text = torch.empty(lead + (spec.res, spec.res, tp), dtype=torch.float32, device=dev)
+        smoothed = torch.empty(lead + (nt, spec.res, spec.res), dtype=torch.float32, device=dev)
+        stats = torch.empty(lead + (nt, abi.GA_STATS), dtype=torch.float32, device=dev)
+        argmax = torch.empty(lead + (nt,), dtype=torch.int32, device=dev)
+        total = torch.empty((S,), dtype=torch.float32, device=dev)
+        nbytes = (sum(a.numel() for a in accs) + attn_text.numel() + smoothed.numel()) * 4 + S * nt * npix
+        with torch.cuda.device(dev), _span("guidance_tail_fwd", (spec.res, T, n, nt, S), nbytes, dev):
             abi.check(lib.ga_guidance_tail_fwd(ptrs, slices, n, C.byref(p), spec.tokens, _ptr(spec.masks),
                                                _ptr(spec.weights), _ptr(attn_text), _ptr(smoothed), _ptr(stats),
-                                               _ptr(argmax), _ptr(total), _ptr(_ticket(dev)), _stream(attn_text)),
+                                               _ptr(argmax), _ptr(total), _ptr(_ticket(dev, S)), _stream(attn_text)),
                       "ga_guidance_tail_fwd")
         _count("guidance_tail_fwd")
         ctx.save_for_backward(attn_text, smoothed, stats, argmax)
@@ -299,30 +301,37 @@ class _GuidanceTailFn(torch.autograd.Function):
         spec, p = ctx.spec, ctx.params
         lib = abi.load()
         dev = attn_text.device
-        npix, T = spec.res * spec.res, spec.n_ctx
+        npix, T, S = spec.res * spec.res, spec.n_ctx, p.n_samples
 
         def prep(g):
             return None if g is None else g.contiguous().float()
         g_attn_text, g_stats, g_total = prep(g_attn_text), prep(g_stats), prep(g_total)
         pitch = (T + 3) // 4 * 4      # rows padded to 16 bytes: K2 reads them with 128-bit loads
-        d_abar = torch.empty((npix, pitch), dtype=torch.float32, device=dev)
+        d_abar = torch.empty((S, npix, pitch), dtype=torch.float32, device=dev)
         nbytes = (attn_text.numel() + d_abar.numel()) * 4
-        with torch.cuda.device(dev), _span("guidance_tail_bwd", (spec.res, T, p.n_tokens), nbytes, dev):
+        with torch.cuda.device(dev), _span("guidance_tail_bwd", (spec.res, T, p.n_tokens, S), nbytes, dev):
             abi.check(lib.ga_guidance_tail_bwd(C.byref(p), spec.tokens, _ptr(spec.masks), _ptr(spec.weights),
                                                _ptr(attn_text), _ptr(smoothed), _ptr(stats), _ptr(argmax),
                                                _ptr(g_total), _ptr(g_stats), _ptr(g_attn_text), _ptr(d_abar), pitch,
                                                _stream(d_abar)), "ga_guidance_tail_bwd")
         _count("guidance_tail_bwd")
-        # every accumulator slice receives the same gradient: hand out stride-0 views, K2 reads them as a broadcast
-        return (None, None) + tuple(d_abar[:, :T].unsqueeze(0).expand(b, npix, T) for b in ctx.batches)
+        # every accumulator slice of a sample receives the same gradient: hand out stride-0 views (K2 reads a broadcast)
+        if S == 1:
+            grads = tuple(d_abar[0, :, :T].unsqueeze(0).expand(b, npix, T) for b in ctx.batches)
+        else:
+            grads = tuple(d_abar[:, None, :, :T].expand(S, b // S, npix, T).reshape(b, npix, T) for b in ctx.batches)
+        return (None, None, None) + grads
 
 
-def guidance_tail(spec: TailSpec, accs: Sequence[torch.Tensor], n_maps: int):
+def guidance_tail(spec: TailSpec, accs: Sequence[torch.Tensor], n_maps: int, n_samples: int = 1):
     """(attn_text (res,res,T'), smoothed (n,res,res), stats (n, GA_STATS), argmax (n), total (1)) -- one launch.
+    With `n_samples` S > 1 (extension, not in the reference: independent samples, e.g. seeds, evaluated by one launch)
+    every accumulator is (S*k, res^2, T), sample-major, `n_maps` counts the maps of ONE sample and every output gains a
+    leading S dimension.
     `accs`: K1 accumulators (B_l, res^2, T), each slice a sum over that layer's heads; `n_maps` = total number of
     head-maps they hold (sum over layers of B_l * heads_l), the divisor of the reference's mean
     (utils/ptp_utils.py:288)."""
-    return _GuidanceTailFn.apply(spec, int(n_maps), *accs)
+    return _GuidanceTailFn.apply(spec, int(n_maps), int(n_samples), *accs)
 
 
 # ===================================================================================== stand-alone stage operators

@@ -254,7 +254,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         p.temperature, p.inv_count = 100.0, 1.0
         p.inside_scale = float(hp["inside_loss_scale"])
         p.outside_scale = float(hp["outside_loss_scale"] * 3)
-        p.custom_total = 0.0
+        p.n_samples = 1
         spec = ops.TailSpec(res=res, n_ctx=n_ctx, first=1, last=last_idx, token_indices=indices,
                             kinds=[_KIND[token_dict[i]['loss_type']] for i in indices], groups=subprompts, tokens=toks,
                             params=p, masks=masks, weights=weights, n_inside=n_inside)

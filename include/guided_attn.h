@@ -84,7 +84,8 @@ typedef struct ga_tail_params {
   float inv_count;      /* 1 / (number of (n_query, n_ctx) head-maps summed into the accumulators)                   */
   float inside_scale;   /* curHyperParams["inside_loss_scale"]                                                       */
   float outside_scale;  /* curHyperParams["outside_loss_scale"] * 3 (:426)                                           */
-  float custom_total;   /* reserved (0)                                                                              */
+  int32_t n_samples;    /* independent samples evaluated by one launch; 1 = the reference's semantics (everything
+                           averaged into one map).  Sample s owns slices [s*slices_i, (s+1)*slices_i) of accumulator i */
 } ga_tail_params_t;
 
 /* ---- library ---------------------------------------------------------------------------------------------------- */
@@ -135,20 +136,21 @@ int ga_rasterize_boxes(const double* boxes_host, int n_boxes, int res, double sh
  * _compute_loss (:398-451):
  *   Abar = inv_count * sum of accumulator slices;  A = softmax(temperature * Abar[:, first:last]);
  *   per token: 3x3 separable Gaussian with reflect padding, max/argmax, normalise, centre of mass, box losses, loss.
- * acc_host[i] points to slices_host[i] consecutive (res*res, n_ctx) fp32 slices (one K1 `acc` tensor).
- * Outputs: attn_text (res*res, last-first) fp32;  smoothed (n_tokens, res*res) fp32;  stats (n_tokens, GA_STATS) fp32;
+ * acc_host[i] points to n_samples * slices_host[i] consecutive (res*res, n_ctx) fp32 slices (one K1 `acc` tensor).
+ * Outputs (each with a leading n_samples dimension): attn_text (res*res, last-first) fp32;  smoothed (n_tokens, res*res) fp32;  stats (n_tokens, GA_STATS) fp32;
  *          argmax (n_tokens) int32 first-occurrence row-major;  total (1) fp32 = sum group_weight * scaled.
  * masks (n_boxes, res, res) u8 and weights (n_boxes, res, res) fp32 (strict mode only, may be NULL otherwise).
- * ticket: 4-byte device workspace that hands the per-pixel stage over to the per-token stage inside the single
- *         launch; zero it once, every launch leaves it zero; launches sharing a ticket must be stream-ordered. */
+ * ticket: n_samples x 4-byte device workspace that hands the per-pixel stage over to the per-token stage inside the
+ *         single launch; zero it once, every launch leaves it zero; launches sharing a ticket must be stream-ordered. */
 int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t* slices_host, int n_acc,
                          const ga_tail_params_t* params_host, const ga_token_t* tokens_host, const uint8_t* masks,
                          const float* weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
                          float* total, uint32_t* ticket, ga_stream_t stream);
 
 /* Backward of the tail, one launch:  d_abar (res*res, n_ctx) fp32 = d loss / d (each accumulator slice), i.e. already
- * multiplied by inv_count; rows are `d_abar_row_stride` (>= n_ctx) floats apart.  Upstream gradients (all DEVICE, any may be NULL = zero): g_total (1), g_stats
- * (n_tokens, GA_STATS; only MAX/COL/ROW/INSIDE/OUTSIDE are differentiable outputs), g_attn_text (res*res, last-first). */
+ * multiplied by inv_count; rows are `d_abar_row_stride` (>= n_ctx) floats apart; one (res*res, stride) slice per
+ * sample.  Upstream gradients (all DEVICE, any may be NULL = zero): g_total (1), g_stats
+ * (n_tokens, GA_STATS), g_attn_text (res*res, last-first) -- each with a leading n_samples dimension. */
 int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* tokens_host, const uint8_t* masks,
                          const float* weights, const float* attn_text, const float* smoothed, const float* stats,
                          const int32_t* argmax, const float* g_total, const float* g_stats, const float* g_attn_text,

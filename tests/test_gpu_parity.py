@@ -344,6 +344,31 @@ def test_tail_custom_loss_plugin_and_upstream_grads():
         assert rel_err(g.cpu().numpy(), go.numpy()) < FP32_RTOL
 
 
+def test_tail_sample_batching_equals_separate_evaluations():
+    """Extension: n_samples independent evaluations in one launch == n separate launches, fwd and bwd."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200 import ops
+    cfg = setup_prompt()
+    pipe = GuidedAttention(unet=None, tokenizer=cfg.stable.tokenizer)
+    pipe.prompt = cfg.prompt
+    S, L, B, res, T = 3, 4, 2, 16, 77
+    g = torch.Generator("cpu").manual_seed(21)
+    layers = [torch.softmax(3 * torch.randn(S * B, res * res, T, generator=g), -1) for _ in range(L)]
+    spec = pipe._tail_spec(res, T, True, 0.5, 3, False, torch.device(DEV))
+    batched = [a.to(DEV).requires_grad_(True) for a in layers]
+    attn_b, sm_b, st_b, am_b, tot_b = ops.guidance_tail(spec, batched, L * B, n_samples=S)
+    w = torch.tensor([1.0, -0.5, 2.0], device=DEV)
+    gb = torch.autograd.grad((tot_b * w).sum(), batched)
+    for s_ in range(S):
+        single = [a[s_ * B:(s_ + 1) * B].to(DEV).requires_grad_(True) for a in layers]
+        attn, sm, st, am, tot = ops.guidance_tail(spec, single, L * B)
+        assert torch.equal(attn, attn_b[s_]) and torch.equal(st, st_b[s_]) and torch.equal(am, am_b[s_])
+        assert torch.equal(tot[0], tot_b[s_])
+        gs = torch.autograd.grad(tot.sum() * w[s_], single)
+        for a, b_ in zip(gs, gb):
+            assert torch.equal(a, b_[s_ * B:(s_ + 1) * B])
+
+
 def test_box_without_inside_pixel_raises_like_reference():
     from guided_attention_b200.pipeline_guided_attention import GuidedAttention
     cfg = setup_prompt('a [dot:.5,.5,.02,.02] here')
