@@ -166,10 +166,10 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
                 const float* __restrict__ weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
                 float* total, unsigned int* ticket) {
   extern __shared__ float simg[];  // kWarps * res*res floats (phase S only)
+  __shared__ __align__(16) float srow[kWarps][4 * GA_MAX_CTX];   // phase R: 4 pixels x T tokens per warp
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npix = p.res * p.res, T = p.n_ctx, tp = p.last - p.first;
-  const int pix = blockIdx.x * kWarps + warp;
   const int smp = blockIdx.y;                       // independent sample
   attn_text += (int64_t)smp * npix * tp;
   smoothed += (int64_t)smp * p.n_tokens * npix;
@@ -177,40 +177,66 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
   argmax += (int64_t)smp * p.n_tokens;
   total += smp;
   ticket += smp;
-  if (pix < npix) {
-    float v[kKPL];
+
+  // Phase R.  A warp owns 4 consecutive pixels = 4*T contiguous floats of every slice = T aligned float4 chunks
+  // (npix % 4 == 0 is guaranteed by the host wrapper): 128-bit coalesced loads, lanes over chunks, slices summed in a
+  // fixed order; the sums are re-distributed through shared memory so that lanes become text tokens for the softmax.
+  const int group = blockIdx.x * kWarps + warp;
+  if (group * 4 < npix) {
+    float4 v[kKPL];
 #pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) v[kk] = 0.f;
+    for (int kk = 0; kk < kKPL; ++kk) v[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t slice4 = (int64_t)npix * T / 4;
     for (int a = 0; a < acc.n; ++a) {
-      const float* base = acc.ptr[a] + ((int64_t)smp * acc.slices[a] * npix + pix) * T;
+      const float4* base = reinterpret_cast<const float4*>(acc.ptr[a]) + (int64_t)smp * acc.slices[a] * slice4 +
+                           (int64_t)group * T;
+#pragma unroll 2
       for (int s = 0; s < acc.slices[a]; ++s) {
 #pragma unroll
         for (int kk = 0; kk < kKPL; ++kk) {
-          const int j = lane + 32 * kk;
-          if (j < T) v[kk] += __ldg(base + (int64_t)s * npix * T + j);
+          const int c = lane + 32 * kk;
+          if (c < T) {
+            const float4 x = __ldg(base + (int64_t)s * slice4 + c);
+            v[kk].x += x.x; v[kk].y += x.y; v[kk].z += x.z; v[kk].w += x.w;
+          }
         }
       }
     }
-    float m = -INFINITY;
+    const float k = p.inv_count * p.temperature;
 #pragma unroll
     for (int kk = 0; kk < kKPL; ++kk) {
-      const int j = lane + 32 * kk;
-      v[kk] = (v[kk] * p.inv_count) * p.temperature;
-      if (j >= p.first && j < p.last) m = fmaxf(m, v[kk]);
+      const int c = lane + 32 * kk;
+      if (c < T)
+        reinterpret_cast<float4*>(srow[warp])[c] =
+            make_float4((v[kk].x * p.inv_count) * p.temperature, (v[kk].y * p.inv_count) * p.temperature,
+                        (v[kk].z * p.inv_count) * p.temperature, (v[kk].w * p.inv_count) * p.temperature);
     }
-    m = warp_max(m);
-    float e[kKPL], sum = 0.f;
+    (void)k;
+    __syncwarp();
+    for (int q = 0; q < 4; ++q) {
+      const int pix = group * 4 + q;
+      const float* row = srow[warp] + q * T;
+      float x[kKPL], m = -INFINITY;
 #pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) {
-      const int j = lane + 32 * kk;
-      e[kk] = (j >= p.first && j < p.last) ? expf(v[kk] - m) : 0.f;
-      sum += e[kk];
-    }
-    sum = warp_sum(sum);
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        x[kk] = (j < T) ? row[j] : 0.f;
+        if (j >= p.first && j < p.last) m = fmaxf(m, x[kk]);
+      }
+      m = warp_max(m);
+      float e[kKPL], sum = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) {
-      const int j = lane + 32 * kk;
-      if (j >= p.first && j < p.last) attn_text[(int64_t)pix * tp + (j - p.first)] = e[kk] / sum;
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        e[kk] = (j >= p.first && j < p.last) ? expf(x[kk] - m) : 0.f;
+        sum += e[kk];
+      }
+      sum = warp_sum(sum);
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        if (j >= p.first && j < p.last) attn_text[(int64_t)pix * tp + (j - p.first)] = e[kk] / sum;
+      }
     }
   }
 
@@ -246,7 +272,7 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
 // then the warp does the x100-softmax backward over the tokens of this pixel.
 struct TokenGrad {
   float g_col, g_row, g_in, g_out, g_max, g_sum, dp_mean, inv_sum, at_most;
-  int argmax, box, strict_box;
+  int argmax, box, strict_box, column;
 };
 
 __device__ __forceinline__ TokenGrad make_token_grad(const ga_tail_params_t& p, const ga_token_t& tk,
@@ -277,6 +303,7 @@ __device__ __forceinline__ TokenGrad make_token_grad(const ga_tail_params_t& p, 
   g.inv_sum = 1.f / st[GA_STAT_SUM];
   g.at_most = st[GA_STAT_NINSIDE] > 0.f ? 1.f / st[GA_STAT_NINSIDE] : 0.f;
   g.argmax = amax;
+  g.column = tk.column;
   g.box = is_box ? tk.box : -1;
   g.strict_box = (is_box && p.strict) ? 1 : 0;
   // sum over pixels of dp * p, in closed form from the saved statistics
@@ -316,11 +343,9 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
                 const float* __restrict__ stats, const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
                 const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar,
                 int d_abar_rstride) {
+  __shared__ TokenGrad tg[GA_MAX_TOKENS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int res = p.res, npix = res * res, T = p.n_ctx, tp = p.last - p.first;
-  const int pix = blockIdx.x * kWarps + warp;
-  if (pix >= npix) return;
-  const int y = pix / res, x = pix - y * res;
+  const int res = p.res, npix = res * res, tp = p.last - p.first;
   const int smp = blockIdx.y;
   attn_text += (int64_t)smp * npix * tp;
   smoothed += (int64_t)smp * p.n_tokens * npix;
@@ -331,38 +356,20 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   if (g_attn_text != nullptr) g_attn_text += (int64_t)smp * npix * tp;
   d_abar += (int64_t)smp * npix * d_abar_rstride;
 
-  // lane t: gradient of the loss w.r.t. the raw (pre-smoothing) map of token t at this pixel
-  float dimg = 0.f;
-  int my_col = -1;
-  if (lane < p.n_tokens) {
-    const ga_token_t& tk = toks.t[lane];
-    my_col = tk.column;
-    const float gt = g_total != nullptr ? g_total[0] : 0.f;
-    const TokenGrad g = make_token_grad(p, tk, stats + (int64_t)lane * GA_STATS, argmax[lane], gt,
-                                        g_stats != nullptr ? g_stats + (int64_t)lane * GA_STATS : nullptr);
-    const float* sm = smoothed + (int64_t)lane * npix;
-    if (p.smooth) {
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= res) continue;
-        const float my = adjoint_tap(y, yy, res, p.w1d);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = x + dx;
-          if (xx < 0 || xx >= res) continue;
-          const float mx = adjoint_tap(x, xx, res, p.w1d);
-          dimg = fmaf(my * mx, dsmoothed_at(g, yy * res + xx, res, masks, weights, sm), dimg);
-        }
-      }
-    } else {
-      dimg = dsmoothed_at(g, pix, res, masks, weights, sm);
-    }
+  // per-token scalars once per CTA: upstream gradients x the forward's saved statistics
+  if ((int)threadIdx.x < p.n_tokens) {
+    const int t = threadIdx.x;
+    tg[t] = make_token_grad(p, toks.t[t], stats + (int64_t)t * GA_STATS, argmax[t],
+                            g_total != nullptr ? g_total[0] : 0.f,
+                            g_stats != nullptr ? g_stats + (int64_t)t * GA_STATS : nullptr);
   }
-  // tokens beyond 32 lanes: GA_MAX_TOKENS (24) < 32, so one pass is enough
+  __syncthreads();
+  const int pix = blockIdx.x * kWarps + warp;
+  if (pix >= npix) return;
+  const int y = pix / res, x = pix - y * res;
 
-  // softmax backward over the text tokens of this pixel
-  float a[kKPL], da[kKPL], dot = 0.f;
+  // softmax backward over the text tokens of this pixel: lanes are tokens
+  float a[kKPL], da[kKPL];
 #pragma unroll
   for (int kk = 0; kk < kKPL; ++kk) {
     const int j = lane + 32 * kk;
@@ -370,13 +377,41 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
     a[kk] = live ? attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
     da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
   }
-  for (int t = 0; t < p.n_tokens; ++t) {
-    const float gv = __shfl_sync(0xffffffffu, dimg, t);
-    const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
+
+  // d loss / d raw map of every tracked token at this pixel: the work items (token, tap of the 3x3 adjoint filter) are
+  // spread over the lanes, then summed per token with shuffles and added to the lane that owns the token's column
+  const int taps = p.smooth ? 9 : 1;
+  const int n_items = p.n_tokens * taps;
+  for (int w0 = 0; w0 < n_items; w0 += 32) {
+    const int w = w0 + lane;
+    float c = 0.f;
+    if (w < n_items) {
+      const int t = w / taps, tap = w - t * taps;
+      const float* sm = smoothed + (int64_t)t * npix;
+      if (p.smooth) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < res && xx >= 0 && xx < res)
+          c = adjoint_tap(y, yy, res, p.w1d) * adjoint_tap(x, xx, res, p.w1d) *
+              dsmoothed_at(tg[t], yy * res + xx, res, masks, weights, sm);
+      } else {
+        c = dsmoothed_at(tg[t], pix, res, masks, weights, sm);
+      }
+    }
+    const int w_end = min(w0 + 32, n_items);
+    for (int t = w0 / taps; t * taps < w_end; ++t) {
+      float sum = 0.f;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int idx = t * taps + tap - w0;
+        if (idx >= 0 && idx < 32) sum += __shfl_sync(0xffffffffu, c, idx);
+      }
+      const int j = tg[t].column + p.first;
 #pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk)
-      if (j == lane + 32 * kk) da[kk] += gv;
+      for (int kk = 0; kk < kKPL; ++kk)
+        if (j == lane + 32 * kk) da[kk] += sum;
+    }
   }
+
+  float dot = 0.f;
 #pragma unroll
   for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
   dot = warp_sum(dot);
@@ -565,7 +600,9 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
     cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  const dim3 grid((npix + tail::kWarps - 1) / tail::kWarps, p.n_samples);
+  GA_CHECK_ARG(npix % 4 == 0, "res*res must be a multiple of 4 (res %d)", p.res);
+  for (int i = 0; i < n_acc; ++i) GA_CHECK_ALIGN(acc_host[i], 16, "accumulator");
+  const dim3 grid((npix / 4 + tail::kWarps - 1) / tail::kWarps, p.n_samples);
   tail::tail_fwd_kernel<<<grid, tail::kThreads, smem, st>>>(acc, p, toks, masks, weights, attn_text, smoothed, stats,
                                                             argmax, total, reinterpret_cast<unsigned int*>(ticket));
   return check_launch("guidance_tail_fwd");
