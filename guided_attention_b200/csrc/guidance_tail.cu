@@ -337,12 +337,15 @@ __device__ __forceinline__ float dsmoothed_at(const TokenGrad& g, int pix, int r
   return ds;
 }
 
+constexpr int kBwdPixPerCta = 64;   // 8 pixels per warp
+
 __global__ void __launch_bounds__(kThreads)
 tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks, const float* __restrict__ weights,
                 const float* __restrict__ attn_text, const float* __restrict__ smoothed,
                 const float* __restrict__ stats, const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
                 const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar,
                 int d_abar_rstride) {
+  extern __shared__ float sds[];            // d loss / d smoothed for [tile - halo, tile + halo), per token
   __shared__ TokenGrad tg[GA_MAX_TOKENS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int res = p.res, npix = res * res, tp = p.last - p.first;
@@ -364,63 +367,73 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
                             g_stats != nullptr ? g_stats + (int64_t)t * GA_STATS : nullptr);
   }
   __syncthreads();
-  const int pix = blockIdx.x * kWarps + warp;
-  if (pix >= npix) return;
-  const int y = pix / res, x = pix - y * res;
-
-  // softmax backward over the text tokens of this pixel: lanes are tokens
-  float a[kKPL], da[kKPL];
-#pragma unroll
-  for (int kk = 0; kk < kKPL; ++kk) {
-    const int j = lane + 32 * kk;
-    const bool live = j >= p.first && j < p.last;
-    a[kk] = live ? attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
-    da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+  // d loss / d smoothed-map for the tile's pixels plus a halo of one row + one pixel on each side, every token:
+  // computed once per CTA (each value is needed by up to 9 output pixels)
+  const int p0 = blockIdx.x * kBwdPixPerCta;
+  const int halo = p.smooth ? res + 1 : 0;
+  const int lo = max(p0 - halo, 0), hi = min(p0 + kBwdPixPerCta + halo, npix), span = kBwdPixPerCta + 2 * halo;
+  for (int i = threadIdx.x; i < p.n_tokens * span; i += blockDim.x) {
+    const int t = i / span, q = lo + (i - t * span);
+    if (q < hi) sds[i] = dsmoothed_at(tg[t], q, res, masks, weights, smoothed + (int64_t)t * npix);
   }
+  __syncthreads();
 
-  // d loss / d raw map of every tracked token at this pixel: the work items (token, tap of the 3x3 adjoint filter) are
-  // spread over the lanes, then summed per token with shuffles and added to the lane that owns the token's column
-  const int taps = p.smooth ? 9 : 1;
-  const int n_items = p.n_tokens * taps;
-  for (int w0 = 0; w0 < n_items; w0 += 32) {
-    const int w = w0 + lane;
-    float c = 0.f;
-    if (w < n_items) {
-      const int t = w / taps, tap = w - t * taps;
-      const float* sm = smoothed + (int64_t)t * npix;
+  const float k = p.temperature * p.inv_count;
+  for (int pi = warp; pi < kBwdPixPerCta; pi += kWarps) {
+    const int pix = p0 + pi;
+    if (pix >= npix) break;
+    const int y = pix / res, x = pix - y * res;
+    // lane t: gradient w.r.t. the raw map of token t at this pixel = adjoint of the reflect-padded 3x3 filter
+    float dimg = 0.f;
+    int my_col = -1;
+    if (lane < p.n_tokens) {
+      my_col = tg[lane].column;
+      const float* ds = sds + lane * span - lo;
       if (p.smooth) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < res && xx >= 0 && xx < res)
-          c = adjoint_tap(y, yy, res, p.w1d) * adjoint_tap(x, xx, res, p.w1d) *
-              dsmoothed_at(tg[t], yy * res + xx, res, masks, weights, sm);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= res) continue;
+          const float wy = p.w1d[1 - dy] + ((y == 1 && dy == -1) ? p.w1d[0] : 0.f) +
+                           ((y == res - 2 && dy == 1) ? p.w1d[2] : 0.f);
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= res) continue;
+            const float wx = p.w1d[1 - dx] + ((x == 1 && dx == -1) ? p.w1d[0] : 0.f) +
+                             ((x == res - 2 && dx == 1) ? p.w1d[2] : 0.f);
+            dimg = fmaf(wy * wx, ds[yy * res + xx], dimg);
+          }
+        }
       } else {
-        c = dsmoothed_at(tg[t], pix, res, masks, weights, sm);
+        dimg = ds[pix];
       }
     }
-    const int w_end = min(w0 + 32, n_items);
-    for (int t = w0 / taps; t * taps < w_end; ++t) {
-      float sum = 0.f;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int idx = t * taps + tap - w0;
-        if (idx >= 0 && idx < 32) sum += __shfl_sync(0xffffffffu, c, idx);
-      }
-      const int j = tg[t].column + p.first;
+    // softmax backward over the text tokens of this pixel: lanes are tokens
+    float a[kKPL], da[kKPL], dot = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int j = lane + 32 * kk;
+      const bool live = j >= p.first && j < p.last;
+      a[kk] = live ? attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+      da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+    }
+    for (int t = 0; t < p.n_tokens; ++t) {
+      const float gv = __shfl_sync(0xffffffffu, dimg, t);
+      const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
 #pragma unroll
       for (int kk = 0; kk < kKPL; ++kk)
-        if (j == lane + 32 * kk) da[kk] += sum;
+        if (j == lane + 32 * kk) da[kk] += gv;
     }
-  }
-
-  float dot = 0.f;
 #pragma unroll
-  for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
-  dot = warp_sum(dot);
-  const float k = p.temperature * p.inv_count;
+    for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
+    dot = warp_sum(dot);
 #pragma unroll
-  for (int kk = 0; kk < kKPL; ++kk) {
-    const int j = lane + 32 * kk;
-    if (j < d_abar_rstride)   // padding columns (>= n_ctx) are written as zeros too
-      d_abar[(int64_t)pix * d_abar_rstride + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int j = lane + 32 * kk;
+      if (j < d_abar_rstride)   // padding columns (>= n_ctx) are written as zeros too
+        d_abar[(int64_t)pix * d_abar_rstride + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
+    }
   }
 }
 
@@ -596,9 +609,15 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
   const size_t smem = (size_t)tail::kWarps * npix * sizeof(float);
   if (smem > 200 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d too large for the fused tail", p.res);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (smem > 48 * 1024) {   // res > 39: not a size the AttentionStore keeps; set per call
-    cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (smem > 24 * 1024) {   // static (phase R rows) + dynamic (phase S maps) can pass the 48 KB default from res 32 up
+    static bool raised[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !raised[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(tail::tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      raised[dev] = true;
+    }
   }
   GA_CHECK_ARG(npix % 4 == 0, "res*res must be a multiple of 4 (res %d)", p.res);
   for (int i = 0; i < n_acc; ++i) GA_CHECK_ALIGN(acc_host[i], 16, "accumulator");
@@ -623,8 +642,10 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   tail::TokArgs toks;
   for (int t = 0; t < p.n_tokens; ++t) toks.t[t] = tokens_host[t];
   const int npix = p.res * p.res;
-  const dim3 grid((npix + tail::kWarps - 1) / tail::kWarps, p.n_samples);
-  tail::tail_bwd_kernel<<<grid, tail::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const dim3 grid((npix + tail::kBwdPixPerCta - 1) / tail::kBwdPixPerCta, p.n_samples);
+  const size_t smem = (size_t)(p.n_tokens > 0 ? p.n_tokens : 1) * (tail::kBwdPixPerCta + 2 * (p.res + 1)) * sizeof(float);
+  if (smem > 40 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d x %d tokens too large for the tail backward", p.res, p.n_tokens);
+  tail::tail_bwd_kernel<<<grid, tail::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar,
       d_abar_row_stride);
   return check_launch("guidance_tail_bwd");
