@@ -337,16 +337,18 @@ __device__ __forceinline__ float dsmoothed_at(const TokenGrad& g, int pix, int r
   return ds;
 }
 
-constexpr int kBwdPixPerCta = 64;   // 8 pixels per warp
-
+// One launch, one warp per group of 4 consecutive pixels (128-bit coalesced loads of the attn_text rows and stores of
+// the d_abar rows, staged through shared memory); `groups_per_warp` groups per warp (1 when the launch is small).
 __global__ void __launch_bounds__(kThreads)
 tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks, const float* __restrict__ weights,
                 const float* __restrict__ attn_text, const float* __restrict__ smoothed,
                 const float* __restrict__ stats, const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
                 const float* __restrict__ g_stats, const float* __restrict__ g_attn_text, float* __restrict__ d_abar,
-                int d_abar_rstride) {
+                int d_abar_rstride, int groups_per_warp) {
   extern __shared__ float sds[];            // d loss / d smoothed for [tile - halo, tile + halo), per token
   __shared__ TokenGrad tg[GA_MAX_TOKENS];
+  __shared__ __align__(16) float s_in[kWarps][4 * GA_MAX_CTX];    // 4 attn_text rows
+  __shared__ __align__(16) float s_out[kWarps][4 * GA_MAX_CTX];   // 4 d_abar rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int res = p.res, npix = res * res, tp = p.last - p.first;
   const int smp = blockIdx.y;
@@ -369,9 +371,10 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   __syncthreads();
   // d loss / d smoothed-map for the tile's pixels plus a halo of one row + one pixel on each side, every token:
   // computed once per CTA (each value is needed by up to 9 output pixels)
-  const int p0 = blockIdx.x * kBwdPixPerCta;
+  const int ppc = 4 * kWarps * groups_per_warp;
+  const int p0 = blockIdx.x * ppc;
   const int halo = p.smooth ? res + 1 : 0;
-  const int lo = max(p0 - halo, 0), hi = min(p0 + kBwdPixPerCta + halo, npix), span = kBwdPixPerCta + 2 * halo;
+  const int lo = max(p0 - halo, 0), hi = min(p0 + ppc + halo, npix), span = ppc + 2 * halo;
   for (int i = threadIdx.x; i < p.n_tokens * span; i += blockDim.x) {
     const int t = i / span, q = lo + (i - t * span);
     if (q < hi) sds[i] = dsmoothed_at(tg[t], q, res, masks, weights, smoothed + (int64_t)t * npix);
@@ -379,61 +382,88 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   __syncthreads();
 
   const float k = p.temperature * p.inv_count;
-  for (int pi = warp; pi < kBwdPixPerCta; pi += kWarps) {
-    const int pix = p0 + pi;
-    if (pix >= npix) break;
-    const int y = pix / res, x = pix - y * res;
-    // lane t: gradient w.r.t. the raw map of token t at this pixel = adjoint of the reflect-padded 3x3 filter
-    float dimg = 0.f;
-    int my_col = -1;
-    if (lane < p.n_tokens) {
-      my_col = tg[lane].column;
-      const float* ds = sds + lane * span - lo;
-      if (p.smooth) {
+  const bool vec_in = (tp & 3) == 0 || true;   // 4 rows of tp floats are 4*tp*4 bytes = a multiple of 16 for any tp
+  (void)vec_in;
+  const bool vec_out = (d_abar_rstride & 3) == 0;
+  for (int gi = 0; gi < groups_per_warp; ++gi) {
+    const int g0 = p0 + (gi * kWarps + warp) * 4;     // first pixel of this warp's group
+    if (g0 >= npix) break;
+    // stage the 4 attn_text rows: tp float4 chunks, contiguous and 16-byte aligned (g0 % 4 == 0)
+    const float4* src = reinterpret_cast<const float4*>(attn_text + (int64_t)g0 * tp);
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= res) continue;
-          const float wy = p.w1d[1 - dy] + ((y == 1 && dy == -1) ? p.w1d[0] : 0.f) +
-                           ((y == res - 2 && dy == 1) ? p.w1d[2] : 0.f);
+    for (int kk = 0; kk < kKPL; ++kk) {
+      const int c = lane + 32 * kk;
+      if (c < tp) reinterpret_cast<float4*>(s_in[warp])[c] = __ldg(src + c);
+    }
+    __syncwarp();
+    for (int q = 0; q < 4; ++q) {
+      const int pix = g0 + q;
+      const int y = pix / res, x = pix - y * res;
+      // lane t: gradient w.r.t. the raw map of token t at this pixel = adjoint of the reflect-padded 3x3 filter
+      float dimg = 0.f;
+      int my_col = -1;
+      if (lane < p.n_tokens) {
+        my_col = tg[lane].column;
+        const float* ds = sds + lane * span - lo;
+        if (p.smooth) {
 #pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= res) continue;
-            const float wx = p.w1d[1 - dx] + ((x == 1 && dx == -1) ? p.w1d[0] : 0.f) +
-                             ((x == res - 2 && dx == 1) ? p.w1d[2] : 0.f);
-            dimg = fmaf(wy * wx, ds[yy * res + xx], dimg);
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= res) continue;
+            const float wy = p.w1d[1 - dy] + ((y == 1 && dy == -1) ? p.w1d[0] : 0.f) +
+                             ((y == res - 2 && dy == 1) ? p.w1d[2] : 0.f);
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int xx = x + dx;
+              if (xx < 0 || xx >= res) continue;
+              const float wx = p.w1d[1 - dx] + ((x == 1 && dx == -1) ? p.w1d[0] : 0.f) +
+                               ((x == res - 2 && dx == 1) ? p.w1d[2] : 0.f);
+              dimg = fmaf(wy * wx, ds[yy * res + xx], dimg);
+            }
           }
+        } else {
+          dimg = ds[pix];
         }
-      } else {
-        dimg = ds[pix];
+      }
+      // softmax backward over the text tokens of this pixel: lanes are tokens
+      float a[kKPL], da[kKPL], dot = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        const bool live = j >= p.first && j < p.last;
+        a[kk] = live ? s_in[warp][q * tp + (j - p.first)] : 0.f;
+        da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+      }
+      for (int t = 0; t < p.n_tokens; ++t) {
+        const float gv = __shfl_sync(0xffffffffu, dimg, t);
+        const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
+#pragma unroll
+        for (int kk = 0; kk < kKPL; ++kk)
+          if (j == lane + 32 * kk) da[kk] += gv;
+      }
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int j = lane + 32 * kk;
+        if (j < d_abar_rstride) {   // padding columns (>= n_ctx) are written as zeros too
+          const float val = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
+          if (vec_out) s_out[warp][q * d_abar_rstride + j] = val;
+          else d_abar[(int64_t)pix * d_abar_rstride + j] = val;
+        }
       }
     }
-    // softmax backward over the text tokens of this pixel: lanes are tokens
-    float a[kKPL], da[kKPL], dot = 0.f;
+    if (vec_out) {
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(d_abar + (int64_t)g0 * d_abar_rstride);
 #pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) {
-      const int j = lane + 32 * kk;
-      const bool live = j >= p.first && j < p.last;
-      a[kk] = live ? attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
-      da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+      for (int kk = 0; kk < kKPL; ++kk) {
+        const int c = lane + 32 * kk;
+        if (c < d_abar_rstride) dst[c] = reinterpret_cast<const float4*>(s_out[warp])[c];
+      }
     }
-    for (int t = 0; t < p.n_tokens; ++t) {
-      const float gv = __shfl_sync(0xffffffffu, dimg, t);
-      const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
-#pragma unroll
-      for (int kk = 0; kk < kKPL; ++kk)
-        if (j == lane + 32 * kk) da[kk] += gv;
-    }
-#pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
-    dot = warp_sum(dot);
-#pragma unroll
-    for (int kk = 0; kk < kKPL; ++kk) {
-      const int j = lane + 32 * kk;
-      if (j < d_abar_rstride)   // padding columns (>= n_ctx) are written as zeros too
-        d_abar[(int64_t)pix * d_abar_rstride + j] = (j >= p.first && j < p.last) ? k * a[kk] * (da[kk] - dot) : 0.f;
-    }
+    __syncwarp();
   }
 }
 
@@ -642,12 +672,22 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   tail::TokArgs toks;
   for (int t = 0; t < p.n_tokens; ++t) toks.t[t] = tokens_host[t];
   const int npix = p.res * p.res;
-  const dim3 grid((npix + tail::kBwdPixPerCta - 1) / tail::kBwdPixPerCta, p.n_samples);
-  const size_t smem = (size_t)(p.n_tokens > 0 ? p.n_tokens : 1) * (tail::kBwdPixPerCta + 2 * (p.res + 1)) * sizeof(float);
-  if (smem > 40 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d x %d tokens too large for the tail backward", p.res, p.n_tokens);
+  GA_CHECK_ARG(npix % 4 == 0, "res*res must be a multiple of 4 (res %d)", p.res);
+  GA_CHECK_ALIGN(attn_text, 16, "attn_text");
+  if ((d_abar_row_stride & 3) == 0) GA_CHECK_ALIGN(d_abar, 16, "d_abar");
+  // small launches: one 4-pixel group per warp (latency); large ones: 4 groups per warp (amortise the halo staging)
+  int groups_per_warp = ((int64_t)p.n_samples * npix >= 128 * 1024) ? 4 : 1;
+  auto halo_bytes = [&](int gpw) {
+    return (size_t)(p.n_tokens > 0 ? p.n_tokens : 1) * (4 * tail::kWarps * gpw + 2 * (p.res + 1)) * sizeof(float);
+  };
+  if (halo_bytes(groups_per_warp) > 14 * 1024) groups_per_warp = 1;
+  const int ppc = 4 * tail::kWarps * groups_per_warp;
+  const dim3 grid((npix + ppc - 1) / ppc, p.n_samples);
+  const size_t smem = halo_bytes(groups_per_warp);
+  if (smem > 14 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d x %d tokens too large for the tail backward", p.res, p.n_tokens);
   tail::tail_bwd_kernel<<<grid, tail::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar,
-      d_abar_row_stride);
+      d_abar_row_stride, groups_per_warp);
   return check_launch("guidance_tail_bwd");
 }
 
