@@ -300,7 +300,24 @@ def run_ours(args):
     pipe.use_cuda_graphs = not args.no_graphs
     roofline, kernel_table = roofline_from(prof)
 
-    # parity self-check of this very process (tiny, oracle as the checker)
+    # (4) extension: S seeds per UNet pass (`generate_batch`), same per-seed semantics; reported next to the headline
+    batched = None
+    if args.seeds_per_batch > 1:
+        Sb = args.seeds_per_batch
+        pipe.use_cuda_graphs = not args.no_graphs
+        emb16 = embeds_dev.to(torch.float16)
+
+        def batch_step(i):
+            seeds = [seed_of(2, i * Sb + j) for j in range(Sb)]
+            return pipe.generate_batch(cfg.prompt, store, seeds, emb16[1:2], emb16[0:1], attention_res=16,
+                                       num_inference_steps=args.denoise_steps, guidance_scale=7.5,
+                                       thresholds=cfg.thresholds)
+        batch_step(0)                                   # warm-up: captures the batch-S graphs
+        ms_b, _ = timed(batch_step, 1)
+        batched = {"seeds_per_batch": Sb, "value": Sb * world / (ms_b / 1e3), "unit": "img/s",
+                   "ms_per_batch": ms_b, "note": "extension (SURVEY 8e): per-seed results equal the one-seed path "
+                   "(tests/test_gpu_parity.py::test_seed_batching_equals_separate_calls)"}
+
     n_img = args.steps * world
     value = n_img / (ms_value / 1e3)
     e2e = n_img / (ms_e2e / 1e3)
@@ -311,7 +328,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(embeds_host.numel() * 4 + 4 * 64 * 64 * 4),
                     "d2h_bytes_per_step": int(4 * 64 * 64 * 2)},
             "gpu_launches": launches, "gpu_launches_by_kernel": counts, "unet_passes": unet_passes,
-            "clocks": clocks, "roofline": roofline, "kernels": kernel_table}
+            "clocks": clocks, "roofline": roofline, "kernels": kernel_table, "batched": batched}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         times, _ = cpu_component_times(args.unet, threads)
@@ -376,6 +393,8 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--seeds-per-batch", type=int, default=8,
+                    help="also measure the seed-batched extension with this many seeds per UNet pass (0/1 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

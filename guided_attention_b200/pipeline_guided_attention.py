@@ -132,6 +132,102 @@ class _StepGraphs:
         return self.outputs[name], (self.lat_out.clone() if name != "eval" else None)
 
 
+class _BatchGraphs:
+    """Seed-batched versions of the three device programs (extension): S independent seeds advance
+    through the same UNet pass, every sample keeps its own attention accumulators (K1 writes `acc[b]` per batch element),
+    the tail kernel evaluates the S losses in one launch (`n_samples = S`) and the latent step takes a per-sample step
+    size, so seeds that must not move in a given pass simply get step 0.  Nothing couples the samples (eval-mode UNet:
+    GroupNorm / LayerNorm / attention are per sample), which the tests check against the one-seed path."""
+
+    def __init__(self, pipe, store, loss_kw, prompt_embeds, guidance_scale, latents_like, eager=False):
+        self.pipe, self.store, self.loss_kw, self.gs, self.eager = pipe, store, loss_kw, float(guidance_scale), eager
+        S = latents_like.shape[0]
+        dev = latents_like.device
+        self.S = S
+        self.lat = torch.zeros_like(latents_like)
+        self.lat_out = torch.zeros_like(latents_like)
+        self.t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step = torch.zeros(S, 1, 1, 1, dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.set_embeds(prompt_embeds)
+        self.graphs, self.outputs, self.launches, self.replays = {}, {}, {}, {}
+        self.pool = None
+
+    def set_embeds(self, prompt_embeds):
+        S = self.S
+        cond = prompt_embeds[1:2].detach().expand(S, -1, -1).contiguous()
+        unc = prompt_embeds[0:1].detach().expand(S, -1, -1).contiguous()
+        if hasattr(self, "cond"):
+            self.cond.copy_(cond)
+            self.both.copy_(torch.cat([unc, cond]))
+        else:
+            self.cond, self.both = cond, torch.cat([unc, cond])
+
+    def _loss(self):
+        kw = self.loss_kw
+        picked = select_maps(self.store, kw["attention_res"], ("up", "down", "mid"), True)
+        if len(picked) == 0:
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")
+        accs = [m.acc for m in picked]                       # each (S, N, T): one slice per sample
+        res, T = kw["attention_res"], accs[0].shape[2]
+        spec = self.pipe._tail_spec(res, T, kw["smooth_attentions"], kw["sigma"], kw["kernel_size"],
+                                    kw["normalize_eot"], accs[0].device)
+        n_maps = sum(m.heads for m in picked)                # maps per sample
+        _, _, stats, _, total = ops.guidance_tail(spec, accs, n_maps, n_samples=self.S)
+        if self.S == 1:
+            stats, total = stats[None], total
+        return stats, total
+
+    def _prog_eval(self):
+        with torch.no_grad():
+            self.pipe.unet(self.lat, self.t, encoder_hidden_states=self.cond)
+            stats, total = self._loss()
+        return {"stats": stats, "total": total}
+
+    def _prog_update(self):
+        with torch.enable_grad():
+            lat = self.lat.detach().clone().requires_grad_(True)
+            self.pipe.unet(lat, self.t, encoder_hidden_states=self.cond)
+            stats, total = self._loss()
+            (g,) = torch.autograd.grad(total.sum(), [lat])   # samples are independent: row s of g is d total[s] / d lat[s]
+        with torch.no_grad():
+            self.lat_out.copy_((lat.detach().float() - self.step * g.float()).to(lat.dtype))
+        return {"stats": stats.detach(), "total": total.detach()}
+
+    def _prog_cfg(self):
+        with torch.no_grad():
+            x2 = torch.cat([self.lat] * 2)
+            noise = self.pipe.unet(x2, self.t, encoder_hidden_states=self.both).sample
+            n_u, n_t = noise.chunk(2)
+            noise = n_u + self.gs * (n_t - n_u)
+            out = self.pipe.scheduler.step(noise, None, self.lat, coeffs=(self.coef[0], self.coef[1], self.coef[2],
+                                                                          self.coef[3]))
+            self.lat_out.copy_(out.prev_sample)
+        return {}
+
+    _graph = _StepGraphs._graph
+
+    def run(self, name, latents, t, step_sizes=None, coeffs=None):
+        self.lat.copy_(latents)
+        self.t.fill_(int(t))
+        if step_sizes is not None:
+            self.step.copy_(torch.tensor(step_sizes, dtype=torch.float32).reshape(-1, 1, 1, 1), non_blocking=True)
+        if coeffs is not None:
+            for n, c in enumerate(coeffs):
+                self.coef[n].fill_(float(c))
+        if self.eager:
+            out = getattr(self, "_prog_" + name)()
+        else:
+            g = self._graph(name)
+            g.replay()
+            for k, v in self.launches[name].items():
+                ops._count(k, v)
+            out = self.outputs[name]
+        self.replays[name] = self.replays.get(name, 0) + 1
+        self.pipe._count_pass(name)
+        return out, (self.lat_out.clone() if name != "eval" else None)
+
+
 class GuidedAttention(StableDiffusionPipelineBase):
     """Pipeline for text-to-image generation with cross-attention guidance (boxes, crosshairs, keyword losses)."""
 
@@ -537,6 +633,139 @@ class GuidedAttention(StableDiffusionPipelineBase):
             latents = ((Bt ** 0.5) * latents.float()
                        + ((1 - Bt) ** 0.5) * noise.to(latents.device)).to(latents.dtype)
         return latents
+
+    # ------------------------------------------------------------------------------------------ seed batching
+    def _unscaled_groups(self, stats_row, spec):
+        """{sub-prompt: summed (or averaged) unscaled loss} for one sample from a host copy of its stats rows."""
+        groups = {}
+        for n, sub in enumerate(spec.groups):
+            if spec.kinds[n] == abi.GA_TOKEN_KEYWORD:
+                continue
+            groups.setdefault(sub, []).append(float(stats_row[n][abi.GA_STAT_UNSCALED]))
+        avg = bool(state.config.sub_prompt_avg_within)
+        return {k: (sum(v) / len(v) if avg else sum(v)) for k, v in groups.items()}
+
+    @staticmethod
+    def _met(i, thresholds, groups):
+        if (i not in thresholds and i != -1) or len(thresholds) == 0:
+            return True
+        thresh = list(thresholds.values())[-1] if i == -1 else thresholds[i]
+        return all(not (v > thresh) for v in groups.values())
+
+    @torch.no_grad()
+    def generate_batch(self, prompt, attention_store, seeds, prompt_embeds, negative_prompt_embeds,
+                       attention_res: int = 16, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                       max_iter_to_alter: int = 25, run_standard_sd: bool = False, thresholds: Optional[dict] = None,
+                       scale_factor: int = 20, scale_range=(1., 0.5), smooth_attentions: bool = True,
+                       sigma: float = 0.5, kernel_size: int = 3, sd_2_1: bool = False, latents=None,
+                       max_refinement_steps: int = 10):
+        """Extension: the guided loop of `__call__` for S seeds at once (one UNet pass serves all of them).  Per-seed
+        semantics are those of S separate `__call__`s: each seed has its own initial noise and re-noise stream, its own
+        threshold tests, refinement iteration count and recursion decisions; seeds that are done with a stage ride along
+        with step size 0 / are masked out of the result.  Returns the final latents (S, C, h, w).  Python custom losses
+        are not supported here."""
+        if getattr(state.config, "custom_loss", None):
+            raise NotImplementedError("generate_batch does not support [CustomLoss:...] annotations")
+        thresholds = dict(thresholds if thresholds is not None else state.config.thresholds)
+        if len(thresholds) == 0:
+            thresholds = {0: float("inf")}
+        cfg = state.config
+        device, dtype = self._execution_device, self.unet.dtype
+        S = len(seeds)
+        self.prompt = prompt
+        embeds = torch.cat([negative_prompt_embeds, prompt_embeds]).to(device=device, dtype=dtype)
+        self.scheduler = DDIMScheduler.from_config(self.scheduler.config)
+        self.scheduler.set_timesteps(num_inference_steps)
+        timesteps = self.scheduler.timesteps
+        hw = self.unet.config.sample_size
+        if latents is None:
+            latents = torch.cat([torch.randn(1, self.unet.in_channels, hw, hw,
+                                             generator=torch.Generator("cpu").manual_seed(int(sd))) for sd in seeds])
+        latents = latents.to(device=device, dtype=dtype) * self.scheduler.init_noise_sigma
+        scale = np.linspace(scale_range[0], scale_range[1], len(timesteps))
+        recurse_steps = max(state.curHyperParams.get("recurse_steps", 1), 1)
+        recurse_until = state.curHyperParams.get("recurse_until", 20)
+        renoise = [torch.Generator("cpu").manual_seed(int(sd)) for sd in seeds] if recurse_steps > 1 else None
+
+        loss_kw = dict(attention_store=attention_store, attention_res=attention_res,
+                       smooth_attentions=smooth_attentions, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
+        key = ("batch", S, id(self.unet), id(attention_store), tuple(embeds.shape), embeds.dtype, float(guidance_scale),
+               attention_res, smooth_attentions, sigma, kernel_size, sd_2_1, num_inference_steps,
+               tuple((i, v['loss_type'], v['subprompt'],
+                      v['loss'].as_tuple() if hasattr(v['loss'], 'as_tuple') else v['loss'])
+                     for i, v in cfg.token_dict.items()),
+               tuple(sorted((k, str(v)) for k, v in state.curHyperParams.items())), bool(cfg.sub_prompt_avg_within),
+               bool(self.use_cuda_graphs), str(device))
+        cached = getattr(self, "_batch_graphs_cache", None)
+        if cached is None or cached[0] != key:
+            self._batch_graphs_cache = (key, _BatchGraphs(self, attention_store, loss_kw, embeds, guidance_scale,
+                                                          latents, eager=not self.use_cuda_graphs))
+        G = self._batch_graphs_cache[1]
+        G.set_embeds(embeds)
+
+        def groups_of(out):
+            rows = out["stats"].detach().cpu().tolist()       # the one D2H read of this evaluation
+            spec = self._tail_spec_cache[1]
+            return [self._unscaled_groups(rows[s_], spec) for s_ in range(S)]
+
+        for i, t in enumerate(timesteps):
+            t = int(t)
+            state.cur_time_step_iter = i
+            step_size = float(scale_factor * np.sqrt(scale[i]))
+            live = [True] * S                        # seeds taking part in this recursion round
+            for recurse_step in range(recurse_steps):
+                if not any(live):
+                    break
+                did_update = [False] * S
+                out, _ = G.run("eval", latents, t)
+                if not run_standard_sd:
+                    update_cond = (not cfg.only_update_on_threshold_steps and i < max_iter_to_alter) or \
+                        (i in cfg.thresholds)
+                    met, do_update = [True] * S, [False] * S
+                    if i in thresholds or update_cond:
+                        g0 = groups_of(out)
+                        met = [self._met(i, thresholds, g0[s_]) or not live[s_] for s_ in range(S)]
+                        do_update = [live[s_] and update_cond and not self._met(-1, cfg.thresholds, g0[s_])
+                                     for s_ in range(S)]
+                    refine = [not m for m in met]
+                    need = list(refine)
+                    iteration = 0
+                    while any(need):
+                        iteration += 1
+                        o, latents = G.run("update", latents, t, step_sizes=[step_size if n_ else 0.0 for n_ in need])
+                        gi = groups_of(o)
+                        need = [need[s_] and not self._met(i, cfg.thresholds, gi[s_]) for s_ in range(S)]
+                        if iteration >= max_refinement_steps:
+                            break
+                    if any(do_update):
+                        # the final evaluation at the (refined) latents carries the threshold-step update (:998-1004)
+                        _, latents = G.run("update", latents, t,
+                                           step_sizes=[step_size if u else 0.0 for u in do_update])
+                    elif any(refine):
+                        G.run("eval", latents, t)
+                    did_update = [refine[s_] or do_update[s_] for s_ in range(S)]
+                _, stepped = G.run("cfg", latents, t, coeffs=self.scheduler.coefficients(t))
+                if all(live):
+                    latents = stepped
+                else:
+                    mask = torch.tensor(live, device=device).reshape(S, 1, 1, 1)
+                    latents = torch.where(mask, stepped, latents)
+                # seeds that updated (and are early enough) are re-noised and repeat this timestep; the others are done
+                again = [live[s_] and did_update[s_] and i <= recurse_until and recurse_step != recurse_steps - 1
+                         for s_ in range(S)]
+                if any(again):
+                    prev_timestep = t - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
+                    if prev_timestep > 0:
+                        Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_timestep])
+                        noise = torch.zeros(latents.shape, dtype=torch.float32)
+                        for s_ in range(S):
+                            if again[s_]:
+                                noise[s_] = torch.randn(latents.shape[1:], generator=renoise[s_], dtype=torch.float32)
+                        mixed = ((Bt ** 0.5) * latents.float() + ((1 - Bt) ** 0.5) * noise.to(device)).to(dtype)
+                        mask = torch.tensor(again, device=device).reshape(S, 1, 1, 1)
+                        latents = torch.where(mask, mixed, latents)
+                live = again
+        return latents.detach()
 
     # ---------------------------------------------------------------------------------------------------- call
     @torch.no_grad()

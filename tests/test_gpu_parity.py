@@ -590,6 +590,30 @@ def test_cuda_graph_image_matches_eager_image():
     assert passes["cfg"] >= case["steps"] and passes["update"] > 0
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_seed_batching_equals_separate_calls(graphs):
+    """Extension: `generate_batch` (S seeds per UNet pass, per-sample losses / step sizes / recursion masks) against S
+    separate `__call__`s, fp32.  Seeds diverge in their refinement counts and recursion decisions with these thresholds."""
+    pipe, store, cfg, embeds, case = _graph_test_pipe(torch.float32)
+    pipe.use_cuda_graphs = graphs
+    seeds = [28, 29, 31]
+    singles = []
+    for sd in seeds:
+        gen = torch.Generator("cpu").manual_seed(sd)
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(sd))
+        out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5, generator=gen,
+                   latents=lat, prompt_embeds=embeds[1:2], negative_prompt_embeds=embeds[0:1],
+                   num_inference_steps=case["steps"], thresholds=cfg.thresholds, output_type="latent")
+        singles.append(out.images.float().cpu().numpy())
+    batch = pipe.generate_batch(cfg.prompt, store, seeds, embeds[1:2], embeds[0:1], attention_res=16,
+                                num_inference_steps=case["steps"], guidance_scale=7.5, thresholds=cfg.thresholds)
+    batch = batch.float().cpu().numpy()
+    for n, single in enumerate(singles):
+        b = batch[n:n + 1]
+        cos = float((b * single).sum() / (np.linalg.norm(b) * np.linalg.norm(single)))
+        assert cos > 0.99999 and _psnr(b, single) > 55, (seeds[n], cos, _psnr(b, single))
+
+
 def test_full_size_sd14_guidance_step_fp16():
     """BASELINE config 2 shapes: SD-1.4-shaped UNet, fp16, one guidance evaluation + latent gradient; compared with the
     fp32 CPU oracle driving the same UNet (loss within 2e-2, gradient cosine > 0.98)."""
