@@ -35,6 +35,11 @@ int bwd(const void*, const void*, const void*, const float*, const void*, const 
         int, int, int, float, int, int, cudaStream_t);
 }  // namespace tc
 
+namespace sa {
+bool supports(int dtype, int head_dim);
+int fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, float, int, cudaStream_t);
+}  // namespace sa
+
 static int check_attn_args(const void* q, const void* k, int batch, int heads, int n_query, int n_ctx, int head_dim,
                            int dtype) {
   GA_CHECK_ARG(q != nullptr && k != nullptr, "NULL operand");
@@ -117,4 +122,14 @@ extern "C" int ga_attn_probs(const void* q, const void* k, void* probs, int batc
   GA_CHECK_ARG(probs != nullptr, "probs is NULL");
   return simt::fwd(q, k, k, nullptr, nullptr, nullptr, probs, batch, heads, n_query, n_ctx, head_dim, scale, dtype,
                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ga_self_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads,
+                                int n_tokens, int head_dim, float scale, int dtype, ga_stream_t stream) {
+  GA_CHECK_ARG(q && k && v && o && lse, "NULL operand");
+  GA_CHECK_ARG(batch >= 1 && heads >= 1 && n_tokens >= 1, "bad batch %d / heads %d / n_tokens %d", batch, heads, n_tokens);
+  if (!sa::supports(dtype, head_dim))
+    return fail(GA_ERR_UNSUPPORTED, "self-attention kernel: dtype %d / head_dim %d not supported", dtype, head_dim);
+  GA_CHECK_ALIGN(q, 16, "q"); GA_CHECK_ALIGN(k, 16, "k"); GA_CHECK_ALIGN(v, 16, "v"); GA_CHECK_ALIGN(o, 16, "o");
+  return sa::fwd(q, k, v, o, lse, batch, heads, n_tokens, head_dim, scale, dtype, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,292 @@
+// Exact self-attention (queries and keys are the same N image tokens) on the tcgen05 tensor cores, without ever
+// materialising the (B*H, N, N) probability tensor that the reference builds, keeps for autograd and streams through
+// four ATen kernels per layer (utils/ptp_utils.py:77-85, 97-146 on the attn1 layers: 268 MB per tensor at 64x64).
+// SURVEY.md section 8 row f4.  These layers are off the guidance path (their maps are never read) but on the autograd
+// path, so the backward is provided too.
+//
+// Forward, one CTA = 128 query rows of one (batch, head), two passes over the keys in blocks of BK (128 or 64):
+//   pass 1   S_j = Q K_j^T -> running row maximum                      (no exponentials)
+//   pass 2   S_j again -> P_j = exp(scale (S_j - max)) (un-normalised, 16-bit, back into TMEM) -> O += P_j V_j
+//            with the row sum accumulated on the side; O is divided by the sum once, in the epilogue.
+// With the final maximum known before the first exponential, O never has to be rescaled (no correction pass over the
+// TMEM accumulator); the price is a second QK^T GEMM per block, which is free here -- the kernel is bound by the
+// exponentials and the TMEM <-> register traffic, not by the tensor pipe or HBM (K and V blocks come from L2).
+//
+//   warp 0      TMA producer   Q tile once, then a ring of K (pass 1) / K+V (pass 2) blocks
+//   warp 1      MMA issuer     MMA1 into S buffer g = item & 1; MMA2(item-2) is issued before MMA1(item), which is what
+//                              orders "P consumed" before "S overwritten" (tcgen05.mma retires in issue order)
+//   warps 4-7   compute group 0 (S buffer 0), warps 8-11 compute group 1 (S buffer 1): thread = query row = TMEM lane;
+//               the two groups own alternate key blocks and merge their row maxima / sums through shared memory.
+#include "tc_common.cuh"
+
+namespace ga {
+namespace sa {
+
+using namespace ga::tc;
+
+constexpr int kM = 128;
+constexpr int kThreads = 384;
+constexpr int kGroupThreads = 128;
+constexpr int kQBlockBytes = kM * 128;
+// TMEM columns: S buffers at 0 and 128 (P overwrites the head of its S buffer), O from 256
+constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+constexpr int kMaxStages = 4;
+
+struct FwdParams {
+  void* o;
+  float* lse;
+  int B, H, N, d;
+  int nblk, npv, bf16;
+  int bk;        // keys per block: 128 (d <= 64) or 64
+  int nb;        // key blocks
+  int stages;    // K/V ring depth (>= 2)
+  float scale;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // q_full, o_ready, kv_full[4], kv_free[4], s_ready[2], p_ready[2]
+  __shared__ __align__(8) uint64_t bars[14];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float xchg[2][kM];          // row maxima / sums of the two compute groups
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = tile * kM;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_block_bytes = (uint32_t)p.bk * 128u;                  // one 64-channel block of K or V
+  const uint32_t k_bytes = (uint32_t)p.nblk * kv_block_bytes;
+  const uint32_t stage_bytes = 2u * k_bytes;
+  const uint32_t sQ = base;
+  const uint32_t sKV = sQ + (uint32_t)p.nblk * kQBlockBytes;
+  auto Q_FULL = [&]() { return smem_u32(&bars[0]); };
+  auto O_READY = [&]() { return smem_u32(&bars[1]); };
+  auto KV_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
+  auto KV_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
+  auto S_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
+  auto P_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(Q_FULL(), 1);
+    mbar_init(O_READY(), 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(S_READY(g), 1); mbar_init(P_READY(g), kGroupThreads); }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const int nb = p.nb, n_items = 2 * nb, NS = p.stages;
+  const int ksteps = (p.d + 15) >> 4;
+  const int fmt = p.bf16 ? 1 : 0;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------------------------------- producer
+      mbar_expect_tx(Q_FULL(), (uint32_t)p.nblk * kQBlockBytes);
+      for (int blk = 0; blk < p.nblk; ++blk)
+        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, Q_FULL(), blk * kBlockCols, h, row0, b);
+      int ss = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < n_items; ++it) {
+        const int j = it < nb ? it : it - nb;
+        const bool with_v = it >= nb;
+        if (it >= NS) mbar_wait(KV_FREE(ss), par ^ 1u);
+        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
+        mbar_expect_tx(KV_FULL(ss), with_v ? stage_bytes : k_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+          if (with_v) tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+        }
+        if (++ss == NS) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ----------------------------------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_qk = make_idesc(fmt, 0, p.bk, kM);
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      mbar_wait(Q_FULL(), 0);
+      bool o_started = false;
+      auto mma2 = [&](int it) {                     // O += P(it) V(it); `it` is a pass-2 item
+        const int g = it & 1, ss = it % NS;
+        const uint32_t sV = sKV + ss * stage_bytes + k_bytes;
+        const uint32_t colP = g ? kColS1 : kColS0;
+        for (int ks = 0; ks < p.bk / 16; ++ks) {
+          mma_ts(tmem + kColO, tmem + colP + ks * 8, smem_desc_sw128(sV + ks * 2048u, kv_block_bytes, 1024), idesc_pv,
+                 (o_started || ks > 0) ? 1u : 0u);
+        }
+        o_started = true;
+        tc_commit(KV_FREE(ss));
+      };
+      for (int it = 0; it < n_items; ++it) {
+        const int g = it & 1, ss = it % NS;
+        if (it >= 2) {
+          // S buffer g was last used by item it-2: its rows have been read (pass 1) / replaced by P (pass 2)
+          mbar_wait(P_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
+          tc_fence_after();
+          if (it - 2 >= nb) mma2(it - 2);
+        }
+        mbar_wait(KV_FULL(ss), (uint32_t)(it / NS) & 1u);
+        tc_fence_after();
+        const uint32_t sK = sKV + ss * stage_bytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + (g ? kColS1 : kColS0), smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sK + off * kv_block_bytes + in, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(S_READY(g));
+        if (it < nb) tc_commit(KV_FREE(ss));        // pass 1: the block is only needed by this GEMM
+      }
+      for (int it = (n_items >= 2 ? n_items - 2 : 0); it < n_items; ++it) {
+        if (it < nb) continue;
+        mbar_wait(P_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        mma2(it);
+      }
+      tc_commit(O_READY());
+    }
+  } else {
+    reg_alloc<232>();
+    // --------------------------------------------------------------------------------------- compute groups
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const int row = row0 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t colS = g ? kColS1 : kColS0;
+    const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
+    const int halves = p.bk / 64;                    // S is processed 64 key columns at a time
+
+    // ---- pass 1: running maximum over this group's key blocks
+    float m = -INFINITY;
+    for (int it = g; it < nb; it += 2) {
+      mbar_wait(S_READY(g), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const int key0 = it * p.bk;
+      const bool ragged = key0 + p.bk > p.N;
+      for (int hf = 0; hf < halves; ++hf) {
+        float s[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + colS + hf * 64 + c * 16, s + c * 16);
+        tmem_ld_wait();
+        if (!ragged) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) m = fmaxf(m, s[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (key0 + hf * 64 + j < p.N) m = fmaxf(m, s[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(P_READY(g));
+    }
+    xchg[g][r] = m;
+    named_bar_sync(1, 2 * kGroupThreads);
+    m = fmaxf(xchg[0][r], xchg[1][r]);
+    named_bar_sync(2, 2 * kGroupThreads);            // both groups have read the maxima before the sums reuse xchg
+    const float mo = m * sc;
+
+    // ---- pass 2: P = exp(scale (S - max)) -> TMEM, row sum on the side
+    float l = 0.f;
+    for (int it = nb + ((nb & 1) ^ g); it < n_items; it += 2) {      // items of this group: it & 1 == g
+      mbar_wait(S_READY(g), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const int key0 = (it - nb) * p.bk;
+      const bool ragged = key0 + p.bk > p.N;
+      for (int hf = 0; hf < halves; ++hf) {
+        float s[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + colS + hf * 64 + c * 16, s + c * 16);
+        tmem_ld_wait();
+        uint32_t packed[32];
+        if (!ragged) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) { s[j] = ex2_approx(fmaf(s[j], sc, -mo)); l += s[j]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            s[j] = (key0 + hf * 64 + j < p.N) ? ex2_approx(fmaf(s[j], sc, -mo)) : 0.f;
+            l += s[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
+        // the second half of S must be in registers before P overwrites the head of the buffer: with bk = 128 the P
+        // columns of half 0 (0..31) do not overlap the S columns of half 1 (64..127), and half 1's P goes to 32..63
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st8(lane_base + colS + hf * 32 + c * 8, packed + c * 8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(P_READY(g));
+    }
+    xchg[g][r] = l;
+    named_bar_sync(3, 2 * kGroupThreads);
+    l = xchg[0][r] + xchg[1][r];
+    const float inv = 1.f / l;
+    if (g == 0 && row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(l);
+
+    // ---- epilogue: the two groups take alternate 16-column chunks of O
+    mbar_wait(O_READY(), 0);
+    tc_fence_after();
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+    for (int cc = g; cc < p.npv / 16; cc += 2) {
+      float ov[16];
+      tmem_ld16(lane_base + kColO + cc * 16, ov);
+      tmem_ld_wait();
+      if (row < p.N) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
+        const int col = cc * 16;
+        if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------------------------ host
+bool supports(int dtype, int head_dim) {
+  return (dtype == GA_F16 || dtype == GA_BF16) && head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 160;
+}
+
+int fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int N, int d, float scale,
+        int dtype, cudaStream_t st) {
+  FwdParams p;
+  p.o = o; p.lse = lse; p.B = B; p.H = H; p.N = N; p.d = d;
+  p.nblk = (d + kBlockCols - 1) / kBlockCols;
+  p.npv = (d + 15) & ~15;
+  p.bf16 = dtype == GA_BF16;
+  p.bk = p.nblk == 1 ? 128 : 64;
+  p.nb = (N + p.bk - 1) / p.bk;
+  p.scale = scale;
+  const size_t q_bytes = (size_t)p.nblk * kQBlockBytes, stage = (size_t)2 * p.nblk * p.bk * 128;
+  p.stages = 0;
+  for (int n = kMaxStages; n >= 2; --n)
+    if (1024 + q_bytes + n * stage <= 226 * 1024) { p.stages = n; break; }
+  if (p.stages == 0) return fail(GA_ERR_UNSUPPORTED, "self-attention: head_dim %d does not fit shared memory", d);
+  const size_t smem = 1024 + q_bytes + p.stages * stage;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+  if ((rc = make_map(&mk, k, dtype, B, N, H, d, p.bk)) != GA_OK) return rc;
+  if ((rc = make_map(&mv, v, dtype, B, N, H, d, p.bk)) != GA_OK) return rc;
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(self_attn_fwd_kernel), 0, smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 grid((N + kM - 1) / kM, H, B);
+  self_attn_fwd_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+  return check_launch("self_attn_fwd");
+}
+
+}  // namespace sa
+}  // namespace ga

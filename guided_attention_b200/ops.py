@@ -181,6 +181,21 @@ def cross_attention(q, k, v, heads: int, scale: float, want_acc: bool = False, i
     return _CrossAttnFn.apply(q, k, v, heads, scale, want_acc, default_impl if impl is None else impl)
 
 
+def self_attention_forward(q, k, v, heads: int, scale: float):
+    """Fused exact self-attention forward (no autograd): returns (o, lse)."""
+    _need_cuda(q, k, v)
+    lib = abi.load()
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    B, N, Cdim = q.shape
+    o = torch.empty_like(q)
+    lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        abi.check(lib.ga_self_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, N, Cdim // heads,
+                                       float(scale), _DTYPES[q.dtype], _stream(q)), "ga_self_attn_fwd")
+    _count("self_attn_fwd")
+    return o, lse
+
+
 def attention_probs(q, k, heads: int, scale: float):
     """Materialised P (B*H, N, T), rows ordered b*H + h like the reference's stored maps.  Not differentiable; exists for
     API compatibility (`AttentionStore.get_average_attention`) and for tests."""

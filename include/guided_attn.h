@@ -124,6 +124,13 @@ int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* 
 int ga_attn_probs(const void* q, const void* k, void* probs, int batch, int heads, int n_query, int n_ctx,
                   int head_dim, float scale, int dtype, ga_stream_t stream);
 
+/* ---- self-attention ------------------------------------------------------------------------------
+ * Exact softmax(scale Q K^T) V where queries and keys are the same N image tokens; q, k, v, o (B, N, H*d) 16-bit,
+ * lse (B, H, N) fp32.  Replaces the attn1 branch of the reference processor (utils/ptp_utils.py:66-93 with
+ * encoder_hidden_states=None): the (B*H, N, N) probability tensor is never materialised.  d % 8 == 0, d <= 160. */
+int ga_self_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads,
+                     int n_tokens, int head_dim, float scale, int dtype, ga_stream_t stream);
+
 /* ---- K5: box-mask rasteriser ------------------------------------------------------------------------------------------
  * masks[i, ii, jj] = inside_box(jj, ii, Rect(box_i, size 1).of_size(res))   (utils/helpers.py:164-173, 28-30)
  * float64, no FMA contraction, the reference's operation order: bit-exact.  boxes_host: n x (x, y, w, h). */

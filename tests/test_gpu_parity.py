@@ -138,6 +138,32 @@ def test_tcgen05_lse_matches_simt():
     assert rel_err(outs[0], outs[1]) < FP16_RTOL
 
 
+SELF_SHAPES = [(8, 40, 4096, 1), (8, 80, 1024, 2), (8, 160, 256, 2), (8, 160, 64, 1),       # SD-1.4 levels
+               (5, 64, 9216, 1), (10, 64, 2304, 1), (20, 64, 576, 1), (20, 64, 144, 2),      # SD-2.x, 96x96 latent
+               (2, 16, 200, 2), (4, 32, 1000, 1), (1, 8, 1, 1)]                              # ragged
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("shape", SELF_SHAPES)
+def test_self_attention_forward(shape, dtype, rtol):
+    """Fused exact self-attention (two-pass, tcgen05) against explicit softmax attention in fp32."""
+    from guided_attention_b200 import ops
+    H, d, N, B = shape
+    g = torch.Generator("cpu").manual_seed(N + d)
+    q = torch.randn(B, N, H * d, generator=g).to(dtype)
+    k = torch.randn(B, N, H * d, generator=g).to(dtype)
+    v = torch.randn(B, N, H * d, generator=g).to(dtype)
+    scale = d ** -0.5
+    o, lse = ops.self_attention_forward(q.to(DEV), k.to(DEV), v.to(DEV), H, scale)
+    torch.cuda.synchronize()
+    qd, kd, vd = (O.head_to_batch(t.to(DEV).float(), H) for t in (q, k, v))
+    S = scale * torch.bmm(qd, kd.transpose(1, 2))
+    want = O.batch_to_head(torch.bmm(torch.softmax(S, -1), vd), H)
+    assert rel_err(o.float().cpu().numpy(), want.cpu().numpy()) < rtol
+    want_lse = torch.logsumexp(S, -1).reshape(B, H, N)
+    assert rel_err(lse.cpu().numpy(), want_lse.cpu().numpy()) < 1e-3
+
+
 # -------------------------------------------------------------------------------------------------- K2 backward
 @pytest.mark.parametrize("dtype,rtol", [(torch.float32, FP32_RTOL), (torch.float16, FP16_RTOL)])
 @pytest.mark.parametrize("shape", [(8, 40, 1024, 77, 1), (8, 160, 256, 77, 2), (5, 64, 576, 77, 1),
