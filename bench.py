@@ -32,12 +32,13 @@ EMBED_SEED = 1234
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, provenance): the measured numbers of this pool's B200s when the driver left them."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json; burst figures: kernel timed alone)"
+    return 6650.0, 1650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------ clock sampling
@@ -354,33 +355,53 @@ def roofline_from(prof):
     """Dominant kernel = the (kernel, shape) class with the largest summed device time inside the profiled image.
     Its launch duration is then measured kernel-only: the same launch (same shape, dtype, variant choice) replayed
     back-to-back from a CUDA graph between two CUDA events on the launching stream, on rotating buffer sets larger than
-    L2 (`microbench.time_cross_attn`).  The in-pipeline event time is kept next to it: it includes the host gaps of the
-    eager profiling pass and only serves to rank the kernels."""
+    L2 (`microbench.time_cross_attn` / `time_self_attn`).  The in-pipeline event time is kept next to it: it includes
+    the host gaps of the eager profiling pass and only serves to rank the kernels.
+    Cross-attention / tail kernels are HBM-bound (algorithmic bytes); the self-attention kernels are tensor-pipe bound
+    (algorithmic FLOPs = the 2 GEMMs of the forward / 5 of the backward, not the recomputation the kernels add)."""
     from guided_attention_b200 import microbench
-    peak, how = peaks()
+    hbm_peak, tf_peak, how = peaks()
     table = []
     for (name, key), d in prof.items():
         avg_us = d["ms"] * 1e3 / d["launches"]
-        table.append({"kernel": name, "shape": list(map(str, key)), "launches": d["launches"],
-                      "pipeline_event_us": avg_us, "total_ms": d["ms"], "bytes_per_launch": d["bytes_per_launch"]})
+        row = {"kernel": name, "shape": list(map(str, key)), "launches": d["launches"],
+               "pipeline_event_us": avg_us, "total_ms": d["ms"]}
+        row["flops_issued_per_launch" if name.startswith("self_attn") else "bytes_per_launch"] = d["bytes_per_launch"]
+        table.append(row)
     table.sort(key=lambda r: -r["total_ms"])
     if not table:
         return None, table
-    for row in table[:6]:
+    dts = {"torch.float16": torch.float16, "torch.bfloat16": torch.bfloat16, "torch.float32": torch.float32}
+    for row in table[:8]:
         if row["kernel"].startswith("cross_attn"):
             B, H, N, T, dd = (int(x) for x in row["shape"][:5])
-            dt = {"torch.float16": torch.float16, "torch.bfloat16": torch.bfloat16, "torch.float32": torch.float32}[
-                row["shape"][5]]
-            m = microbench.time_cross_attn(B, H, N, T, dd, dt, with_acc=row["shape"][6] == "True",
+            m = microbench.time_cross_attn(B, H, N, T, dd, dts[row["shape"][5]], with_acc=row["shape"][6] == "True",
                                            direction=row["kernel"].split("_")[-1])
             row["kernel_us"], row["gbs"] = m["us"], m["gbs"]
+        elif row["kernel"].startswith("self_attn"):
+            B, H, N, dd = (int(x) for x in row["shape"][:4])
+            m = microbench.time_self_attn(B, H, N, dd, dts[row["shape"][4]], direction=row["kernel"].split("_")[-1])
+            row["kernel_us"], row["tflops"], row["tflops_issued"] = m["us"], m["tflops_algorithmic"], m["tflops_issued"]
+            row["algorithmic_flops_per_launch"] = m["tflops_algorithmic"] * m["us"] * 1e6
     top = next((r for r in table if "kernel_us" in r), table[0])
-    roof = {"bound": "hbm", "kernel": top["kernel"], "shape": top["shape"], "achieved": top.get("gbs"), "peak": peak,
-            "unit": "GB/s", "frac": (top["gbs"] / peak) if "gbs" in top else None, "traffic": None, "peak_source": how,
-            "avg_launch_us": top.get("kernel_us"), "algorithmic_bytes_per_launch": top["bytes_per_launch"],
-            "note": "one launch at the pipeline's batch (B=1 text-cond pass, B=2 CFG pass) moves 0.7-11 MB: launch-"
-                    "latency bound by size; profiles/ holds the batch sweep where the same kernels run bandwidth-bound"}
-    return roof, table[:8]
+    if "tflops" in top:
+        roof = {"bound": "tensor", "kernel": top["kernel"], "shape": top["shape"], "achieved": top["tflops"],
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak, "traffic": None,
+                "peak_source": how, "avg_launch_us": top["kernel_us"],
+                "algorithmic_flops_per_launch": top["algorithmic_flops_per_launch"],
+                "issued_tflops": top["tflops_issued"],
+                "note": "fused exact self-attention at head_dim 40: per exponential only 4*d = 160 FLOPs of GEMM work "
+                        "exist, so the SFU (16 ex2/clk/SM) caps this kernel far below the dense-GEMM peak; the "
+                        "cross-attention / tail kernels (HBM-bound) are listed in `kernels` and in profiles/"}
+    else:
+        roof = {"bound": "hbm", "kernel": top["kernel"], "shape": top["shape"], "achieved": top.get("gbs"),
+                "peak": hbm_peak, "unit": "GB/s", "frac": (top["gbs"] / hbm_peak) if "gbs" in top else None,
+                "traffic": None, "peak_source": how, "avg_launch_us": top.get("kernel_us"),
+                "algorithmic_bytes_per_launch": top.get("bytes_per_launch"),
+                "note": "one launch at the pipeline's batch (B=1 text-cond pass, B=2 CFG pass) moves 0.7-11 MB: launch-"
+                        "latency bound by size; profiles/ holds the batch sweep where the same kernels run "
+                        "bandwidth-bound"}
+    return roof, table[:10]
 
 
 def main():

@@ -48,6 +48,7 @@ PROTOTYPES = {
                                 _vp]),
     "ga_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_self_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "ga_self_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_rasterize_boxes": (_i, [C.POINTER(C.c_double), _i, _i, C.c_double, _vp, _vp]),
     "ga_guidance_tail_fwd": (_i, [C.POINTER(_vp), C.POINTER(C.c_int32), _i, C.POINTER(GaTailParams), C.POINTER(GaToken),
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -38,6 +38,8 @@ int bwd(const void*, const void*, const void*, const float*, const void*, const 
 namespace sa {
 bool supports(int dtype, int head_dim);
 int fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, float, int, cudaStream_t);
+int bwd(const void*, const void*, const void*, const void*, const float*, const void*, void*, void*, void*, float*, int,
+        int, int, int, float, int, cudaStream_t);
 }  // namespace sa
 
 static int check_attn_args(const void* q, const void* k, int batch, int heads, int n_query, int n_ctx, int head_dim,
@@ -132,4 +134,18 @@ extern "C" int ga_self_attn_fwd(const void* q, const void* k, const void* v, voi
     return fail(GA_ERR_UNSUPPORTED, "self-attention kernel: dtype %d / head_dim %d not supported", dtype, head_dim);
   GA_CHECK_ALIGN(q, 16, "q"); GA_CHECK_ALIGN(k, 16, "k"); GA_CHECK_ALIGN(v, 16, "v"); GA_CHECK_ALIGN(o, 16, "o");
   return sa::fwd(q, k, v, o, lse, batch, heads, n_tokens, head_dim, scale, dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ga_self_attn_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                                const void* d_o, void* d_q, void* d_k, void* d_v, float* dvec, int batch, int heads,
+                                int n_tokens, int head_dim, float scale, int dtype, ga_stream_t stream) {
+  GA_CHECK_ARG(q && k && v && o && lse && d_o && d_q && d_k && d_v && dvec, "NULL operand");
+  GA_CHECK_ARG(batch >= 1 && heads >= 1 && n_tokens >= 1, "bad batch %d / heads %d / n_tokens %d", batch, heads, n_tokens);
+  if (!sa::supports(dtype, head_dim))
+    return fail(GA_ERR_UNSUPPORTED, "self-attention kernel: dtype %d / head_dim %d not supported", dtype, head_dim);
+  GA_CHECK_ALIGN(q, 16, "q"); GA_CHECK_ALIGN(k, 16, "k"); GA_CHECK_ALIGN(v, 16, "v"); GA_CHECK_ALIGN(o, 16, "o");
+  GA_CHECK_ALIGN(d_o, 16, "d_o"); GA_CHECK_ALIGN(d_q, 16, "d_q"); GA_CHECK_ALIGN(d_k, 16, "d_k");
+  GA_CHECK_ALIGN(d_v, 16, "d_v");
+  return sa::bwd(q, k, v, o, lse, d_o, d_q, d_k, d_v, dvec, batch, heads, n_tokens, head_dim, scale, dtype,
+                 static_cast<cudaStream_t>(stream));
 }

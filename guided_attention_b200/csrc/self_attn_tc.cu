@@ -288,5 +288,507 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B,
   return check_launch("self_attn_fwd");
 }
 
+
+// ===================================================================================================== backward
+// Autograd of the forward above (reference: torch autograd through utils/ptp_utils.py:77-85 on the attn1 layers, which
+// keeps the (B*H, N, N) probabilities and streams them through softmax-backward and four batched GEMMs).  Here P is
+// recomputed from the saved row log-sum-exp; two launches, no atomics (results are bit-stable run to run):
+//
+//   dQ kernel   one CTA = 128 query rows of one (batch, head); streams the keys in blocks of 64:
+//                 S = Q K_j^T, dP = dO V_j^T (two K-major GEMMs into TMEM) -> P = exp(scale S - lse),
+//                 dS = P o (dP - D) * scale -> 16-bit into TMEM -> dQ += dS K_j (K_j as the MN-major B operand).
+//               It also produces D[row] = sum_c dO[row, c] O[row, c] for the second kernel.
+//   dK/dV kernel one CTA = 128 keys of one (batch, head) (TMEM lane = key); streams the queries in blocks of BQ:
+//                 S^T = K Q_i^T, dP^T = V dO_i^T -> P^T, dS^T (lse and D are per COLUMN here: staged in shared memory)
+//                 -> dV += P^T dO_i, dK += dS^T Q_i (Q_i / dO_i tiles as MN-major B operands).
+// Both kernels use the forward's warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 / 8-11 compute groups
+// that own alternate blocks (TMEM stage = block & 1).
+constexpr int kBK = 64;        // keys per block in the dQ kernel
+
+struct BwdParams {
+  const void* o;
+  const void* d_o;
+  const float* lse;
+  float* dvec;                 // (B, H, N) fp32: D, written by the dQ kernel, read by the dK/dV kernel
+  void* d_q;
+  void* d_k;
+  void* d_v;
+  int B, H, N, d;
+  int nblk, npv, bf16;
+  int nb;                      // streamed blocks (keys for dQ, queries for dK/dV)
+  int bq;                      // queries per block in the dK/dV kernel (64 or 32)
+  int stages;
+  float scale;
+};
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, bool bf16) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa, fb;
+    if (bf16) {
+      fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[i]));
+      fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pb[i]));
+    } else {
+      fa = __half22float2(*reinterpret_cast<const __half2*>(&pa[i]));
+      fb = __half22float2(*reinterpret_cast<const __half2*>(&pb[i]));
+    }
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------------ dQ
+__global__ void __launch_bounds__(kThreads, 1)
+self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                        const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                        const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // qg_full, dq_ready, kv_full[4], kv_free[4], sd_ready[2], ds_ready[2]
+  __shared__ __align__(8) uint64_t bars[14];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = tile * kM;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_block_bytes = (uint32_t)kBK * 128u;
+  const uint32_t k_bytes = (uint32_t)p.nblk * kv_block_bytes;
+  const uint32_t stage_bytes = 2u * k_bytes;
+  const uint32_t sQ = base;
+  const uint32_t sG = sQ + (uint32_t)p.nblk * kQBlockBytes;
+  const uint32_t sKV = sG + (uint32_t)p.nblk * kQBlockBytes;
+  auto QG_FULL = [&]() { return smem_u32(&bars[0]); };
+  auto DQ_READY = [&]() { return smem_u32(&bars[1]); };
+  auto KV_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
+  auto KV_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
+  auto SD_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
+  auto DS_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
+  constexpr int kColDQ = 256;
+  auto colS = [](int g) { return g * 128; };          // S at +0 (dS written over it), dP at +64
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(QG_FULL(), 1);
+    mbar_init(DQ_READY(), 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(SD_READY(g), 1); mbar_init(DS_READY(g), kGroupThreads); }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const int nb = p.nb, NS = p.stages;
+  const int ksteps = (p.d + 15) >> 4;
+  const int fmt = p.bf16 ? 1 : 0;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------------------------------- producer
+      mbar_expect_tx(QG_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, QG_FULL(), blk * kBlockCols, h, row0, b);
+        tma_load_4d(sG + blk * kQBlockBytes, &map_do, QG_FULL(), blk * kBlockCols, h, row0, b);
+      }
+      int ss = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < nb; ++it) {
+        if (it >= NS) mbar_wait(KV_FREE(ss), par ^ 1u);
+        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
+        mbar_expect_tx(KV_FULL(ss), stage_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
+          tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
+        }
+        if (++ss == NS) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ----------------------------------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = make_idesc(fmt, 0, kBK, kM);
+      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      mbar_wait(QG_FULL(), 0);
+      bool dq_started = false;
+      auto mma3 = [&](int it) {                     // dQ += dS(it) K(it)
+        const int g = it & 1, ss = it % NS;
+        const uint32_t sK = sKV + ss * stage_bytes;
+        for (int ks = 0; ks < kBK / 16; ++ks)
+          mma_ts(tmem + kColDQ, tmem + colS(g) + ks * 8, smem_desc_sw128(sK + ks * 2048u, kv_block_bytes, 1024),
+                 idesc_dq, (dq_started || ks > 0) ? 1u : 0u);
+        dq_started = true;
+        tc_commit(KV_FREE(ss));
+      };
+      for (int it = 0; it < nb; ++it) {
+        const int g = it & 1, ss = it % NS;
+        if (it >= 2) {
+          mbar_wait(DS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
+          tc_fence_after();
+          mma3(it - 2);
+        }
+        mbar_wait(KV_FULL(ss), (uint32_t)(it / NS) & 1u);
+        tc_fence_after();
+        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + colS(g), smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sK + off * kv_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + colS(g) + kBK, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sV + off * kv_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(SD_READY(g));
+      }
+      for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
+        mbar_wait(DS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        mma3(it);
+      }
+      tc_commit(DQ_READY());
+    }
+  } else {
+    reg_alloc<232>();
+    // --------------------------------------------------------------------------------------- compute groups
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const int row = row0 + r;
+    const bool live = row < p.N;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
+
+    // D = rowsum(dO o O) for this thread's row (both groups compute it; group 0 publishes it for the dK/dV kernel)
+    float Drow = 0.f, l2 = 0.f;
+    if (live) {
+      const int64_t off = (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d;
+      const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.o) + off * 2);
+      const uint4* pg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.d_o) + off * 2);
+      for (int c = 0; c < p.d / 8; ++c) Drow += dot8(__ldg(po + c), __ldg(pg + c), bf16);
+      const int64_t vi = ((int64_t)b * p.H + h) * p.N + row;
+      l2 = __ldg(p.lse + vi) * 1.4426950408889634f;
+      if (g == 0) p.dvec[vi] = Drow;
+    }
+
+    for (int it = g; it < nb; it += 2) {
+      mbar_wait(SD_READY(g), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      float s[kBK], dp[kBK];
+#pragma unroll
+      for (int c = 0; c < kBK / 16; ++c) {
+        tmem_ld16(lane_base + colS(g) + c * 16, s + c * 16);
+        tmem_ld16(lane_base + colS(g) + kBK + c * 16, dp + c * 16);
+      }
+      tmem_ld_wait();
+      const int key0 = it * kBK;
+      const bool ragged = key0 + kBK > p.N;
+      uint32_t packed[kBK / 2];
+#pragma unroll
+      for (int j = 0; j < kBK; ++j) {
+        float pr = ex2_approx(fmaf(s[j], sc, -l2));
+        if (ragged && key0 + j >= p.N) pr = 0.f;
+        s[j] = pr * (dp[j] - Drow) * p.scale;
+      }
+#pragma unroll
+      for (int j = 0; j < kBK; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
+#pragma unroll
+      for (int c = 0; c < kBK / 16; ++c) tmem_st8(lane_base + colS(g) + c * 8, packed + c * 8);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(DS_READY(g));
+    }
+
+    // ---- epilogue: the two groups take alternate 16-column chunks of dQ
+    mbar_wait(DQ_READY(), 0);
+    tc_fence_after();
+    uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+    for (int cc = g; cc < p.npv / 16; cc += 2) {
+      float ov[16];
+      tmem_ld16(lane_base + kColDQ + cc * 16, ov);
+      tmem_ld_wait();
+      if (live) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
+        const int col = cc * 16;
+        if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+// --------------------------------------------------------------------------------------------------- dK, dV
+template <int BQ>
+__global__ void __launch_bounds__(kThreads, 1)
+self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                         const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                         const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // kv_full, acc_ready, qg_full[4], qg_free[4], sd_ready[2], pds_ready[2]
+  __shared__ __align__(8) uint64_t bars[14];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float xl[2][2][BQ];       // [group][block parity][query]: lse * log2(e)
+  __shared__ __align__(16) float xd[2][2][BQ];       //                                D
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int key0 = tile * kM;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_block_bytes = (uint32_t)BQ * 128u;
+  const uint32_t q_bytes = (uint32_t)p.nblk * q_block_bytes;
+  const uint32_t stage_bytes = 2u * q_bytes;
+  const uint32_t sK = base;
+  const uint32_t sV = sK + (uint32_t)p.nblk * kQBlockBytes;
+  const uint32_t sQG = sV + (uint32_t)p.nblk * kQBlockBytes;
+  auto KV_FULL = [&]() { return smem_u32(&bars[0]); };
+  auto ACC_READY = [&]() { return smem_u32(&bars[1]); };
+  auto QG_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
+  auto QG_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
+  auto SD_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
+  auto PDS_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
+  // TMEM: stage g at g*2*BQ: S^T at +0 (P^T written over it), dP^T at +BQ (dS^T written over it); accumulators after
+  auto colST = [](int g) { return g * 2 * BQ; };
+  constexpr int kColDV = 4 * BQ;
+  const int colDK = kColDV + p.npv;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(KV_FULL(), 1);
+    mbar_init(ACC_READY(), 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(QG_FULL(s), 1); mbar_init(QG_FREE(s), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(SD_READY(g), 1); mbar_init(PDS_READY(g), kGroupThreads); }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const int nb = p.nb, NS = p.stages;
+  const int ksteps = (p.d + 15) >> 4;
+  const int fmt = p.bf16 ? 1 : 0;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------------------------------- producer
+      mbar_expect_tx(KV_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        tma_load_4d(sK + blk * kQBlockBytes, &map_k, KV_FULL(), blk * kBlockCols, h, key0, b);
+        tma_load_4d(sV + blk * kQBlockBytes, &map_v, KV_FULL(), blk * kBlockCols, h, key0, b);
+      }
+      int ss = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < nb; ++it) {
+        if (it >= NS) mbar_wait(QG_FREE(ss), par ^ 1u);
+        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
+        mbar_expect_tx(QG_FULL(ss), stage_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sQi + blk * q_block_bytes, &map_q, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
+          tma_load_4d(sGi + blk * q_block_bytes, &map_do, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
+        }
+        if (++ss == NS) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ----------------------------------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = make_idesc(fmt, 0, BQ, kM);
+      const uint32_t idesc_acc = make_idesc(fmt, 1, p.npv, kM);
+      mbar_wait(KV_FULL(), 0);
+      bool started = false;
+      auto mma34 = [&](int it) {                    // dV += P^T(it) dO(it);  dK += dS^T(it) Q(it)
+        const int g = it & 1, ss = it % NS;
+        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
+        for (int ks = 0; ks < BQ / 16; ++ks)
+          mma_ts(tmem + kColDV, tmem + colST(g) + ks * 8, smem_desc_sw128(sGi + ks * 2048u, q_block_bytes, 1024),
+                 idesc_acc, (started || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < BQ / 16; ++ks)
+          mma_ts(tmem + colDK, tmem + colST(g) + BQ + ks * 8, smem_desc_sw128(sQi + ks * 2048u, q_block_bytes, 1024),
+                 idesc_acc, (started || ks > 0) ? 1u : 0u);
+        started = true;
+        tc_commit(QG_FREE(ss));
+      };
+      for (int it = 0; it < nb; ++it) {
+        const int g = it & 1, ss = it % NS;
+        if (it >= 2) {
+          mbar_wait(PDS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
+          tc_fence_after();
+          mma34(it - 2);
+        }
+        mbar_wait(QG_FULL(ss), (uint32_t)(it / NS) & 1u);
+        tc_fence_after();
+        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + colST(g), smem_desc_sw128(sK + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sQi + off * q_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + colST(g) + BQ, smem_desc_sw128(sV + off * kQBlockBytes + in, 16, 1024),
+                 smem_desc_sw128(sGi + off * q_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(SD_READY(g));
+      }
+      for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
+        mbar_wait(PDS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        mma34(it);
+      }
+      tc_commit(ACC_READY());
+    }
+  } else {
+    reg_alloc<232>();
+    // --------------------------------------------------------------------------------------- compute groups
+    const int g = (warp - 4) >> 2;
+    const int gt = tid - 128 - g * kGroupThreads;    // thread index inside the group
+    const int r = ((warp & 3) << 5) + lane;          // key row of the tile = TMEM lane
+    const int key = key0 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
+    const int64_t vbase = ((int64_t)b * p.H + h) * p.N;
+
+    int n = 0;
+    for (int it = g; it < nb; it += 2, ++n) {
+      // stage the per-query log-sum-exp and D of this block (columns of S^T) in shared memory
+      const int buf = n & 1;
+      if (gt < BQ) {
+        const int q = it * BQ + gt;
+        xl[g][buf][gt] = q < p.N ? __ldg(p.lse + vbase + q) * 1.4426950408889634f : INFINITY;
+        xd[g][buf][gt] = q < p.N ? __ldg(p.dvec + vbase + q) : 0.f;
+      }
+      named_bar_sync(1 + g, kGroupThreads);
+      mbar_wait(SD_READY(g), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      float s[BQ], dp[BQ];
+#pragma unroll
+      for (int c = 0; c < BQ / 16; ++c) {
+        tmem_ld16(lane_base + colST(g) + c * 16, s + c * 16);
+        tmem_ld16(lane_base + colST(g) + BQ + c * 16, dp + c * 16);
+      }
+      tmem_ld_wait();
+      uint32_t pk[BQ / 2], dk[BQ / 2];
+#pragma unroll
+      for (int j = 0; j < BQ; j += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(&xl[g][buf][j]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&xd[g][buf][j]);
+        const float lj[4] = {l4.x, l4.y, l4.z, l4.w}, dj[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float pr = ex2_approx(fmaf(s[j + u], sc, -lj[u]));
+          s[j + u] = pr;
+          dp[j + u] = pr * (dp[j + u] - dj[u]) * p.scale;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BQ; j += 2) {
+        pk[j >> 1] = pack16(s[j], s[j + 1], bf16);
+        dk[j >> 1] = pack16(dp[j], dp[j + 1], bf16);
+      }
+#pragma unroll
+      for (int c = 0; c < BQ / 16; ++c) {
+        tmem_st8(lane_base + colST(g) + c * 8, pk + c * 8);
+        tmem_st8(lane_base + colST(g) + BQ + c * 8, dk + c * 8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(PDS_READY(g));
+    }
+
+    // ---- epilogue: group 0 stores dV, group 1 stores dK
+    mbar_wait(ACC_READY(), 0);
+    tc_fence_after();
+    const int col0 = g == 0 ? kColDV : colDK;
+    uint8_t* out = reinterpret_cast<uint8_t*>(g == 0 ? p.d_v : p.d_k) +
+                   (((int64_t)b * p.N + key) * p.H + h) * (int64_t)p.d * 2;
+    for (int cc = 0; cc < p.npv / 16; ++cc) {
+      float ov[16];
+      tmem_ld16(lane_base + col0 + cc * 16, ov);
+      tmem_ld_wait();
+      if (key < p.N) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
+        const int col = cc * 16;
+        if (col < p.d) *reinterpret_cast<uint4*>(out + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (col + 8 < p.d) *reinterpret_cast<uint4*>(out + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+template <int BQ>
+static int launch_dkv(const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mq, const CUtensorMap& mg,
+                      BwdParams p, int slot, cudaStream_t st) {
+  const size_t kv_bytes = (size_t)2 * p.nblk * kQBlockBytes, stage = (size_t)2 * p.nblk * BQ * 128;
+  p.bq = BQ;
+  p.nb = (p.N + BQ - 1) / BQ;
+  p.stages = 0;
+  for (int n = kMaxStages; n >= 2; --n)
+    if (1024 + kv_bytes + n * stage <= 226 * 1024) { p.stages = n; break; }
+  if (p.stages == 0) return fail(GA_ERR_UNSUPPORTED, "self-attention dK/dV: head_dim %d does not fit shared memory", p.d);
+  const size_t smem = 1024 + kv_bytes + p.stages * stage;
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(self_attn_bwd_dkv_kernel<BQ>), slot, smem);
+  if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 grid((p.N + kM - 1) / kM, p.H, p.B);
+  self_attn_bwd_dkv_kernel<BQ><<<grid, kThreads, smem, st>>>(mk, mv, mq, mg, p);
+  return check_launch("self_attn_bwd_dkv");
+}
+
+int bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* d_o, void* d_q,
+        void* d_k, void* d_v, float* dvec, int B, int H, int N, int d, float scale, int dtype, cudaStream_t st) {
+  BwdParams p;
+  p.o = o; p.d_o = d_o; p.lse = lse; p.dvec = dvec; p.d_q = d_q; p.d_k = d_k; p.d_v = d_v;
+  p.B = B; p.H = H; p.N = N; p.d = d;
+  p.nblk = (d + kBlockCols - 1) / kBlockCols;
+  p.npv = (d + 15) & ~15;
+  p.bf16 = dtype == GA_BF16;
+  p.scale = scale;
+  p.bq = 0;
+  int rc;
+  // ---- dQ (+ D)
+  {
+    p.nb = (N + kBK - 1) / kBK;
+    const size_t qg_bytes = (size_t)2 * p.nblk * kQBlockBytes, stage = (size_t)2 * p.nblk * kBK * 128;
+    p.stages = 0;
+    for (int n = kMaxStages; n >= 2; --n)
+      if (1024 + qg_bytes + n * stage <= 226 * 1024) { p.stages = n; break; }
+    if (p.stages == 0) return fail(GA_ERR_UNSUPPORTED, "self-attention dQ: head_dim %d does not fit shared memory", d);
+    const size_t smem = 1024 + qg_bytes + p.stages * stage;
+    CUtensorMap mq, mg, mk, mv;
+    if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+    if ((rc = make_map(&mg, d_o, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+    if ((rc = make_map(&mk, k, dtype, B, N, H, d, kBK)) != GA_OK) return rc;
+    if ((rc = make_map(&mv, v, dtype, B, N, H, d, kBK)) != GA_OK) return rc;
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(self_attn_bwd_dq_kernel), 1, smem);
+    if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    dim3 grid((N + kM - 1) / kM, H, B);
+    self_attn_bwd_dq_kernel<<<grid, kThreads, smem, st>>>(mq, mg, mk, mv, p);
+    if ((rc = check_launch("self_attn_bwd_dq")) != GA_OK) return rc;
+  }
+  // ---- dK, dV
+  {
+    const int bq = (4 * 64 + 2 * p.npv <= 512) ? 64 : 32;
+    CUtensorMap mk, mv, mq, mg;
+    if ((rc = make_map(&mk, k, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+    if ((rc = make_map(&mv, v, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+    if ((rc = make_map(&mq, q, dtype, B, N, H, d, bq)) != GA_OK) return rc;
+    if ((rc = make_map(&mg, d_o, dtype, B, N, H, d, bq)) != GA_OK) return rc;
+    return bq == 64 ? launch_dkv<64>(mk, mv, mq, mg, p, 2, st) : launch_dkv<32>(mk, mv, mq, mg, p, 3, st);
+  }
+}
+
 }  // namespace sa
 }  // namespace ga

@@ -82,6 +82,47 @@ def time_cross_attn(B, H, N, T, d, dtype=torch.float16, with_acc=True, direction
             "buffer_sets": n_sets}
 
 
+def time_self_attn(B, H, N, d, dtype=torch.float16, direction="fwd", device="cuda:0"):
+    """One fused self-attention forward launch (or the backward's two launches).  Tensor-core bound: reports TFLOP/s of
+    the GEMM work the kernels issue (`ops.self_attn_flops`) and of the algorithm's minimum (2 GEMMs fwd, 5 bwd)."""
+    lib = abi.load()
+    flops = ops.self_attn_flops(B, H, N, d, direction)
+    need = 2 * B * H * N * N * d * (2 if direction == "fwd" else 5)
+    nbytes = B * N * H * d * 2 * (4 if direction == "fwd" else 8)
+    n_sets = max(2, min(16, (2 * L2_BYTES) // max(nbytes, 1) + 1))
+    g = torch.Generator(device=device).manual_seed(0)
+    sets = []
+    for _ in range(n_sets):
+        q, k, v, do = (torch.randn(B, N, H * d, device=device, dtype=dtype, generator=g) for _ in range(4))
+        o, lse = ops.self_attention_forward(q, k, v, H, d ** -0.5)
+        sets.append((q, k, v, o, lse, do, torch.empty_like(q), torch.empty_like(q), torch.empty_like(q),
+                     torch.empty(B, H, N, device=device, dtype=torch.float32)))
+    dt, scale = ops._DTYPES[dtype], d ** -0.5
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)   # noqa: E731
+
+    def fwd(i):
+        q, k, v, o, lse = sets[i][:5]
+        abi.check(lib.ga_self_attn_fwd(ops._ptr(q), ops._ptr(k), ops._ptr(v), ops._ptr(o), ops._ptr(lse), B, H, N, d,
+                                       scale, dt, st()), "ga_self_attn_fwd")
+
+    def bwd(i):
+        q, k, v, o, lse, do, dq, dk, dv, dvec = sets[i]
+        abi.check(lib.ga_self_attn_bwd(ops._ptr(q), ops._ptr(k), ops._ptr(v), ops._ptr(o), ops._ptr(lse), ops._ptr(do),
+                                       ops._ptr(dq), ops._ptr(dk), ops._ptr(dv), ops._ptr(dvec), B, H, N, d, scale, dt,
+                                       st()), "ga_self_attn_bwd")
+    us = _time_graph(fwd if direction == "fwd" else bwd, n_sets)
+    return {"kernel": f"self_attn_{direction}", "B": B, "H": H, "N": N, "d": d, "dtype": str(dtype), "us": us,
+            "flops_issued": flops, "tflops_issued": flops / us / 1e6, "tflops_algorithmic": need / us / 1e6,
+            "bytes": nbytes, "buffer_sets": n_sets}
+
+
+def sweep_self(device="cuda:0"):
+    for (N, d) in ((4096, 40), (1024, 80), (256, 160), (64, 160)):
+        for B in (1, 2, 8):
+            for direction in ("fwd", "bwd"):
+                yield time_self_attn(B, 8, N, d, torch.float16, direction, device)
+
+
 def time_tail(res, n_layers, slices_per_layer, n_samples=1, T=77, direction="fwd", device="cuda:0"):
     """One guidance-tail launch (forward or backward): `n_samples` independent evaluations, each over `n_layers`
     accumulators of `slices_per_layer` (N, T) slices (the reference's shape is n_samples = 1, 5 layers, 1-2 slices)."""
@@ -151,6 +192,13 @@ def single(argv):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--single":
         single(sys.argv[2:])
+    elif len(sys.argv) > 1 and sys.argv[1] == "--single-self":
+        a = sys.argv[2:]
+        print(json.dumps(time_self_attn(int(a[1]), 8, int(a[2]), int(a[3]), torch.float16, a[0])))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--self":
+        for r in sweep_self():
+            print(json.dumps(r))
+            sys.stdout.flush()
     else:
         for r in sweep():
             print(json.dumps(r))

@@ -181,6 +181,11 @@ def cross_attention(q, k, v, heads: int, scale: float, want_acc: bool = False, i
     return _CrossAttnFn.apply(q, k, v, heads, scale, want_acc, default_impl if impl is None else impl)
 
 
+def self_attn_flops(B, H, N, d, direction="fwd"):
+    """Tensor-core FLOPs one launch pair issues (the forward recomputes QK^T once: 3 GEMMs; the backward runs 7)."""
+    return (3 if direction == "fwd" else 7) * 2 * B * H * N * N * d
+
+
 def self_attention_forward(q, k, v, heads: int, scale: float):
     """Fused exact self-attention forward (no autograd): returns (o, lse)."""
     _need_cuda(q, k, v)
@@ -189,11 +194,50 @@ def self_attention_forward(q, k, v, heads: int, scale: float):
     B, N, Cdim = q.shape
     o = torch.empty_like(q)
     lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
-    with torch.cuda.device(q.device):
-        abi.check(lib.ga_self_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, N, Cdim // heads,
+    d = Cdim // heads
+    with torch.cuda.device(q.device), _span("self_attn_fwd", (B, heads, N, d, str(q.dtype)),
+                                            self_attn_flops(B, heads, N, d, "fwd"), q.device):
+        abi.check(lib.ga_self_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, N, d,
                                        float(scale), _DTYPES[q.dtype], _stream(q)), "ga_self_attn_fwd")
     _count("self_attn_fwd")
     return o, lse
+
+
+class _SelfAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float):
+        o, lse = self_attention_forward(q, k, v, heads, scale)
+        ctx.save_for_backward(q.contiguous(), k.contiguous(), v.contiguous(), o, lse)
+        ctx.meta = (heads, float(scale))
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        heads, scale = ctx.meta
+        lib = abi.load()
+        B, N, Cdim = q.shape
+        d = Cdim // heads
+        d_o = d_o.contiguous()
+        d_q, d_k, d_v = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dvec = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device), _span("self_attn_bwd", (B, heads, N, d, str(q.dtype)),
+                                                self_attn_flops(B, heads, N, d, "bwd"), q.device):
+            abi.check(lib.ga_self_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(d_o), _ptr(d_q),
+                                           _ptr(d_k), _ptr(d_v), _ptr(dvec), B, heads, N, d, scale,
+                                           _DTYPES[q.dtype], _stream(q)), "ga_self_attn_bwd")
+        _count("self_attn_bwd", 2)
+        return d_q, d_k, d_v, None, None
+
+
+def self_attention(q, k, v, heads: int, scale: float):
+    """O = softmax(scale Q K^T) V per head over the same N tokens; q, k, v (B, N, H*d) fp16/bf16.  Differentiable in
+    q, k and v; the (B*H, N, N) probabilities are never materialised (forward: one launch, backward: two)."""
+    return _SelfAttnFn.apply(q, k, v, heads, scale)
+
+
+def self_attention_supported(dtype, head_dim: int) -> bool:
+    return dtype in (torch.float16, torch.bfloat16) and head_dim % 8 == 0 and 8 <= head_dim <= 160
 
 
 def attention_probs(q, k, heads: int, scale: float):

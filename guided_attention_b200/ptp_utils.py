@@ -11,9 +11,11 @@ Same public names, signatures and bookkeeping (`register_attention_control`, `At
   * what the controller receives for a cross layer is therefore a `HeadSummedMaps` handle instead of a probability
     tensor.  It has the `.shape` the reference tensor would have, so `AttentionStore.forward`'s size test is unchanged,
     and `.probs()` materialises the per-head maps on demand (API compatibility, off the hot path).
-  * self-attention layers are off the guidance path; they run the same explicit math as the reference in PyTorch and
-    their maps are only stored when `AttentionStore(save_self_attention=True)` (the reference stores them
-    unconditionally although nothing reads them: `pipeline_guided_attention.py:309` hard-wires the reader off).
+  * self-attention layers are off the guidance path but on the autograd path: with 16-bit operands they run the fused
+    exact self-attention kernels (`ops.self_attention`, forward + backward, no (B*H, N, N) tensor); with fp32 operands,
+    or when `AttentionStore(save_self_attention=True)` asks for the maps, they run the reference's explicit math in
+    PyTorch (the reference stores the self maps unconditionally although nothing reads them:
+    `pipeline_guided_attention.py:309` hard-wires the reader off).
 """
 from __future__ import annotations
 
@@ -89,15 +91,28 @@ class AttendExciteCrossAttnProcessor:
             self.attnstore(maps, True, self.place_in_unet)
             hidden_states = out
         else:
-            # self-attention: off the guidance path, same explicit math as the reference (utils/ptp_utils.py:77-85)
             key = attn.to_k(hidden_states)
             value = attn.to_v(hidden_states)
-            query = attn.head_to_batch_dim(query)
-            key = attn.head_to_batch_dim(key)
-            value = attn.head_to_batch_dim(value)
-            attention_probs = attn.get_attention_scores(query, key, attention_mask)
-            self.attnstore(attention_probs, False, self.place_in_unet)
-            hidden_states = attn.batch_to_head_dim(torch.bmm(attention_probs, value))
+            want_maps = bool(getattr(self.attnstore, "save_self_attention", False))
+            fused = (not want_maps and attention_mask is None and hidden_states.is_cuda
+                     and ops.self_attention_supported(query.dtype, query.shape[-1] // attn.heads)
+                     and not (attn.upcast_attention or attn.upcast_softmax))
+            if fused:
+                # self-attention, 16-bit operands: fused exact attention; the (B*H, N, N) probabilities
+                # the reference materialises and keeps for autograd never exist.  The controller still gets its call
+                # (layer counting, utils/ptp_utils.py:194-201) with a shape-only stand-in: nothing reads these maps
+                # (pipeline_guided_attention.py:309 hard-wires the reader off).
+                hidden_states = ops.self_attention(query, key, value, attn.heads, attn.scale)
+                self.attnstore(_ShapeOnly(batch_size * attn.heads, sequence_length, sequence_length), False,
+                               self.place_in_unet)
+            else:
+                # fp32 operands / stored self maps: the reference's explicit math (utils/ptp_utils.py:77-85) in PyTorch
+                query = attn.head_to_batch_dim(query)
+                key = attn.head_to_batch_dim(key)
+                value = attn.head_to_batch_dim(value)
+                attention_probs = attn.get_attention_scores(query, key, attention_mask)
+                self.attnstore(attention_probs, False, self.place_in_unet)
+                hidden_states = attn.batch_to_head_dim(torch.bmm(attention_probs, value))
 
         hidden_states = attn.to_out[0](hidden_states)
         hidden_states = attn.to_out[1](hidden_states)

@@ -131,6 +131,13 @@ int ga_attn_probs(const void* q, const void* k, void* probs, int batch, int head
 int ga_self_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads,
                      int n_tokens, int head_dim, float scale, int dtype, ga_stream_t stream);
 
+/* Backward of ga_self_attn_fwd (autograd of the reference's attn1 branch): P is recomputed from `lse`; two launches
+ * (dQ, then dK/dV), no atomics.  o, d_o, d_q, d_k, d_v (B, N, H*d) 16-bit; dvec (B, H, N) fp32 caller-owned workspace
+ * (receives rowsum(dO o O)). */
+int ga_self_attn_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* d_o,
+                     void* d_q, void* d_k, void* d_v, float* dvec, int batch, int heads, int n_tokens, int head_dim,
+                     float scale, int dtype, ga_stream_t stream);
+
 /* ---- K5: box-mask rasteriser ------------------------------------------------------------------------------------------
  * masks[i, ii, jj] = inside_box(jj, ii, Rect(box_i, size 1).of_size(res))   (utils/helpers.py:164-173, 28-30)
  * float64, no FMA contraction, the reference's operation order: bit-exact.  boxes_host: n x (x, y, w, h). */

@@ -164,6 +164,55 @@ def test_self_attention_forward(shape, dtype, rtol):
     assert rel_err(lse.cpu().numpy(), want_lse.cpu().numpy()) < 1e-3
 
 
+@pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("shape", SELF_SHAPES)
+def test_self_attention_backward(shape, dtype, rtol):
+    """dQ, dK, dV of the fused self-attention (two launches, P recomputed from the LSE) against torch autograd through
+    the reference's explicit math (utils/ptp_utils.py:77-85) in fp32."""
+    from guided_attention_b200 import ops
+    H, d, N, B = shape
+    g = torch.Generator("cpu").manual_seed(3 * N + d)
+    q, k, v, go = (torch.randn(B, N, H * d, generator=g).to(dtype).to(DEV) for _ in range(4))
+    scale = d ** -0.5
+    qf, kf, vf = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    o = ops.self_attention(qf, kf, vf, H, scale)
+    dq, dk, dv = torch.autograd.grad(o, [qf, kf, vf], go)
+    torch.cuda.synchronize()
+    qr, kr, vr = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    S = scale * torch.bmm(O.head_to_batch(qr, H), O.head_to_batch(kr, H).transpose(1, 2))
+    want = O.batch_to_head(torch.bmm(torch.softmax(S, -1), O.head_to_batch(vr, H)), H)
+    wq, wk, wv = torch.autograd.grad(want, [qr, kr, vr], go.float())
+    for got, ref, name in ((dq, wq, "dq"), (dk, wk, "dk"), (dv, wv, "dv")):
+        err = rel_err(got.float().cpu().numpy(), ref.cpu().numpy())
+        assert err < rtol, (name, err)
+    # bit-stable: no atomics anywhere in the backward
+    dq2, dk2, dv2 = torch.autograd.grad(ops.self_attention(qf, kf, vf, H, scale), [qf, kf, vf], go)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
+
+
+def test_processor_uses_fused_self_attention():
+    """16-bit self-attention layers go through the fused kernels (forward and backward) and match the explicit math."""
+    from guided_attention_b200 import ops
+    from guided_attention_b200.ptp_utils import AttentionStore, AttendExciteCrossAttnProcessor
+    from guided_attention_b200.substrate.unet import CrossAttention
+    torch.manual_seed(0)
+    attn = CrossAttention(320, None, 8, 40).to(DEV).half()
+    x = torch.randn(2, 1024, 320, device=DEV, dtype=torch.float16, requires_grad=True)
+    store = AttentionStore()
+    store.num_att_layers = 1
+    ops.reset_launch_counts()
+    y = AttendExciteCrossAttnProcessor(store, "down")(attn, x)
+    (gx,) = torch.autograd.grad(y.float().square().sum(), x)
+    assert ops.launch_counts.get("self_attn_fwd") == 1 and ops.launch_counts.get("self_attn_bwd") == 2
+    store2 = AttentionStore(save_self_attention=True)       # explicit PyTorch path
+    store2.num_att_layers = 1
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = AttendExciteCrossAttnProcessor(store2, "down")(attn, x2)
+    (gx2,) = torch.autograd.grad(y2.float().square().sum(), x2)
+    assert rel_err(y.detach().float().cpu().numpy(), y2.detach().float().cpu().numpy()) < FP16_RTOL
+    assert rel_err(gx.float().cpu().numpy(), gx2.float().cpu().numpy()) < 5e-2
+
+
 # -------------------------------------------------------------------------------------------------- K2 backward
 @pytest.mark.parametrize("dtype,rtol", [(torch.float32, FP32_RTOL), (torch.float16, FP16_RTOL)])
 @pytest.mark.parametrize("shape", [(8, 40, 1024, 77, 1), (8, 160, 256, 77, 2), (5, 64, 576, 77, 1),
