@@ -58,7 +58,7 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tile = blockIdx.y, b = blockIdx.z;
   const int head0 = blockIdx.x * p.heads_per_cta;
   const int row0 = tile * kM;
@@ -84,7 +84,7 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's quarter of the 128 TMEM lanes
 
   const int fmt = p.bf16 ? 1 : 0;
@@ -101,26 +101,26 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint32_t ph_load = 0, ph_mma = 0;   // mbarrier phase parities: bar_load flips once per head, bar_mma twice
   for (int hh = 0; hh < p.heads_per_cta; ++hh) {
     const int h = head0 + hh;
-    // ---- TMA: Q tile + K + V of this head; MMA 1 -----------------------------------------------------------
-    if (tid == 0) {
-      mbar_expect_tx(bar_load, tx_bytes);
-      for (int blk = 0; blk < p.nblk; ++blk) {
-        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
-        tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
-        tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+    // ---- TMA: Q tile + K + V of this head; MMA 1 (warp 0, warp-uniform; one elected lane issues) ---------------
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(bar_load, tx_bytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
+          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
+          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+        }
       }
       mbar_wait(bar_load, ph_load);
       tc_fence_after();
-      // S = Q K^T: K-major operands; a k-step of 16 elements is 32 bytes inside the 128-byte swizzled row
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t off = (uint32_t)(ks >> 2) , in = (uint32_t)(ks & 3) * 32u;
-        const uint64_t da = smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024);
-        const uint64_t db = smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024);
-        mma_ss(tmem + kColS, da, db, idesc_qk, ks > 0 ? 1u : 0u);
+      if (elect_one()) {
+        // S = Q K^T: K-major operands; a k-step of 16 elements is 32 bytes inside the 128-byte swizzled row
+        issue_kmajor_gemm(tmem + kColS, smem_desc_sw128(sQ, 16, 1024), kQBlockBytes, smem_desc_sw128(sK, 16, 1024),
+                          kKVBlockBytes, ksteps, idesc_qk);
+        tc_commit(bar_mma);
       }
-      tc_commit(bar_mma);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
@@ -148,16 +148,15 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     __syncthreads();
 
     // ---- MMA 2: O = P V  (V is MN-major: rows = keys, 128-byte rows of 64 channels) -------------------------
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      for (int ks = 0; ks < kTpad / 16; ++ks) {
+      if (elect_one()) {
         // 16 keys = two 8-row swizzle atoms (SBO = 1024 B apart); channel blocks are LBO = one K/V block apart
-        const uint64_t db = smem_desc_sw128(sV + ks * 2048u, kKVBlockBytes, 1024);
-        mma_ts(tmem + kColO, tmem + kColP + ks * 8, db, idesc_pv, ks > 0 ? 1u : 0u);
+        issue_tmem_gemm(tmem + kColO, tmem + kColP, smem_desc_sw128(sV, kKVBlockBytes, 1024), kTpad / 16, idesc_pv, false);
+        tc_commit(bar_mma);
       }
-      tc_commit(bar_mma);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
@@ -195,17 +194,28 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 #pragma unroll
     for (int j = 0; j < kTpad; ++j) sAcc[tid * kAccStride + j] = pacc[j];
     cluster.sync();
+    // every remote load of a row is issued before the first add (one DSMEM round trip per row instead of one per
+    // peer); the sum itself runs in rank order, so the result does not depend on timing
+    const float* peer[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) peer[c] = cluster.map_shared_rank(sAcc, c < (int)csize ? c : 0);
     for (int i = (int)crank + (int)csize * warp; i < kM; i += (int)csize * (kThreads / 32)) {
       const int r = row0 + i;
       if (r >= p.N) continue;
-      float v[3] = {0.f, 0.f, 0.f};
-      for (unsigned c = 0; c < csize; ++c) {
-        const float* remote = cluster.map_shared_rank(sAcc, c) + i * kAccStride;
+      float part[8][3];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
           const int j = lane + 32 * kk;
-          if (j < p.T) v[kk] += remote[j];
+          part[c][kk] = (c < (int)csize && j < p.T) ? peer[c][i * kAccStride + j] : 0.f;
         }
+      }
+      float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) v[kk] += part[c][kk];
       }
 #pragma unroll
       for (int kk = 0; kk < 3; ++kk) {
@@ -257,7 +267,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
@@ -288,50 +298,62 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const int fmt = p.bf16 ? 1 : 0;
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
 
   if (warp < 4) {
     reg_dealloc<40>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ------------------------------------------------------------------------------------- TMA producer
-      // coordinates advance incrementally (no divisions in the loop)
+      // warp-uniform; coordinates advance incrementally (no divisions in the loop); one elected lane issues
       int unit = blockIdx.x, h = 0, ss = 0;
+      int b0 = 0, tile0 = 0, hh0 = 0;
+      if (p.grouped) { b0 = unit / p.tiles; tile0 = unit - b0 * p.tiles; }
+      else { tile0 = unit % p.tiles; const int bh = unit / p.tiles; b0 = bh / p.H; hh0 = bh - b0 * p.H; }
       uint32_t par = 0;                                 // parity of the use of stage ss that is about to start
       for (int k = 0; k < n_items; ++k) {
-        int b, tile, hh;
-        if (p.grouped) { b = unit / p.tiles; tile = unit - b * p.tiles; hh = h; }
-        else { tile = unit % p.tiles; const int bh = unit / p.tiles; b = bh / p.H; hh = bh - b * p.H; }
+        const int b = b0, tile = tile0, hh = p.grouped ? h : hh0;
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
-        const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
-        mbar_expect_tx(FULL(ss), stage_bytes);
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, hh, tile * kM, b);
-          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, hh, 0, b);
-          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, hh, 0, b);
+        if (elect_one()) {
+          const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
+          mbar_expect_tx(FULL(ss), stage_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, hh, tile * kM, b);
+            tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, hh, 0, b);
+            tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, hh, 0, b);
+          }
         }
-        if (p.grouped) { if (++h == p.H) { h = 0; unit += gridDim.x; } } else unit += gridDim.x;
+        __syncwarp();
+        bool next_unit = true;
+        if (p.grouped) { if (++h == p.H) h = 0; else next_unit = false; }
+        if (next_unit) {
+          unit += gridDim.x;
+          if (p.grouped) { b0 = unit / p.tiles; tile0 = unit - b0 * p.tiles; }
+          else { tile0 = unit % p.tiles; const int bh = unit / p.tiles; b0 = bh / p.H; hh0 = bh - b0 * p.H; }
+        }
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // -------------------------------------------------------------------------------------- MMA issuer
       // tcgen05.mma instructions retire in issue order, so MMA1(k+2) -- which overwrites the S/P columns of its TMEM
       // stage -- needs no wait on MMA2(k); only the O columns are handed back by the compute group (TMEM_FREE).
       const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(base + p.nblk * kQBlockBytes, 16, 1024);
+      const uint64_t dV0 = smem_desc_sw128(base + p.nblk * (kQBlockBytes + kKVBlockBytes), kKVBlockBytes, 1024);
       auto mma1 = [&](int k, int ss, uint32_t par) {
         const int ts = k & 1;
         mbar_wait(FULL(ss), par);
         tc_fence_after();
-        const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + ts * kStageCols + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + ts * kStageCols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
+                            desc_advance(dK0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_qk);
+          tc_commit(S_READY(ts));
         }
-        tc_commit(S_READY(ts));
+        __syncwarp();
       };
       auto mma2 = [&](int k, int ss) {
         const int ts = k & 1;
@@ -339,12 +361,13 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         mbar_wait(P_READY(ts), ph);
         if (k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);      // the epilogue of item k-2 has drained the O columns
         tc_fence_after();
-        const uint32_t sV = base + ss * stage_bytes + p.nblk * (kQBlockBytes + kKVBlockBytes);
-        for (int ks = 0; ks < kTpad / 16; ++ks)
-          mma_ts(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP + ks * 8,
-                 smem_desc_sw128(sV + ks * 2048u, kKVBlockBytes, 1024), idesc_pv, ks > 0 ? 1u : 0u);
-        tc_commit(O_READY(ts));
-        tc_commit(SMEM_FREE(ss));
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP,
+                          desc_advance(dV0, ss * stage_bytes), kTpad / 16, idesc_pv, false);
+          tc_commit(O_READY(ts));
+          tc_commit(SMEM_FREE(ss));
+        }
+        __syncwarp();
       };
       int ss = 0, ss_prev = 0;
       uint32_t par = 0;
@@ -491,7 +514,7 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = uniform_warp_idx();
   const int h = blockIdx.x, tile = blockIdx.y, b = blockIdx.z;
   const int row0 = tile * kM, row = row0 + tid;
 
@@ -512,7 +535,7 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
 
   const int fmt = p.bf16 ? 1 : 0;
@@ -520,29 +543,27 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
   const int ksteps = (p.d + 15) >> 4;
 
-  if (tid == 0) {
-    mbar_expect_tx(bar_load, (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes));
-    for (int blk = 0; blk < p.nblk; ++blk) {
-      tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
-      tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
-      tma_load_4d(sG + blk * kQBlockBytes, &map_do, bar_load, blk * kBlockCols, h, row0, b);
-      tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_load, (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes));
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, bar_load, blk * kBlockCols, h, row0, b);
+        tma_load_4d(sK + blk * kKVBlockBytes, &map_k, bar_load, blk * kBlockCols, h, 0, b);
+        tma_load_4d(sG + blk * kQBlockBytes, &map_do, bar_load, blk * kBlockCols, h, row0, b);
+        tma_load_4d(sV + blk * kKVBlockBytes, &map_v, bar_load, blk * kBlockCols, h, 0, b);
+      }
     }
     mbar_wait(bar_load, 0);
     tc_fence_after();
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-      mma_ss(tmem + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
-             smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+    if (elect_one()) {
+      issue_kmajor_gemm(tmem + kColS, smem_desc_sw128(sQ, 16, 1024), kQBlockBytes, smem_desc_sw128(sK, 16, 1024),
+                        kKVBlockBytes, ksteps, idesc_nt);
+      issue_kmajor_gemm(tmem + kColDP, smem_desc_sw128(sG, 16, 1024), kQBlockBytes, smem_desc_sw128(sV, 16, 1024),
+                        kKVBlockBytes, ksteps, idesc_nt);
+      tc_commit(bar_mma);
     }
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-      mma_ss(tmem + kColDP, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
-             smem_desc_sw128(sV + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
-    }
-    tc_commit(bar_mma);
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
@@ -558,13 +579,27 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const float l2 = live ? p.lse[((int64_t)b * p.H + h) * p.N + row] * 1.4426950408889634f : 0.f;
   const float* dacc = (p.d_acc != nullptr && live)
                           ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.d_acc_rstride : nullptr;
+  if (dacc != nullptr) {
+    if ((p.d_acc_rstride & 3) == 0) {            // 16-byte aligned rows (the tail kernel pads them to 80 floats)
+#pragma unroll
+      for (int j = 0; j < kTpad; j += 4) {
+        if (j + 3 < p.d_acc_rstride) {
+          const float4 v4 = __ldg(reinterpret_cast<const float4*>(dacc + j));
+          dp[j] += v4.x; dp[j + 1] += v4.y; dp[j + 2] += v4.z; dp[j + 3] += v4.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTpad; ++j)
+        if (j < p.T) dp[j] += __ldg(dacc + j);
+    }
+  }
   float dsum = 0.f;
 #pragma unroll
   for (int j = 0; j < kTpad; ++j) {
     const bool ok = live && j < p.T;
     const float pr = ok ? ex2_approx(fmaf(s[j], sc, -l2)) : 0.f;
-    float g = ok ? dp[j] : 0.f;
-    if (dacc != nullptr && j < p.T) g += __ldg(dacc + j);
+    const float g = ok ? dp[j] : 0.f;
     s[j] = pr;
     dp[j] = g;
     dsum = fmaf(pr, g, dsum);
@@ -579,14 +614,14 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   tc_fence_before();
   __syncthreads();
 
-  if (tid == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    for (int ks = 0; ks < kTpad / 16; ++ks)
-      mma_ts(tmem + kColDP, tmem + kColP + ks * 8, smem_desc_sw128(sK + ks * 2048u, kKVBlockBytes, 1024), idesc_dq,
-             ks > 0 ? 1u : 0u);
-    tc_commit(bar_mma);
+    if (elect_one()) {
+      issue_tmem_gemm(tmem + kColDP, tmem + kColP, smem_desc_sw128(sK, kKVBlockBytes, 1024), kTpad / 16, idesc_dq, false);
+      tc_commit(bar_mma);
+    }
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
 
@@ -635,7 +670,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes);
   auto FULL = [&](int s) { return smem_u32(&bars[s]); };
@@ -662,7 +697,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const int fmt = p.bf16 ? 1 : 0;
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
@@ -677,46 +712,50 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (warp < 4) {
     reg_dealloc<40>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      // TMA producer (warp-uniform, one elected lane issues)
       int ss = 0;
       uint32_t par = 0;
       for (int k = 0; k < n_items; ++k) {
         int b, h, tile;
         coords(k, b, h, tile);
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
-        const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
-                       sV = sK + p.nblk * kKVBlockBytes;
-        mbar_expect_tx(FULL(ss), stage_bytes);
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, h, tile * kM, b);
-          tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, h, 0, b);
-          tma_load_4d(sG + blk * kQBlockBytes, &map_do, FULL(ss), blk * kBlockCols, h, tile * kM, b);
-          tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, h, 0, b);
+        if (elect_one()) {
+          const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
+                         sV = sK + p.nblk * kKVBlockBytes;
+          mbar_expect_tx(FULL(ss), stage_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, h, tile * kM, b);
+            tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, h, 0, b);
+            tma_load_4d(sG + blk * kQBlockBytes, &map_do, FULL(ss), blk * kBlockCols, h, tile * kM, b);
+            tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, h, 0, b);
+          }
         }
+        __syncwarp();
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+      // MMA issuer (warp-uniform, one elected lane issues)
       const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
       const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      const uint32_t oG = p.nblk * kQBlockBytes, oK = 2u * p.nblk * kQBlockBytes, oV = oK + p.nblk * kKVBlockBytes;
+      const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024), dG0 = smem_desc_sw128(base + oG, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(base + oK, 16, 1024), dV0 = smem_desc_sw128(base + oV, 16, 1024);
+      const uint64_t dKmn0 = smem_desc_sw128(base + oK, kKVBlockBytes, 1024);
       auto mma12 = [&](int k, int ss, uint32_t par) {
         const int ts = k & 1;
         mbar_wait(FULL(ss), par);
         // dQ over dP: the epilogue of item k-2 must have drained those columns before dP(k) is written
         if (dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), (((uint32_t)(k >> 1)) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
-                       sV = sK + p.nblk * kKVBlockBytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + ts * kStageCols + kColS, smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sK + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + ts * kStageCols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
+                            desc_advance(dK0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_nt);
+          issue_kmajor_gemm(tmem + ts * kStageCols + kColDP, desc_advance(dG0, ss * stage_bytes), kQBlockBytes,
+                            desc_advance(dV0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_nt);
+          tc_commit(SD_READY(ts));
         }
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + ts * kStageCols + kColDP, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sV + off * kKVBlockBytes + in, 16, 1024), idesc_nt, ks > 0 ? 1u : 0u);
-        }
-        tc_commit(SD_READY(ts));
+        __syncwarp();
       };
       auto mma3 = [&](int k, int ss) {
         const int ts = k & 1;
@@ -724,12 +763,13 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         mbar_wait(DS_READY(ts), ph);
         if (!dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
         tc_fence_after();
-        const uint32_t sK = base + ss * stage_bytes + 2u * p.nblk * kQBlockBytes;
-        for (int ks = 0; ks < kTpad / 16; ++ks)
-          mma_ts(tmem + ts * kStageCols + p.col_dq, tmem + ts * kStageCols + kColP + ks * 8,
-                 smem_desc_sw128(sK + ks * 2048u, kKVBlockBytes, 1024), idesc_dq, ks > 0 ? 1u : 0u);
-        tc_commit(DQ_READY(ts));
-        tc_commit(SMEM_FREE(ss));
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + ts * kStageCols + p.col_dq, tmem + ts * kStageCols + kColP,
+                          desc_advance(dKmn0, ss * stage_bytes), kTpad / 16, idesc_dq, false);
+          tc_commit(DQ_READY(ts));
+          tc_commit(SMEM_FREE(ss));
+        }
+        __syncwarp();
       };
       int ss = 0, ss_prev = 0;
       uint32_t par = 0;

@@ -52,7 +52,7 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __shared__ uint32_t tmem_base_slot;
   __shared__ float xchg[2][kM];          // row maxima / sums of the two compute groups
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row0 = tile * kM;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -80,75 +80,91 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const int nb = p.nb, n_items = 2 * nb, NS = p.stages;
   const int ksteps = (p.d + 15) >> 4;
   const int fmt = p.bf16 ? 1 : 0;
 
   if (warp < 4) {
     reg_dealloc<40>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ------------------------------------------------------------------------------------------- producer
-      mbar_expect_tx(Q_FULL(), (uint32_t)p.nblk * kQBlockBytes);
-      for (int blk = 0; blk < p.nblk; ++blk)
-        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, Q_FULL(), blk * kBlockCols, h, row0, b);
-      int ss = 0;
+      if (elect_one()) {
+        mbar_expect_tx(Q_FULL(), (uint32_t)p.nblk * kQBlockBytes);
+        for (int blk = 0; blk < p.nblk; ++blk)
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, Q_FULL(), blk * kBlockCols, h, row0, b);
+      }
+      int ss = 0, j = 0;
       uint32_t par = 0;
       for (int it = 0; it < n_items; ++it) {
-        const int j = it < nb ? it : it - nb;
         const bool with_v = it >= nb;
         if (it >= NS) mbar_wait(KV_FREE(ss), par ^ 1u);
-        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
-        mbar_expect_tx(KV_FULL(ss), with_v ? stage_bytes : k_bytes);
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
-          if (with_v) tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+        if (elect_one()) {
+          const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
+          mbar_expect_tx(KV_FULL(ss), with_v ? stage_bytes : k_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+            if (with_v) tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+          }
         }
+        __syncwarp();
+        if (++j == nb) j = 0;
         if (++ss == NS) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ----------------------------------------------------------------------------------------- MMA issuer
       const uint32_t idesc_qk = make_idesc(fmt, 0, p.bk, kM);
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dQ0 = smem_desc_sw128(sQ, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(sKV, 16, 1024);                          // stage 0, K-major
+      const uint64_t dV0 = smem_desc_sw128(sKV + k_bytes, kv_block_bytes, 1024);    // stage 0, MN-major
+      const int pv_steps = p.bk / 16;
       mbar_wait(Q_FULL(), 0);
       bool o_started = false;
-      auto mma2 = [&](int it) {                     // O += P(it) V(it); `it` is a pass-2 item
-        const int g = it & 1, ss = it % NS;
-        const uint32_t sV = sKV + ss * stage_bytes + k_bytes;
-        const uint32_t colP = g ? kColS1 : kColS0;
-        for (int ks = 0; ks < p.bk / 16; ++ks) {
-          mma_ts(tmem + kColO, tmem + colP + ks * 8, smem_desc_sw128(sV + ks * 2048u, kv_block_bytes, 1024), idesc_pv,
-                 (o_started || ks > 0) ? 1u : 0u);
-        }
-        o_started = true;
-        tc_commit(KV_FREE(ss));
-      };
+      int ss = 0, ss2 = 0;                          // ring stage of item `it` / of item `it - 2`
+      uint32_t par = 0;
       for (int it = 0; it < n_items; ++it) {
-        const int g = it & 1, ss = it % NS;
+        const int g = it & 1;
         if (it >= 2) {
           // S buffer g was last used by item it-2: its rows have been read (pass 1) / replaced by P (pass 2)
           mbar_wait(P_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
           tc_fence_after();
-          if (it - 2 >= nb) mma2(it - 2);
+          if (it - 2 >= nb) {                       // O += P(it-2) V(it-2)
+            if (elect_one()) {
+              issue_tmem_gemm(tmem + kColO, tmem + (g ? kColS1 : kColS0), desc_advance(dV0, ss2 * stage_bytes), pv_steps,
+                              idesc_pv, o_started);
+              tc_commit(KV_FREE(ss2));
+            }
+            o_started = true;
+          }
+          if (++ss2 == NS) ss2 = 0;
         }
-        mbar_wait(KV_FULL(ss), (uint32_t)(it / NS) & 1u);
+        mbar_wait(KV_FULL(ss), par);
         tc_fence_after();
-        const uint32_t sK = sKV + ss * stage_bytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + (g ? kColS1 : kColS0), smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sK + off * kv_block_bytes + in, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + (g ? kColS1 : kColS0), dQ0, kQBlockBytes, desc_advance(dK0, ss * stage_bytes),
+                            kv_block_bytes, ksteps, idesc_qk);
+          tc_commit(S_READY(g));
+          if (it < nb) tc_commit(KV_FREE(ss));      // pass 1: the block is only needed by this GEMM
         }
-        tc_commit(S_READY(g));
-        if (it < nb) tc_commit(KV_FREE(ss));        // pass 1: the block is only needed by this GEMM
+        __syncwarp();
+        if (++ss == NS) { ss = 0; par ^= 1u; }
       }
-      for (int it = (n_items >= 2 ? n_items - 2 : 0); it < n_items; ++it) {
-        if (it < nb) continue;
-        mbar_wait(P_READY(it & 1), (uint32_t)(it >> 1) & 1u);
-        tc_fence_after();
-        mma2(it);
+      for (int it = n_items - 2; it < n_items; ++it) {       // n_items = 2 nb >= 2
+        if (it >= nb) {
+          mbar_wait(P_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_tmem_gemm(tmem + kColO, tmem + ((it & 1) ? kColS1 : kColS0), desc_advance(dV0, ss2 * stage_bytes),
+                            pv_steps, idesc_pv, o_started);
+            tc_commit(KV_FREE(ss2));
+          }
+          o_started = true;
+        }
+        if (++ss2 == NS) ss2 = 0;
       }
-      tc_commit(O_READY());
+      if (elect_one()) tc_commit(O_READY());
+      __syncwarp();
     }
   } else {
     reg_alloc<232>();
@@ -351,7 +367,7 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   __shared__ __align__(8) uint64_t bars[14];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row0 = tile * kM;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -382,75 +398,86 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const int nb = p.nb, NS = p.stages;
   const int ksteps = (p.d + 15) >> 4;
   const int fmt = p.bf16 ? 1 : 0;
 
   if (warp < 4) {
     reg_dealloc<40>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ------------------------------------------------------------------------------------------- producer
-      mbar_expect_tx(QG_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
-      for (int blk = 0; blk < p.nblk; ++blk) {
-        tma_load_4d(sQ + blk * kQBlockBytes, &map_q, QG_FULL(), blk * kBlockCols, h, row0, b);
-        tma_load_4d(sG + blk * kQBlockBytes, &map_do, QG_FULL(), blk * kBlockCols, h, row0, b);
+      if (elect_one()) {
+        mbar_expect_tx(QG_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, QG_FULL(), blk * kBlockCols, h, row0, b);
+          tma_load_4d(sG + blk * kQBlockBytes, &map_do, QG_FULL(), blk * kBlockCols, h, row0, b);
+        }
       }
       int ss = 0;
       uint32_t par = 0;
       for (int it = 0; it < nb; ++it) {
         if (it >= NS) mbar_wait(KV_FREE(ss), par ^ 1u);
-        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
-        mbar_expect_tx(KV_FULL(ss), stage_bytes);
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
-          tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
+        if (elect_one()) {
+          const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
+          mbar_expect_tx(KV_FULL(ss), stage_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
+            tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, it * kBK, b);
+          }
         }
+        __syncwarp();
         if (++ss == NS) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ----------------------------------------------------------------------------------------- MMA issuer
       const uint32_t idesc_s = make_idesc(fmt, 0, kBK, kM);
       const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dQ0 = smem_desc_sw128(sQ, 16, 1024), dG0 = smem_desc_sw128(sG, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(sKV, 16, 1024), dV0 = smem_desc_sw128(sKV + k_bytes, 16, 1024);   // K-major
+      const uint64_t dKmn0 = smem_desc_sw128(sKV, kv_block_bytes, 1024);                                   // MN-major
       mbar_wait(QG_FULL(), 0);
       bool dq_started = false;
-      auto mma3 = [&](int it) {                     // dQ += dS(it) K(it)
-        const int g = it & 1, ss = it % NS;
-        const uint32_t sK = sKV + ss * stage_bytes;
-        for (int ks = 0; ks < kBK / 16; ++ks)
-          mma_ts(tmem + kColDQ, tmem + colS(g) + ks * 8, smem_desc_sw128(sK + ks * 2048u, kv_block_bytes, 1024),
-                 idesc_dq, (dq_started || ks > 0) ? 1u : 0u);
-        dq_started = true;
-        tc_commit(KV_FREE(ss));
-      };
+      int ss = 0, ss2 = 0;
+      uint32_t par = 0;
       for (int it = 0; it < nb; ++it) {
-        const int g = it & 1, ss = it % NS;
+        const int g = it & 1;
         if (it >= 2) {
           mbar_wait(DS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
           tc_fence_after();
-          mma3(it - 2);
+          if (elect_one()) {                        // dQ += dS(it-2) K(it-2)
+            issue_tmem_gemm(tmem + kColDQ, tmem + colS(g), desc_advance(dKmn0, ss2 * stage_bytes), kBK / 16, idesc_dq,
+                            dq_started);
+            tc_commit(KV_FREE(ss2));
+          }
+          dq_started = true;
+          if (++ss2 == NS) ss2 = 0;
         }
-        mbar_wait(KV_FULL(ss), (uint32_t)(it / NS) & 1u);
+        mbar_wait(KV_FULL(ss), par);
         tc_fence_after();
-        const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + colS(g), smem_desc_sw128(sQ + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sK + off * kv_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + colS(g), dQ0, kQBlockBytes, desc_advance(dK0, ss * stage_bytes), kv_block_bytes, ksteps,
+                            idesc_s);
+          issue_kmajor_gemm(tmem + colS(g) + kBK, dG0, kQBlockBytes, desc_advance(dV0, ss * stage_bytes), kv_block_bytes,
+                            ksteps, idesc_s);
+          tc_commit(SD_READY(g));
         }
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + colS(g) + kBK, smem_desc_sw128(sG + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sV + off * kv_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
-        }
-        tc_commit(SD_READY(g));
+        __syncwarp();
+        if (++ss == NS) { ss = 0; par ^= 1u; }
       }
       for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
         mbar_wait(DS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
-        mma3(it);
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + kColDQ, tmem + colS(it & 1), desc_advance(dKmn0, ss2 * stage_bytes), kBK / 16, idesc_dq,
+                          dq_started);
+          tc_commit(KV_FREE(ss2));
+        }
+        dq_started = true;
+        if (++ss2 == NS) ss2 = 0;
       }
-      tc_commit(DQ_READY());
+      if (elect_one()) tc_commit(DQ_READY());
+      __syncwarp();
     }
   } else {
     reg_alloc<232>();
@@ -539,7 +566,7 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
   __shared__ __align__(16) float xl[2][2][BQ];       // [group][block parity][query]: lse * log2(e)
   __shared__ __align__(16) float xd[2][2][BQ];       //                                D
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int key0 = tile * kM;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -572,78 +599,87 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
   const int nb = p.nb, NS = p.stages;
   const int ksteps = (p.d + 15) >> 4;
   const int fmt = p.bf16 ? 1 : 0;
 
   if (warp < 4) {
     reg_dealloc<40>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ------------------------------------------------------------------------------------------- producer
-      mbar_expect_tx(KV_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
-      for (int blk = 0; blk < p.nblk; ++blk) {
-        tma_load_4d(sK + blk * kQBlockBytes, &map_k, KV_FULL(), blk * kBlockCols, h, key0, b);
-        tma_load_4d(sV + blk * kQBlockBytes, &map_v, KV_FULL(), blk * kBlockCols, h, key0, b);
+      if (elect_one()) {
+        mbar_expect_tx(KV_FULL(), 2u * (uint32_t)p.nblk * kQBlockBytes);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(sK + blk * kQBlockBytes, &map_k, KV_FULL(), blk * kBlockCols, h, key0, b);
+          tma_load_4d(sV + blk * kQBlockBytes, &map_v, KV_FULL(), blk * kBlockCols, h, key0, b);
+        }
       }
       int ss = 0;
       uint32_t par = 0;
       for (int it = 0; it < nb; ++it) {
         if (it >= NS) mbar_wait(QG_FREE(ss), par ^ 1u);
-        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
-        mbar_expect_tx(QG_FULL(ss), stage_bytes);
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(sQi + blk * q_block_bytes, &map_q, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
-          tma_load_4d(sGi + blk * q_block_bytes, &map_do, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
+        if (elect_one()) {
+          const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
+          mbar_expect_tx(QG_FULL(ss), stage_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sQi + blk * q_block_bytes, &map_q, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
+            tma_load_4d(sGi + blk * q_block_bytes, &map_do, QG_FULL(ss), blk * kBlockCols, h, it * BQ, b);
+          }
         }
+        __syncwarp();
         if (++ss == NS) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ----------------------------------------------------------------------------------------- MMA issuer
       const uint32_t idesc_s = make_idesc(fmt, 0, BQ, kM);
       const uint32_t idesc_acc = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dK0 = smem_desc_sw128(sK, 16, 1024), dV0 = smem_desc_sw128(sV, 16, 1024);
+      const uint64_t dQ0 = smem_desc_sw128(sQG, 16, 1024), dG0 = smem_desc_sw128(sQG + q_bytes, 16, 1024);       // K-major
+      const uint64_t dQmn0 = smem_desc_sw128(sQG, q_block_bytes, 1024);                                       // MN-major
+      const uint64_t dGmn0 = smem_desc_sw128(sQG + q_bytes, q_block_bytes, 1024);
       mbar_wait(KV_FULL(), 0);
       bool started = false;
-      auto mma34 = [&](int it) {                    // dV += P^T(it) dO(it);  dK += dS^T(it) Q(it)
-        const int g = it & 1, ss = it % NS;
-        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
-        for (int ks = 0; ks < BQ / 16; ++ks)
-          mma_ts(tmem + kColDV, tmem + colST(g) + ks * 8, smem_desc_sw128(sGi + ks * 2048u, q_block_bytes, 1024),
-                 idesc_acc, (started || ks > 0) ? 1u : 0u);
-        for (int ks = 0; ks < BQ / 16; ++ks)
-          mma_ts(tmem + colDK, tmem + colST(g) + BQ + ks * 8, smem_desc_sw128(sQi + ks * 2048u, q_block_bytes, 1024),
-                 idesc_acc, (started || ks > 0) ? 1u : 0u);
+      int ss = 0, ss2 = 0;
+      uint32_t par = 0;
+      auto mma34 = [&](int g, int st) {             // dV += P^T dO_i;  dK += dS^T Q_i
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + kColDV, tmem + colST(g), desc_advance(dGmn0, st * stage_bytes), BQ / 16, idesc_acc,
+                          started);
+          issue_tmem_gemm(tmem + colDK, tmem + colST(g) + BQ, desc_advance(dQmn0, st * stage_bytes), BQ / 16, idesc_acc,
+                          started);
+          tc_commit(QG_FREE(st));
+        }
         started = true;
-        tc_commit(QG_FREE(ss));
       };
       for (int it = 0; it < nb; ++it) {
-        const int g = it & 1, ss = it % NS;
+        const int g = it & 1;
         if (it >= 2) {
           mbar_wait(PDS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
           tc_fence_after();
-          mma34(it - 2);
+          mma34(g, ss2);
+          if (++ss2 == NS) ss2 = 0;
         }
-        mbar_wait(QG_FULL(ss), (uint32_t)(it / NS) & 1u);
+        mbar_wait(QG_FULL(ss), par);
         tc_fence_after();
-        const uint32_t sQi = sQG + ss * stage_bytes, sGi = sQi + q_bytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + colST(g), smem_desc_sw128(sK + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sQi + off * q_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + colST(g), dK0, kQBlockBytes, desc_advance(dQ0, ss * stage_bytes), q_block_bytes, ksteps,
+                            idesc_s);
+          issue_kmajor_gemm(tmem + colST(g) + BQ, dV0, kQBlockBytes, desc_advance(dG0, ss * stage_bytes), q_block_bytes,
+                            ksteps, idesc_s);
+          tc_commit(SD_READY(g));
         }
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2), in = (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + colST(g) + BQ, smem_desc_sw128(sV + off * kQBlockBytes + in, 16, 1024),
-                 smem_desc_sw128(sGi + off * q_block_bytes + in, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
-        }
-        tc_commit(SD_READY(g));
+        __syncwarp();
+        if (++ss == NS) { ss = 0; par ^= 1u; }
       }
       for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
         mbar_wait(PDS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
-        mma34(it);
+        mma34(it & 1, ss2);
+        if (++ss2 == NS) ss2 = 0;
       }
-      tc_commit(ACC_READY());
+      if (elect_one()) tc_commit(ACC_READY());
+      __syncwarp();
     }
   } else {
     reg_alloc<232>();

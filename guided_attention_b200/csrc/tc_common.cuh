@@ -153,6 +153,40 @@ __device__ __forceinline__ void row_softmax(float* s, uint32_t* packed, int T, f
 }
 
 
+// ---- warp-uniform role helpers ----------------------------------------------------------------------------------
+// The TMA-producer and MMA-issuer roles run as WHOLE warps in warp-uniform control flow and pick one lane with
+// elect.sync for the asynchronous instructions.  A role entered through a divergent `lane == 0` branch makes the
+// compiler wrap every UTCHMMA / UTMALDG in an ELECT / BRA.U.ANY loop and keep descriptors in vector registers
+// (~13 SASS instructions per MMA): the single issuing thread then becomes the critical path of the whole CTA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// start-address field of a shared-memory descriptor advanced by `bytes` (stays inside the 14-bit field: < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
+// D[tmem] = A . B^T with A and B K-major in 64-column blocks of 128-byte swizzled rows; one k-step = 16 columns =
+// 32 bytes inside the row, four k-steps per block.
+__device__ __forceinline__ void issue_kmajor_gemm(uint32_t d_tmem, uint64_t a_desc, uint32_t a_block_bytes, uint64_t b_desc,
+                                                  uint32_t b_block_bytes, int ksteps, uint32_t idesc) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t blk = (uint32_t)ks >> 2, in = ((uint32_t)ks & 3u) * 32u;
+    mma_ss(d_tmem, desc_advance(a_desc, blk * a_block_bytes + in), desc_advance(b_desc, blk * b_block_bytes + in), idesc,
+           ks > 0 ? 1u : 0u);
+  }
+}
+// D[tmem] (+)= A[tmem, packed 16-bit: 8 columns per k-step] . B with B MN-major (k-step = 16 rows of 128 bytes)
+__device__ __forceinline__ void issue_tmem_gemm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, int ksteps, uint32_t idesc,
+                                                bool accumulate) {
+  for (int ks = 0; ks < ksteps; ++ks)
+    mma_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, desc_advance(b_desc, (uint32_t)ks * 2048u), idesc,
+           (accumulate || ks > 0) ? 1u : 0u);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
