@@ -131,18 +131,22 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     for (int c = 0; c < kTpad / 16; ++c) tmem_ld16(lane_addr + kColS + c * 16, s + c * 16);
     tmem_ld_wait();
     float m, sum;
-    uint32_t packed[kTpad / 2];
-    row_softmax(s, packed, p.T, sc, p.bf16 != 0, m, sum);
-    const float inv = 1.f / sum;
+    row_softmax_ilp(s, p.T, sc, m, sum);
+    // P (un-normalised, 16-bit) -> TMEM (A operand of the second GEMM), over the columns S occupied
+#pragma unroll
+    for (int c = 0; c < kTpad / 16; ++c) {
+      uint32_t packed[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) packed[i] = pack16(s[c * 16 + 2 * i], s[c * 16 + 2 * i + 1], p.bf16 != 0);
+      tmem_st8(lane_addr + kColP + c * 8, packed);
+    }
+    const float inv = __fdividef(1.f, sum);
     if (p.acc != nullptr) {
 #pragma unroll
       for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
     }
     const int row = row0 + tid;
-    if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(sum);
-    // P -> TMEM (A operand of the second GEMM), over the columns S occupied
-#pragma unroll
-    for (int c = 0; c < kTpad / 16; ++c) tmem_st8(lane_addr + kColP + c * 8, packed + c * 8);
+    if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = (m * sc + lg2_approx(sum)) * 0.6931471805599453f;
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
@@ -229,20 +233,26 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 
 
 // ============================================================================= K1, persistent pipelined variant
-// The single-shot kernel above is latency-bound per CTA (TMA -> MMA -> softmax -> MMA -> epilogue in sequence, two CTAs
-// per SM).  For launches with enough work per SM this variant keeps ONE persistent CTA per SM and overlaps the stages
-// of consecutive work items with warp specialisation:
+// The single-shot kernel above is latency-bound per CTA (TMA -> MMA -> softmax -> MMA -> epilogue in sequence).  For
+// launches with enough work per SM this variant keeps ONE persistent CTA per SM (512 threads, four warpgroups) and
+// overlaps the stages of consecutive work items:
 //
-//   warp 0          TMA producer     runs up to `smem_stages` items ahead (full / smem_free mbarriers)
-//   warp 1          MMA issuer       MMA1(k) is issued before MMA2(k-1): the softmax of item k-1 overlaps the loads
-//                                    and the first GEMM of item k
-//   warps 4-7       compute group 0  items 0, 2, 4, ...   TMEM stage 0 (columns   0-255: S/P at +0, O at +96)
-//   warps 8-11      compute group 1  items 1, 3, 5, ...   TMEM stage 1 (columns 256-511)
+//   WG0  warps  0-3   epilogue        O (TMEM) * 1/rowsum -> 16-bit -> shared memory (the item's dead Q tile, TMA swizzle)
+//                                     -> TMA store; hands the TMEM O columns and the shared-memory stage back
+//   WG1  warps  4-7   softmax group 0 items 0, 2, 4, ...   TMEM stage 0 (columns   0-255: S/P at +0, O at +96)
+//   WG2  warps  8-11  softmax group 1 items 1, 3, 5, ...   TMEM stage 1 (columns 256-511)
+//   WG3  warp  12     TMA producer    runs up to `smem_stages` items ahead (full / smem_free mbarriers)
+//        warp  13     MMA issuer      MMA1(k) is issued before MMA2(k-1)
 //
-// Work items: flat (b, h, tile) when no maps are kept; with maps a CTA takes whole (b, tile) groups and streams the H
-// heads through the pipeline, so the head-sum of P stays in the two groups' registers and is combined once per group
-// through one shared staging tile, in a fixed order, then written coalesced: deterministic, no atomics, no cluster.
-constexpr int kPipeThreads = 384;
+// A softmax group never waits for the second GEMM or for global stores: its per-item critical path is
+// tcgen05.ld -> max / exp2 / sum -> tcgen05.st.  The O rows leave through the TMA (no per-thread 16-byte stores with
+// a row stride between lanes, which is what saturated the LSU in the first pipelined version: profiles/).
+//
+// Work items: flat (b, tile, h) with h fastest (the heads of one row tile run on neighbouring SMs at the same time, so
+// the 32-byte sectors two heads share are fetched / written once); with maps a CTA takes whole (b, tile) groups and
+// streams the H heads through the pipeline, so the head-sum of P stays in the two groups' registers and is combined
+// once per group through one shared staging tile, in a fixed order, then written coalesced: deterministic, no atomics.
+constexpr int kPipeThreads = 512;
 constexpr int kStageCols = 256;
 constexpr int kGroupThreads = 128;
 
@@ -253,19 +263,64 @@ struct PipeParams {
   int B, H, N, T, d;
   int nblk, npv, bf16;
   int tiles;        // row tiles per (b, h)
-  int units;        // work units: B*tiles (grouped) or B*H*tiles (flat)
+  int units;        // row tiles B*tiles: the work units of the grouped mode, the ranges the flat mode splits
   int grouped;      // 1: a unit is a (b, tile) group of H items
-  int smem_stages;  // 1 or 2
+  int smem_stages;  // 1 .. 4
   float scale;
+};
+
+// Coordinates of the work items of one CTA, advanced incrementally.
+//   grouped (maps kept): units (b, tile) dealt round-robin over the grid, H items (heads) per unit.
+//   flat: the grid is `gridDim.x / H` teams of H CTAs; a team owns a contiguous range of the B * tiles row tiles and CTA
+//         `blockIdx.x % H` of the team streams head h of that range in (b, tile) order.  Consecutive items of a CTA then
+//         share (b, h) -- K and V stay in the shared-memory stage and are not re-loaded -- while the H CTAs of a team
+//         sweep the same rows at the same time, so the 32-byte sectors neighbouring heads share are fetched once.
+struct ItemIter {
+  int unit, b, tile, h;
+  __device__ __forceinline__ void init(const PipeParams& p) {
+    if (p.grouped) {
+      unit = blockIdx.x;
+      h = 0;
+      b = unit / p.tiles;
+      tile = unit - b * p.tiles;
+    } else {
+      h = blockIdx.x % p.H;
+      unit = flat_begin(p);                       // row tile index b * tiles + tile
+      b = unit / p.tiles;
+      tile = unit - b * p.tiles;
+    }
+  }
+  __device__ __forceinline__ void next(const PipeParams& p) {
+    if (p.grouped) {
+      if (++h < p.H) return;
+      h = 0;
+      unit += gridDim.x;
+      b = unit / p.tiles;
+      tile = unit - b * p.tiles;
+    } else {
+      ++unit;
+      if (++tile == p.tiles) { tile = 0; ++b; }
+    }
+  }
+  static __device__ __forceinline__ int flat_begin(const PipeParams& p) {
+    const int teams = gridDim.x / p.H, team = blockIdx.x / p.H;
+    return (int)(((int64_t)p.units * team) / teams);
+  }
+  static __device__ __forceinline__ int flat_count(const PipeParams& p) {
+    const int teams = gridDim.x / p.H, team = blockIdx.x / p.H;
+    return (int)(((int64_t)p.units * (team + 1)) / teams) - (int)(((int64_t)p.units * team) / teams);
+  }
 };
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                              const __grid_constant__ CUtensorMap map_v, const PipeParams p) {
+                              const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                              const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
   // full[4], smem_free[4] (per shared-memory stage); s_ready[2], p_ready[2], o_ready[2], tmem_free[2] (per TMEM stage)
   __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_inv[2][2][kM];      // [TMEM stage][use parity][row]: 1 / rowsum, softmax group -> epilogue
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -281,10 +336,10 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   // number of work units / items this CTA owns (units are dealt round-robin over the grid)
   const int my_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_items = p.grouped ? my_units * p.H : my_units;
+  const int n_items = p.grouped ? my_units * p.H : ItemIter::flat_count(p);
 
   if (tid == 0) {
-    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_o);
     for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(S_READY(s), 1);
@@ -302,43 +357,44 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int fmt = p.bf16 ? 1 : 0;
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
+  const bool bf16 = p.bf16 != 0;
 
-  if (warp < 4) {
-    reg_dealloc<40>();
-    if (warp == 0) {
+  if (warp >= 12) {
+    reg_dealloc<56>();
+    if (warp == 12) {
       // ------------------------------------------------------------------------------------- TMA producer
-      // warp-uniform; coordinates advance incrementally (no divisions in the loop); one elected lane issues
-      int unit = blockIdx.x, h = 0, ss = 0;
-      int b0 = 0, tile0 = 0, hh0 = 0;
-      if (p.grouped) { b0 = unit / p.tiles; tile0 = unit - b0 * p.tiles; }
-      else { tile0 = unit % p.tiles; const int bh = unit / p.tiles; b0 = bh / p.H; hh0 = bh - b0 * p.H; }
+      // K and V of a stage are re-loaded only when the stage's batch element changes (flat mode: same head throughout):
+      // the TMA handles one box row (<= 128 bytes) per few cycles, and at d = 40 the 2 x 80 K/V rows of an item would
+      // otherwise cost more TMA slots than its 128 Q rows.
+      ItemIter it;
+      it.init(p);
+      int kv_tag[4] = {-1, -1, -1, -1};
+      int ss = 0;
       uint32_t par = 0;                                 // parity of the use of stage ss that is about to start
+      const uint32_t q_bytes = (uint32_t)p.nblk * kQBlockBytes;
       for (int k = 0; k < n_items; ++k) {
-        const int b = b0, tile = tile0, hh = p.grouped ? h : hh0;
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
+        const bool with_kv = p.grouped || kv_tag[ss] != it.b;
+        kv_tag[ss] = it.b;
         if (elect_one()) {
           const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
-          mbar_expect_tx(FULL(ss), stage_bytes);
+          mbar_expect_tx(FULL(ss), with_kv ? stage_bytes : q_bytes);
           for (int blk = 0; blk < p.nblk; ++blk) {
-            tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, hh, tile * kM, b);
-            tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, hh, 0, b);
-            tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, hh, 0, b);
+            tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, it.h, it.tile * kM, it.b);
+            if (with_kv) {
+              tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
+              tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
+            }
           }
         }
         __syncwarp();
-        bool next_unit = true;
-        if (p.grouped) { if (++h == p.H) h = 0; else next_unit = false; }
-        if (next_unit) {
-          unit += gridDim.x;
-          if (p.grouped) { b0 = unit / p.tiles; tile0 = unit - b0 * p.tiles; }
-          else { tile0 = unit % p.tiles; const int bh = unit / p.tiles; b0 = bh / p.H; hh0 = bh - b0 * p.H; }
-        }
+        it.next(p);
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1) {
+    } else if (warp == 13) {
       // -------------------------------------------------------------------------------------- MMA issuer
       // tcgen05.mma instructions retire in issue order, so MMA1(k+2) -- which overwrites the S/P columns of its TMEM
-      // stage -- needs no wait on MMA2(k); only the O columns are handed back by the compute group (TMEM_FREE).
+      // stage -- needs no wait on MMA2(k); only the O columns are handed back by the epilogue (TMEM_FREE).
       const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024);
@@ -365,14 +421,13 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           issue_tmem_gemm(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP,
                           desc_advance(dV0, ss * stage_bytes), kTpad / 16, idesc_pv, false);
           tc_commit(O_READY(ts));
-          tc_commit(SMEM_FREE(ss));
         }
         __syncwarp();
       };
       int ss = 0, ss_prev = 0;
       uint32_t par = 0;
       for (int k = 0; k < n_items; ++k) {
-        if (S == 1) {            // one smem stage: the loads of item k can only start once MMA2(k-1) has retired
+        if (S == 1) {            // one smem stage: the loads of item k can only start once the epilogue of k-1 is done
           if (k >= 1) mma2(k - 1, 0);
           mma1(k, 0, (uint32_t)k & 1u);
         } else {
@@ -384,14 +439,58 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       }
       if (n_items >= 1) mma2(n_items - 1, S == 1 ? 0 : ss_prev);
     }
+  } else if (warp < 4) {
+    reg_dealloc<88>();
+    // ---------------------------------------------------------------------------------------- epilogue
+    const int r = (warp << 5) + lane;                 // row of the tile = TMEM lane
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    ItemIter it;
+    it.init(p);
+    int ss = 0;
+    for (int k = 0; k < n_items; ++k) {
+      const int ts = k & 1;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      mbar_wait(O_READY(ts), ph);
+      tc_fence_after();
+      const float inv = s_inv[ts][ph][r];
+      const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage is dead once MMA1 has retired
+      for (int cc = 0; cc < p.npv / 16; ++cc) {
+        float ov[16];
+        tmem_ld16(lane_base + ts * kStageCols + kColO + cc * 16, ov);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
+        st_swizzled_32B(sO + (uint32_t)(cc >> 2) * kQBlockBytes, r, (cc & 3) * 2, w);
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(ts));
+      fence_proxy_async_smem();
+      named_bar_sync(4, kGroupThreads);
+      if (warp == 0) {
+        if (elect_one()) {
+          for (int blk = 0; blk < p.nblk; ++blk)
+            tma_store_4d(&map_o, sO + blk * kQBlockBytes, blk * kBlockCols, it.h, it.tile * kM, it.b);
+          bulk_commit_group();
+          bulk_wait_read0();                          // the stage may be refilled once the store has read it
+          mbar_arrive(SMEM_FREE(ss));
+        }
+        __syncwarp();
+      }
+      it.next(p);
+      if (++ss == S) ss = 0;
+    }
+    if (warp == 0) {
+      if (elect_one()) bulk_wait_all0();
+      __syncwarp();
+    }
   } else {
-    reg_alloc<232>();
-    // ------------------------------------------------------------------------------------ compute groups
+    reg_alloc<184>();
+    // ------------------------------------------------------------------------------------ softmax groups
     const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage; handles items k with k % 2 == g
     const int r = ((warp & 3) << 5) + lane;           // row of the tile = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
     const float sc = p.scale * 1.4426950408889634f;
-    const bool bf16 = p.bf16 != 0;
     float pacc[kTpad];
     if (p.grouped) {
 #pragma unroll
@@ -408,46 +507,35 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
       tmem_ld_wait();
       float m, sum;
-      uint32_t packed[kTpad / 2];
-      row_softmax(s, packed, p.T, sc, bf16, m, sum);
+      row_softmax_ilp(s, p.T, sc, m, sum);
 #pragma unroll
-      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
+      for (int cc = 0; cc < kTpad / 16; ++cc) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) packed[i] = pack16(s[cc * 16 + 2 * i], s[cc * 16 + 2 * i + 1], bf16);
+        tmem_st8(lane_addr + kColP + cc * 8, packed);
+      }
+      const float inv = __fdividef(1.f, sum);
+      s_inv[g][ph][r] = inv;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(P_READY(g));
-      const float inv = 1.f / sum;
       if (p.grouped) {
 #pragma unroll
         for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
       }
-      if (row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(sum);
-
-      mbar_wait(O_READY(g), ph);
-      tc_fence_after();
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
-      for (int cc = 0; cc < p.npv / 16; ++cc) {
-        float ov[16];
-        tmem_ld16(lane_addr + kColO + cc * 16, ov);
-        tmem_ld_wait();
-        if (row < p.N) {
-          uint32_t w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
-          const int col = cc * 16;
-          if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-          if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(TMEM_FREE(g));
+      if (row < p.N)
+        p.lse[((int64_t)b * p.H + h) * p.N + row] = (m * sc + lg2_approx(sum)) * 0.6931471805599453f;
     };
 
+    ItemIter it;
+    it.init(p);
     if (!p.grouped) {
-      // flat items: this group takes every second unit of the CTA
+      if (g == 1) it.next(p);
       for (int k = g; k < n_items; k += 2) {
-        const int unit = blockIdx.x + k * gridDim.x;
-        const int tile = unit % p.tiles, bh = unit / p.tiles, b = bh / p.H;
-        process(k, b, bh - b * p.H, tile);
+        process(k, it.b, it.h, it.tile);
+        it.next(p);
+        it.next(p);
       }
     } else {
       int k = 0;
@@ -645,10 +733,11 @@ cross_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 }
 
 // ============================================================================ K2, persistent pipelined variant
-// Same warp roles as the pipelined forward.  Per item: TMA brings Q, dO, K, V; the MMA warp issues S = QK^T and
-// dP = dO V^T back to back into two TMEM regions; a compute group turns them into dS (16-bit, written over S), the MMA
-// warp issues dQ = dS K (K as the MN-major B operand), the group converts and stores dQ.  dQ has its own TMEM columns
-// when they fit (d <= 80), so the next item's first two GEMMs never wait for an epilogue.
+// Same warpgroup roles as the pipelined forward.  Per item: TMA brings Q, dO, K, V; the MMA warp issues S = QK^T and
+// dP = dO V^T back to back into two TMEM regions; a compute group turns them into dS (16-bit, written over S); the MMA
+// warp issues dQ = dS K (K as the MN-major B operand); the epilogue warpgroup converts dQ, stages it in the item's dead
+// Q tile and hands it to the TMA.  dQ has its own TMEM columns when they fit (d <= 80), so the next item's first two
+// GEMMs never wait for an epilogue.
 struct BwdPipeParams {
   void* d_q;
   const float* lse;
@@ -665,7 +754,7 @@ struct BwdPipeParams {
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                               const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                              const BwdPipeParams p) {
+                              const __grid_constant__ CUtensorMap map_dq, const BwdPipeParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_slot;
@@ -679,11 +768,14 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   auto DS_READY = [&](int s) { return smem_u32(&bars[10 + s]); };
   auto DQ_READY = [&](int s) { return smem_u32(&bars[12 + s]); };
   auto TMEM_FREE = [&](int s) { return smem_u32(&bars[14 + s]); };
-  const int n_items = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // flat work split of the forward kernel: teams of H CTAs own contiguous ranges of the B * tiles row tiles
+  const int teams = gridDim.x / p.H, team = blockIdx.x / p.H, my_h = blockIdx.x % p.H;
+  const int rt0 = (int)(((int64_t)p.units * team) / teams);
+  const int n_items = (int)(((int64_t)p.units * (team + 1)) / teams) - rt0;
   const bool dq_aliased = p.col_dq == kColDP;
 
   if (tid == 0) {
-    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_dq);
     for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(SD_READY(s), 1);
@@ -701,40 +793,47 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int fmt = p.bf16 ? 1 : 0;
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
+  const bool bf16 = p.bf16 != 0;
 
   auto coords = [&](int k, int& b, int& h, int& tile) {
-    const int unit = blockIdx.x + k * gridDim.x;
-    tile = unit % p.tiles;
-    const int bh = unit / p.tiles;
-    b = bh / p.H;
-    h = bh - b * p.H;
+    const int rt = rt0 + k;
+    h = my_h;
+    b = rt / p.tiles;
+    tile = rt - b * p.tiles;
   };
 
-  if (warp < 4) {
-    reg_dealloc<40>();
-    if (warp == 0) {
-      // TMA producer (warp-uniform, one elected lane issues)
+  if (warp >= 12) {
+    reg_dealloc<56>();
+    if (warp == 12) {
+      // TMA producer (warp-uniform, one elected lane issues); K and V are re-loaded only when the stage's batch element
+      // changes (see the forward kernel)
+      int kv_tag[4] = {-1, -1, -1, -1};
       int ss = 0;
       uint32_t par = 0;
+      const uint32_t qg_bytes = 2u * (uint32_t)p.nblk * kQBlockBytes;
       for (int k = 0; k < n_items; ++k) {
         int b, h, tile;
         coords(k, b, h, tile);
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
+        const bool with_kv = kv_tag[ss] != b;
+        kv_tag[ss] = b;
         if (elect_one()) {
           const uint32_t sQ = base + ss * stage_bytes, sG = sQ + p.nblk * kQBlockBytes, sK = sG + p.nblk * kQBlockBytes,
                          sV = sK + p.nblk * kKVBlockBytes;
-          mbar_expect_tx(FULL(ss), stage_bytes);
+          mbar_expect_tx(FULL(ss), with_kv ? stage_bytes : qg_bytes);
           for (int blk = 0; blk < p.nblk; ++blk) {
             tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, h, tile * kM, b);
-            tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, h, 0, b);
             tma_load_4d(sG + blk * kQBlockBytes, &map_do, FULL(ss), blk * kBlockCols, h, tile * kM, b);
-            tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, h, 0, b);
+            if (with_kv) {
+              tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, h, 0, b);
+              tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, h, 0, b);
+            }
           }
         }
         __syncwarp();
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 1) {
+    } else if (warp == 13) {
       // MMA issuer (warp-uniform, one elected lane issues)
       const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
       const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
@@ -767,7 +866,6 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           issue_tmem_gemm(tmem + ts * kStageCols + p.col_dq, tmem + ts * kStageCols + kColP,
                           desc_advance(dKmn0, ss * stage_bytes), kTpad / 16, idesc_dq, false);
           tc_commit(DQ_READY(ts));
-          tc_commit(SMEM_FREE(ss));
         }
         __syncwarp();
       };
@@ -786,13 +884,55 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       }
       if (n_items >= 1) mma3(n_items - 1, S == 1 ? 0 : ss_prev);
     }
+  } else if (warp < 4) {
+    reg_dealloc<88>();
+    // ---------------------------------------------------------------------------------------- epilogue (dQ)
+    const int r = (warp << 5) + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    int ss = 0;
+    for (int k = 0; k < n_items; ++k) {
+      const int ts = k & 1;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      mbar_wait(DQ_READY(ts), ph);
+      tc_fence_after();
+      const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage: dead since S = Q K^T retired
+      for (int cc = 0; cc < p.npv / 16; ++cc) {
+        float ov[16];
+        tmem_ld16(lane_base + ts * kStageCols + p.col_dq + cc * 16, ov);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
+        st_swizzled_32B(sO + (uint32_t)(cc >> 2) * kQBlockBytes, r, (cc & 3) * 2, w);
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(ts));
+      fence_proxy_async_smem();
+      named_bar_sync(4, kGroupThreads);
+      if (warp == 0) {
+        int b, h, tile;
+        coords(k, b, h, tile);
+        if (elect_one()) {
+          for (int blk = 0; blk < p.nblk; ++blk)
+            tma_store_4d(&map_dq, sO + blk * kQBlockBytes, blk * kBlockCols, h, tile * kM, b);
+          bulk_commit_group();
+          bulk_wait_read0();
+          mbar_arrive(SMEM_FREE(ss));
+        }
+        __syncwarp();
+      }
+      if (++ss == S) ss = 0;
+    }
+    if (warp == 0) {
+      if (elect_one()) bulk_wait_all0();
+      __syncwarp();
+    }
   } else {
-    reg_alloc<232>();
+    reg_alloc<184>();
     const int g = (warp - 4) >> 2;
     const int r = ((warp & 3) << 5) + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
     const float sc = p.scale * 1.4426950408889634f;
-    const bool bf16 = p.bf16 != 0;
     for (int k = g; k < n_items; k += 2) {
       int b, h, tile;
       coords(k, b, h, tile);
@@ -827,42 +967,28 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
             if (j < p.T) dp[j] += __ldg(dacc + j);
         }
       }
-      float dsum = 0.f;
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains for rowsum(P o dP)
 #pragma unroll
       for (int j = 0; j < kTpad; ++j) {
         const bool ok = live && (j < kTpad - 16 || j < p.T);
         const float pr = ok ? ex2_approx(fmaf(s[j], sc, -l2)) : 0.f;
         s[j] = pr;
-        dsum = fmaf(pr, dp[j], dsum);
+        d4[j & 3] = fmaf(pr, dp[j], d4[j & 3]);
       }
-      uint32_t packed[kTpad / 2];
+      const float dsum = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-      for (int j = 0; j < kTpad; j += 2)
-        packed[j >> 1] = pack16(s[j] * (dp[j] - dsum) * p.scale, s[j + 1] * (dp[j + 1] - dsum) * p.scale, bf16);
+      for (int cc = 0; cc < kTpad / 16; ++cc) {
+        uint32_t packed[8];
 #pragma unroll
-      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_st8(lane_addr + kColP + cc * 8, packed + cc * 8);
+        for (int i = 0; i < 8; ++i) {
+          const int j = cc * 16 + 2 * i;
+          packed[i] = pack16(s[j] * (dp[j] - dsum) * p.scale, s[j + 1] * (dp[j + 1] - dsum) * p.scale, bf16);
+        }
+        tmem_st8(lane_addr + kColP + cc * 8, packed);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(DS_READY(g));
-
-      mbar_wait(DQ_READY(g), ph);
-      tc_fence_after();
-      uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
-      for (int cc = 0; cc < p.npv / 16; ++cc) {
-        float ov[16];
-        tmem_ld16(lane_addr + p.col_dq + cc * 16, ov);
-        tmem_ld_wait();
-        if (live) {
-          uint32_t w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
-          const int col = cc * 16;
-          if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-          if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(TMEM_FREE(g));
     }
   }
   tc_fence_before();
@@ -898,7 +1024,7 @@ static int pipe_override() {
   return v;
 }
 
-static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdParams& f,
+static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdParams& f, int dtype,
                     cudaStream_t st) {
   PipeParams p;
   p.o = f.o; p.lse = f.lse; p.acc = f.acc;
@@ -906,18 +1032,29 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   p.nblk = f.nblk; p.npv = f.npv; p.bf16 = f.bf16; p.scale = f.scale;
   p.tiles = (f.N + kM - 1) / kM;
   p.grouped = f.acc != nullptr ? 1 : 0;
-  p.units = p.grouped ? f.B * p.tiles : f.B * f.H * p.tiles;
+  p.units = f.B * p.tiles;
+  CUtensorMap mo;
+  int rc;
+  if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, kM)) != GA_OK) return rc;
   const size_t stage = (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 0);
   p.smem_stages = 1;
   for (int n = 4; n >= 2; --n)
-    if (n * stage + extra <= 226 * 1024) { p.smem_stages = n; break; }
+    if (n * stage + extra <= 224 * 1024) { p.smem_stages = n; break; }
   const size_t smem = p.smem_stages * stage + extra;
-  if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
+  if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel), 2, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = p.units < sm_count() ? p.units : sm_count();
-  cross_attn_fwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mk, mv, p);
+  int grid;
+  if (p.grouped) {
+    grid = p.units < sm_count() ? p.units : sm_count();
+  } else {                                   // teams of H CTAs, each team a contiguous range of row tiles
+    if (f.H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention: %d heads", f.H);
+    int teams = sm_count() / f.H;
+    if (teams > p.units) teams = p.units;
+    grid = teams * f.H;
+  }
+  cross_attn_fwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mk, mv, mo, p);
   return check_launch("cross_attn_fwd_tc_pipe");
 }
 
@@ -962,7 +1099,7 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
       if (d > 160) return fail(GA_ERR_UNSUPPORTED, "pipelined tcgen05 cross-attention needs head_dim <= 160");
       use_pipe = true;
     }
-    if (use_pipe) return fwd_pipe(mq, mk, mv, p, st);
+    if (use_pipe) return fwd_pipe(mq, mk, mv, p, dtype, st);
   }
   size_t smem = 1024 + (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   if (acc != nullptr) smem += (size_t)kM * kAccStride * sizeof(float);
@@ -998,7 +1135,7 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
   if ((rc = make_map(&mv, v, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
   const int nblk = (d + kBlockCols - 1) / kBlockCols, npv = (d + 15) & ~15;
   const int tiles = (N + kM - 1) / kM, units = B * H * tiles;
-  bool use_pipe = d <= 160 && units >= 2 * sm_count();
+  bool use_pipe = d <= 160 && units >= 2 * sm_count() && H <= sm_count();
   if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
   if (force_variant == 0) use_pipe = false;
   if (force_variant == 1) {
@@ -1010,18 +1147,23 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
     p.d_q = d_q; p.lse = lse; p.d_acc = d_acc; p.d_acc_bstride = d_acc_bstride; p.d_acc_rstride = d_acc_rstride;
     p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
     p.nblk = nblk; p.npv = npv; p.bf16 = dtype == GA_BF16; p.scale = scale;
-    p.tiles = tiles; p.units = units;
+    p.tiles = tiles; p.units = B * tiles;      // row tiles, split over teams of H CTAs
     p.col_dq = (2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP;
     const size_t stage = (size_t)nblk * 2 * (kQBlockBytes + kKVBlockBytes);
     p.smem_stages = 1;
     for (int n = 4; n >= 2; --n)
-      if (n * stage + 1024 <= 226 * 1024) { p.smem_stages = n; break; }
+      if (n * stage + 1024 <= 224 * 1024) { p.smem_stages = n; break; }
     const size_t smem = p.smem_stages * stage + 1024;
-    if (smem > 226 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined bwd: %zu B of shared memory", smem);
+    if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined bwd: %zu B of shared memory", smem);
+    CUtensorMap mdq;
+    if ((rc = make_map(&mdq, d_q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_pipe_kernel), 3, smem);
     if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = units < sm_count() ? units : sm_count();
-    cross_attn_bwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mg, mk, mv, p);
+    if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);
+    int teams = sm_count() / H;
+    if (teams > p.units) teams = p.units;
+    const int grid = teams * H;
+    cross_attn_bwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mg, mk, mv, mdq, p);
     return check_launch("cross_attn_bwd_tc_pipe");
   }
   BwdParams p;

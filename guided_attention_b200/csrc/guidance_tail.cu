@@ -381,10 +381,43 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   }
   __syncthreads();
 
+  // d loss / d raw-map for the tile's own pixels, every token: the adjoint of the reflect-padded 3x3 filter applied to
+  // the staged values, again once per CTA and spread over all threads (in the per-pixel loop below this used to run
+  // on n_tokens lanes of every warp)
+  float* sdi = sds + p.n_tokens * span;            // [token][pixel of the tile]
+  for (int i = threadIdx.x; i < p.n_tokens * ppc; i += blockDim.x) {
+    const int t = i / ppc, pix = p0 + (i - t * ppc);
+    float dimg = 0.f;
+    if (pix < npix) {
+      const float* ds = sds + t * span - lo;
+      if (p.smooth) {
+        const int y = pix / res, x = pix - y * res;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= res) continue;
+          const float wy = p.w1d[1 - dy] + ((y == 1 && dy == -1) ? p.w1d[0] : 0.f) +
+                           ((y == res - 2 && dy == 1) ? p.w1d[2] : 0.f);
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= res) continue;
+            const float wx = p.w1d[1 - dx] + ((x == 1 && dx == -1) ? p.w1d[0] : 0.f) +
+                             ((x == res - 2 && dx == 1) ? p.w1d[2] : 0.f);
+            dimg = fmaf(wy * wx, ds[yy * res + xx], dimg);
+          }
+        }
+      } else {
+        dimg = ds[pix];
+      }
+    }
+    sdi[i] = dimg;
+  }
+  __syncthreads();
+
   const float k = p.temperature * p.inv_count;
-  const bool vec_in = (tp & 3) == 0 || true;   // 4 rows of tp floats are 4*tp*4 bytes = a multiple of 16 for any tp
-  (void)vec_in;
   const bool vec_out = (d_abar_rstride & 3) == 0;
+  const bool sparse = g_attn_text == nullptr;      // the map gradient is non-zero only in the tracked tokens' columns
   for (int gi = 0; gi < groups_per_warp; ++gi) {
     const int g0 = p0 + (gi * kWarps + warp) * 4;     // first pixel of this warp's group
     if (g0 >= npix) break;
@@ -398,52 +431,29 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
     __syncwarp();
     for (int q = 0; q < 4; ++q) {
       const int pix = g0 + q;
-      const int y = pix / res, x = pix - y * res;
-      // lane t: gradient w.r.t. the raw map of token t at this pixel = adjoint of the reflect-padded 3x3 filter
-      float dimg = 0.f;
-      int my_col = -1;
-      if (lane < p.n_tokens) {
-        my_col = tg[lane].column;
-        const float* ds = sds + lane * span - lo;
-        if (p.smooth) {
-#pragma unroll
-          for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= res) continue;
-            const float wy = p.w1d[1 - dy] + ((y == 1 && dy == -1) ? p.w1d[0] : 0.f) +
-                             ((y == res - 2 && dy == 1) ? p.w1d[2] : 0.f);
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int xx = x + dx;
-              if (xx < 0 || xx >= res) continue;
-              const float wx = p.w1d[1 - dx] + ((x == 1 && dx == -1) ? p.w1d[0] : 0.f) +
-                               ((x == res - 2 && dx == 1) ? p.w1d[2] : 0.f);
-              dimg = fmaf(wy * wx, ds[yy * res + xx], dimg);
-            }
-          }
-        } else {
-          dimg = ds[pix];
-        }
-      }
+      const float* arow = s_in[warp] + q * tp;
       // softmax backward over the text tokens of this pixel: lanes are tokens
       float a[kKPL], da[kKPL], dot = 0.f;
 #pragma unroll
       for (int kk = 0; kk < kKPL; ++kk) {
         const int j = lane + 32 * kk;
         const bool live = j >= p.first && j < p.last;
-        a[kk] = live ? s_in[warp][q * tp + (j - p.first)] : 0.f;
-        da[kk] = (live && g_attn_text != nullptr) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
+        a[kk] = live ? arow[j - p.first] : 0.f;
+        da[kk] = (live && !sparse) ? g_attn_text[(int64_t)pix * tp + (j - p.first)] : 0.f;
       }
-      for (int t = 0; t < p.n_tokens; ++t) {
-        const float gv = __shfl_sync(0xffffffffu, dimg, t);
-        const int j = __shfl_sync(0xffffffffu, my_col, t) + p.first;
+      for (int t = 0; t < p.n_tokens; ++t) {         // smem broadcasts: every lane reads the same words
+        const float gv = sdi[t * ppc + (pix - p0)];
+        const int col = tg[t].column;
+        if (sparse) dot = fmaf(arow[col], gv, dot);   // sum_j a_j da_j has n_tokens terms: no warp reduction
 #pragma unroll
         for (int kk = 0; kk < kKPL; ++kk)
-          if (j == lane + 32 * kk) da[kk] += gv;
+          if (col + p.first == lane + 32 * kk) da[kk] += gv;
       }
+      if (!sparse) {
 #pragma unroll
-      for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
-      dot = warp_sum(dot);
+        for (int kk = 0; kk < kKPL; ++kk) dot = fmaf(a[kk], da[kk], dot);
+        dot = warp_sum(dot);
+      }
 #pragma unroll
       for (int kk = 0; kk < kKPL; ++kk) {
         const int j = lane + 32 * kk;
@@ -678,7 +688,8 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   // small launches: one 4-pixel group per warp (latency); large ones: 4 groups per warp (amortise the halo staging)
   int groups_per_warp = ((int64_t)p.n_samples * npix >= 128 * 1024) ? 4 : 1;
   auto halo_bytes = [&](int gpw) {
-    return (size_t)(p.n_tokens > 0 ? p.n_tokens : 1) * (4 * tail::kWarps * gpw + 2 * (p.res + 1)) * sizeof(float);
+    // staged d loss / d smoothed (tile + halo) and d loss / d raw map (tile), per token
+    return (size_t)(p.n_tokens > 0 ? p.n_tokens : 1) * (2 * 4 * tail::kWarps * gpw + 2 * (p.res + 1)) * sizeof(float);
   };
   if (halo_bytes(groups_per_warp) > 14 * 1024) groups_per_warp = 1;
   const int ppc = 4 * tail::kWarps * groups_per_warp;

@@ -47,6 +47,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Pull a tile into L2 without touching shared memory: lets a producer keep far more HBM requests in flight than its
+// shared-memory ring has stages (the later cp.async.bulk.tensor of the same tile then hits L2).
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -125,34 +132,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Row softmax over up to kTpad keys held by one thread, un-normalised: on return s[j] = exp(scale*(s[j] - max)) for
-// j < T and 0 beyond, packed[] holds the same values as 16-bit pairs (the A operand of the second GEMM), and the row sum
-// is returned through `sum` (the normalisation 1/sum is applied to the fp32 O accumulator and to the map accumulator,
-// not to the 16-bit operand).  Only the last 16 columns are predicated on T: the callers guarantee T > kTpad - 16.
-__device__ __forceinline__ void row_softmax(float* s, uint32_t* packed, int T, float sc, bool bf16, float& m, float& sum) {
-  m = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < kTpad - 16; ++j) m = fmaxf(m, s[j]);
-#pragma unroll
-  for (int j = kTpad - 16; j < kTpad; ++j)
-    if (j < T) m = fmaxf(m, s[j]);
-  const float mo = m * sc;
-  sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < kTpad - 16; ++j) {
-    s[j] = ex2_approx(fmaf(s[j], sc, -mo));
-    sum += s[j];
-  }
-#pragma unroll
-  for (int j = kTpad - 16; j < kTpad; ++j) {
-    s[j] = (j < T) ? ex2_approx(fmaf(s[j], sc, -mo)) : 0.f;
-    sum += s[j];
-  }
-#pragma unroll
-  for (int j = 0; j < kTpad; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
-}
-
-
 // ---- warp-uniform role helpers ----------------------------------------------------------------------------------
 // The TMA-producer and MMA-issuer roles run as WHOLE warps in warp-uniform control flow and pick one lane with
 // elect.sync for the asynchronous instructions.  A role entered through a divergent `lane == 0` branch makes the
@@ -185,6 +164,61 @@ __device__ __forceinline__ void issue_tmem_gemm(uint32_t d_tmem, uint32_t a_tmem
   for (int ks = 0; ks < ksteps; ++ks)
     mma_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, desc_advance(b_desc, (uint32_t)ks * 2048u), idesc,
            (accumulate || ks > 0) ? 1u : 0u);
+}
+
+// ---- TMA stores (shared -> global, bulk async group) ---------------------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk stores issued by this thread have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (globally visible)
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory made visible to the async proxy (TMA) before the store is issued
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One thread's 16 consecutive 16-bit values (32 bytes: two 16-byte chunks) of row `r` written into a [rows x 64-column]
+// block laid out with the 128-byte swizzle the TMA expects: chunk index XOR (row & 7).  `col16` = first column / 8.
+__device__ __forceinline__ void st_swizzled_32B(uint32_t block_base, int r, int chunk, const uint32_t* w) {
+  const uint32_t row_base = block_base + (uint32_t)r * 128u;
+  const uint32_t a0 = row_base + (uint32_t)(((chunk) ^ (r & 7)) << 4);
+  const uint32_t a1 = row_base + (uint32_t)(((chunk + 1) ^ (r & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+// Row softmax with four independent max / sum chains (the serial 80-long chains of `row_softmax` leave a warp stalled on
+// its own dependencies).  On return s[j] = exp2(sc * (s[j] - max)) for j < T and 0 beyond; `sum` is their sum.
+__device__ __forceinline__ void row_softmax_ilp(float* s, int T, float sc, float& m, float& sum) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int j = 0; j < kTpad - 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+#pragma unroll
+  for (int j = kTpad - 16; j < kTpad; ++j)
+    if (j < T) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+  m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  const float mo = m * sc;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < kTpad - 16; ++j) {
+    s[j] = ex2_approx(fmaf(s[j], sc, -mo));
+    a4[j & 3] += s[j];
+  }
+#pragma unroll
+  for (int j = kTpad - 16; j < kTpad; ++j) {
+    s[j] = (j < T) ? ex2_approx(fmaf(s[j], sc, -mo)) : 0.f;
+    a4[j & 3] += s[j];
+  }
+  sum = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+}
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
