@@ -253,6 +253,7 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 // streams the H heads through the pipeline, so the head-sum of P stays in the two groups' registers and is combined
 // once per group through one shared staging tile, in a fixed order, then written coalesced: deterministic, no atomics.
 constexpr int kPipeThreads = 512;
+constexpr int kMaxStages = 6;   // shared-memory ring depth of the pipelined kernels
 constexpr int kStageCols = 256;
 constexpr int kGroupThreads = 128;
 
@@ -265,7 +266,10 @@ struct PipeParams {
   int tiles;        // row tiles per (b, h)
   int units;        // row tiles B*tiles: the work units of the grouped mode, the ranges the flat mode splits
   int grouped;      // 1: a unit is a (b, tile) group of H items
-  int smem_stages;  // 1 .. 4
+  int smem_stages;  // 1 .. kMaxStages
+  int n_sbuf;       // S/P buffers in TMEM: 4 when 4*80 + 2*npv <= 512, else 2
+  int n_obuf;       // O buffers in TMEM: as many as fit behind the S buffers (2 .. 4)
+  int ablate;       // debugging aid (GA_ABLATE): 1 = no O store, 2 = no exponentials, 4 = no Q loads.  WRONG RESULTS.
   float scale;
 };
 
@@ -317,10 +321,11 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
                               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                               const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // full[4], smem_free[4] (per shared-memory stage); s_ready[2], p_ready[2], o_ready[2], tmem_free[2] (per TMEM stage)
-  __shared__ __align__(8) uint64_t bars[16];
+  // full[6], smem_free[6] (per shared-memory stage); s_ready[4], p_ready[4], p_free[4] (per S/P buffer); o_ready[4],
+  // tmem_free[4] (per O buffer)
+  __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_inv[2][2][kM];      // [TMEM stage][use parity][row]: 1 / rowsum, softmax group -> epilogue
+  __shared__ float s_inv[8][kM];         // [item & 7][row]: 1 / rowsum, softmax group -> epilogue
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -328,11 +333,25 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const uint32_t stage_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)p.smem_stages * stage_bytes);
   auto FULL = [&](int s) { return smem_u32(&bars[s]); };
-  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[4 + s]); };
-  auto S_READY = [&](int s) { return smem_u32(&bars[8 + s]); };
-  auto P_READY = [&](int s) { return smem_u32(&bars[10 + s]); };
-  auto O_READY = [&](int s) { return smem_u32(&bars[12 + s]); };
-  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[14 + s]); };
+  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  auto S_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
+  auto P_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
+  auto O_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 8 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 12 + s]); };
+  auto P_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 16 + s]); };
+  // TMEM: nS score buffers of 80 columns (P, packed 16-bit, overwrites the head of its S buffer), then two O buffers.
+  // With four S buffers (d <= 96) a softmax group finds the scores of its NEXT item already computed when it finishes
+  // one: MMA1(k + 2) no longer has to wait for MMA2(k) to consume P(k) out of the same columns -- that round trip
+  // (arrive -> issue -> tensor pipe -> commit -> wake-up, ~1.4 us) used to sit on every group's critical path.
+  // (buffer counts are powers of two: index = k & mask, use parity = (k >> shift) & 1 -- no divisions on the issue path)
+  const int nS = p.n_sbuf, nO = p.n_obuf;
+  const int sMask = nS - 1, oMask = nO - 1, sShift = nS == 4 ? 2 : 1, oShift = nO == 4 ? 2 : 1;
+  auto sIdx = [&](int k) { return k & sMask; };
+  auto oIdx = [&](int k) { return k & oMask; };
+  auto colS = [&](int k) { return (uint32_t)((k & sMask) * kTpad); };
+  auto colO = [&](int k) { return (uint32_t)(nS * kTpad + (k & oMask) * p.npv); };
+  auto sPar = [&](int k) { return (uint32_t)(k >> sShift) & 1u; };
+  auto oPar = [&](int k) { return (uint32_t)(k >> oShift) & 1u; };
 
   // number of work units / items this CTA owns (units are dealt round-robin over the grid)
   const int my_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -340,12 +359,13 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_o);
-    for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 4); }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(S_READY(s), 1);
       mbar_init(P_READY(s), kGroupThreads);
       mbar_init(O_READY(s), 1);
       mbar_init(TMEM_FREE(s), kGroupThreads);
+      mbar_init(P_FREE(s), 1);
     }
     fence_mbar_init();
   }
@@ -368,7 +388,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       // otherwise cost more TMA slots than its 128 Q rows.
       ItemIter it;
       it.init(p);
-      int kv_tag[4] = {-1, -1, -1, -1};
+      int kv_tag[kMaxStages] = {-1, -1, -1, -1, -1, -1};
       int ss = 0;
       uint32_t par = 0;                                 // parity of the use of stage ss that is about to start
       const uint32_t q_bytes = (uint32_t)p.nblk * kQBlockBytes;
@@ -378,9 +398,10 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         kv_tag[ss] = it.b;
         if (elect_one()) {
           const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
-          mbar_expect_tx(FULL(ss), with_kv ? stage_bytes : q_bytes);
+          const bool load_q = !(p.ablate & 4);
+          mbar_expect_tx(FULL(ss), (with_kv ? stage_bytes : q_bytes) - (load_q ? 0u : q_bytes));
           for (int blk = 0; blk < p.nblk; ++blk) {
-            tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, it.h, it.tile * kM, it.b);
+            if (load_q) tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, it.h, it.tile * kM, it.b);
             if (with_kv) {
               tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
               tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
@@ -392,104 +413,115 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
     } else if (warp == 13) {
-      // -------------------------------------------------------------------------------------- MMA issuer
-      // tcgen05.mma instructions retire in issue order, so MMA1(k+2) -- which overwrites the S/P columns of its TMEM
-      // stage -- needs no wait on MMA2(k); only the O columns are handed back by the epilogue (TMEM_FREE).
+      // ------------------------------------------------------------------------------ MMA issuer 1: S = Q K^T
+      // Two issuer warps, one per GEMM: a single thread issuing both was the critical path of the CTA once everything
+      // else overlapped (its ~150 instructions per item take longer than the item's data movement).  Cross-warp
+      // ordering is by completion: MMA1(k) overwrites the columns P(k - nS) lived in, so it waits for P_FREE of that
+      // buffer, which MMA2's commit signals.
       const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
-      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024);
       const uint64_t dK0 = smem_desc_sw128(base + p.nblk * kQBlockBytes, 16, 1024);
-      const uint64_t dV0 = smem_desc_sw128(base + p.nblk * (kQBlockBytes + kKVBlockBytes), kKVBlockBytes, 1024);
-      auto mma1 = [&](int k, int ss, uint32_t par) {
-        const int ts = k & 1;
+      int ss = 0;
+      uint32_t par = 0;
+      for (int k = 0; k < n_items; ++k) {
+        if (k >= nS) mbar_wait(P_FREE(sIdx(k)), sPar(k) ^ 1u);
         mbar_wait(FULL(ss), par);
         tc_fence_after();
         if (elect_one()) {
-          issue_kmajor_gemm(tmem + ts * kStageCols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
+          issue_kmajor_gemm(tmem + colS(k), desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
                             desc_advance(dK0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_qk);
-          tc_commit(S_READY(ts));
+          tc_commit(S_READY(sIdx(k)));
         }
         __syncwarp();
-      };
-      auto mma2 = [&](int k, int ss) {
-        const int ts = k & 1;
-        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        mbar_wait(P_READY(ts), ph);
-        if (k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);      // the epilogue of item k-2 has drained the O columns
+        if (++ss == S) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 14) {
+      // ------------------------------------------------------------------------------ MMA issuer 2: O = P V
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dV0 = smem_desc_sw128(base + p.nblk * (kQBlockBytes + kKVBlockBytes), kKVBlockBytes, 1024);
+      int ss = 0;
+      for (int k = 0; k < n_items; ++k) {
+        mbar_wait(P_READY(sIdx(k)), sPar(k));
+        if (k >= nO) mbar_wait(TMEM_FREE(oIdx(k)), oPar(k) ^ 1u);  // the epilogue of item k-nO has drained this O buffer
         tc_fence_after();
         if (elect_one()) {
-          issue_tmem_gemm(tmem + ts * kStageCols + kColO, tmem + ts * kStageCols + kColP,
-                          desc_advance(dV0, ss * stage_bytes), kTpad / 16, idesc_pv, false);
-          tc_commit(O_READY(ts));
+          issue_tmem_gemm(tmem + colO(k), tmem + colS(k), desc_advance(dV0, ss * stage_bytes), kTpad / 16, idesc_pv,
+                          false);
+          tc_commit(O_READY(oIdx(k)));
+          tc_commit(P_FREE(sIdx(k)));
         }
         __syncwarp();
-      };
-      int ss = 0, ss_prev = 0;
-      uint32_t par = 0;
-      for (int k = 0; k < n_items; ++k) {
-        if (S == 1) {            // one smem stage: the loads of item k can only start once the epilogue of k-1 is done
-          if (k >= 1) mma2(k - 1, 0);
-          mma1(k, 0, (uint32_t)k & 1u);
-        } else {
-          mma1(k, ss, par);
-          if (k >= 1) mma2(k - 1, ss_prev);
-          ss_prev = ss;
-          if (++ss == S) { ss = 0; par ^= 1u; }
-        }
+        if (++ss == S) ss = 0;
       }
-      if (n_items >= 1) mma2(n_items - 1, S == 1 ? 0 : ss_prev);
     }
   } else if (warp < 4) {
     reg_dealloc<88>();
     // ---------------------------------------------------------------------------------------- epilogue
+    // The four warps run independently (no warpgroup barrier): each converts its 32 TMEM lanes, stages them in its
+    // quarter of the tile and issues its own TMA store (box of 32 rows); the stage is handed back to the producer when
+    // all four stores have read it (SMEM_FREE counts 4 arrivals).
     const int r = (warp << 5) + lane;                 // row of the tile = TMEM lane
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     ItemIter it;
     it.init(p);
     int ss = 0;
     for (int k = 0; k < n_items; ++k) {
-      const int ts = k & 1;
-      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-      mbar_wait(O_READY(ts), ph);
+      const int ob = oIdx(k);
+      mbar_wait(O_READY(ob), oPar(k));
       tc_fence_after();
-      const float inv = s_inv[ts][ph][r];
+      const float inv = s_inv[k & 7][r];
       const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage is dead once MMA1 has retired
-      for (int cc = 0; cc < p.npv / 16; ++cc) {
-        float ov[16];
-        tmem_ld16(lane_base + ts * kStageCols + kColO + cc * 16, ov);
-        tmem_ld_wait();
-        uint32_t w[8];
+      for (int c0 = 0; c0 < p.npv / 16 && !(p.ablate & 8); c0 += 4) {    // up to 64 columns per TMEM round trip
+        float ov[64];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
-        st_swizzled_32B(sO + (uint32_t)(cc >> 2) * kQBlockBytes, r, (cc & 3) * 2, w);
+        for (int u = 0; u < 4; ++u)
+          if (c0 + u < p.npv / 16) tmem_ld16(lane_base + colO(k) + (c0 + u) * 16, ov + u * 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < p.npv / 16) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[u * 16 + 2 * i] * inv, ov[u * 16 + 2 * i + 1] * inv, bf16);
+            st_swizzled_32B(sO + (uint32_t)((c0 + u) >> 2) * kQBlockBytes, r, ((c0 + u) & 3) * 2, w);
+          }
+        }
       }
       tc_fence_before();
-      mbar_arrive(TMEM_FREE(ts));
+      mbar_arrive(TMEM_FREE(ob));
       fence_proxy_async_smem();
-      named_bar_sync(4, kGroupThreads);
-      if (warp == 0) {
-        if (elect_one()) {
-          for (int blk = 0; blk < p.nblk; ++blk)
-            tma_store_4d(&map_o, sO + blk * kQBlockBytes, blk * kBlockCols, it.h, it.tile * kM, it.b);
-          bulk_commit_group();
-          bulk_wait_read0();                          // the stage may be refilled once the store has read it
+      __syncwarp();
+      if (elect_one()) {
+        for (int blk = 0; blk < p.nblk && !(p.ablate & 1); ++blk)
+          tma_store_4d(&map_o, sO + blk * kQBlockBytes + (uint32_t)warp * 4096u, blk * kBlockCols, it.h,
+                       it.tile * kM + warp * 32, it.b);
+        bulk_commit_group();
+        // a stage may be refilled once its stores have read it.  Long rings wait for the PREVIOUS item's store only, so
+        // the read of this one overlaps the next item's TMEM loads; short rings cannot afford the one-item delay.
+        if (S < 5) {
+          bulk_wait_read0();
           mbar_arrive(SMEM_FREE(ss));
+        } else if (k >= 1) {
+          bulk_wait_read1();
+          mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
         }
-        __syncwarp();
       }
+      __syncwarp();
       it.next(p);
       if (++ss == S) ss = 0;
     }
-    if (warp == 0) {
-      if (elect_one()) bulk_wait_all0();
-      __syncwarp();
+    if (elect_one()) {
+      bulk_wait_read0();
+      if (n_items >= 1 && S >= 5) mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
+      bulk_wait_all0();
     }
+    __syncwarp();
   } else {
     reg_alloc<184>();
     // ------------------------------------------------------------------------------------ softmax groups
     const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage; handles items k with k % 2 == g
     const int r = ((warp & 3) << 5) + lane;           // row of the tile = TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sc = p.scale * 1.4426950408889634f;
     float pacc[kTpad];
     if (p.grouped) {
@@ -499,27 +531,34 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
     auto process = [&](int k, int b, int h, int tile) {
       const int row = tile * kM + r;
-      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-      mbar_wait(S_READY(g), ph);
+      const uint32_t lane_addr = lane_base + colS(k);
+      mbar_wait(S_READY(sIdx(k)), sPar(k));
       tc_fence_after();
+      if (p.ablate & 16) {                           // hand the buffer straight back
+        s_inv[k & 7][r] = 1.f;
+        tc_fence_before();
+        mbar_arrive(P_READY(sIdx(k)));
+        return;
+      }
       float s[kTpad];
 #pragma unroll
-      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
+      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + cc * 16, s + cc * 16);
       tmem_ld_wait();
       float m, sum;
-      row_softmax_ilp(s, p.T, sc, m, sum);
+      if (p.ablate & 2) { m = 0.f; sum = 1.f; }
+      else row_softmax_ilp(s, p.T, sc, m, sum);
 #pragma unroll
       for (int cc = 0; cc < kTpad / 16; ++cc) {
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) packed[i] = pack16(s[cc * 16 + 2 * i], s[cc * 16 + 2 * i + 1], bf16);
-        tmem_st8(lane_addr + kColP + cc * 8, packed);
+        tmem_st8(lane_addr + cc * 8, packed);
       }
       const float inv = __fdividef(1.f, sum);
-      s_inv[g][ph][r] = inv;
+      s_inv[k & 7][r] = inv;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(P_READY(g));
+      mbar_arrive(P_READY(sIdx(k)));
       if (p.grouped) {
 #pragma unroll
         for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
@@ -756,18 +795,18 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
                               const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                               const __grid_constant__ CUtensorMap map_dq, const BwdPipeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ __align__(8) uint64_t bars[20];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = (uint32_t)p.nblk * 2u * (kQBlockBytes + kKVBlockBytes);
   auto FULL = [&](int s) { return smem_u32(&bars[s]); };
-  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[4 + s]); };
-  auto SD_READY = [&](int s) { return smem_u32(&bars[8 + s]); };
-  auto DS_READY = [&](int s) { return smem_u32(&bars[10 + s]); };
-  auto DQ_READY = [&](int s) { return smem_u32(&bars[12 + s]); };
-  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[14 + s]); };
+  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  auto SD_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
+  auto DS_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 2 + s]); };
+  auto DQ_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 6 + s]); };
   // flat work split of the forward kernel: teams of H CTAs own contiguous ranges of the B * tiles row tiles
   const int teams = gridDim.x / p.H, team = blockIdx.x / p.H, my_h = blockIdx.x % p.H;
   const int rt0 = (int)(((int64_t)p.units * team) / teams);
@@ -776,7 +815,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_dq);
-    for (int s = 0; s < 4; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 4); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(SD_READY(s), 1);
       mbar_init(DS_READY(s), kGroupThreads);
@@ -807,7 +846,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     if (warp == 12) {
       // TMA producer (warp-uniform, one elected lane issues); K and V are re-loaded only when the stage's batch element
       // changes (see the forward kernel)
-      int kv_tag[4] = {-1, -1, -1, -1};
+      int kv_tag[kMaxStages] = {-1, -1, -1, -1, -1, -1};
       int ss = 0;
       uint32_t par = 0;
       const uint32_t qg_bytes = 2u * (uint32_t)p.nblk * kQBlockBytes;
@@ -834,18 +873,23 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
     } else if (warp == 13) {
-      // MMA issuer (warp-uniform, one elected lane issues)
+      // MMA issuer 1: S = Q K^T and dP = dO V^T (two issuer warps, see the forward kernel).  Its outputs overwrite the
+      // columns dS(k-2) lives in (and dQ(k-2) when dQ aliases dP): wait for MMA3(k-2) to complete (DQ_READY) and, if
+      // aliased, for the epilogue of k-2 (TMEM_FREE).
       const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
-      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
       const uint32_t oG = p.nblk * kQBlockBytes, oK = 2u * p.nblk * kQBlockBytes, oV = oK + p.nblk * kKVBlockBytes;
       const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024), dG0 = smem_desc_sw128(base + oG, 16, 1024);
       const uint64_t dK0 = smem_desc_sw128(base + oK, 16, 1024), dV0 = smem_desc_sw128(base + oV, 16, 1024);
-      const uint64_t dKmn0 = smem_desc_sw128(base + oK, kKVBlockBytes, 1024);
-      auto mma12 = [&](int k, int ss, uint32_t par) {
+      int ss = 0;
+      uint32_t par = 0;
+      for (int k = 0; k < n_items; ++k) {
         const int ts = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        if (k >= 2) {
+          mbar_wait(DQ_READY(ts), ph ^ 1u);
+          if (dq_aliased) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
+        }
         mbar_wait(FULL(ss), par);
-        // dQ over dP: the epilogue of item k-2 must have drained those columns before dP(k) is written
-        if (dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), (((uint32_t)(k >> 1)) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           issue_kmajor_gemm(tmem + ts * kStageCols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
@@ -855,8 +899,15 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           tc_commit(SD_READY(ts));
         }
         __syncwarp();
-      };
-      auto mma3 = [&](int k, int ss) {
+        if (++ss == S) { ss = 0; par ^= 1u; }
+      }
+    } else if (warp == 14) {
+      // MMA issuer 2: dQ = dS K
+      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      const uint32_t oK = 2u * p.nblk * kQBlockBytes;
+      const uint64_t dKmn0 = smem_desc_sw128(base + oK, kKVBlockBytes, 1024);
+      int ss = 0;
+      for (int k = 0; k < n_items; ++k) {
         const int ts = k & 1;
         const uint32_t ph = (uint32_t)(k >> 1) & 1u;
         mbar_wait(DS_READY(ts), ph);
@@ -868,25 +919,13 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
           tc_commit(DQ_READY(ts));
         }
         __syncwarp();
-      };
-      int ss = 0, ss_prev = 0;
-      uint32_t par = 0;
-      for (int k = 0; k < n_items; ++k) {
-        if (S == 1) {
-          if (k >= 1) mma3(k - 1, 0);
-          mma12(k, 0, (uint32_t)k & 1u);
-        } else {
-          mma12(k, ss, par);
-          if (k >= 1) mma3(k - 1, ss_prev);
-          ss_prev = ss;
-          if (++ss == S) { ss = 0; par ^= 1u; }
-        }
+        if (++ss == S) ss = 0;
       }
-      if (n_items >= 1) mma3(n_items - 1, S == 1 ? 0 : ss_prev);
     }
   } else if (warp < 4) {
     reg_dealloc<88>();
     // ---------------------------------------------------------------------------------------- epilogue (dQ)
+    // four independent warps, one 32-row TMA store each (see the forward kernel)
     const int r = (warp << 5) + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     int ss = 0;
@@ -896,37 +935,50 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       mbar_wait(DQ_READY(ts), ph);
       tc_fence_after();
       const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage: dead since S = Q K^T retired
-      for (int cc = 0; cc < p.npv / 16; ++cc) {
-        float ov[16];
-        tmem_ld16(lane_base + ts * kStageCols + p.col_dq + cc * 16, ov);
-        tmem_ld_wait();
-        uint32_t w[8];
+      for (int c0 = 0; c0 < p.npv / 16; c0 += 4) {
+        float ov[64];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
-        st_swizzled_32B(sO + (uint32_t)(cc >> 2) * kQBlockBytes, r, (cc & 3) * 2, w);
+        for (int u = 0; u < 4; ++u)
+          if (c0 + u < p.npv / 16) tmem_ld16(lane_base + ts * kStageCols + p.col_dq + (c0 + u) * 16, ov + u * 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < p.npv / 16) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[u * 16 + 2 * i], ov[u * 16 + 2 * i + 1], bf16);
+            st_swizzled_32B(sO + (uint32_t)((c0 + u) >> 2) * kQBlockBytes, r, ((c0 + u) & 3) * 2, w);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(TMEM_FREE(ts));
       fence_proxy_async_smem();
-      named_bar_sync(4, kGroupThreads);
-      if (warp == 0) {
-        int b, h, tile;
-        coords(k, b, h, tile);
-        if (elect_one()) {
-          for (int blk = 0; blk < p.nblk; ++blk)
-            tma_store_4d(&map_dq, sO + blk * kQBlockBytes, blk * kBlockCols, h, tile * kM, b);
-          bulk_commit_group();
+      __syncwarp();
+      int b, h, tile;
+      coords(k, b, h, tile);
+      if (elect_one()) {
+        for (int blk = 0; blk < p.nblk; ++blk)
+          tma_store_4d(&map_dq, sO + blk * kQBlockBytes + (uint32_t)warp * 4096u, blk * kBlockCols, h, tile * kM + warp * 32,
+                       b);
+        bulk_commit_group();
+        if (S < 5) {
           bulk_wait_read0();
           mbar_arrive(SMEM_FREE(ss));
+        } else if (k >= 1) {
+          bulk_wait_read1();
+          mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
         }
-        __syncwarp();
       }
+      __syncwarp();
       if (++ss == S) ss = 0;
     }
-    if (warp == 0) {
-      if (elect_one()) bulk_wait_all0();
-      __syncwarp();
+    if (elect_one()) {
+      bulk_wait_read0();
+      if (n_items >= 1 && S >= 5) mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
+      bulk_wait_all0();
     }
+    __syncwarp();
   } else {
     reg_alloc<184>();
     const int g = (warp - 4) >> 2;
@@ -1033,13 +1085,19 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   p.tiles = (f.N + kM - 1) / kM;
   p.grouped = f.acc != nullptr ? 1 : 0;
   p.units = f.B * p.tiles;
+  p.n_sbuf = (4 * kTpad + 2 * p.npv <= 512) ? 4 : 2;
+  p.n_obuf = (512 - p.n_sbuf * kTpad) / p.npv >= 4 ? 4 : 2;
+  {
+    const char* e = getenv("GA_ABLATE");
+    p.ablate = e != nullptr ? atoi(e) : 0;
+  }
   CUtensorMap mo;
   int rc;
-  if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, kM)) != GA_OK) return rc;
+  if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, 32)) != GA_OK) return rc;   // one store per epilogue warp
   const size_t stage = (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
   const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 0);
   p.smem_stages = 1;
-  for (int n = 4; n >= 2; --n)
+  for (int n = kMaxStages; n >= 2; --n)
     if (n * stage + extra <= 224 * 1024) { p.smem_stages = n; break; }
   const size_t smem = p.smem_stages * stage + extra;
   if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
@@ -1151,12 +1209,12 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
     p.col_dq = (2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP;
     const size_t stage = (size_t)nblk * 2 * (kQBlockBytes + kKVBlockBytes);
     p.smem_stages = 1;
-    for (int n = 4; n >= 2; --n)
+    for (int n = kMaxStages; n >= 2; --n)
       if (n * stage + 1024 <= 224 * 1024) { p.smem_stages = n; break; }
     const size_t smem = p.smem_stages * stage + 1024;
     if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined bwd: %zu B of shared memory", smem);
     CUtensorMap mdq;
-    if ((rc = make_map(&mdq, d_q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
+    if ((rc = make_map(&mdq, d_q, dtype, B, N, H, d, 32)) != GA_OK) return rc;   // one store per epilogue warp
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_pipe_kernel), 3, smem);
     if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);

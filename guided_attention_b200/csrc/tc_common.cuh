@@ -142,6 +142,20 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// warp-uniform non-blocking test (a completed phase stays completed, so "any lane saw it" is the right vote)
+// (test_wait returns at once; try_wait may suspend the thread for an implementation-defined time when the phase is
+// still pending, which would turn a poll over several barriers back into a blocking wait on the first one)
+__device__ __forceinline__ bool mbar_test_uniform(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return __any_sync(0xffffffffu, (int)ok) != 0;
+}
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
@@ -175,6 +189,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the bulk stores issued by this thread have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk store of this thread have finished reading shared memory
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // ... have completed (globally visible)
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory made visible to the async proxy (TMA) before the store is issued
