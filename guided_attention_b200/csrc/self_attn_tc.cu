@@ -28,9 +28,8 @@ constexpr int kM = 128;
 constexpr int kThreads = 384;
 constexpr int kGroupThreads = 128;
 constexpr int kQBlockBytes = kM * 128;
-// TMEM columns: S buffers at 0 and 128 (P overwrites the head of its S buffer), O from 256
-constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
 constexpr int kMaxStages = 4;
+constexpr int kSBuf = 3;       // score buffers in TMEM (P overwrites the head of its S buffer); O follows them
 
 struct FwdParams {
   void* o;
@@ -43,12 +42,30 @@ struct FwdParams {
   float scale;
 };
 
+// position in a ring of `n` buffers + parity of the current use of that buffer
+struct RingPos {
+  int idx;
+  uint32_t par;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) { idx = 0; par ^= 1u; }
+  }
+};
+
+// Forward roles:
+//   warp 0      TMA producer   Q tile once, then a ring of K (pass 1) / K+V (pass 2) blocks
+//   warp 1      MMA issuer 1   S(it) = Q K_j^T into score buffer it % 3
+//   warp 2      MMA issuer 2   O += P(it) V_j for the pass-2 items; its commit also frees the score buffer
+//   warps 4-7   compute group 0, warps 8-11 compute group 1: thread = query row = TMEM lane; the groups own alternate
+//               key blocks and merge their row maxima / sums through shared memory.
+// Three score buffers for two groups: the scores of a group's next block are computed while it works on the current
+// one, and the two issuers are ordered by completion (P_FREE), not by sharing one instruction stream -- with a single
+// issuer warp and two buffers every group waited a full issue -> tensor pipe -> commit round trip per block.
 __global__ void __launch_bounds__(kThreads, 1)
 self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // q_full, o_ready, kv_full[4], kv_free[4], s_ready[2], p_ready[2]
-  __shared__ __align__(8) uint64_t bars[14];
+  // q_full, o_ready, kv_full[4], kv_free[4], s_ready[3], p_ready[3], p_free[3]
+  __shared__ __align__(8) uint64_t bars[19];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float xchg[2][kM];          // row maxima / sums of the two compute groups
 
@@ -65,15 +82,21 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   auto O_READY = [&]() { return smem_u32(&bars[1]); };
   auto KV_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
   auto KV_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
-  auto S_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
-  auto P_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
+  auto S_READY = [&](int i) { return smem_u32(&bars[10 + i]); };
+  auto P_READY = [&](int i) { return smem_u32(&bars[13 + i]); };
+  auto P_FREE = [&](int i) { return smem_u32(&bars[16 + i]); };
+  const uint32_t colO = (uint32_t)(kSBuf * p.bk);
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
     mbar_init(Q_FULL(), 1);
     mbar_init(O_READY(), 1);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(S_READY(g), 1); mbar_init(P_READY(g), kGroupThreads); }
+    for (int i = 0; i < kSBuf; ++i) {
+      mbar_init(S_READY(i), 1);
+      mbar_init(P_READY(i), kGroupThreads);
+      mbar_init(P_FREE(i), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
@@ -94,74 +117,74 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int blk = 0; blk < p.nblk; ++blk)
           tma_load_4d(sQ + blk * kQBlockBytes, &map_q, Q_FULL(), blk * kBlockCols, h, row0, b);
       }
-      int ss = 0, j = 0;
-      uint32_t par = 0;
+      RingPos st = {0, 0};
+      int j = 0;
       for (int it = 0; it < n_items; ++it) {
         const bool with_v = it >= nb;
-        if (it >= NS) mbar_wait(KV_FREE(ss), par ^ 1u);
+        if (it >= NS) mbar_wait(KV_FREE(st.idx), st.par ^ 1u);
         if (elect_one()) {
-          const uint32_t sK = sKV + ss * stage_bytes, sV = sK + k_bytes;
-          mbar_expect_tx(KV_FULL(ss), with_v ? stage_bytes : k_bytes);
+          const uint32_t sK = sKV + st.idx * stage_bytes, sV = sK + k_bytes;
+          mbar_expect_tx(KV_FULL(st.idx), with_v ? stage_bytes : k_bytes);
           for (int blk = 0; blk < p.nblk; ++blk) {
-            tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
-            if (with_v) tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(ss), blk * kBlockCols, h, j * p.bk, b);
+            tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(st.idx), blk * kBlockCols, h, j * p.bk, b);
+            if (with_v) tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(st.idx), blk * kBlockCols, h, j * p.bk, b);
           }
         }
         __syncwarp();
         if (++j == nb) j = 0;
-        if (++ss == NS) { ss = 0; par ^= 1u; }
+        st.advance(NS);
       }
     } else if (warp == 1) {
-      // ----------------------------------------------------------------------------------------- MMA issuer
+      // ----------------------------------------------------------------------------- MMA issuer 1: S = Q K^T
       const uint32_t idesc_qk = make_idesc(fmt, 0, p.bk, kM);
-      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dQ0 = smem_desc_sw128(sQ, 16, 1024);
       const uint64_t dK0 = smem_desc_sw128(sKV, 16, 1024);                          // stage 0, K-major
-      const uint64_t dV0 = smem_desc_sw128(sKV + k_bytes, kv_block_bytes, 1024);    // stage 0, MN-major
-      const int pv_steps = p.bk / 16;
       mbar_wait(Q_FULL(), 0);
-      bool o_started = false;
-      int ss = 0, ss2 = 0;                          // ring stage of item `it` / of item `it - 2`
-      uint32_t par = 0;
+      RingPos st = {0, 0}, sb = {0, 0};
+      uint32_t pfree_par[kSBuf] = {0, 0, 0};       // parity of the next P_FREE completion to consume, per buffer
       for (int it = 0; it < n_items; ++it) {
-        const int g = it & 1;
-        if (it >= 2) {
-          // S buffer g was last used by item it-2: its rows have been read (pass 1) / replaced by P (pass 2)
-          mbar_wait(P_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
-          tc_fence_after();
-          if (it - 2 >= nb) {                       // O += P(it-2) V(it-2)
-            if (elect_one()) {
-              issue_tmem_gemm(tmem + kColO, tmem + (g ? kColS1 : kColS0), desc_advance(dV0, ss2 * stage_bytes), pv_steps,
-                              idesc_pv, o_started);
-              tc_commit(KV_FREE(ss2));
-            }
-            o_started = true;
+        if (it >= kSBuf) {
+          // the buffer's previous item (it - 3): its rows have been read (pass 1) / its P written (pass 2) ...
+          mbar_wait(P_READY(sb.idx), sb.par ^ 1u);
+          if (it - kSBuf >= nb) {                  // ... and consumed by its PV GEMM
+#pragma unroll
+            for (int i = 0; i < kSBuf; ++i)
+              if (i == sb.idx) { mbar_wait(P_FREE(i), pfree_par[i]); pfree_par[i] ^= 1u; }
           }
-          if (++ss2 == NS) ss2 = 0;
         }
-        mbar_wait(KV_FULL(ss), par);
+        mbar_wait(KV_FULL(st.idx), st.par);
         tc_fence_after();
         if (elect_one()) {
-          issue_kmajor_gemm(tmem + (g ? kColS1 : kColS0), dQ0, kQBlockBytes, desc_advance(dK0, ss * stage_bytes),
+          issue_kmajor_gemm(tmem + (uint32_t)(sb.idx * p.bk), dQ0, kQBlockBytes, desc_advance(dK0, st.idx * stage_bytes),
                             kv_block_bytes, ksteps, idesc_qk);
-          tc_commit(S_READY(g));
-          if (it < nb) tc_commit(KV_FREE(ss));      // pass 1: the block is only needed by this GEMM
+          tc_commit(S_READY(sb.idx));
+          if (it < nb) tc_commit(KV_FREE(st.idx));     // pass 1: the block is only needed by this GEMM
         }
         __syncwarp();
-        if (++ss == NS) { ss = 0; par ^= 1u; }
+        st.advance(NS);
+        sb.advance(kSBuf);
       }
-      for (int it = n_items - 2; it < n_items; ++it) {       // n_items = 2 nb >= 2
-        if (it >= nb) {
-          mbar_wait(P_READY(it & 1), (uint32_t)(it >> 1) & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_tmem_gemm(tmem + kColO, tmem + ((it & 1) ? kColS1 : kColS0), desc_advance(dV0, ss2 * stage_bytes),
-                            pv_steps, idesc_pv, o_started);
-            tc_commit(KV_FREE(ss2));
-          }
-          o_started = true;
+    } else if (warp == 2) {
+      // ----------------------------------------------------------------------------- MMA issuer 2: O += P V
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dV0 = smem_desc_sw128(sKV + k_bytes, kv_block_bytes, 1024);    // stage 0, MN-major
+      const int pv_steps = p.bk / 16;
+      // Every item's P_READY is waited for in order, pass-1 items included: a parity wait can only tell "this use" from
+      // "the previous one", so jumping straight to the first pass-2 use of a buffer would sail through a phase that has
+      // not even started.
+      RingPos st = {0, 0}, sb = {0, 0};
+      for (int it = 0; it < n_items; ++it) {
+        mbar_wait(P_READY(sb.idx), sb.par);
+        tc_fence_after();
+        if (it >= nb && elect_one()) {
+          issue_tmem_gemm(tmem + colO, tmem + (uint32_t)(sb.idx * p.bk), desc_advance(dV0, st.idx * stage_bytes), pv_steps,
+                          idesc_pv, it > nb);
+          tc_commit(KV_FREE(st.idx));
+          tc_commit(P_FREE(sb.idx));
         }
-        if (++ss2 == NS) ss2 = 0;
+        __syncwarp();
+        st.advance(NS);
+        sb.advance(kSBuf);
       }
       if (elect_one()) tc_commit(O_READY());
       __syncwarp();
@@ -173,15 +196,16 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int r = ((warp & 3) << 5) + lane;
     const int row = row0 + r;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t colS = g ? kColS1 : kColS0;
     const float sc = p.scale * 1.4426950408889634f;
     const bool bf16 = p.bf16 != 0;
     const int halves = p.bk / 64;                    // S is processed 64 key columns at a time
 
-    // ---- pass 1: running maximum over this group's key blocks
-    float m = -INFINITY;
+    // ---- pass 1: running maximum over this group's key blocks (four independent chains)
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int it = g; it < nb; it += 2) {
-      mbar_wait(S_READY(g), (uint32_t)(it >> 1) & 1u);
+      const int buf = it % kSBuf;
+      const uint32_t colS = (uint32_t)(buf * p.bk);
+      mbar_wait(S_READY(buf), (uint32_t)(it / kSBuf) & 1u);
       tc_fence_after();
       const int key0 = it * p.bk;
       const bool ragged = key0 + p.bk > p.N;
@@ -192,16 +216,17 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tmem_ld_wait();
         if (!ragged) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) m = fmaxf(m, s[j]);
+          for (int j = 0; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 64; ++j)
-            if (key0 + hf * 64 + j < p.N) m = fmaxf(m, s[j]);
+            if (key0 + hf * 64 + j < p.N) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
         }
       }
       tc_fence_before();
-      mbar_arrive(P_READY(g));
+      mbar_arrive(P_READY(buf));
     }
+    float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     xchg[g][r] = m;
     named_bar_sync(1, 2 * kGroupThreads);
     m = fmaxf(xchg[0][r], xchg[1][r]);
@@ -209,9 +234,11 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const float mo = m * sc;
 
     // ---- pass 2: P = exp(scale (S - max)) -> TMEM, row sum on the side
-    float l = 0.f;
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it = nb + ((nb & 1) ^ g); it < n_items; it += 2) {      // items of this group: it & 1 == g
-      mbar_wait(S_READY(g), (uint32_t)(it >> 1) & 1u);
+      const int buf = it % kSBuf;
+      const uint32_t colS = (uint32_t)(buf * p.bk);
+      mbar_wait(S_READY(buf), (uint32_t)(it / kSBuf) & 1u);
       tc_fence_after();
       const int key0 = (it - nb) * p.bk;
       const bool ragged = key0 + p.bk > p.N;
@@ -220,28 +247,31 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + colS + hf * 64 + c * 16, s + c * 16);
         tmem_ld_wait();
-        uint32_t packed[32];
         if (!ragged) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) { s[j] = ex2_approx(fmaf(s[j], sc, -mo)); l += s[j]; }
+          for (int j = 0; j < 64; ++j) { s[j] = ex2_approx(fmaf(s[j], sc, -mo)); l4[j & 3] += s[j]; }
         } else {
 #pragma unroll
           for (int j = 0; j < 64; ++j) {
             s[j] = (key0 + hf * 64 + j < p.N) ? ex2_approx(fmaf(s[j], sc, -mo)) : 0.f;
-            l += s[j];
+            l4[j & 3] += s[j];
           }
         }
-#pragma unroll
-        for (int j = 0; j < 64; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
         // the second half of S must be in registers before P overwrites the head of the buffer: with bk = 128 the P
         // columns of half 0 (0..31) do not overlap the S columns of half 1 (64..127), and half 1's P goes to 32..63
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_st8(lane_base + colS + hf * 32 + c * 8, packed + c * 8);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) packed[i] = pack16(s[c * 16 + 2 * i], s[c * 16 + 2 * i + 1], bf16);
+          tmem_st8(lane_base + colS + hf * 32 + c * 8, packed);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(P_READY(g));
+      mbar_arrive(P_READY(buf));
     }
+    float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
     xchg[g][r] = l;
     named_bar_sync(3, 2 * kGroupThreads);
     l = xchg[0][r] + xchg[1][r];
@@ -254,7 +284,7 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
     for (int cc = g; cc < p.npv / 16; cc += 2) {
       float ov[16];
-      tmem_ld16(lane_base + kColO + cc * 16, ov);
+      tmem_ld16(lane_base + colO + cc * 16, ov);
       tmem_ld_wait();
       if (row < p.N) {
         uint32_t w[8];
@@ -333,6 +363,7 @@ struct BwdParams {
   int nblk, npv, bf16;
   int nb;                      // streamed blocks (keys for dQ, queries for dK/dV)
   int bq;                      // queries per block in the dK/dV kernel (64 or 32)
+  int tstages;                 // TMEM stages of the streamed GEMM outputs: 3 when the accumulators fit behind them
   int stages;
   float scale;
 };
@@ -363,8 +394,8 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                         const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                         const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // qg_full, dq_ready, kv_full[4], kv_free[4], sd_ready[2], ds_ready[2]
-  __shared__ __align__(8) uint64_t bars[14];
+  // qg_full, dq_ready, kv_full[4], kv_free[4], sd_ready[3], ds_ready[3], ds_free[3]
+  __shared__ __align__(8) uint64_t bars[19];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -381,17 +412,25 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   auto DQ_READY = [&]() { return smem_u32(&bars[1]); };
   auto KV_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
   auto KV_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
-  auto SD_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
-  auto DS_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
-  constexpr int kColDQ = 256;
-  auto colS = [](int g) { return g * 128; };          // S at +0 (dS written over it), dP at +64
+  auto SD_READY = [&](int i) { return smem_u32(&bars[10 + i]); };
+  auto DS_READY = [&](int i) { return smem_u32(&bars[13 + i]); };
+  auto DS_FREE = [&](int i) { return smem_u32(&bars[16 + i]); };
+  // TMEM: nT stages of 128 columns (S at +0 -- dS is written over it -- and dP at +64), dQ after them.  Three stages
+  // when dQ fits behind them (d <= 128): see the forward kernel for why two groups want three buffers.
+  const int nT = p.tstages;
+  const uint32_t kColDQ = (uint32_t)(nT * 128);
+  auto colS = [](int i) { return (uint32_t)(i * 128); };
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
     mbar_init(QG_FULL(), 1);
     mbar_init(DQ_READY(), 1);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(SD_READY(g), 1); mbar_init(DS_READY(g), kGroupThreads); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(SD_READY(i), 1);
+      mbar_init(DS_READY(i), kGroupThreads);
+      mbar_init(DS_FREE(i), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
@@ -430,51 +469,44 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         if (++ss == NS) { ss = 0; par ^= 1u; }
       }
     } else if (warp == 1) {
-      // ----------------------------------------------------------------------------------------- MMA issuer
+      // ------------------------------------------------------------------ MMA issuer 1: S = Q K^T, dP = dO V^T
       const uint32_t idesc_s = make_idesc(fmt, 0, kBK, kM);
-      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dQ0 = smem_desc_sw128(sQ, 16, 1024), dG0 = smem_desc_sw128(sG, 16, 1024);
       const uint64_t dK0 = smem_desc_sw128(sKV, 16, 1024), dV0 = smem_desc_sw128(sKV + k_bytes, 16, 1024);   // K-major
-      const uint64_t dKmn0 = smem_desc_sw128(sKV, kv_block_bytes, 1024);                                   // MN-major
       mbar_wait(QG_FULL(), 0);
-      bool dq_started = false;
-      int ss = 0, ss2 = 0;
-      uint32_t par = 0;
+      RingPos st = {0, 0}, tb = {0, 0};
       for (int it = 0; it < nb; ++it) {
-        const int g = it & 1;
-        if (it >= 2) {
-          mbar_wait(DS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
-          tc_fence_after();
-          if (elect_one()) {                        // dQ += dS(it-2) K(it-2)
-            issue_tmem_gemm(tmem + kColDQ, tmem + colS(g), desc_advance(dKmn0, ss2 * stage_bytes), kBK / 16, idesc_dq,
-                            dq_started);
-            tc_commit(KV_FREE(ss2));
-          }
-          dq_started = true;
-          if (++ss2 == NS) ss2 = 0;
-        }
-        mbar_wait(KV_FULL(ss), par);
+        if (it >= nT) mbar_wait(DS_FREE(tb.idx), tb.par ^ 1u);   // dS of the stage's previous block consumed by its GEMM
+        mbar_wait(KV_FULL(st.idx), st.par);
         tc_fence_after();
         if (elect_one()) {
-          issue_kmajor_gemm(tmem + colS(g), dQ0, kQBlockBytes, desc_advance(dK0, ss * stage_bytes), kv_block_bytes, ksteps,
-                            idesc_s);
-          issue_kmajor_gemm(tmem + colS(g) + kBK, dG0, kQBlockBytes, desc_advance(dV0, ss * stage_bytes), kv_block_bytes,
+          issue_kmajor_gemm(tmem + colS(tb.idx), dQ0, kQBlockBytes, desc_advance(dK0, st.idx * stage_bytes), kv_block_bytes,
                             ksteps, idesc_s);
-          tc_commit(SD_READY(g));
+          issue_kmajor_gemm(tmem + colS(tb.idx) + kBK, dG0, kQBlockBytes, desc_advance(dV0, st.idx * stage_bytes),
+                            kv_block_bytes, ksteps, idesc_s);
+          tc_commit(SD_READY(tb.idx));
         }
         __syncwarp();
-        if (++ss == NS) { ss = 0; par ^= 1u; }
+        st.advance(NS);
+        tb.advance(nT);
       }
-      for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
-        mbar_wait(DS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------ MMA issuer 2: dQ += dS K
+      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dKmn0 = smem_desc_sw128(sKV, kv_block_bytes, 1024);                                   // MN-major
+      RingPos st = {0, 0}, tb = {0, 0};
+      for (int it = 0; it < nb; ++it) {
+        mbar_wait(DS_READY(tb.idx), tb.par);
         tc_fence_after();
         if (elect_one()) {
-          issue_tmem_gemm(tmem + kColDQ, tmem + colS(it & 1), desc_advance(dKmn0, ss2 * stage_bytes), kBK / 16, idesc_dq,
-                          dq_started);
-          tc_commit(KV_FREE(ss2));
+          issue_tmem_gemm(tmem + kColDQ, tmem + colS(tb.idx), desc_advance(dKmn0, st.idx * stage_bytes), kBK / 16, idesc_dq,
+                          it > 0);
+          tc_commit(KV_FREE(st.idx));
+          tc_commit(DS_FREE(tb.idx));
         }
-        dq_started = true;
-        if (++ss2 == NS) ss2 = 0;
+        __syncwarp();
+        st.advance(NS);
+        tb.advance(nT);
       }
       if (elect_one()) tc_commit(DQ_READY());
       __syncwarp();
@@ -503,13 +535,14 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     }
 
     for (int it = g; it < nb; it += 2) {
-      mbar_wait(SD_READY(g), (uint32_t)(it >> 1) & 1u);
+      const int ti = nT == 3 ? it % 3 : (it & 1);     // constant divisors: no runtime division per block
+      mbar_wait(SD_READY(ti), (uint32_t)(nT == 3 ? it / 3 : it >> 1) & 1u);
       tc_fence_after();
       float s[kBK], dp[kBK];
 #pragma unroll
       for (int c = 0; c < kBK / 16; ++c) {
-        tmem_ld16(lane_base + colS(g) + c * 16, s + c * 16);
-        tmem_ld16(lane_base + colS(g) + kBK + c * 16, dp + c * 16);
+        tmem_ld16(lane_base + colS(ti) + c * 16, s + c * 16);
+        tmem_ld16(lane_base + colS(ti) + kBK + c * 16, dp + c * 16);
       }
       tmem_ld_wait();
       const int key0 = it * kBK;
@@ -524,10 +557,10 @@ self_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
       for (int j = 0; j < kBK; j += 2) packed[j >> 1] = pack16(s[j], s[j + 1], bf16);
 #pragma unroll
-      for (int c = 0; c < kBK / 16; ++c) tmem_st8(lane_base + colS(g) + c * 8, packed + c * 8);
+      for (int c = 0; c < kBK / 16; ++c) tmem_st8(lane_base + colS(ti) + c * 8, packed + c * 8);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(DS_READY(g));
+      mbar_arrive(DS_READY(ti));
     }
 
     // ---- epilogue: the two groups take alternate 16-column chunks of dQ
@@ -560,8 +593,8 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
                          const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                          const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // kv_full, acc_ready, qg_full[4], qg_free[4], sd_ready[2], pds_ready[2]
-  __shared__ __align__(8) uint64_t bars[14];
+  // kv_full, acc_ready, qg_full[4], qg_free[4], sd_ready[3], pds_ready[3], pds_free[3]
+  __shared__ __align__(8) uint64_t bars[19];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float xl[2][2][BQ];       // [group][block parity][query]: lse * log2(e)
   __shared__ __align__(16) float xd[2][2][BQ];       //                                D
@@ -580,19 +613,25 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
   auto ACC_READY = [&]() { return smem_u32(&bars[1]); };
   auto QG_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
   auto QG_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
-  auto SD_READY = [&](int g) { return smem_u32(&bars[10 + g]); };
-  auto PDS_READY = [&](int g) { return smem_u32(&bars[12 + g]); };
+  auto SD_READY = [&](int i) { return smem_u32(&bars[10 + i]); };
+  auto PDS_READY = [&](int i) { return smem_u32(&bars[13 + i]); };
+  auto PDS_FREE = [&](int i) { return smem_u32(&bars[16 + i]); };
   // TMEM: stage g at g*2*BQ: S^T at +0 (P^T written over it), dP^T at +BQ (dS^T written over it); accumulators after
-  auto colST = [](int g) { return g * 2 * BQ; };
-  constexpr int kColDV = 4 * BQ;
-  const int colDK = kColDV + p.npv;
+  const int nT = p.tstages;                          // 3 when the two accumulators fit behind three stages
+  auto colST = [](int i) { return (uint32_t)(i * 2 * BQ); };
+  const uint32_t kColDV = (uint32_t)(nT * 2 * BQ);
+  const uint32_t colDK = kColDV + (uint32_t)p.npv;
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
     mbar_init(KV_FULL(), 1);
     mbar_init(ACC_READY(), 1);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(QG_FULL(s), 1); mbar_init(QG_FREE(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(SD_READY(g), 1); mbar_init(PDS_READY(g), kGroupThreads); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(SD_READY(i), 1);
+      mbar_init(PDS_READY(i), kGroupThreads);
+      mbar_init(PDS_FREE(i), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
@@ -631,52 +670,47 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
         if (++ss == NS) { ss = 0; par ^= 1u; }
       }
     } else if (warp == 1) {
-      // ----------------------------------------------------------------------------------------- MMA issuer
+      // ------------------------------------------------------------ MMA issuer 1: S^T = K Q_i^T, dP^T = V dO_i^T
       const uint32_t idesc_s = make_idesc(fmt, 0, BQ, kM);
-      const uint32_t idesc_acc = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dK0 = smem_desc_sw128(sK, 16, 1024), dV0 = smem_desc_sw128(sV, 16, 1024);
       const uint64_t dQ0 = smem_desc_sw128(sQG, 16, 1024), dG0 = smem_desc_sw128(sQG + q_bytes, 16, 1024);       // K-major
-      const uint64_t dQmn0 = smem_desc_sw128(sQG, q_block_bytes, 1024);                                       // MN-major
-      const uint64_t dGmn0 = smem_desc_sw128(sQG + q_bytes, q_block_bytes, 1024);
       mbar_wait(KV_FULL(), 0);
-      bool started = false;
-      int ss = 0, ss2 = 0;
-      uint32_t par = 0;
-      auto mma34 = [&](int g, int st) {             // dV += P^T dO_i;  dK += dS^T Q_i
-        if (elect_one()) {
-          issue_tmem_gemm(tmem + kColDV, tmem + colST(g), desc_advance(dGmn0, st * stage_bytes), BQ / 16, idesc_acc,
-                          started);
-          issue_tmem_gemm(tmem + colDK, tmem + colST(g) + BQ, desc_advance(dQmn0, st * stage_bytes), BQ / 16, idesc_acc,
-                          started);
-          tc_commit(QG_FREE(st));
-        }
-        started = true;
-      };
+      RingPos st = {0, 0}, tb = {0, 0};
       for (int it = 0; it < nb; ++it) {
-        const int g = it & 1;
-        if (it >= 2) {
-          mbar_wait(PDS_READY(g), (((uint32_t)(it >> 1)) - 1u) & 1u);
-          tc_fence_after();
-          mma34(g, ss2);
-          if (++ss2 == NS) ss2 = 0;
-        }
-        mbar_wait(QG_FULL(ss), par);
+        if (it >= nT) mbar_wait(PDS_FREE(tb.idx), tb.par ^ 1u);
+        mbar_wait(QG_FULL(st.idx), st.par);
         tc_fence_after();
         if (elect_one()) {
-          issue_kmajor_gemm(tmem + colST(g), dK0, kQBlockBytes, desc_advance(dQ0, ss * stage_bytes), q_block_bytes, ksteps,
-                            idesc_s);
-          issue_kmajor_gemm(tmem + colST(g) + BQ, dV0, kQBlockBytes, desc_advance(dG0, ss * stage_bytes), q_block_bytes,
+          issue_kmajor_gemm(tmem + colST(tb.idx), dK0, kQBlockBytes, desc_advance(dQ0, st.idx * stage_bytes), q_block_bytes,
                             ksteps, idesc_s);
-          tc_commit(SD_READY(g));
+          issue_kmajor_gemm(tmem + colST(tb.idx) + BQ, dV0, kQBlockBytes, desc_advance(dG0, st.idx * stage_bytes),
+                            q_block_bytes, ksteps, idesc_s);
+          tc_commit(SD_READY(tb.idx));
         }
         __syncwarp();
-        if (++ss == NS) { ss = 0; par ^= 1u; }
+        st.advance(NS);
+        tb.advance(nT);
       }
-      for (int it = (nb >= 2 ? nb - 2 : 0); it < nb; ++it) {
-        mbar_wait(PDS_READY(it & 1), (uint32_t)(it >> 1) & 1u);
+    } else if (warp == 2) {
+      // ------------------------------------------------------------ MMA issuer 2: dV += P^T dO_i, dK += dS^T Q_i
+      const uint32_t idesc_acc = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dQmn0 = smem_desc_sw128(sQG, q_block_bytes, 1024);                                       // MN-major
+      const uint64_t dGmn0 = smem_desc_sw128(sQG + q_bytes, q_block_bytes, 1024);
+      RingPos st = {0, 0}, tb = {0, 0};
+      for (int it = 0; it < nb; ++it) {
+        mbar_wait(PDS_READY(tb.idx), tb.par);
         tc_fence_after();
-        mma34(it & 1, ss2);
-        if (++ss2 == NS) ss2 = 0;
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + kColDV, tmem + colST(tb.idx), desc_advance(dGmn0, st.idx * stage_bytes), BQ / 16,
+                          idesc_acc, it > 0);
+          issue_tmem_gemm(tmem + colDK, tmem + colST(tb.idx) + BQ, desc_advance(dQmn0, st.idx * stage_bytes), BQ / 16,
+                          idesc_acc, it > 0);
+          tc_commit(QG_FREE(st.idx));
+          tc_commit(PDS_FREE(tb.idx));
+        }
+        __syncwarp();
+        st.advance(NS);
+        tb.advance(nT);
       }
       if (elect_one()) tc_commit(ACC_READY());
       __syncwarp();
@@ -703,13 +737,14 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
         xd[g][buf][gt] = q < p.N ? __ldg(p.dvec + vbase + q) : 0.f;
       }
       named_bar_sync(1 + g, kGroupThreads);
-      mbar_wait(SD_READY(g), (uint32_t)(it >> 1) & 1u);
+      const int ti = nT == 3 ? it % 3 : (it & 1);     // constant divisors: no runtime division per block
+      mbar_wait(SD_READY(ti), (uint32_t)(nT == 3 ? it / 3 : it >> 1) & 1u);
       tc_fence_after();
       float s[BQ], dp[BQ];
 #pragma unroll
       for (int c = 0; c < BQ / 16; ++c) {
-        tmem_ld16(lane_base + colST(g) + c * 16, s + c * 16);
-        tmem_ld16(lane_base + colST(g) + BQ + c * 16, dp + c * 16);
+        tmem_ld16(lane_base + colST(ti) + c * 16, s + c * 16);
+        tmem_ld16(lane_base + colST(ti) + BQ + c * 16, dp + c * 16);
       }
       tmem_ld_wait();
       uint32_t pk[BQ / 2], dk[BQ / 2];
@@ -732,18 +767,18 @@ self_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid
       }
 #pragma unroll
       for (int c = 0; c < BQ / 16; ++c) {
-        tmem_st8(lane_base + colST(g) + c * 8, pk + c * 8);
-        tmem_st8(lane_base + colST(g) + BQ + c * 8, dk + c * 8);
+        tmem_st8(lane_base + colST(ti) + c * 8, pk + c * 8);
+        tmem_st8(lane_base + colST(ti) + BQ + c * 8, dk + c * 8);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(PDS_READY(g));
+      mbar_arrive(PDS_READY(ti));
     }
 
     // ---- epilogue: group 0 stores dV, group 1 stores dK
     mbar_wait(ACC_READY(), 0);
     tc_fence_after();
-    const int col0 = g == 0 ? kColDV : colDK;
+    const uint32_t col0 = g == 0 ? kColDV : colDK;
     uint8_t* out = reinterpret_cast<uint8_t*>(g == 0 ? p.d_v : p.d_k) +
                    (((int64_t)b * p.N + key) * p.H + h) * (int64_t)p.d * 2;
     for (int cc = 0; cc < p.npv / 16; ++cc) {
@@ -771,6 +806,7 @@ static int launch_dkv(const CUtensorMap& mk, const CUtensorMap& mv, const CUtens
   const size_t kv_bytes = (size_t)2 * p.nblk * kQBlockBytes, stage = (size_t)2 * p.nblk * BQ * 128;
   p.bq = BQ;
   p.nb = (p.N + BQ - 1) / BQ;
+  p.tstages = (3 * 2 * BQ + 2 * p.npv <= 512) ? 3 : 2;
   p.stages = 0;
   for (int n = kMaxStages; n >= 2; --n)
     if (1024 + kv_bytes + n * stage <= 226 * 1024) { p.stages = n; break; }
@@ -797,6 +833,7 @@ int bwd(const void* q, const void* k, const void* v, const void* o, const float*
   // ---- dQ (+ D)
   {
     p.nb = (N + kBK - 1) / kBK;
+    p.tstages = (3 * 128 + p.npv <= 512) ? 3 : 2;
     const size_t qg_bytes = (size_t)2 * p.nblk * kQBlockBytes, stage = (size_t)2 * p.nblk * kBK * 128;
     p.stages = 0;
     for (int n = kMaxStages; n >= 2; --n)
