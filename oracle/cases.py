@@ -28,6 +28,59 @@ PARSE_CASES = [
     'time: a [robot:.6,.3,.4,.55] now',              # a colon before the bracket wins
 ]
 
+def fuzz_parse_cases(n: int = 400, seed: int = 20261018):
+    """Seeded random meta-prompts from the bracket grammar: plain words, [words:x,y] crosshairs,
+    [words:x,y,w,h] boxes, 1/3/5-number payloads, blanks, nested and unmatched brackets, missing colons, non-numeric
+    payloads, glued brackets, repeated sub-prompts and a trailing [CustomLoss:...] -- including the malformed ones: the
+    error TYPE the reference raises is part of the fixture."""
+    import random
+    rng = random.Random(seed)
+    words = ["a", "the", "robot", "vase", "cat", "dog", "bird", "blue", "red", "big", "car", "tree", "on", "and",
+             "of", "grass", "photo", "near", "left", "table"]
+
+    def num():
+        r = rng.random()
+        if r < .08:
+            return rng.choice(["a", "", "1e-1", "-.2", "1.", "0", "1"])
+        v = rng.random()
+        return rng.choice(["%.2f" % v, ("%.2f" % v).lstrip("0") or "0", "%.3f" % v, repr(round(v, 1))])
+
+    def phrase(k):
+        return " ".join(rng.choice(words) for _ in range(k))
+
+    def bracket():
+        body = phrase(rng.randint(1, 3))
+        if rng.random() < .06:
+            body = body + " [" + phrase(1) + "]"                   # nested bracket inside the sub-prompt
+        n_num = rng.choice([2, 2, 4, 4, 4, 4, 1, 3, 5])
+        sep = rng.choice([",", ",", ", ", " ,"])
+        payload = sep.join(num() for _ in range(n_num))
+        colon = ":" if rng.random() > .05 else rng.choice(["", " ", ";"])
+        pad = rng.choice(["", "", " "])
+        close = "]" if rng.random() > .04 else ""
+        return "[" + pad + body + pad + colon + pad + payload + pad + close
+
+    cases = []
+    for _ in range(n):
+        parts = []
+        for _ in range(rng.randint(1, 5)):
+            r = rng.random()
+            if r < .45:
+                parts.append(phrase(rng.randint(1, 3)))
+            else:
+                parts.append(bracket())
+        glue = " " if rng.random() > .08 else ""
+        text = glue.join(parts) if glue == "" else " ".join(parts)
+        if rng.random() < .12:
+            args = ",".join(rng.choice(words) for _ in range(2))
+            name = rng.choice(["toLeftOf", "toLeftOf", "unknown"])
+            text += " [CustomLoss:" + name + " (" + args + ")]"
+        if rng.random() < .05:
+            text = "  " + text + " "
+        cases.append(text)
+    return cases
+
+
 # ------------------------------------------------------------------------------------------------- mask cases
 # (unit box, res, shrink)
 MASK_CASES = [

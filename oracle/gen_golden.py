@@ -72,6 +72,22 @@ def gen_parse(ref):
     return res
 
 
+def gen_parse_fuzz(ref):
+    """Reference behaviour on the seeded random meta-prompts of `cases.fuzz_parse_cases` -> reference_parse_fuzz.json."""
+    from oracle.cases import fuzz_parse_cases
+    res = []
+    for mp in fuzz_parse_cases():
+        try:
+            cfg, tok = _setup(ref, mp)
+            td = {str(k): {"word": v["word"], "kind": v["loss_type"].name, "subprompt": v["subprompt"]}
+                  for k, v in cfg.token_dict.items()}
+            res.append({"meta_prompt": mp, "prompt": cfg.prompt, "meta_info": _meta_to_json(ref, cfg.meta_info),
+                        "custom": {k: v[1] for k, v in cfg.custom_loss.items()}, "token_dict": td})
+        except Exception as e:
+            res.append({"meta_prompt": mp, "error": type(e).__name__})
+    return res
+
+
 def gen_masks(ref):
     out = []
     for box, res, shrink in MASK_CASES:
@@ -202,6 +218,12 @@ def gen_e2e(ref, arrays):
 def main():
     ref = ref_loader.load()
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--skip-parse-fuzz" not in sys.argv:
+        with open(os.path.join(GOLDEN, "reference_parse_fuzz.json"), "w") as f:
+            json.dump({"generator": "oracle/gen_golden.py::gen_parse_fuzz", "cases": gen_parse_fuzz(ref)}, f, indent=0)
+    if "--only-parse-fuzz" in sys.argv:
+        print("parser fuzz fixture written to", GOLDEN)
+        return
     arrays = {}
     doc = {"generator": "oracle/gen_golden.py", "torch": torch.__version__,
            "parse": gen_parse(ref), "masks": gen_masks(ref), "gaussian": gen_gaussian(ref),

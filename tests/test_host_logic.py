@@ -44,6 +44,34 @@ def test_parse_and_token_dict_bit_exact(kat):
         assert list(td.keys()) == list(rec["token_dict"].keys())   # insertion order = output order
 
 
+def test_parser_fuzz_against_reference():
+    """400 seeded random meta-prompts (valid and malformed) through parse_prompt + parseMetaPrompt +
+    get_indices; prompt, meta_info, custom-loss table, token table (values and order) and the exception TYPE all equal
+    what the unmodified reference produced (tests/golden/reference_parse_fuzz.json, oracle/gen_golden.py)."""
+    import json
+    import os
+    from oracle.cases import fuzz_parse_cases
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_parse_fuzz.json")) as f:
+        recs = json.load(f)["cases"]
+    assert [r["meta_prompt"] for r in recs] == fuzz_parse_cases()      # the fixture matches the seeded generator
+    n_err = 0
+    for rec in recs:
+        if "error" in rec:
+            n_err += 1
+            with pytest.raises(Exception) as ei:
+                setup_prompt(rec["meta_prompt"])
+            assert type(ei.value).__name__ == rec["error"], rec["meta_prompt"]
+            continue
+        cfg = setup_prompt(rec["meta_prompt"])
+        assert cfg.prompt == rec["prompt"], rec["meta_prompt"]
+        assert _meta_json(cfg.meta_info) == rec["meta_info"], rec["meta_prompt"]
+        assert {k: v[1] for k, v in cfg.custom_loss.items()} == rec["custom"], rec["meta_prompt"]
+        td = {str(k): {"word": v["word"], "kind": v["loss_type"].name, "subprompt": v["subprompt"]}
+              for k, v in cfg.token_dict.items()}
+        assert td == rec["token_dict"] and list(td.keys()) == list(rec["token_dict"].keys()), rec["meta_prompt"]
+    assert 10 < n_err < len(recs) - 100        # the fuzz exercises both the error paths and the happy path
+
+
 def test_shipped_hyperparameters():
     """effective thresholds and hyper-parameters after overrideConfig."""
     cfg = setup_prompt()
