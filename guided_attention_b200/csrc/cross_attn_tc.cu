@@ -269,6 +269,7 @@ struct PipeParams {
   int smem_stages;  // 1 .. kMaxStages
   int n_sbuf;       // S/P buffers in TMEM: 4 when 4*80 + 2*npv <= 512, else 2
   int n_obuf;       // O buffers in TMEM: as many as fit behind the S buffers (2 .. 4)
+  int direct_store; // 1: epilogue stores from registers (short rings), 0: staged in the dead Q tile + TMA store
   int ablate;       // debugging aid (GA_ABLATE): 1 = no O store, 2 = no exponentials, 4 = no Q loads.  WRONG RESULTS.
   float scale;
 };
@@ -359,7 +360,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_o);
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 4); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), p.direct_store ? 1 : 4); }
     for (int s = 0; s < 4; ++s) {
       mbar_init(S_READY(s), 1);
       mbar_init(P_READY(s), kGroupThreads);
@@ -378,6 +379,9 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
   const bool bf16 = p.bf16 != 0;
+  // Short rings (big tiles: d > 64) cannot afford to hold a stage until the epilogue's TMA store has read it: there the
+  // epilogue stores its rows straight from registers and the stage is released by the second GEMM's commit.
+  const bool direct = p.direct_store != 0;
 
   if (warp >= 12) {
     reg_dealloc<56>();
@@ -449,6 +453,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
                           false);
           tc_commit(O_READY(oIdx(k)));
           tc_commit(P_FREE(sIdx(k)));
+          if (direct) tc_commit(SMEM_FREE(ss));          // nothing is staged in the stage: free it as soon as V is read
         }
         __syncwarp();
         if (++ss == S) ss = 0;
@@ -465,7 +470,34 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     ItemIter it;
     it.init(p);
     int ss = 0;
-    for (int k = 0; k < n_items; ++k) {
+    if (direct) {
+      // short rings: rows go from registers to global memory (the stage was handed back by MMA2's commit)
+      for (int k = 0; k < n_items; ++k) {
+        const int ob = oIdx(k);
+        mbar_wait(O_READY(ob), oPar(k));
+        tc_fence_after();
+        const float inv = s_inv[k & 7][r];
+        const int row = it.tile * kM + r;
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)it.b * p.N + row) * p.H + it.h) * (int64_t)p.d * 2;
+        for (int cc = 0; cc < p.npv / 16; ++cc) {
+          float ov[16];
+          tmem_ld16(lane_base + colO(k) + cc * 16, ov);
+          tmem_ld_wait();
+          if (row < p.N) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i] * inv, ov[2 * i + 1] * inv, bf16);
+            const int col = cc * 16;
+            if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(TMEM_FREE(ob));
+        it.next(p);
+      }
+    }
+    for (int k = 0; k < n_items && !direct; ++k) {
       const int ob = oIdx(k);
       mbar_wait(O_READY(ob), oPar(k));
       tc_fence_after();
@@ -510,7 +542,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       it.next(p);
       if (++ss == S) ss = 0;
     }
-    if (elect_one()) {
+    if (!direct && elect_one()) {
       bulk_wait_read0();
       if (n_items >= 1 && S >= 5) mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
       bulk_wait_all0();
@@ -787,6 +819,8 @@ struct BwdPipeParams {
   int nblk, npv, bf16;
   int tiles, units, smem_stages;
   int col_dq;          // TMEM column of dQ inside a stage: 160 (own columns) or 80 (over dP)
+  int tstages;         // TMEM stages: 3 (160 columns each, dQ over dP) when npv <= 80, else 2 (256 columns each)
+  int direct_store;    // 1: dQ rows stored from registers (short rings), 0: staged + TMA store
   float scale;
 };
 
@@ -795,7 +829,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
                               const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                               const __grid_constant__ CUtensorMap map_dq, const BwdPipeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ __align__(8) uint64_t bars[24];   // full[6], smem_free[6], then sd_ready / ds_ready / dq_ready / tmem_free x 3
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -804,9 +838,16 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   auto FULL = [&](int s) { return smem_u32(&bars[s]); };
   auto SMEM_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   auto SD_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
-  auto DS_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 2 + s]); };
-  auto DQ_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
-  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 6 + s]); };
+  auto DS_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 3 + s]); };
+  auto DQ_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 6 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 9 + s]); };
+  // TMEM stages: nT = 3 stages of 160 columns (S | dP, dQ over dP) when dQ fits in dP's 80 columns (d <= 80), else two
+  // stages of 256 columns.  With three stages a compute group finds the GEMM outputs of its next item ready when it
+  // finishes one (see the forward kernel).
+  const int nT = p.tstages;
+  const uint32_t stage_cols = nT == 3 ? 160u : (uint32_t)kStageCols;
+  auto tIdx = [&](int k) { return nT == 3 ? k % 3 : (k & 1); };
+  auto tPar = [&](int k) { return (uint32_t)(nT == 3 ? k / 3 : k >> 1) & 1u; };
   // flat work split of the forward kernel: teams of H CTAs own contiguous ranges of the B * tiles row tiles
   const int teams = gridDim.x / p.H, team = blockIdx.x / p.H, my_h = blockIdx.x % p.H;
   const int rt0 = (int)(((int64_t)p.units * team) / teams);
@@ -815,8 +856,8 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_dq);
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), 4); }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), p.direct_store ? 1 : 4); }
+    for (int s = 0; s < 3; ++s) {
       mbar_init(SD_READY(s), 1);
       mbar_init(DS_READY(s), kGroupThreads);
       mbar_init(DQ_READY(s), 1);
@@ -833,6 +874,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int ksteps = (p.d + 15) >> 4;
   const int S = p.smem_stages;
   const bool bf16 = p.bf16 != 0;
+  const bool direct = p.direct_store != 0;          // see the forward kernel
 
   auto coords = [&](int k, int& b, int& h, int& tile) {
     const int rt = rt0 + k;
@@ -883,18 +925,18 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       int ss = 0;
       uint32_t par = 0;
       for (int k = 0; k < n_items; ++k) {
-        const int ts = k & 1;
-        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        if (k >= 2) {
+        const int ts = tIdx(k);
+        const uint32_t ph = tPar(k);
+        if (k >= nT) {
           mbar_wait(DQ_READY(ts), ph ^ 1u);
           if (dq_aliased) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
         }
         mbar_wait(FULL(ss), par);
         tc_fence_after();
         if (elect_one()) {
-          issue_kmajor_gemm(tmem + ts * kStageCols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
+          issue_kmajor_gemm(tmem + ts * stage_cols + kColS, desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
                             desc_advance(dK0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_nt);
-          issue_kmajor_gemm(tmem + ts * kStageCols + kColDP, desc_advance(dG0, ss * stage_bytes), kQBlockBytes,
+          issue_kmajor_gemm(tmem + ts * stage_cols + kColDP, desc_advance(dG0, ss * stage_bytes), kQBlockBytes,
                             desc_advance(dV0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_nt);
           tc_commit(SD_READY(ts));
         }
@@ -908,15 +950,16 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       const uint64_t dKmn0 = smem_desc_sw128(base + oK, kKVBlockBytes, 1024);
       int ss = 0;
       for (int k = 0; k < n_items; ++k) {
-        const int ts = k & 1;
-        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        const int ts = tIdx(k);
+        const uint32_t ph = tPar(k);
         mbar_wait(DS_READY(ts), ph);
-        if (!dq_aliased && k >= 2) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
+        if (!dq_aliased && k >= nT) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
         tc_fence_after();
         if (elect_one()) {
-          issue_tmem_gemm(tmem + ts * kStageCols + p.col_dq, tmem + ts * kStageCols + kColP,
+          issue_tmem_gemm(tmem + ts * stage_cols + p.col_dq, tmem + ts * stage_cols + kColP,
                           desc_advance(dKmn0, ss * stage_bytes), kTpad / 16, idesc_dq, false);
           tc_commit(DQ_READY(ts));
+          if (direct) tc_commit(SMEM_FREE(ss));
         }
         __syncwarp();
         if (++ss == S) ss = 0;
@@ -929,9 +972,36 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     const int r = (warp << 5) + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     int ss = 0;
-    for (int k = 0; k < n_items; ++k) {
-      const int ts = k & 1;
-      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+    if (direct) {
+      // short rings: rows go from registers to global memory (the stage was handed back by MMA3's commit)
+      for (int k = 0; k < n_items; ++k) {
+        const int ts = tIdx(k);
+        mbar_wait(DQ_READY(ts), tPar(k));
+        tc_fence_after();
+        int b, h, tile;
+        coords(k, b, h, tile);
+        const int row = tile * kM + r;
+        uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+        for (int cc = 0; cc < p.npv / 16; ++cc) {
+          float ov[16];
+          tmem_ld16(lane_base + ts * stage_cols + p.col_dq + cc * 16, ov);
+          tmem_ld_wait();
+          if (row < p.N) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[2 * i], ov[2 * i + 1], bf16);
+            const int col = cc * 16;
+            if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(TMEM_FREE(ts));
+      }
+    }
+    for (int k = 0; k < n_items && !direct; ++k) {
+      const int ts = tIdx(k);
+      const uint32_t ph = tPar(k);
       mbar_wait(DQ_READY(ts), ph);
       tc_fence_after();
       const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage: dead since S = Q K^T retired
@@ -939,7 +1009,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         float ov[64];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (c0 + u < p.npv / 16) tmem_ld16(lane_base + ts * kStageCols + p.col_dq + (c0 + u) * 16, ov + u * 16);
+          if (c0 + u < p.npv / 16) tmem_ld16(lane_base + ts * stage_cols + p.col_dq + (c0 + u) * 16, ov + u * 16);
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -973,7 +1043,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       __syncwarp();
       if (++ss == S) ss = 0;
     }
-    if (elect_one()) {
+    if (!direct && elect_one()) {
       bulk_wait_read0();
       if (n_items >= 1 && S >= 5) mbar_arrive(SMEM_FREE(ss == 0 ? S - 1 : ss - 1));
       bulk_wait_all0();
@@ -983,19 +1053,21 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     reg_alloc<184>();
     const int g = (warp - 4) >> 2;
     const int r = ((warp & 3) << 5) + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kStageCols;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sc = p.scale * 1.4426950408889634f;
     for (int k = g; k < n_items; k += 2) {
       int b, h, tile;
       coords(k, b, h, tile);
       const int row = tile * kM + r;
       const bool live = row < p.N;
-      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      const int ts = tIdx(k);
+      const uint32_t ph = tPar(k);
+      const uint32_t lane_addr = lane_base + ts * stage_cols;
       // issue the row's LSE load before waiting for the GEMMs
       const float l2 = live ? __ldg(p.lse + ((int64_t)b * p.H + h) * p.N + row) * 1.4426950408889634f : 0.f;
       const float* dacc = (p.d_acc != nullptr && live)
                               ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.d_acc_rstride : nullptr;
-      mbar_wait(SD_READY(g), ph);
+      mbar_wait(SD_READY(ts), ph);
       tc_fence_after();
       float s[kTpad], dp[kTpad];
 #pragma unroll
@@ -1040,7 +1112,7 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(DS_READY(g));
+      mbar_arrive(DS_READY(ts));
     }
   }
   tc_fence_before();
@@ -1101,6 +1173,7 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     if (n * stage + extra <= 224 * 1024) { p.smem_stages = n; break; }
   const size_t smem = p.smem_stages * stage + extra;
   if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
+  p.direct_store = p.smem_stages < 4 ? 1 : 0;
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel), 2, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid;
@@ -1206,13 +1279,15 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
     p.B = B; p.H = H; p.N = N; p.T = T; p.d = d;
     p.nblk = nblk; p.npv = npv; p.bf16 = dtype == GA_BF16; p.scale = scale;
     p.tiles = tiles; p.units = B * tiles;      // row tiles, split over teams of H CTAs
-    p.col_dq = (2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP;
+    p.tstages = npv <= kTpad ? 3 : 2;
+    p.col_dq = p.tstages == 3 ? kColDP : ((2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP);
     const size_t stage = (size_t)nblk * 2 * (kQBlockBytes + kKVBlockBytes);
     p.smem_stages = 1;
     for (int n = kMaxStages; n >= 2; --n)
       if (n * stage + 1024 <= 224 * 1024) { p.smem_stages = n; break; }
     const size_t smem = p.smem_stages * stage + 1024;
     if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined bwd: %zu B of shared memory", smem);
+    p.direct_store = (p.smem_stages == 2 || p.smem_stages == 3) ? 1 : 0;   // measured: staged wins again at 1 stage
     CUtensorMap mdq;
     if ((rc = make_map(&mdq, d_q, dtype, B, N, H, d, 32)) != GA_OK) return rc;   // one store per epilogue warp
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_pipe_kernel), 3, smem);
