@@ -25,7 +25,7 @@ import torch
 from . import _cabi as abi
 from . import helpers, ops
 from . import shared_state as state
-from .ptp_utils import AttentionStore, HeadSummedMaps, aggregate_attention, select_maps
+from .ptp_utils import AttentionStore, HeadSummedMaps, TextKVCache, aggregate_attention, select_maps
 from .substrate import DDIMScheduler, StableDiffusionPipelineBase, StableDiffusionPipelineOutput
 
 AT = helpers.AnnotationType
@@ -56,6 +56,12 @@ class _StepGraphs:
         self.embeds = prompt_embeds.detach().clone()
         self.graphs, self.outputs, self.launches, self.replays = {}, {}, {}, {}
         self.pool = None
+        # text K/V projections are computed once per embedding buffer instead of once per UNet pass (ptp_utils.TextKVCache)
+        self.text_kv = TextKVCache()
+
+    def set_embeds(self, prompt_embeds):
+        self.embeds.copy_(prompt_embeds)
+        self.text_kv.refresh()
 
     # -- the three programs ---------------------------------------------------------------------------------------
     def _prog_eval(self):
@@ -116,6 +122,7 @@ class _StepGraphs:
     def run(self, name, latents, t, step_size=None, coeffs=None):
         """Copies the inputs into the static buffers and replays `name`; returns (static outputs, new latents | None).
         The static outputs are overwritten by the next replay of the same program."""
+        self.store.text_kv = self.text_kv
         g = self._graph(name)
         self.lat.copy_(latents)
         self.t.fill_(int(t))
@@ -149,6 +156,7 @@ class _BatchGraphs:
         self.t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.step = torch.zeros(S, 1, 1, 1, dtype=torch.float32, device=dev)
         self.coef = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.text_kv = TextKVCache()
         self.set_embeds(prompt_embeds)
         self.graphs, self.outputs, self.launches, self.replays = {}, {}, {}, {}
         self.pool = None
@@ -162,6 +170,7 @@ class _BatchGraphs:
             self.both.copy_(torch.cat([unc, cond]))
         else:
             self.cond, self.both = cond, torch.cat([unc, cond])
+        self.text_kv.refresh()
 
     def _loss(self):
         kw = self.loss_kw
@@ -208,6 +217,7 @@ class _BatchGraphs:
     _graph = _StepGraphs._graph
 
     def run(self, name, latents, t, step_sizes=None, coeffs=None):
+        self.store.text_kv = self.text_kv
         self.lat.copy_(latents)
         self.t.fill_(int(t))
         if step_sizes is not None:
@@ -571,7 +581,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
             self._graphs_cache = (key, _StepGraphs(self, attention_store, loss_kw, prompt_embeds, guidance_scale,
                                                    latents))
         G = self._graphs_cache[1]
-        G.embeds.copy_(prompt_embeds)
+        G.set_embeds(prompt_embeds)
         return G
 
     def _denoise_graphed(self, G, latents, timesteps, thresholds, scale_range, scale_factor, recurse_steps,
@@ -830,6 +840,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         graphed = (self.use_cuda_graphs and latents.is_cuda and state.config.diagnostic_level == 0
                    and do_classifier_free_guidance and latents.shape[0] == 1
                    and not state.curHyperParams.get("use_optimizer", False) and cross_attention_kwargs is None)
+        attention_store.text_kv = None      # the eager loop does not own the embedding buffers: no K/V caching
         if graphed:
             G = self._step_graphs(attention_store, loss_kw, prompt_embeds, guidance_scale, latents)
             latents = self._denoise_graphed(G, latents, timesteps, thresholds, scale_range, scale_factor,

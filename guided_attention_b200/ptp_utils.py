@@ -79,8 +79,7 @@ class AttendExciteCrossAttnProcessor:
             if stop and state.cur_time_step_iter is not None and state.cur_time_step_iter < stop:
                 raise NotImplementedError("paint-with-words score bias (reference utils/ptp_utils.py:113-138) is not "
                                           "implemented in the fused kernel yet (off by default in the reference)")
-            key = attn.to_k(encoder_hidden_states)
-            value = attn.to_v(encoder_hidden_states)
+            key, value = self._text_kv(attn, encoder_hidden_states)
             keep = self.attnstore.wants_maps(sequence_length) if hasattr(self.attnstore, "wants_maps") \
                 else sequence_length <= 32 ** 2
             out, acc = ops.cross_attention(query, key, value, attn.heads, attn.scale, want_acc=keep)
@@ -117,6 +116,45 @@ class AttendExciteCrossAttnProcessor:
         hidden_states = attn.to_out[0](hidden_states)
         hidden_states = attn.to_out[1](hidden_states)
         return hidden_states
+
+
+def _text_kv_method(self, attn, encoder_hidden_states):
+    """K and V of a cross-attention layer.  They depend on the text embeddings and the layer's weights only, yet the
+    reference recomputes them in every one of the ~500 UNet passes of an image (utils/ptp_utils.py:72-75).  When the
+    caller owns the embedding buffer for the lifetime of the run and says so by installing `controller.text_kv`
+    (`TextKVCache`; the pipeline's CUDA-graph programs do, the eager path does not), the projections are computed once
+    per (layer, buffer) and refreshed in place when the buffer's contents change."""
+    cache = getattr(self.attnstore, "text_kv", None)
+    if cache is None or encoder_hidden_states.requires_grad or torch.is_grad_enabled() and (
+            attn.to_k.weight.requires_grad or attn.to_v.weight.requires_grad):
+        return attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)
+    return cache.get(attn, encoder_hidden_states)
+
+
+AttendExciteCrossAttnProcessor._text_kv = _text_kv_method
+
+
+class TextKVCache:
+    """(layer, embedding buffer) -> (K, V).  Entries keep the tensors they were computed from, so `refresh()` can
+    recompute them IN PLACE after the owner overwrote the buffer (captured CUDA graphs keep reading the same memory)."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, attn, ehs):
+        key = (id(attn), ehs.data_ptr(), tuple(ehs.shape), ehs.dtype)
+        e = self.entries.get(key)
+        if e is None:
+            with torch.no_grad():
+                e = (attn, ehs, attn.to_k(ehs), attn.to_v(ehs))
+            self.entries[key] = e
+        return e[2], e[3]
+
+    @torch.no_grad()
+    def refresh(self):
+        for attn, ehs, k, v in self.entries.values():
+            k.copy_(attn.to_k(ehs))
+            v.copy_(attn.to_v(ehs))
 
 
 class _ShapeOnly:

@@ -665,6 +665,32 @@ def test_cuda_graph_image_matches_eager_image():
     assert passes["cfg"] >= case["steps"] and passes["update"] > 0
 
 
+def test_text_kv_cache_follows_the_embeddings():
+    """The graph programs compute the text K/V projections once per embedding buffer (ptp_utils.TextKVCache) instead of
+    once per UNet pass; when the next call brings different embeddings the cached projections are refreshed in place and
+    the replayed graphs see them: graphed(embeds B) == eager(embeds B), and differs from graphed(embeds A)."""
+    pipe, store, cfg, embeds, case = _graph_test_pipe(torch.float32)
+    embeds_b = embeds + 0.25 * torch.randn(embeds.shape, generator=torch.Generator("cpu").manual_seed(7)).to(embeds)
+
+    def run(e):
+        gen = torch.Generator("cpu").manual_seed(28)
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(28))
+        out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5, generator=gen,
+                   latents=lat, prompt_embeds=e[1:2], negative_prompt_embeds=e[0:1],
+                   num_inference_steps=case["steps"], thresholds=cfg.thresholds, output_type="latent")
+        return out.images.float().cpu().numpy()
+    pipe.use_cuda_graphs = True
+    graph_a = run(embeds)
+    assert store.text_kv is not None and len(store.text_kv.entries) > 0
+    graph_b = run(embeds_b)                      # same graphs, refreshed projections
+    pipe.use_cuda_graphs = False
+    eager_b = run(embeds_b)
+    assert store.text_kv is None                 # the eager loop never caches
+    cos = float((graph_b * eager_b).sum() / (np.linalg.norm(graph_b) * np.linalg.norm(eager_b)))
+    assert cos > 0.99999 and _psnr(graph_b, eager_b) > 55, (cos, _psnr(graph_b, eager_b))
+    assert not np.allclose(graph_a, graph_b, atol=1e-3)
+
+
 @pytest.mark.parametrize("graphs", [False, True])
 def test_seed_batching_equals_separate_calls(graphs):
     """Extension: `generate_batch` (S seeds per UNet pass, per-sample losses / step sizes / recursion masks) against S
