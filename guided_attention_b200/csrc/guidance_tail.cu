@@ -429,6 +429,48 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
       if (c < tp) reinterpret_cast<float4*>(s_in[warp])[c] = __ldg(src + c);
     }
     __syncwarp();
+    if (sparse && vec_out) {
+      // Fast path (no upstream gradient on attn_text: the map gradient is non-zero only in the tracked tokens' columns,
+      // so sum_j a_j da_j has n_tokens terms and everything else is elementwise).  Lanes 0..3 compute the dot product of
+      // "their" pixel; then the warp writes the 4 rows as aligned float4 chunks straight to global memory with
+      // da = 0, and 4 * n_tokens lanes patch the tracked columns.
+      const int rs4 = d_abar_rstride >> 2;
+      float dotq = 0.f;
+      if (lane < 4 && g0 + lane < npix) {
+        for (int t = 0; t < p.n_tokens; ++t)
+          dotq = fmaf(s_in[warp][lane * tp + tg[t].column], sdi[t * ppc + (g0 + lane - p0)], dotq);
+      }
+      float dots[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dots[q] = __shfl_sync(0xffffffffu, dotq, q);
+      float* dst = d_abar + (int64_t)g0 * d_abar_rstride;
+      for (int c = lane; c < 4 * rs4; c += 32) {
+        const int q = c / rs4, jc = (c - q * rs4) << 2;
+        if (g0 + q >= npix) break;
+        const float* arow = s_in[warp] + q * tp - p.first;
+        const float nk = -k * (q == 0 ? dots[0] : q == 1 ? dots[1] : q == 2 ? dots[2] : dots[3]);
+        float4 o;
+        o.x = (jc + 0 >= p.first && jc + 0 < p.last) ? nk * arow[jc + 0] : 0.f;
+        o.y = (jc + 1 >= p.first && jc + 1 < p.last) ? nk * arow[jc + 1] : 0.f;
+        o.z = (jc + 2 >= p.first && jc + 2 < p.last) ? nk * arow[jc + 2] : 0.f;
+        o.w = (jc + 3 >= p.first && jc + 3 < p.last) ? nk * arow[jc + 3] : 0.f;
+        *reinterpret_cast<float4*>(dst + q * d_abar_rstride + jc) = o;
+      }
+      __syncwarp();                                   // orders the patch stores below after the row stores above
+      for (int i = lane; i < 4 * p.n_tokens; i += 32) {
+        const int q = i & 3, t = i >> 2;
+        if (g0 + q < npix) {
+          const int col = tg[t].column;
+          float da = 0.f;
+          for (int t2 = 0; t2 < p.n_tokens; ++t2)     // tokens that share a column (never in practice) add up
+            if (tg[t2].column == col) da += sdi[t2 * ppc + (g0 + q - p0)];
+          const float dq = q == 0 ? dots[0] : q == 1 ? dots[1] : q == 2 ? dots[2] : dots[3];
+          dst[q * d_abar_rstride + col + p.first] = k * s_in[warp][q * tp + col] * (da - dq);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     for (int q = 0; q < 4; ++q) {
       const int pix = g0 + q;
       const float* arow = s_in[warp] + q * tp;

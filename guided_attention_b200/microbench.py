@@ -192,6 +192,9 @@ def single(argv):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--single":
         single(sys.argv[2:])
+    elif len(sys.argv) > 1 and sys.argv[1] == "--single-tail":
+        a = sys.argv[2:]
+        print(json.dumps(time_tail(int(a[1]), 5, 2, n_samples=int(a[2]), direction=a[0])))
     elif len(sys.argv) > 1 and sys.argv[1] == "--single-self":
         a = sys.argv[2:]
         print(json.dumps(time_self_attn(int(a[1]), 8, int(a[2]), int(a[3]), torch.float16, a[0])))
