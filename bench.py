@@ -351,6 +351,20 @@ def run_ours(args):
     return 0
 
 
+def ncu_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed `ncu --set full`
+    summary (profiles/r01_ncu_final_summary.json, captured with tools/ncu_all.sh at the shape the bench reports)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_final_summary.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        rows = json.load(f)
+    tot = [r.get("dram_traffic_bytes") for r in rows if r["kernel"].split("::")[-1].replace("void ", "").startswith(kernel_prefix)
+           and r["report"].endswith("_b1.ncu-rep")]
+    tot = [t for t in tot if t is not None]
+    return float(sum(tot)) if tot else None
+
+
 def roofline_from(prof):
     """Dominant kernel = the (kernel, shape) class with the largest summed device time inside the profiled image.
     Its launch duration is then measured kernel-only: the same launch (same shape, dtype, variant choice) replayed
@@ -386,7 +400,8 @@ def roofline_from(prof):
     top = next((r for r in table if "kernel_us" in r), table[0])
     if "tflops" in top:
         roof = {"bound": "tensor", "kernel": top["kernel"], "shape": top["shape"], "achieved": top["tflops"],
-                "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak, "traffic": None,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
+                "traffic": ncu_traffic(top["kernel"]) if top["shape"][:4] == ["1", "8", "4096", "40"] else None,
                 "peak_source": how, "avg_launch_us": top["kernel_us"],
                 "algorithmic_flops_per_launch": top["algorithmic_flops_per_launch"],
                 "issued_tflops": top["tflops_issued"],
