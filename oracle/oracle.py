@@ -403,6 +403,9 @@ class OraclePipeline:
 
     def _loss(self, attention_res, smooth_attentions, sigma, kernel_size, last_idx):
         abar = aggregate_attention(self.store.attention_store, attention_res)
+        # the loss restatement is host code; when a test drives the UNet on a device (full-size configs whose explicit
+        # self-attention maps would take minutes on the host) the averaged map comes back here, autograd-connected
+        abar = abar.cpu()
         return guidance_loss(abar, self.tokens, attention_res, self.hp, smooth_attentions, sigma, kernel_size,
                              last_idx, self.custom_losses)
 

@@ -750,3 +750,58 @@ def test_full_size_sd14_guidance_step_fp16():
     a, b = gd.float().cpu().flatten(), go.flatten()
     cos = float((a @ b) / (a.norm() * b.norm()))
     assert cos > 0.98, cos
+
+
+def test_full_size_sd21_config4_guidance_step_fp16():
+    """BASELINE config 4: SD-2.x-shaped UNet (heads 5/10/20/20, d = 64, 1024-wide text), 96x96 latent -> stored levels
+    24x24 and 12x12 only, attention_res 24, normalize_eot, four subjects mixing two boxes, a crosshair and a keyword
+    (toLeftOf) annotation.  One guidance evaluation + latent gradient of the fused fp16 path against the oracle driving
+    the same UNet in fp32 (on the device: the explicit (5, 9216, 9216) self-attention maps would take minutes on the
+    host).  Also the reference's failure mode: attention_res 16 matches no stored level."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
+    from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, build_unet
+    from guided_attention_b200.run import synthetic_prompt_embeds
+    cfg = setup_prompt('a [cat:.1,.3,.3,.4] and a [dog:.55,.3,.35,.4] with a [bird:.5,.15] a lamp and a tree '
+                       '[CustomLoss:toLeftOf (lamp,tree)]')
+    kinds = sorted(v['loss_type'].name for v in cfg.token_dict.values())
+    assert kinds == ["BOX", "BOX", "COOR", "KEYWORD", "KEYWORD"]
+    words = cfg.prompt.lower().split()
+    last_idx = len(cfg.stable.tokenizer(cfg.prompt)['input_ids']) - 1
+    ucfg = UNetConfig.sd21_base(96)
+    embeds = synthetic_prompt_embeds(cfg.prompt, 1024)
+    lat = torch.randn(1, 4, 96, 96, generator=torch.Generator("cpu").manual_seed(28))
+    # oracle: fp32, explicit attention, same weights
+    unet = build_unet(ucfg, seed=0, device=DEV)
+    fn = lambda A: O.to_left_of(A, [words.index("lamp")], [words.index("tree")])   # noqa: E731
+    opipe = O.OraclePipeline(unet, DDIMScheduler(), oracle_tokens(cfg), oracle_hyper(cfg), custom_losses=[fn])
+    with torch.enable_grad():
+        lo = lat.to(DEV).requires_grad_(True)
+        unet(lo, 981, encoder_hidden_states=embeds[1:2].to(DEV))
+        r = opipe._loss(attention_res=24, smooth_attentions=True, sigma=0.5, kernel_size=3, last_idx=last_idx)
+        (go,) = torch.autograd.grad(r.loss, lo)
+    ref_loss, go = float(r.loss), go.float().cpu()
+    del unet, opipe, r, lo
+    torch.cuda.empty_cache()
+    # product: fp16, fused kernels
+    unet_h = build_unet(ucfg, seed=0, dtype=torch.float16, device=DEV)
+    pipe = GuidedAttention(unet=unet_h, scheduler=DDIMScheduler(), tokenizer=cfg.stable.tokenizer)
+    pipe.prompt = cfg.prompt
+    store = AttentionStore()
+    register_attention_control(pipe, store)
+    with torch.enable_grad():
+        ld_ = lat.to(DEV, torch.float16).requires_grad_(True)
+        unet_h(ld_, 981, encoder_hidden_states=embeds[1:2].to(DEV, torch.float16))
+        sizes = sorted({m.shape[1] for v in store.get_average_attention().values() for m in v})
+        assert sizes == [144, 576]                       # 48x48 = 2304 is not stored (utils/ptp_utils.py:228)
+        with pytest.raises(RuntimeError):                # reference: torch.cat([]) at utils/ptp_utils.py:287
+            pipe._aggregate_and_get_max_attention_per_token(store, 16, True, 0.5, 3, True)
+        d = pipe._aggregate_and_get_max_attention_per_token(store, 24, True, 0.5, 3, True)
+        loss, losses, _ = pipe._compute_loss(d)
+        (gd,) = torch.autograd.grad(loss, ld_)
+    assert torch.isfinite(gd).all()
+    assert losses[-1][0] is None                          # the keyword loss rides at the end of the list
+    assert float(loss) == pytest.approx(ref_loss, rel=FP16_RTOL)
+    a, b = gd.float().cpu().flatten(), go.flatten()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    assert cos > 0.98, cos
