@@ -375,6 +375,7 @@ def roofline_from(prof):
     (algorithmic FLOPs = the 2 GEMMs of the forward / 5 of the backward, not the recomputation the kernels add)."""
     from guided_attention_b200 import microbench
     hbm_peak, tf_peak, how = peaks()
+    dev = f"cuda:{torch.cuda.current_device()}"      # every rank measures on its own GPU
     table = []
     for (name, key), d in prof.items():
         avg_us = d["ms"] * 1e3 / d["launches"]
@@ -390,11 +391,12 @@ def roofline_from(prof):
         if row["kernel"].startswith("cross_attn"):
             B, H, N, T, dd = (int(x) for x in row["shape"][:5])
             m = microbench.time_cross_attn(B, H, N, T, dd, dts[row["shape"][5]], with_acc=row["shape"][6] == "True",
-                                           direction=row["kernel"].split("_")[-1])
+                                           direction=row["kernel"].split("_")[-1], device=dev)
             row["kernel_us"], row["gbs"] = m["us"], m["gbs"]
         elif row["kernel"].startswith("self_attn"):
             B, H, N, dd = (int(x) for x in row["shape"][:4])
-            m = microbench.time_self_attn(B, H, N, dd, dts[row["shape"][4]], direction=row["kernel"].split("_")[-1])
+            m = microbench.time_self_attn(B, H, N, dd, dts[row["shape"][4]], direction=row["kernel"].split("_")[-1],
+                                          device=dev)
             row["kernel_us"], row["tflops"], row["tflops_issued"] = m["us"], m["tflops_algorithmic"], m["tflops_issued"]
             row["algorithmic_flops_per_launch"] = m["tflops_algorithmic"] * m["us"] * 1e6
     top = next((r for r in table if "kernel_us" in r), table[0])
