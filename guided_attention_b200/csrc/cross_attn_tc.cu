@@ -317,7 +317,11 @@ struct ItemIter {
   }
 };
 
-__global__ void __launch_bounds__(kPipeThreads, 1)
+// NG softmax groups: 2 (16 warps; needed when maps are kept: the head-sum lives in the groups' registers) or 3 (20
+// warps, flat mode: the softmax groups are the busiest role of the flat kernel, a third one raises its throughput 1.5x;
+// 128 registers per softmax thread are enough without the map accumulator).
+template <int NG>
+__global__ void __launch_bounds__(128 * (NG + 2), 1)
 cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                               const PipeParams p) {
@@ -383,9 +387,10 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   // epilogue stores its rows straight from registers and the stage is released by the second GEMM's commit.
   const bool direct = p.direct_store != 0;
 
-  if (warp >= 12) {
-    reg_dealloc<56>();
-    if (warp == 12) {
+  constexpr int kCtlWarp = 4 + 4 * NG;               // control warpgroup: producer, MMA issuer 1, MMA issuer 2, idle
+  if (warp >= kCtlWarp) {
+    reg_dealloc<(NG == 2 ? 56 : 40)>();
+    if (warp == kCtlWarp) {
       // ------------------------------------------------------------------------------------- TMA producer
       // K and V of a stage are re-loaded only when the stage's batch element changes (flat mode: same head throughout):
       // the TMA handles one box row (<= 128 bytes) per few cycles, and at d = 40 the 2 x 80 K/V rows of an item would
@@ -416,7 +421,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         it.next(p);
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 13) {
+    } else if (warp == kCtlWarp + 1) {
       // ------------------------------------------------------------------------------ MMA issuer 1: S = Q K^T
       // Two issuer warps, one per GEMM: a single thread issuing both was the critical path of the CTA once everything
       // else overlapped (its ~150 instructions per item take longer than the item's data movement).  Cross-warp
@@ -439,7 +444,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         __syncwarp();
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
-    } else if (warp == 14) {
+    } else if (warp == kCtlWarp + 2) {
       // ------------------------------------------------------------------------------ MMA issuer 2: O = P V
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
       const uint64_t dV0 = smem_desc_sw128(base + p.nblk * (kQBlockBytes + kKVBlockBytes), kKVBlockBytes, 1024);
@@ -549,16 +554,19 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     }
     __syncwarp();
   } else {
-    reg_alloc<184>();
+    // setmaxnreg moves registers inside the CTA's OWN launch allocation (threads x registers at launch), not the SM's
+    // file: 512 x 128 = 64 K for NG == 2 (56 + 88 + 2 x 184 per 128 threads), 640 x 96 = 60 K for NG == 3
+    // (40 + 88 + 3 x 112 = 464 <= 480); asking for more spins forever in USETMAXREG.TRY_ALLOC.
+    reg_alloc<(NG == 2 ? 184 : 112)>();
     // ------------------------------------------------------------------------------------ softmax groups
-    const int g = (warp - 4) >> 2;                    // 0 or 1 = TMEM stage; handles items k with k % 2 == g
+    const int g = (warp - 4) >> 2;                    // handles items k with k % NG == g
     const int r = ((warp & 3) << 5) + lane;           // row of the tile = TMEM lane
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sc = p.scale * 1.4426950408889634f;
-    float pacc[kTpad];
-    if (p.grouped) {
+    float pacc[NG == 2 ? kTpad : 1];                  // head-sum of P (maps kept: NG == 2 only)
+    if (NG == 2 && p.grouped) {
 #pragma unroll
-      for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+      for (int j = 0; j < (NG == 2 ? kTpad : 1); ++j) pacc[j] = 0.f;
     }
 
     auto process = [&](int k, int b, int h, int tile) {
@@ -591,9 +599,11 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(P_READY(sIdx(k)));
-      if (p.grouped) {
+      if constexpr (NG == 2) {
+        if (p.grouped) {
 #pragma unroll
-        for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
+          for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
+        }
       }
       if (row < p.N)
         p.lse[((int64_t)b * p.H + h) * p.N + row] = (m * sc + lg2_approx(sum)) * 0.6931471805599453f;
@@ -602,13 +612,13 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     ItemIter it;
     it.init(p);
     if (!p.grouped) {
-      if (g == 1) it.next(p);
-      for (int k = g; k < n_items; k += 2) {
+      for (int i = 0; i < g; ++i) it.next(p);
+      for (int k = g; k < n_items; k += NG) {
         process(k, it.b, it.h, it.tile);
-        it.next(p);
-        it.next(p);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) it.next(p);
       }
-    } else {
+    } else if constexpr (NG == 2) {
       int k = 0;
       for (int u = 0; u < my_units; ++u) {
         const int unit = blockIdx.x + u * gridDim.x;
@@ -1174,7 +1184,7 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   const size_t smem = p.smem_stages * stage + extra;
   if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
   p.direct_store = p.smem_stages < 4 ? 1 : 0;
-  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel), 2, smem);
+  cudaError_t e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel<2>), 2, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid;
   if (p.grouped) {
@@ -1185,7 +1195,21 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     if (teams > p.units) teams = p.units;
     grid = teams * f.H;
   }
-  cross_attn_fwd_tc_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(mq, mk, mv, mo, p);
+  // GA_TC_GROUPS=3 selects the three-softmax-group variant in flat mode (d <= 64).  Measured SLOWER than two groups
+  // (3 445 vs 3 629 GB/s at B=128, N=4096, d=40): the softmax groups are not what bounds the flat kernel.  Kept for A/B runs.
+  static int force_groups = -1;
+  if (force_groups < 0) {
+    const char* e3 = getenv("GA_TC_GROUPS");
+    force_groups = e3 != nullptr ? atoi(e3) : 0;
+  }
+  const bool three = !p.grouped && p.nblk == 1 && force_groups == 3;
+  if (three) {
+    e = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_pipe_kernel<3>), 4, smem);
+    if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cross_attn_fwd_tc_pipe_kernel<3><<<grid, 128 * 5, smem, st>>>(mq, mk, mv, mo, p);
+  } else {
+    cross_attn_fwd_tc_pipe_kernel<2><<<grid, 128 * 4, smem, st>>>(mq, mk, mv, mo, p);
+  }
   return check_launch("cross_attn_fwd_tc_pipe");
 }
 
