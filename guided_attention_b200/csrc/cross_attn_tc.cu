@@ -253,7 +253,8 @@ cross_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 // streams the H heads through the pipeline, so the head-sum of P stays in the two groups' registers and is combined
 // once per group through one shared staging tile, in a fixed order, then written coalesced: deterministic, no atomics.
 constexpr int kPipeThreads = 512;
-constexpr int kMaxStages = 6;   // shared-memory ring depth of the pipelined kernels
+constexpr int kMaxStages = 6;   // shared-memory ring depth of the pipelined backward / grouped forward
+constexpr int kFwdStages = 12;  // flat forward: Q-only stages
 constexpr int kStageCols = 256;
 constexpr int kGroupThreads = 128;
 
@@ -326,24 +327,33 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
                               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                               const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // full[6], smem_free[6] (per shared-memory stage); s_ready[4], p_ready[4], p_free[4] (per S/P buffer); o_ready[4],
-  // tmem_free[4] (per O buffer)
-  __shared__ __align__(8) uint64_t bars[32];
+  // full[12], smem_free[12] (per shared-memory stage); s_ready[4], p_ready[4], p_free[4] (per S/P buffer); o_ready[4],
+  // tmem_free[4] (per O buffer); kv_full[2], kv_free[2] (flat mode: K/V slots outside the ring)
+  __shared__ __align__(8) uint64_t bars[2 * kFwdStages + 24];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_inv[8][kM];         // [item & 7][row]: 1 / rowsum, softmax group -> epilogue
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t stage_bytes = (uint32_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
+  // Flat mode (no maps): consecutive items of a CTA share (b, h), so K and V live in two slots OUTSIDE the ring and a ring
+  // stage holds the Q tile only (16 KB per 64 channels instead of 36): up to 12 Q tiles in flight.  The ablation runs
+  // showed the flat kernel bound by ring latency (load + store-read + seven barrier hand-offs ~ 5 us per item) times ring
+  // depth, not by any unit.  Grouped mode (maps kept): every item has its own head -> K/V stay inside the stage.
+  const bool kvres = !p.grouped;
+  const uint32_t q_bytes = (uint32_t)p.nblk * kQBlockBytes, kv_bytes = 2u * (uint32_t)p.nblk * kKVBlockBytes;
+  const uint32_t stage_bytes = kvres ? q_bytes : q_bytes + kv_bytes;
+  const uint32_t kv_base = base + (uint32_t)p.smem_stages * stage_bytes;        // flat mode: two (K, V) slots
   float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)p.smem_stages * stage_bytes);
+  auto KV_FULL = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 20 + s]); };
+  auto KV_FREE = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 22 + s]); };
   auto FULL = [&](int s) { return smem_u32(&bars[s]); };
-  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
-  auto S_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
-  auto P_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
-  auto O_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 8 + s]); };
-  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 12 + s]); };
-  auto P_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 16 + s]); };
+  auto SMEM_FREE = [&](int s) { return smem_u32(&bars[kFwdStages + s]); };
+  auto S_READY = [&](int s) { return smem_u32(&bars[2 * kFwdStages + s]); };
+  auto P_READY = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 4 + s]); };
+  auto O_READY = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 8 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 12 + s]); };
+  auto P_FREE = [&](int s) { return smem_u32(&bars[2 * kFwdStages + 16 + s]); };
   // TMEM: nS score buffers of 80 columns (P, packed 16-bit, overwrites the head of its S buffer), then two O buffers.
   // With four S buffers (d <= 96) a softmax group finds the scores of its NEXT item already computed when it finishes
   // one: MMA1(k + 2) no longer has to wait for MMA2(k) to consume P(k) out of the same columns -- that round trip
@@ -364,7 +374,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_o);
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), p.direct_store ? 1 : 4); }
+    for (int s = 0; s < kFwdStages; ++s) { mbar_init(FULL(s), 1); mbar_init(SMEM_FREE(s), p.direct_store ? 1 : 4); }
     for (int s = 0; s < 4; ++s) {
       mbar_init(S_READY(s), 1);
       mbar_init(P_READY(s), kGroupThreads);
@@ -372,6 +382,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       mbar_init(TMEM_FREE(s), kGroupThreads);
       mbar_init(P_FREE(s), 1);
     }
+    for (int s = 0; s < 2; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
@@ -392,26 +403,36 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
     reg_dealloc<(NG == 2 ? 56 : 40)>();
     if (warp == kCtlWarp) {
       // ------------------------------------------------------------------------------------- TMA producer
-      // K and V of a stage are re-loaded only when the stage's batch element changes (flat mode: same head throughout):
-      // the TMA handles one box row (<= 128 bytes) per few cycles, and at d = 40 the 2 x 80 K/V rows of an item would
-      // otherwise cost more TMA slots than its 128 Q rows.
+      // Flat mode: K and V are loaded once per batch element of the CTA's range (the TMA handles one box row of <= 128
+      // bytes per few cycles; at d = 40 the 2 x 80 K/V rows of an item would cost more TMA slots than its 128 Q rows).
       ItemIter it;
       it.init(p);
-      int kv_tag[kMaxStages] = {-1, -1, -1, -1, -1, -1};
-      int ss = 0;
+      int ss = 0, cur_b = -1, unit = -1;
       uint32_t par = 0;                                 // parity of the use of stage ss that is about to start
-      const uint32_t q_bytes = (uint32_t)p.nblk * kQBlockBytes;
       for (int k = 0; k < n_items; ++k) {
+        if (kvres && it.b != cur_b) {                   // flat mode: a new batch element -> its K, V into the next slot
+          cur_b = it.b;
+          ++unit;
+          const int slot = unit & 1;
+          if (unit >= 2) mbar_wait(KV_FREE(slot), (((uint32_t)(unit >> 1)) & 1u) ^ 1u);
+          if (elect_one()) {
+            const uint32_t sK = kv_base + slot * kv_bytes, sV = sK + p.nblk * kKVBlockBytes;
+            mbar_expect_tx(KV_FULL(slot), kv_bytes);
+            for (int blk = 0; blk < p.nblk; ++blk) {
+              tma_load_4d(sK + blk * kKVBlockBytes, &map_k, KV_FULL(slot), blk * kBlockCols, it.h, 0, it.b);
+              tma_load_4d(sV + blk * kKVBlockBytes, &map_v, KV_FULL(slot), blk * kBlockCols, it.h, 0, it.b);
+            }
+          }
+          __syncwarp();
+        }
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
-        const bool with_kv = p.grouped || kv_tag[ss] != it.b;
-        kv_tag[ss] = it.b;
         if (elect_one()) {
           const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
           const bool load_q = !(p.ablate & 4);
-          mbar_expect_tx(FULL(ss), (with_kv ? stage_bytes : q_bytes) - (load_q ? 0u : q_bytes));
+          mbar_expect_tx(FULL(ss), stage_bytes - (load_q ? 0u : q_bytes));
           for (int blk = 0; blk < p.nblk; ++blk) {
             if (load_q) tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, it.h, it.tile * kM, it.b);
-            if (with_kv) {
+            if (!kvres) {
               tma_load_4d(sK + blk * kKVBlockBytes, &map_k, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
               tma_load_4d(sV + blk * kKVBlockBytes, &map_v, FULL(ss), blk * kBlockCols, it.h, 0, it.b);
             }
@@ -429,38 +450,55 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       // buffer, which MMA2's commit signals.
       const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
       const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024);
-      const uint64_t dK0 = smem_desc_sw128(base + p.nblk * kQBlockBytes, 16, 1024);
-      int ss = 0;
+      const uint64_t dK0 = smem_desc_sw128(kvres ? kv_base : base + p.nblk * kQBlockBytes, 16, 1024);
+      ItemIter it;
+      it.init(p);
+      int ss = 0, cur_b = -1, unit = -1;
       uint32_t par = 0;
       for (int k = 0; k < n_items; ++k) {
+        if (kvres && it.b != cur_b) {                   // first item of a batch element: its K, V must have landed
+          cur_b = it.b;
+          ++unit;
+          mbar_wait(KV_FULL(unit & 1), ((uint32_t)(unit >> 1)) & 1u);
+        }
         if (k >= nS) mbar_wait(P_FREE(sIdx(k)), sPar(k) ^ 1u);
         mbar_wait(FULL(ss), par);
         tc_fence_after();
         if (elect_one()) {
           issue_kmajor_gemm(tmem + colS(k), desc_advance(dQ0, ss * stage_bytes), kQBlockBytes,
-                            desc_advance(dK0, ss * stage_bytes), kKVBlockBytes, ksteps, idesc_qk);
+                            desc_advance(dK0, kvres ? (unit & 1) * kv_bytes : ss * stage_bytes), kKVBlockBytes, ksteps,
+                            idesc_qk);
           tc_commit(S_READY(sIdx(k)));
         }
         __syncwarp();
+        it.next(p);
         if (++ss == S) { ss = 0; par ^= 1u; }
       }
     } else if (warp == kCtlWarp + 2) {
       // ------------------------------------------------------------------------------ MMA issuer 2: O = P V
       const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
-      const uint64_t dV0 = smem_desc_sw128(base + p.nblk * (kQBlockBytes + kKVBlockBytes), kKVBlockBytes, 1024);
-      int ss = 0;
+      const uint64_t dV0 = smem_desc_sw128((kvres ? kv_base : base + p.nblk * kQBlockBytes) + p.nblk * kKVBlockBytes,
+                                           kKVBlockBytes, 1024);
+      ItemIter it;
+      it.init(p);
+      int ss = 0, cur_b = it.b, unit = 0;
       for (int k = 0; k < n_items; ++k) {
         mbar_wait(P_READY(sIdx(k)), sPar(k));
         if (k >= nO) mbar_wait(TMEM_FREE(oIdx(k)), oPar(k) ^ 1u);  // the epilogue of item k-nO has drained this O buffer
         tc_fence_after();
+        const int slot = unit & 1;
+        it.next(p);
+        const bool last_of_unit = kvres && (k == n_items - 1 || it.b != cur_b);
         if (elect_one()) {
-          issue_tmem_gemm(tmem + colO(k), tmem + colS(k), desc_advance(dV0, ss * stage_bytes), kTpad / 16, idesc_pv,
-                          false);
+          issue_tmem_gemm(tmem + colO(k), tmem + colS(k), desc_advance(dV0, kvres ? slot * kv_bytes : ss * stage_bytes),
+                          kTpad / 16, idesc_pv, false);
           tc_commit(O_READY(oIdx(k)));
           tc_commit(P_FREE(sIdx(k)));
           if (direct) tc_commit(SMEM_FREE(ss));          // nothing is staged in the stage: free it as soon as V is read
+          if (last_of_unit) tc_commit(KV_FREE(slot));    // every GEMM that reads this slot has been issued (and S(k) done)
         }
         __syncwarp();
+        if (last_of_unit) { cur_b = it.b; ++unit; }
         if (++ss == S) ss = 0;
       }
     }
@@ -1176,10 +1214,11 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   CUtensorMap mo;
   int rc;
   if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, 32)) != GA_OK) return rc;   // one store per epilogue warp
-  const size_t stage = (size_t)p.nblk * (kQBlockBytes + 2 * kKVBlockBytes);
-  const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 0);
+  const size_t kv = (size_t)2 * p.nblk * kKVBlockBytes;
+  const size_t stage = (size_t)p.nblk * kQBlockBytes + (p.grouped ? kv : 0);            // flat: Q-only stages
+  const size_t extra = 1024 + (p.grouped ? (size_t)kM * kAccStride * sizeof(float) : 2 * kv);   // flat: two K/V slots
   p.smem_stages = 1;
-  for (int n = kMaxStages; n >= 2; --n)
+  for (int n = (p.grouped ? kMaxStages : kFwdStages); n >= 2; --n)
     if (n * stage + extra <= 224 * 1024) { p.smem_stages = n; break; }
   const size_t smem = p.smem_stages * stage + extra;
   if (smem > 224 * 1024) return fail(GA_ERR_UNSUPPORTED, "tcgen05 pipelined cross-attention: %zu B of shared memory", smem);
