@@ -316,10 +316,9 @@ __device__ __forceinline__ TokenGrad make_token_grad(const ga_tail_params_t& p, 
 }
 
 // d loss / d smoothed[pix] for one token
-__device__ __forceinline__ float dsmoothed_at(const TokenGrad& g, int pix, int res, const uint8_t* masks,
+__device__ __forceinline__ float dsmoothed_at(const TokenGrad& g, int pix, int y, int x, int res, const uint8_t* masks,
                                               const float* weights, const float* sm) {
   const int npix = res * res;
-  const int y = pix / res, x = pix - y * res;
   float dp = g.g_col * ((float)x + 0.5f) + g.g_row * ((float)y + 0.5f);
   if (g.box >= 0) {
     const bool in = masks[(int64_t)g.box * npix + pix] != 0;
@@ -375,9 +374,15 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   const int p0 = blockIdx.x * ppc;
   const int halo = p.smooth ? res + 1 : 0;
   const int lo = max(p0 - halo, 0), hi = min(p0 + ppc + halo, npix), span = ppc + 2 * halo;
+  // (row / column of a pixel without an integer division: (pix + 0.5) / res in fp32 is exact for res <= 256)
+  const float inv_res = 1.f / (float)res;
+  const float inv_span = 1.f / (float)span;
   for (int i = threadIdx.x; i < p.n_tokens * span; i += blockDim.x) {
-    const int t = i / span, q = lo + (i - t * span);
-    if (q < hi) sds[i] = dsmoothed_at(tg[t], q, res, masks, weights, smoothed + (int64_t)t * npix);
+    const int t = (int)(((float)i + 0.5f) * inv_span), q = lo + (i - t * span);
+    if (q < hi) {
+      const int y = (int)(((float)q + 0.5f) * inv_res);
+      sds[i] = dsmoothed_at(tg[t], q, y, q - y * res, res, masks, weights, smoothed + (int64_t)t * npix);
+    }
   }
   __syncthreads();
 
@@ -386,12 +391,12 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   // on n_tokens lanes of every warp)
   float* sdi = sds + p.n_tokens * span;            // [token][pixel of the tile]
   for (int i = threadIdx.x; i < p.n_tokens * ppc; i += blockDim.x) {
-    const int t = i / ppc, pix = p0 + (i - t * ppc);
+    const int t = (int)(((float)i + 0.5f) / (float)ppc), pix = p0 + (i - t * ppc);
     float dimg = 0.f;
     if (pix < npix) {
       const float* ds = sds + t * span - lo;
       if (p.smooth) {
-        const int y = pix / res, x = pix - y * res;
+        const int y = (int)(((float)pix + 0.5f) * inv_res), x = pix - y * res;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
           const int yy = y + dy;
@@ -445,7 +450,8 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
       for (int q = 0; q < 4; ++q) dots[q] = __shfl_sync(0xffffffffu, dotq, q);
       float* dst = d_abar + (int64_t)g0 * d_abar_rstride;
       for (int c = lane; c < 4 * rs4; c += 32) {
-        const int q = c / rs4, jc = (c - q * rs4) << 2;
+        const int q = (c >= rs4) + (c >= 2 * rs4) + (c >= 3 * rs4);      // c / rs4 without the runtime division
+        const int jc = (c - q * rs4) << 2;
         if (g0 + q >= npix) break;
         const float* arow = s_in[warp] + q * tp - p.first;
         const float nk = -k * (q == 0 ? dots[0] : q == 1 ? dots[1] : q == 2 ? dots[2] : dots[3]);
