@@ -319,6 +319,15 @@ def run_ours(args):
                    "ms_per_batch": ms_b, "note": "extension (SURVEY 8e): per-seed results equal the one-seed path "
                    "(tests/test_gpu_parity.py::test_seed_batching_equals_separate_calls)"}
 
+    # (5) the HBM-bound kernels at GPU-filling batch sizes (rank 0; last, because the tail timer re-installs the prompt)
+    saturated = None
+    if rank == 0 and not args.no_saturated:
+        keep = (S.config, S.curHyperParams)
+        torch.cuda.empty_cache()
+        saturated = saturated_rooflines(dev)
+        S.config, S.curHyperParams = keep
+        torch.cuda.empty_cache()
+
     n_img = args.steps * world
     value = n_img / (ms_value / 1e3)
     e2e = n_img / (ms_e2e / 1e3)
@@ -329,7 +338,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(embeds_host.numel() * 4 + 4 * 64 * 64 * 4),
                     "d2h_bytes_per_step": int(4 * 64 * 64 * 2)},
             "gpu_launches": launches, "gpu_launches_by_kernel": counts, "unet_passes": unet_passes,
-            "clocks": clocks, "roofline": roofline, "kernels": kernel_table, "batched": batched}
+            "clocks": clocks, "roofline": roofline, "kernels": kernel_table, "saturated_kernels": saturated,
+            "batched": batched}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         times, _ = cpu_component_times(args.unet, threads)
@@ -349,6 +359,31 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def saturated_rooflines(dev):
+    """The HBM-bound guidance kernels timed live at batch sizes that fill the GPU (the pipeline's own launches move
+    0.7-11 MB and are launch-latency bound by size): same timing method as the roofline leg (CUDA graph of back-to-back
+    launches between two CUDA events on the launching stream, rotating buffer sets larger than L2)."""
+    from guided_attention_b200 import microbench
+    peak = peaks()[0]
+    out = []
+    try:
+        for direction in ("fwd", "bwd"):
+            m = microbench.time_cross_attn(128, 8, 4096, 77, 40, torch.float16, with_acc=False, direction=direction,
+                                           device=str(dev))
+            out.append({"kernel": m["kernel"], "shape": "B=128 H=8 N=4096 T=77 d=40 fp16", "us": m["us"],
+                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
+            m = microbench.time_cross_attn(256, 8, 1024, 77, 80, torch.float16, with_acc=True, direction=direction,
+                                           device=str(dev))
+            out.append({"kernel": m["kernel"], "shape": "B=256 H=8 N=1024 T=77 d=80 fp16 (maps)", "us": m["us"],
+                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
+            m = microbench.time_tail(16, 5, 2, n_samples=2048, direction=direction, device=str(dev))
+            out.append({"kernel": m["kernel"], "shape": "res 16, 5 layers x 2 slices, 2048 samples", "us": m["us"],
+                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
+    except Exception as e:   # never lose the headline line to an auxiliary measurement
+        out.append({"error": f"{type(e).__name__}: {e}"})
+    return out
 
 
 def ncu_traffic(kernel_prefix):
@@ -431,6 +466,7 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-saturated", action="store_true", help="skip the large-batch kernel rooflines")
     ap.add_argument("--seeds-per-batch", type=int, default=8,
                     help="also measure the seed-batched extension with this many seeds per UNet pass (0/1 = skip)")
     args = ap.parse_args()
