@@ -17,6 +17,7 @@ from . import _cabi as abi
 from . import ops
 
 L2_BYTES = 126 * 1024 * 1024
+DEFAULT_PROMPT = 'a [robot:.6,.3,.4,.55] and a [blue vase:.2,.3,.4,.55]'   # BASELINE config 1 / 2
 
 
 def _time_graph(launch, n_sets, reps=20, replays=5):
@@ -126,9 +127,9 @@ def sweep_self(device="cuda:0"):
 def time_tail(res, n_layers, slices_per_layer, n_samples=1, T=77, direction="fwd", device="cuda:0"):
     """One guidance-tail launch (forward or backward): `n_samples` independent evaluations, each over `n_layers`
     accumulators of `slices_per_layer` (N, T) slices (the reference's shape is n_samples = 1, 5 layers, 1-2 slices)."""
-    from tests.gpu_harness import setup_prompt   # prompt/config fixture shared with the tests
     from .pipeline_guided_attention import GuidedAttention
-    cfg = setup_prompt()
+    from .run import setup_prompt
+    cfg = setup_prompt(DEFAULT_PROMPT)
     pipe = GuidedAttention(unet=None, tokenizer=cfg.stable.tokenizer)
     pipe.prompt = cfg.prompt
     npix, S = res * res, n_samples

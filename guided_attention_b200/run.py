@@ -223,5 +223,28 @@ def main(argv=None):
     print(execute(config))
 
 
+
+def setup_prompt(meta_prompt: str, hyper=None, cfg_kw=None, register: bool = True):
+    """`setup` + `parseMetaPrompt` of the reference (run.py:81-91, 139-145) for stacks without a CLIP tokenizer: installs a
+    RunConfig with the whitespace tokenizer as `shared_state.config`, the shipped hyper-parameters (plus `hyper`
+    overrides) as `shared_state.curHyperParams`, and builds `config.token_dict`.  Used by the microbenchmarks and, through
+    tests/gpu_harness.py, by the tests."""
+    import tempfile
+    import types
+    from .config import RunConfig
+    from .substrate import WhitespaceTokenizer
+    cfg = RunConfig(meta_prompt=meta_prompt, output_path=tempfile.mkdtemp(prefix="ga_run_"), **(cfg_kw or {}))
+    shared_state.config = cfg
+    cfg.stable = types.SimpleNamespace(tokenizer=WhitespaceTokenizer())
+    if register:
+        register_custom_loss("toLeftOf", ToLeftOf())
+    hp = shared_state.get_hyperparam_states()[0]
+    hp.update(hyper or {})
+    shared_state.curHyperParams = hp
+    overrideConfig(cfg)
+    parseMetaPrompt(cfg)
+    shared_state.cur_time_step_iter, shared_state.cur_seed, shared_state.sub_iteration = 0, 0, 0
+    return cfg
+
 if __name__ == '__main__':
     main()

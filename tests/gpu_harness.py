@@ -14,21 +14,8 @@ from oracle.cases import DEFAULT_PROMPT
 
 def setup_prompt(meta_prompt=DEFAULT_PROMPT, hyper=None, cfg_kw=None, register=True):
     """Product-side equivalent of reference run.setup + parseMetaPrompt, with the whitespace tokenizer."""
-    from guided_attention_b200 import run as R, shared_state as S
-    from guided_attention_b200.config import RunConfig
-    from guided_attention_b200.substrate import WhitespaceTokenizer
-    cfg = RunConfig(meta_prompt=meta_prompt, output_path=tempfile.mkdtemp(prefix="ga_test_"), **(cfg_kw or {}))
-    S.config = cfg
-    cfg.stable = types.SimpleNamespace(tokenizer=WhitespaceTokenizer())
-    if register:
-        R.register_custom_loss("toLeftOf", R.ToLeftOf())
-    hp = S.get_hyperparam_states()[0]
-    hp.update(hyper or {})
-    S.curHyperParams = hp
-    R.overrideConfig(cfg)
-    R.parseMetaPrompt(cfg)
-    S.cur_time_step_iter, S.cur_seed, S.sub_iteration = 0, 0, 0
-    return cfg
+    from guided_attention_b200 import run as R
+    return R.setup_prompt(meta_prompt, hyper, cfg_kw, register)
 
 
 def oracle_tokens(cfg):
