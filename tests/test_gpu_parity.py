@@ -92,7 +92,10 @@ def test_cross_attention_forward(shape, dtype, rtol):
 @pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
 @pytest.mark.parametrize("with_acc", [False, True])
 @pytest.mark.parametrize("variant", ["single", "pipe"])
-@pytest.mark.parametrize("shape", SHAPES + [(8, 40, 4096, 77, 4), (8, 160, 256, 77, 40), (5, 64, 576, 77, 9)])
+@pytest.mark.parametrize("shape", SHAPES + [(8, 40, 4096, 77, 4), (8, 160, 256, 77, 40), (5, 64, 576, 77, 9),
+                                            # one tile per batch element (a new K/V slot every item), ragged second tile,
+                                            # more batch elements than ring stages
+                                            (8, 40, 64, 77, 12), (8, 40, 192, 77, 7), (8, 48, 128, 77, 30)])
 def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, with_acc, variant):
     """The tcgen05/TMA/TMEM kernels explicitly -- the single-shot one and the persistent pipelined one -- against the
     oracle and the SIMT variant."""
@@ -252,7 +255,8 @@ def test_cross_attention_backward(shape, dtype, rtol, broadcast):
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.float16, FP16_RTOL), (torch.bfloat16, 6e-2)])
 @pytest.mark.parametrize("shape", [(8, 40, 4096, 77, 1), (8, 80, 1024, 77, 2), (8, 160, 256, 77, 2), (8, 160, 64, 77, 1),
-                                   (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 70, 2)])
+                                   (5, 64, 576, 77, 1), (20, 64, 144, 77, 1), (2, 16, 100, 70, 2),
+                                   (8, 40, 64, 77, 12), (8, 40, 192, 77, 7), (8, 80, 128, 77, 9)])
 @pytest.mark.parametrize("with_dacc", [False, True])
 @pytest.mark.parametrize("variant", ["single", "pipe"])
 def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc, variant):
