@@ -18,9 +18,10 @@ GA_IMPL_AUTO, GA_IMPL_SIMT, GA_IMPL_TCGEN05, GA_IMPL_TCGEN05_SINGLE, GA_IMPL_TCG
 GA_TOKEN_COOR, GA_TOKEN_BOX, GA_TOKEN_KEYWORD = 0, 1, 2
 GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
 (GA_STAT_MAX, GA_STAT_SUM, GA_STAT_COL, GA_STAT_ROW, GA_STAT_INSIDE, GA_STAT_OUTSIDE, GA_STAT_SCALED,
- GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER) = range(12)
-GA_STATS = 12
-GA_ABI_VERSION = 1
+ GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER, GA_STAT_RAW_SUM,
+ GA_STAT_RAW_COL, GA_STAT_RAW_ROW) = range(15)
+GA_STATS = 16
+GA_ABI_VERSION = 2
 
 
 class GaToken(C.Structure):

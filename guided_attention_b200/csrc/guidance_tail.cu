@@ -92,11 +92,15 @@ __device__ void token_stage(const ga_tail_params_t& p, const ga_token_t& tk, int
   const float* wts = (is_box && p.strict && weights != nullptr) ? weights + (int64_t)tk.box * npix : nullptr;
   float* sm = smoothed + (int64_t)t * npix;
 
-  float vmax = -INFINITY, sum = 0.f;
+  float vmax = -INFINITY, sum = 0.f, rsum = 0.f, rcol = 0.f, rrow = 0.f;
   int imax = 0x7fffffff, nin = 0;
   for (int pix = lane; pix < npix; pix += 32) {
     const int y = pix / res, x = pix - y * res;
     const float s = p.smooth ? smooth_at(img, y, x, res, p.w1d) : img[pix];
+    const float a = img[pix];                         // un-smoothed map: custom-loss statistics
+    rsum += a;
+    rcol = fmaf((float)x + 0.5f, a, rcol);
+    rrow = fmaf((float)y + 0.5f, a, rrow);
     sm[pix] = s;
     if (s > vmax) { vmax = s; imax = pix; }
     sum += s;
@@ -110,6 +114,7 @@ __device__ void token_stage(const ga_tail_params_t& p, const ga_token_t& tk, int
     nin += __shfl_xor_sync(0xffffffffu, nin, o);
   }
   sum = warp_sum(sum);
+  rsum = warp_sum(rsum); rcol = warp_sum(rcol); rrow = warp_sum(rrow);
 
   const float at_most = nin > 0 ? 1.f / (float)nin : 0.f;
   float col = 0.f, row = 0.f, sin_ = 0.f, sout = 0.f, hin = 0.f, hout = 0.f;
@@ -155,6 +160,8 @@ __device__ void token_stage(const ga_tail_params_t& p, const ga_token_t& tk, int
     st[GA_STAT_INSIDE] = inside; st[GA_STAT_OUTSIDE] = outside; st[GA_STAT_SCALED] = scaled;
     st[GA_STAT_UNSCALED] = unscaled; st[GA_STAT_HINGE_IN] = hin; st[GA_STAT_HINGE_OUT] = hout;
     st[GA_STAT_NINSIDE] = (float)nin; st[GA_STAT_CENTER] = center;
+    st[GA_STAT_RAW_SUM] = rsum; st[GA_STAT_RAW_COL] = rcol / rsum; st[GA_STAT_RAW_ROW] = rrow / rsum;
+    st[15] = 0.f;
     argmax[t] = imax;
   }
 }
@@ -272,6 +279,7 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
 // then the warp does the x100-softmax backward over the tokens of this pixel.
 struct TokenGrad {
   float g_col, g_row, g_in, g_out, g_max, g_sum, dp_mean, inv_sum, at_most;
+  float r_gsum, r_gcol, r_grow, r_col, r_row, r_inv_sum;   // upstream gradients on / saved values of the raw statistics
   int argmax, box, strict_box, column;
 };
 
@@ -300,6 +308,12 @@ __device__ __forceinline__ TokenGrad make_token_grad(const ga_tail_params_t& p, 
   g.g_row = (gs ? gs[GA_STAT_ROW] : 0.f) + g_center * 4.f * sgn_r / denom;
   g.g_max = gs ? gs[GA_STAT_MAX] : 0.f;
   g.g_sum = gs ? gs[GA_STAT_SUM] : 0.f;
+  g.r_gsum = gs ? gs[GA_STAT_RAW_SUM] : 0.f;
+  g.r_gcol = gs ? gs[GA_STAT_RAW_COL] : 0.f;
+  g.r_grow = gs ? gs[GA_STAT_RAW_ROW] : 0.f;
+  g.r_col = st[GA_STAT_RAW_COL];
+  g.r_row = st[GA_STAT_RAW_ROW];
+  g.r_inv_sum = 1.f / st[GA_STAT_RAW_SUM];
   g.inv_sum = 1.f / st[GA_STAT_SUM];
   g.at_most = st[GA_STAT_NINSIDE] > 0.f ? 1.f / st[GA_STAT_NINSIDE] : 0.f;
   g.argmax = amax;
@@ -414,6 +428,13 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
         }
       } else {
         dimg = ds[pix];
+      }
+      // raw-map statistics (custom losses) act on the un-smoothed map directly:
+      // d rcol / d A[pix] = ((x + .5) - rcol) / rsum, d rsum / d A[pix] = 1
+      const TokenGrad& g = tg[t];
+      if (g.r_gcol != 0.f || g.r_grow != 0.f || g.r_gsum != 0.f) {
+        const int y = (int)(((float)pix + 0.5f) * inv_res), x = pix - y * res;
+        dimg += g.r_gsum + (g.r_gcol * (((float)x + 0.5f) - g.r_col) + g.r_grow * (((float)y + 0.5f) - g.r_row)) * g.r_inv_sum;
       }
     }
     sdi[i] = dimg;

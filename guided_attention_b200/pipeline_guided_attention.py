@@ -399,7 +399,12 @@ class GuidedAttention(StableDiffusionPipelineBase):
         if hasattr(state.config, "custom_loss"):
             custom = torch.zeros(1, dtype=torch.float32, device=stats.device)
             for _, (loss_obj, args) in state.config.custom_loss.items():
-                custom = custom + loss_obj.calc_loss(attn_text, args)
+                term = None
+                if hasattr(loss_obj, "calc_loss_from_stats"):     # built-in losses: scalars from the tail's statistics
+                    term = loss_obj.calc_loss_from_stats(stats, spec.token_indices, res, args)
+                if term is None:                                  # plug-in contract of the reference (run.py:148-232)
+                    term = loss_obj.calc_loss(attn_text, args)
+                custom = custom + term
             losses_dict["custom_loss"] = custom
         if state.config.diagnostic_level > 0 or state.config.save_all_maps:
             self._log_maps(losses_dict)

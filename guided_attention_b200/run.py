@@ -177,6 +177,25 @@ class ToLeftOf(CustomLossBase):
         loss = (left_c + .2 * width - right_c) / width * 9
         return torch.clamp(loss, min=0).reshape(1)
 
+    def calc_loss_from_stats(self, stats, token_indices, res: int, text_args: str) -> torch.Tensor:
+        """Fused path: the same loss from the tail kernel's per-token raw-map statistics -- the centre of
+        mass of the un-smoothed map of every tracked token is `stats[n, GA_STAT_RAW_COL]`, differentiable through the
+        tail backward kernel -- instead of reductions over the materialised (res, res, 75) maps.  `token_indices[n]` is
+        the token index of stats row n (token index = map column + 1).  Returns None when a token of the two
+        sub-prompts is not tracked (the caller then falls back to `calc_loss`)."""
+        from . import _cabi as abi
+        args = self.parse_text_args(self.quote_items_in_tuple(text_args))
+        left = self.find_indices_for_sub_prompt(args[0])
+        right = self.find_indices_for_sub_prompt(args[1])
+        rows = {idx - 1: n for n, idx in enumerate(token_indices)}
+        if any(i not in rows for i in left + right):
+            return None
+        cx = stats[:, abi.GA_STAT_RAW_COL]
+        left_c = sum(cx[rows[i]] / len(left) for i in left)
+        right_c = sum(cx[rows[i]] / len(left) for i in right)      # the reference divides by len(left) here too
+        loss = (left_c + .2 * res - right_c) / res * 9
+        return torch.clamp(loss, min=0).reshape(1)
+
     def subprompts_of_interest(self, text_args: str) -> list:
         return list(self.parse_text_args(self.quote_items_in_tuple(text_args)))
 

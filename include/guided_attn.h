@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 1
+#define GA_ABI_VERSION 2
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -56,7 +56,13 @@ enum ga_stat {
   GA_STAT_HINGE_OUT = 9,/* strict mode only: sum_out w [p > 0] p                                                    */
   GA_STAT_NINSIDE = 10, /* number of inside pixels                                                                  */
   GA_STAT_CENTER = 11,  /* centring loss |col-cx*res|/(res-1) + 4|row-cy*res|/(res-1)   (:390-395)                  */
-  GA_STATS = 12
+  /* statistics of the UN-smoothed renormalised map A[:, :, token] -- what the custom-loss plug-ins read
+   * (run.py:157-161, 203-225: CustomLossBase.get_map_for_token + calc_weighted_center); differentiable, so the built-in
+   * toLeftOf loss is a few scalar operations on them and its gradient re-enters the tail backward through g_stats   */
+  GA_STAT_RAW_SUM = 12, /* sum of the raw map                                                                         */
+  GA_STAT_RAW_COL = 13, /* sum (jj+.5) A / sum A                                                                      */
+  GA_STAT_RAW_ROW = 14, /* sum (ii+.5) A / sum A                                                                      */
+  GA_STATS = 16
 };
 
 /* One tracked text token = one entry of the reference's `config.token_dict` (run.py:81-91). */

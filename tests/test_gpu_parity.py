@@ -387,12 +387,20 @@ def test_tail_vs_oracle_other_resolutions(res, variant):
         assert rel_err(g.cpu().numpy(), go.numpy()) < FP32_RTOL
 
 
-def test_tail_custom_loss_plugin_and_upstream_grads():
-    """Python CustomLoss plug-in on the materialised maps (gradient enters through g_attn_text) and arbitrary upstream
-    gradients on the per-token outputs."""
+@pytest.mark.parametrize("path", ["fused", "plugin"])
+def test_tail_custom_loss_plugin_and_upstream_grads(path):
+    """The keyword loss both ways -- "plugin": a Python CustomLoss on the materialised maps (reference contract,
+    run.py:148-232; gradient enters through g_attn_text), "fused": the built-in toLeftOf from the tail kernel's raw-map
+    statistics (gradient enters through g_stats, the tail backward stays on its sparse fast path) -- plus arbitrary
+    upstream gradients on the per-token outputs."""
     from guided_attention_b200.pipeline_guided_attention import GuidedAttention
-    from guided_attention_b200 import _cabi as abi
+    from guided_attention_b200 import _cabi as abi, ops, run as R
     cfg = setup_prompt('a [cat:.2,.3,.3,.4] and a dog with a bird [CustomLoss:toLeftOf (dog,bird)]')
+    if path == "plugin":
+        class PluginOnly(R.ToLeftOf):
+            def calc_loss_from_stats(self, *a, **k):
+                return None
+        cfg.custom_loss = {k: (PluginOnly(), args) for k, (_, args) in cfg.custom_loss.items()}
     case = dict(seed=77, bh=8, layers=2, gain=3.0)
     Ps, _ = make_loss_inputs(case)
     words = cfg.prompt.lower().split()
