@@ -185,23 +185,34 @@ class _BatchGraphs:
         _, _, stats, _, total = ops.guidance_tail(spec, accs, n_maps, n_samples=self.S)
         if self.S == 1:
             stats, total = stats[None], total
-        return stats, total
+        custom = None
+        if getattr(state.config, "custom_loss", None):
+            # built-in keyword losses per sample, from the tail's raw-map statistics (scalars; differentiable via g_stats)
+            terms = []
+            for s_ in range(self.S):
+                c = torch.zeros(1, dtype=torch.float32, device=stats.device)
+                for _, (loss_obj, args) in state.config.custom_loss.items():
+                    c = c + loss_obj.calc_loss_from_stats(stats[s_], spec.token_indices, res, args)
+                terms.append(c)
+            custom = torch.cat(terms)
+            total = total + custom
+        return stats, total, custom
 
     def _prog_eval(self):
         with torch.no_grad():
             self.pipe.unet(self.lat, self.t, encoder_hidden_states=self.cond)
-            stats, total = self._loss()
-        return {"stats": stats, "total": total}
+            stats, total, custom = self._loss()
+        return {"stats": stats, "total": total, "custom": custom}
 
     def _prog_update(self):
         with torch.enable_grad():
             lat = self.lat.detach().clone().requires_grad_(True)
             self.pipe.unet(lat, self.t, encoder_hidden_states=self.cond)
-            stats, total = self._loss()
+            stats, total, custom = self._loss()
             (g,) = torch.autograd.grad(total.sum(), [lat])   # samples are independent: row s of g is d total[s] / d lat[s]
         with torch.no_grad():
             self.lat_out.copy_((lat.detach().float() - self.step * g.float()).to(lat.dtype))
-        return {"stats": stats.detach(), "total": total.detach()}
+        return {"stats": stats.detach(), "total": total.detach(), "custom": None if custom is None else custom.detach()}
 
     def _prog_cfg(self):
         with torch.no_grad():
@@ -677,10 +688,13 @@ class GuidedAttention(StableDiffusionPipelineBase):
         """Extension: the guided loop of `__call__` for S seeds at once (one UNet pass serves all of them).  Per-seed
         semantics are those of S separate `__call__`s: each seed has its own initial noise and re-noise stream, its own
         threshold tests, refinement iteration count and recursion decisions; seeds that are done with a stage ride along
-        with step size 0 / are masked out of the result.  Returns the final latents (S, C, h, w).  Python custom losses
-        are not supported here."""
-        if getattr(state.config, "custom_loss", None):
-            raise NotImplementedError("generate_batch does not support [CustomLoss:...] annotations")
+        with step size 0 / are masked out of the result.  Returns the final latents (S, C, h, w).  Keyword losses are
+        supported when they can be computed from the tail's statistics (the built-in toLeftOf); Python plug-ins that
+        need the materialised maps are not."""
+        for _, (loss_obj, _args) in (getattr(state.config, "custom_loss", None) or {}).items():
+            if not hasattr(loss_obj, "calc_loss_from_stats"):
+                raise NotImplementedError("generate_batch supports [CustomLoss:...] only for losses with a fused "
+                                          "calc_loss_from_stats (the built-in toLeftOf)")
         thresholds = dict(thresholds if thresholds is not None else state.config.thresholds)
         if len(thresholds) == 0:
             thresholds = {0: float("inf")}
@@ -721,7 +735,12 @@ class GuidedAttention(StableDiffusionPipelineBase):
         def groups_of(out):
             rows = out["stats"].detach().cpu().tolist()       # the one D2H read of this evaluation
             spec = self._tail_spec_cache[1]
-            return [self._unscaled_groups(rows[s_], spec) for s_ in range(S)]
+            groups = [self._unscaled_groups(rows[s_], spec) for s_ in range(S)]
+            if hasattr(state.config, "custom_loss"):          # the reference appends (None, custom) even when it is 0
+                cust = out["custom"].detach().cpu().tolist() if out.get("custom") is not None else [0.0] * S
+                for s_ in range(S):
+                    groups[s_][None] = groups[s_].get(None, 0.0) + float(cust[s_])
+            return groups
 
         for i, t in enumerate(timesteps):
             t = int(t)

@@ -587,7 +587,7 @@ def test_pipeline_matches_reference_call_on_tiny_unet(e2e_golden):
     assert _psnr(got, gold) > 60, _psnr(got, gold)
 
 
-def _graph_test_pipe(dtype):
+def _graph_test_pipe(dtype, meta_prompt=None):
     from guided_attention_b200.pipeline_guided_attention import GuidedAttention
     from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
     from guided_attention_b200.substrate import DDIMScheduler
@@ -595,7 +595,7 @@ def _graph_test_pipe(dtype):
     torch.backends.cuda.matmul.allow_tf32 = False
     case = E2E_CASE
     unet, embeds, latents, _ = make_e2e_inputs(case)
-    cfg = setup_prompt(case["meta_prompt"], case["hyper"])
+    cfg = setup_prompt(meta_prompt or case["meta_prompt"], case["hyper"])
     cfg.thresholds = case["hyper"]["thresholds"]
     unet = unet.to(DEV, dtype)
     pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=cfg.stable.tokenizer)
@@ -725,6 +725,41 @@ def test_seed_batching_equals_separate_calls(graphs):
         b = batch[n:n + 1]
         cos = float((b * single).sum() / (np.linalg.norm(b) * np.linalg.norm(single)))
         assert cos > 0.99999 and _psnr(b, single) > 55, (seeds[n], cos, _psnr(b, single))
+
+
+def test_seed_batching_with_keyword_loss_equals_separate_calls():
+    """`generate_batch` with a [CustomLoss:toLeftOf ...] annotation (computed per sample from the tail's raw-map
+    statistics) against separate `__call__`s; a plug-in that needs the materialised maps is refused."""
+    from guided_attention_b200 import run as R
+    prompt = 'a [robot:.55,.3,.4,.55] and a vase with a lamp [CustomLoss:toLeftOf (vase,lamp)]'
+    pipe, store, cfg, embeds, case = _graph_test_pipe(torch.float32, prompt)
+    from guided_attention_b200.run import synthetic_prompt_embeds
+    embeds = synthetic_prompt_embeds(cfg.prompt, embeds.shape[-1])
+    pipe.use_cuda_graphs = True
+    seeds = [28, 31]
+    singles = []
+    for sd in seeds:
+        gen = torch.Generator("cpu").manual_seed(sd)
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(sd))
+        out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5, generator=gen,
+                   latents=lat, prompt_embeds=embeds[1:2], negative_prompt_embeds=embeds[0:1],
+                   num_inference_steps=case["steps"], thresholds=cfg.thresholds, output_type="latent")
+        singles.append(out.images.float().cpu().numpy())
+    batch = pipe.generate_batch(cfg.prompt, store, seeds, embeds[1:2], embeds[0:1], attention_res=16,
+                                num_inference_steps=case["steps"], guidance_scale=7.5, thresholds=cfg.thresholds)
+    batch = batch.float().cpu().numpy()
+    for n, single in enumerate(singles):
+        b = batch[n:n + 1]
+        cos = float((b * single).sum() / (np.linalg.norm(b) * np.linalg.norm(single)))
+        assert cos > 0.99999 and _psnr(b, single) > 55, (seeds[n], cos, _psnr(b, single))
+
+    class MapsOnly(R.CustomLossBase):
+        def calc_loss(self, maps, args):
+            return maps.sum().reshape(1) * 0
+    cfg.custom_loss = {k: (MapsOnly(), args) for k, (_, args) in cfg.custom_loss.items()}
+    with pytest.raises(NotImplementedError):
+        pipe.generate_batch(cfg.prompt, store, seeds, embeds[1:2], embeds[0:1], attention_res=16,
+                            num_inference_steps=case["steps"], guidance_scale=7.5, thresholds=cfg.thresholds)
 
 
 def test_full_size_sd14_guidance_step_fp16():
