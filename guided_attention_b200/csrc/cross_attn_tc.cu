@@ -258,6 +258,12 @@ constexpr int kFwdStages = 12;  // flat forward: Q-only stages
 constexpr int kStageCols = 256;
 constexpr int kGroupThreads = 128;
 
+#ifdef GA_DEBUG
+#define GA_ABL(p, bit) (((p).ablate & (bit)) != 0)
+#else
+#define GA_ABL(p, bit) false   // the ablation switch does not exist in release builds
+#endif
+
 struct PipeParams {
   void* o;
   float* lse;
@@ -271,7 +277,9 @@ struct PipeParams {
   int n_sbuf;       // S/P buffers in TMEM: 4 when 4*80 + 2*npv <= 512, else 2
   int n_obuf;       // O buffers in TMEM: as many as fit behind the S buffers (2 .. 4)
   int direct_store; // 1: epilogue stores from registers (short rings), 0: staged in the dead Q tile + TMA store
-  int ablate;       // debugging aid (GA_ABLATE): 1 = no O store, 2 = no exponentials, 4 = no Q loads.  WRONG RESULTS.
+#ifdef GA_DEBUG
+  int ablate;       // debug builds only (-DGA_DEBUG, env GA_ABLATE): 1 = no O store, 2 = no exponentials, 4 = no Q loads.  WRONG RESULTS.
+#endif
   float scale;
 };
 
@@ -428,7 +436,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
         if (k >= S) mbar_wait(SMEM_FREE(ss), par ^ 1u);
         if (elect_one()) {
           const uint32_t sQ = base + ss * stage_bytes, sK = sQ + p.nblk * kQBlockBytes, sV = sK + p.nblk * kKVBlockBytes;
-          const bool load_q = !(p.ablate & 4);
+          const bool load_q = !GA_ABL(p, 4);
           mbar_expect_tx(FULL(ss), stage_bytes - (load_q ? 0u : q_bytes));
           for (int blk = 0; blk < p.nblk; ++blk) {
             if (load_q) tma_load_4d(sQ + blk * kQBlockBytes, &map_q, FULL(ss), blk * kBlockCols, it.h, it.tile * kM, it.b);
@@ -546,7 +554,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       tc_fence_after();
       const float inv = s_inv[k & 7][r];
       const uint32_t sO = base + ss * stage_bytes;    // the Q tile of this stage is dead once MMA1 has retired
-      for (int c0 = 0; c0 < p.npv / 16 && !(p.ablate & 8); c0 += 4) {    // up to 64 columns per TMEM round trip
+      for (int c0 = 0; c0 < p.npv / 16 && !GA_ABL(p, 8); c0 += 4) {    // up to 64 columns per TMEM round trip
         float ov[64];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -567,7 +575,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
-        for (int blk = 0; blk < p.nblk && !(p.ablate & 1); ++blk)
+        for (int blk = 0; blk < p.nblk && !GA_ABL(p, 1); ++blk)
           tma_store_4d(&map_o, sO + blk * kQBlockBytes + (uint32_t)warp * 4096u, blk * kBlockCols, it.h,
                        it.tile * kM + warp * 32, it.b);
         bulk_commit_group();
@@ -612,7 +620,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       const uint32_t lane_addr = lane_base + colS(k);
       mbar_wait(S_READY(sIdx(k)), sPar(k));
       tc_fence_after();
-      if (p.ablate & 16) {                           // hand the buffer straight back
+      if (GA_ABL(p, 16)) {                           // hand the buffer straight back
         s_inv[k & 7][r] = 1.f;
         tc_fence_before();
         mbar_arrive(P_READY(sIdx(k)));
@@ -623,7 +631,7 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
       for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + cc * 16, s + cc * 16);
       tmem_ld_wait();
       float m, sum;
-      if (p.ablate & 2) { m = 0.f; sum = 1.f; }
+      if (GA_ABL(p, 2)) { m = 0.f; sum = 1.f; }
       else row_softmax_ilp(s, p.T, sc, m, sum);
 #pragma unroll
       for (int cc = 0; cc < kTpad / 16; ++cc) {
@@ -1207,10 +1215,12 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
   p.units = f.B * p.tiles;
   p.n_sbuf = (4 * kTpad + 2 * p.npv <= 512) ? 4 : 2;
   p.n_obuf = (512 - p.n_sbuf * kTpad) / p.npv >= 4 ? 4 : 2;
+#ifdef GA_DEBUG
   {
     const char* e = getenv("GA_ABLATE");
     p.ablate = e != nullptr ? atoi(e) : 0;
   }
+#endif
   CUtensorMap mo;
   int rc;
   if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, 32)) != GA_OK) return rc;   // one store per epilogue warp

@@ -209,7 +209,6 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
         }
       }
     }
-    const float k = p.inv_count * p.temperature;
 #pragma unroll
     for (int kk = 0; kk < kKPL; ++kk) {
       const int c = lane + 32 * kk;
@@ -218,7 +217,6 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
             make_float4((v[kk].x * p.inv_count) * p.temperature, (v[kk].y * p.inv_count) * p.temperature,
                         (v[kk].z * p.inv_count) * p.temperature, (v[kk].w * p.inv_count) * p.temperature);
     }
-    (void)k;
     __syncwarp();
     for (int q = 0; q < 4; ++q) {
       const int pix = group * 4 + q;

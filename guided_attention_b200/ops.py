@@ -136,6 +136,9 @@ class _CrossAttnFn(torch.autograd.Function):
         _count("cross_attn_fwd")
         ctx.save_for_backward(q, k, v, lse)
         ctx.meta = (heads, float(scale), impl)
+        # layers whose maps do not feed the loss (32^2 and 8^2 at attention_res 16) get d_acc = None, not a
+        # materialised all-zero (B, N, 77) tensor that K2 would still read
+        ctx.set_materialize_grads(False)
         if acc is None:
             return o, None
         return o, acc
@@ -240,7 +243,7 @@ def self_attention_supported(dtype, head_dim: int) -> bool:
     return dtype in (torch.float16, torch.bfloat16) and head_dim % 8 == 0 and 8 <= head_dim <= 160
 
 
-def attention_probs(q, k, heads: int, scale: float):
+def attention_probs(q, k, heads: int, scale: float, bias=None):
     """Materialised P (B*H, N, T), rows ordered b*H + h like the reference's stored maps.  Not differentiable; exists for
     API compatibility (`AttentionStore.get_average_attention`) and for tests."""
     _need_cuda(q, k)

@@ -33,6 +33,15 @@ _KIND = {AT.COOR: abi.GA_TOKEN_COOR, AT.BOX: abi.GA_TOKEN_BOX, AT.KEYWORD: abi.G
 
 
 
+def _token_table_key(token_dict):
+    """Hashable snapshot of `config.token_dict` (run.py:81-91): everything the tail spec and the captured graphs bake in."""
+    def payload(v):
+        if hasattr(v, 'as_tuple'):
+            return tuple(v.as_tuple()) + (getattr(v, 'size', None),)
+        return tuple(v) if isinstance(v, (list, tuple)) else v
+    return tuple((i, v['loss_type'], v['subprompt'], payload(v['loss'])) for i, v in token_dict.items())
+
+
 class _StepGraphs:
     """CUDA-graph execution of the three device programs the guided loop keeps re-issuing (DESIGN.md "CUDA graphs"):
 
@@ -303,7 +312,9 @@ class GuidedAttention(StableDiffusionPipelineBase):
             prompt = self.prompt[0] if isinstance(self.prompt, list) else self.prompt
             last_idx = len(self.tokenizer(prompt)['input_ids']) - 1
         token_dict = cfg.token_dict
-        key = (id(token_dict), tuple(token_dict.keys()), attention_res, n_ctx, last_idx, bool(smooth_attentions),
+        # keyed on the CONTENTS of the token table (the reference re-derives all of this on every evaluation): a dict
+        # mutated in place, or a new dict at a recycled address, must not hit a stale spec
+        key = (_token_table_key(token_dict), attention_res, n_ctx, last_idx, bool(smooth_attentions),
                float(sigma), int(kernel_size), bool(hp["strict"]), float(hp["shrink_factor"]),
                float(hp["inside_loss_scale"]), float(hp["outside_loss_scale"]), float(hp.get("bb_center_weight", .05)),
                bool(getattr(cfg, "sub_prompt_avg_within", False)), str(device))
@@ -578,7 +589,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         self.pass_counts[name] += n
 
     # ------------------------------------------------------------------------------------- CUDA-graph execution
-    use_cuda_graphs = False   # opt-in: `pipe.use_cuda_graphs = True` (bench.py and run.py turn it on)
+    use_cuda_graphs = False   # `run.load_model` (the `run.py --meta_prompt` entry point) and bench.py turn it on for CUDA
 
     def _step_graphs(self, attention_store, loss_kw, prompt_embeds, guidance_scale, latents) -> "_StepGraphs":
         """Graphs are cached on the pipeline and reused across calls (seeds) while everything baked into them is
@@ -587,9 +598,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         key = (id(self.unet), id(attention_store), tuple(prompt_embeds.shape), prompt_embeds.dtype, tuple(latents.shape),
                float(guidance_scale), (loss_kw["attention_res"], loss_kw["smooth_attentions"], loss_kw["sigma"],
                                        loss_kw["kernel_size"], loss_kw["normalize_eot"]),
-               tuple((i, v['loss_type'], v['subprompt'],
-                      v['loss'].as_tuple() if hasattr(v['loss'], 'as_tuple') else v['loss'])
-                     for i, v in cfg.token_dict.items()),
+               _token_table_key(cfg.token_dict),
                tuple(sorted((k, str(v)) for k, v in hp.items())), bool(cfg.sub_prompt_avg_within),
                tuple(getattr(cfg, "custom_loss", {}).keys()), self.scheduler.num_inference_steps, str(latents.device))
         cached = getattr(self, "_graphs_cache", None)
@@ -720,9 +729,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                        smooth_attentions=smooth_attentions, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
         key = ("batch", S, id(self.unet), id(attention_store), tuple(embeds.shape), embeds.dtype, float(guidance_scale),
                attention_res, smooth_attentions, sigma, kernel_size, sd_2_1, num_inference_steps,
-               tuple((i, v['loss_type'], v['subprompt'],
-                      v['loss'].as_tuple() if hasattr(v['loss'], 'as_tuple') else v['loss'])
-                     for i, v in cfg.token_dict.items()),
+               _token_table_key(cfg.token_dict),
                tuple(sorted((k, str(v)) for k, v in state.curHyperParams.items())), bool(cfg.sub_prompt_avg_within),
                bool(self.use_cuda_graphs), str(device))
         cached = getattr(self, "_batch_graphs_cache", None)

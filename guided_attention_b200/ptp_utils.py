@@ -35,9 +35,11 @@ class HeadSummedMaps:
     shape (B*H, N, T): the shape of the probability tensor the reference hands to the controller.
     """
 
-    def __init__(self, acc: torch.Tensor, heads: int, q: torch.Tensor, k: torch.Tensor, scale: float):
+    _cache = None
+
+    def __init__(self, acc: torch.Tensor, heads: int, q: torch.Tensor, k: torch.Tensor, scale: float, bias=None):
         self.acc, self.heads, self.scale = acc, heads, scale
-        self._q, self._k = q, k
+        self._q, self._k, self._bias = q, k, bias
         self.shape = torch.Size((acc.shape[0] * heads, acc.shape[1], acc.shape[2]))
         self.dtype, self.device = q.dtype, acc.device
 
@@ -47,14 +49,44 @@ class HeadSummedMaps:
 
     def probs(self) -> torch.Tensor:
         """Per-head probabilities (B*H, N, T), recomputed by `ga_attn_probs`; detached."""
-        return ops.attention_probs(self._q.detach(), self._k.detach(), self.heads, self.scale)
+        return ops.attention_probs(self._q.detach(), self._k.detach(), self.heads, self.scale, bias=self._bias)
+
+    # -- tensor-like on demand (SURVEY 8b: "lazily materialised only if someone asks").  Code written against the
+    # reference's store -- e.g. its own aggregate_attention, `item.reshape(1, -1, res, res, item.shape[-1])`
+    # (utils/ptp_utils.py:286), or `torch.cat(out, dim=0)` (:287) -- sees the (B*H, N, T) probability tensor: any
+    # attribute this handle does not have, and any torch function it is passed to, goes to the materialised maps.
+    def _materialised(self) -> torch.Tensor:
+        if self._cache is None:
+            self._cache = self.probs()
+        return self._cache
+
+    def __getattr__(self, name):
+        if name.startswith("__") or name in ("acc", "heads", "scale", "_q", "_k", "_bias", "shape", "dtype", "device"):
+            raise AttributeError(name)
+        return getattr(self._materialised(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def conv(x):
+            if isinstance(x, HeadSummedMaps):
+                return x._materialised()
+            if isinstance(x, (list, tuple)):
+                return type(x)(conv(y) for y in x)
+            return x
+        return func(*conv(args), **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+    def __getitem__(self, idx):
+        return self._materialised()[idx]
+
+    def __len__(self):
+        return self.shape[0]
 
     def mean_map(self) -> torch.Tensor:
         """(N, T) mean over batch x heads, differentiable."""
         return self.acc.sum(0) / self.n_maps
 
     def detach(self):
-        return HeadSummedMaps(self.acc.detach(), self.heads, self._q.detach(), self._k.detach(), self.scale)
+        return HeadSummedMaps(self.acc.detach(), self.heads, self._q.detach(), self._k.detach(), self.scale, self._bias)
 
 
 class AttendExciteCrossAttnProcessor:
@@ -182,6 +214,12 @@ def register_attention_control(model, controller):
         attn_procs[name] = AttendExciteCrossAttnProcessor(attnstore=controller, place_in_unet=place)
     model.unet.set_attn_processor(attn_procs)
     controller.num_att_layers = count
+    # The guidance path differentiates with respect to the latents only (pipeline_guided_attention.py:466); a UNet
+    # fresh from `from_pretrained` still has requires_grad=True on its weights, which would make every cross layer's
+    # K/V "need" gradients: K2 would leave the tcgen05 path to compute dK/dV nobody reads, and the text K/V cache would
+    # be bypassed.  Freezing the weights does not change any value the reference computes.
+    if hasattr(model.unet, "requires_grad_"):
+        model.unet.requires_grad_(False)
 
 
 class AttentionControl(abc.ABC):

@@ -32,7 +32,11 @@ def load_model(config: RunConfig, device=None, unet_config: UNetConfig = None, u
         unet_config = UNetConfig.sd21_base() if config.sd_2_1 else UNetConfig.sd14()
     dtype = torch.float16 if config.half_precision else torch.float32
     unet = build_unet(unet_config, seed=unet_seed, dtype=dtype, device=device)
-    return GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=WhitespaceTokenizer())
+    pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=WhitespaceTokenizer())
+    # the guided loop replays three captured device programs instead of re-issuing ~10^3 launches per UNet pass; the
+    # eager loop stays available (`pipe.use_cuda_graphs = False`, diagnostics, use_optimizer=False only for graphs)
+    pipe.use_cuda_graphs = device.type == "cuda"
+    return pipe
 
 
 def synthetic_prompt_embeds(prompt: str, cross_attention_dim: int, n_ctx: int = 77, seed: int = 1234):
@@ -96,11 +100,19 @@ def parseMetaPrompt(config):
 
 
 def execute(config, output_type="pil", save=True):
-    """All seeds x hyper-parameter states, sequentially on this process's GPU (reference run.py:93-135).  For the
-    multi-GPU seed sweep see `guided_attention_b200.sweep`."""
+    """All seeds x hyper-parameter states (reference run.py:93-135).  Launched plainly, every seed runs sequentially on
+    this process's GPU like the reference; launched under `torchrun` (one process per GPU), `config.seeds` is sharded
+    round-robin `seed_idx % world_size` (`sweep.shard_seeds`, BASELINE config 5) with no collective on the hot path, and
+    for `output_type="latent"` the per-seed results are gathered once at the end so that every rank returns the full
+    list in (seed, hyper-state) order.  One `AttentionStore` serves every seed (`reset()` between images, which is all
+    a fresh store would give) so the CUDA graphs captured for the first image are replayed for the rest."""
+    from . import sweep
+    rank, world, _ = sweep.init_distributed() if sweep.dist_env()[1] > 1 else (0, 1, 0)
     images = []
     image_path = None
-    for seed in config.seeds:
+    controller = AttentionStore()
+    n_states = len(shared_state.get_hyperparam_states())
+    for seed in sweep.shard_seeds(list(config.seeds), rank, world):
         for hyper in shared_state.get_hyperparam_states():
             shared_state.curHyperParams = hyper
             overrideConfig(config)
@@ -108,7 +120,7 @@ def execute(config, output_type="pil", save=True):
             helpers.log_clear()
             shared_state.cur_seed = seed
             g = torch.Generator('cpu').manual_seed(seed)   # CPU stream: same latents on every device
-            controller = AttentionStore()
+            controller.reset()
             image = run_on_prompt(prompt=config.prompt, model=config.stable, controller=controller, seed=g,
                                   config=config, output_type=output_type)
             if save and output_type == "pil":
@@ -123,6 +135,15 @@ def execute(config, output_type="pil", save=True):
                     image.save(image_path)
                 helpers.log_save(out_dir / f'{seed}.txt')
             images.append(image)
+    if output_type == "latent" and world > 1:
+        local = torch.cat(images) if images else None
+        # the only communication of the sweep: final latents, 32 KB per image (NCCL over NVLink on the GPU box)
+        like = local if local is not None else torch.zeros((0, config.stable.unet.in_channels) + (
+            config.stable.unet.config.sample_size,) * 2, dtype=config.stable.unet.dtype,
+            device=config.stable._execution_device)
+        per_seed = like.reshape((-1, n_states) + tuple(like.shape[1:]))
+        full = sweep.gather_results(per_seed, len(config.seeds), rank, world)
+        return list(full.reshape((-1, 1) + tuple(like.shape[1:])))
     return images if output_type != "pil" else image_path
 
 

@@ -52,14 +52,3 @@ def to_str(t):
 
 def get_name():
     return "".join(str(t) + "_" + to_str(globals()[t]) + "_" for t in tags)
-
-
-class TurnOffRequiresGradDeepLatent(object):
-    def __enter__(self):
-        global deepLatentRequiresGrad
-        deepLatentRequiresGrad = False
-        return deepLatentRequiresGrad
-
-    def __exit__(self, *args):
-        global deepLatentRequiresGrad
-        deepLatentRequiresGrad = True

@@ -3,8 +3,11 @@
 
 diffusers is absent offline, so this is a *definition* shared by the oracle and the product path.  Settings follow
 what `DDIMScheduler.from_config(<SD-1.4 PNDM config>)` is assumed to yield in diffusers 0.12.1 (SURVEY.md 8c [memory]):
-scaled_linear betas 0.00085 -> 0.012 over 1000 train steps, steps_offset=1, set_alpha_to_one=False, clip_sample=True
-(DDIM default, so pred_x0 is clamped to [-1, 1]), eta=0, epsilon prediction.  For 50 steps: timesteps 981, 961, ..., 1
+scaled_linear betas 0.00085 -> 0.012 over 1000 train steps, steps_offset=1, set_alpha_to_one=False, eta=0, epsilon
+prediction, and clip_sample=False: the checkpoints' own scheduler_config.json files (CompVis/stable-diffusion-v1-4,
+stabilityai/stable-diffusion-2-1-base) carry `"clip_sample": false` and `from_config` honours the key [memory, not
+checkable offline], so latent-space pred_x0 is NOT clamped.  The key stays overridable (`DDIMScheduler(clip_sample=True)`
+gives the class default of diffusers' DDIMScheduler) and `from_config` passes it through when the config has it.  For 50 steps: timesteps 981, 961, ..., 1
 (matches the comment at reference `utils/shared_state.py:8`).
 """
 from __future__ import annotations
@@ -27,7 +30,7 @@ class DDIMScheduler:
     init_noise_sigma = 1.0
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1,
-                 clip_sample=True, set_alpha_to_one=False):
+                 clip_sample=False, set_alpha_to_one=False):
         self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start,
                                       beta_end=beta_end, steps_offset=steps_offset, clip_sample=clip_sample,
                                       set_alpha_to_one=set_alpha_to_one, beta_schedule="scaled_linear")

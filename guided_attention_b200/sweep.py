@@ -53,10 +53,24 @@ def gather_results(local: torch.Tensor, n_total: int, rank: int, world: int) -> 
     return out
 
 
+def _agree_on_template(local_template: Optional[torch.Tensor], rank: int, world: int, device=None):
+    """(shape, dtype) of one result, agreed across ranks: the lowest rank that has a result describes it to everybody.
+    Every rank takes part (no early return before a collective); returns None on every rank when nobody has a result."""
+    if world == 1:
+        return None if local_template is None else (tuple(local_template.shape), local_template.dtype)
+    mine = None if local_template is None else (tuple(local_template.shape), str(local_template.dtype).split(".")[-1])
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    desc = next((d for d in everyone if d is not None), None)
+    return None if desc is None else (tuple(desc[0]), getattr(torch, desc[1]))
+
+
 def run_seed_sweep(generate: Callable[[int], torch.Tensor], seeds: Sequence[int], rank: int, world: int,
-                   gather: bool = True):
+                   gather: bool = True, device=None):
     """`generate(seed) -> (C, H, W) tensor`.  Returns (all results in seed order or None, this rank's results, failures).
-    A failing seed is reported and skipped (zeros in its slot); the other seeds continue."""
+    A failing seed is reported and skipped (zeros in its slot); the other seeds continue.  A rank whose shard is empty
+    or whose seeds all failed still joins the final gather with a zero chunk, so per-seed failures never turn into a
+    job-wide hang; when no rank has any result every rank returns (None, [], failures)."""
     mine = shard_seeds(seeds, rank, world)
     results, failures = [], []
     for s in mine:
@@ -66,8 +80,15 @@ def run_seed_sweep(generate: Callable[[int], torch.Tensor], seeds: Sequence[int]
             failures.append((s, repr(e)))
             results.append(None)
     template = next((r for r in results if r is not None), None)
-    if template is None:
+    desc = _agree_on_template(template, rank, world) if gather else (
+        None if template is None else (tuple(template.shape), template.dtype))
+    if desc is None:
         return None, [], failures
-    local = torch.stack([r if r is not None else torch.zeros_like(template) for r in results])
+    shape, dtype = desc
+    dev = template.device if template is not None else (device if device is not None else (
+        torch.device("cuda", torch.cuda.current_device()) if dist.is_initialized() and dist.get_backend() == "nccl"
+        else torch.device("cpu")))
+    zero = torch.zeros(shape, dtype=dtype, device=dev)
+    local = torch.stack([r if r is not None else zero for r in results]) if results else zero.new_zeros((0,) + shape)
     full = gather_results(local, len(seeds), rank, world) if gather else None
     return full, local, failures
