@@ -21,7 +21,7 @@ GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
  GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER, GA_STAT_RAW_SUM,
  GA_STAT_RAW_COL, GA_STAT_RAW_ROW) = range(15)
 GA_STATS = 16
-GA_ABI_VERSION = 2
+GA_ABI_VERSION = 3
 
 
 class GaToken(C.Structure):
@@ -37,7 +37,14 @@ class GaTailParams(C.Structure):
                 ("inside_scale", C.c_float), ("outside_scale", C.c_float), ("n_samples", C.c_int32)]
 
 
+class GaScoreBias(C.Structure):
+    _fields_ = [("mask", C.c_void_p), ("mask_stride_bh", C.c_int64), ("mask_stride_n", C.c_int64),
+                ("pww_masks", C.c_void_p), ("pww_coef", C.c_void_p), ("pww_smax", C.c_void_p),
+                ("pww_count", C.c_int32), ("pww_column", C.c_int32 * GA_MAX_TOKENS)]
+
+
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_bias = C.POINTER(GaScoreBias)
 
 # name -> (restype, argtypes); every symbol declared in include/guided_attn.h
 PROTOTYPES = {
@@ -48,6 +55,11 @@ PROTOTYPES = {
     "ga_cross_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i,
                                 _vp]),
     "ga_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "ga_cross_attn_smax": (_i, [_vp, _vp, _vp, _bias, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "ga_cross_attn_fwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _bias, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_cross_attn_bwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _bias, _vp, _i, _i, _i, _i, _i,
+                                   _f, _i, _i, _vp]),
+    "ga_attn_probs_ex": (_i, [_vp, _vp, _vp, _bias, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_self_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_self_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "ga_rasterize_boxes": (_i, [C.POINTER(C.c_double), _i, _i, C.c_double, _vp, _vp]),

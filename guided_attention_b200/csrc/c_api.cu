@@ -22,9 +22,11 @@ int fail(int code, const char* fmt, ...) {
 
 namespace simt {
 int fwd(const void*, const void*, const void*, void*, float*, float*, void*, int, int, int, int, int, float, int,
-        cudaStream_t);
+        const ga_score_bias_t*, cudaStream_t);
 int bwd(const void*, const void*, const void*, const float*, const void*, const float*, int64_t, int, void*, float*,
-        float*, int, int, int, int, int, float, int, cudaStream_t);
+        float*, int, int, int, int, int, float, int, const ga_score_bias_t*, float*, cudaStream_t);
+int smax(const void*, const void*, unsigned long long*, int, int, int, int, int, float, int, const ga_score_bias_t*,
+         cudaStream_t);
 }  // namespace simt
 namespace tc {
 bool supports_fwd(int dtype, int n_ctx, int head_dim, int heads, bool with_acc);
@@ -69,11 +71,34 @@ extern "C" int ga_device_supported(int device) {
   return prop.major == 10 ? 1 : 0;
 }
 
+static int check_bias(const ga_score_bias_t* b, int batch, int heads, int n_query, int n_ctx, int impl) {
+  if (b == nullptr) return GA_OK;
+  GA_CHECK_ARG(impl == GA_IMPL_AUTO || impl == GA_IMPL_SIMT, "the score bias is implemented by the SIMT variant only");
+  GA_CHECK_ARG(b->pww_count >= 0 && b->pww_count <= GA_MAX_TOKENS, "pww_count %d out of range", b->pww_count);
+  if (b->pww_count > 0) {
+    GA_CHECK_ARG(b->pww_masks && b->pww_coef && b->pww_smax, "paint-with-words needs pww_masks, pww_coef and pww_smax");
+    GA_CHECK_ARG((int64_t)batch * heads * n_query * n_ctx < (int64_t)0xffffffffll, "launch too large for the packed max");
+    GA_CHECK_ALIGN(b->pww_smax, 8, "pww_smax");
+    for (int i = 0; i < b->pww_count; ++i)
+      GA_CHECK_ARG(b->pww_column[i] >= 0 && b->pww_column[i] < n_ctx, "pww_column[%d] = %d", i, b->pww_column[i]);
+  }
+  return GA_OK;
+}
+
 extern "C" int ga_cross_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* acc,
                                  int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
                                  int impl, ga_stream_t stream) {
+  return ga_cross_attn_fwd_ex(q, k, v, o, lse, acc, nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, impl,
+                              stream);
+}
+
+extern "C" int ga_cross_attn_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, float* acc,
+                                    const ga_score_bias_t* bias, int batch, int heads, int n_query, int n_ctx,
+                                    int head_dim, float scale, int dtype, int impl, ga_stream_t stream) {
   int rc = check_attn_args(q, k, batch, heads, n_query, n_ctx, head_dim, dtype);
   if (rc != GA_OK) return rc;
+  if ((rc = check_bias(bias, batch, heads, n_query, n_ctx, impl)) != GA_OK) return rc;
+  if (bias != nullptr) impl = GA_IMPL_SIMT;
   GA_CHECK_ARG(v != nullptr && o != nullptr && lse != nullptr, "NULL operand");
   GA_CHECK_ALIGN(v, 16, "v");
   GA_CHECK_ALIGN(o, 16, "o");
@@ -87,15 +112,41 @@ extern "C" int ga_cross_attn_fwd(const void* q, const void* k, const void* v, vo
     const int force = impl == GA_IMPL_TCGEN05_SINGLE ? 0 : (impl == GA_IMPL_TCGEN05_PIPE ? 1 : -1);
     return tc::fwd(q, k, v, o, lse, acc, batch, heads, n_query, n_ctx, head_dim, scale, dtype, force, st);
   }
-  return simt::fwd(q, k, v, o, lse, acc, nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, st);
+  return simt::fwd(q, k, v, o, lse, acc, nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, bias, st);
+}
+
+extern "C" int ga_cross_attn_smax(const void* q, const void* k, unsigned long long* smax, const ga_score_bias_t* bias,
+                                  int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
+                                  ga_stream_t stream) {
+  int rc = check_attn_args(q, k, batch, heads, n_query, n_ctx, head_dim, dtype);
+  if (rc != GA_OK) return rc;
+  GA_CHECK_ARG(smax != nullptr, "smax is NULL");
+  GA_CHECK_ALIGN(smax, 8, "smax");
+  GA_CHECK_ARG((int64_t)batch * heads * n_query * n_ctx < (int64_t)0xffffffffll, "launch too large for the packed max");
+  return simt::smax(q, k, smax, batch, heads, n_query, n_ctx, head_dim, scale, dtype, bias,
+                    static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
                                  const float* d_acc, int64_t d_acc_batch_stride, int d_acc_row_stride, void* d_q,
                                  float* d_k, float* d_v, int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
                                  int impl, ga_stream_t stream) {
+  return ga_cross_attn_bwd_ex(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_acc_row_stride, d_q, d_k, d_v, nullptr,
+                              nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, impl, stream);
+}
+
+extern "C" int ga_cross_attn_bwd_ex(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
+                                    const float* d_acc, int64_t d_acc_batch_stride, int d_acc_row_stride, void* d_q,
+                                    float* d_k, float* d_v, const ga_score_bias_t* bias, float* pww_partials, int batch,
+                                    int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl,
+                                    ga_stream_t stream) {
   int rc = check_attn_args(q, k, batch, heads, n_query, n_ctx, head_dim, dtype);
   if (rc != GA_OK) return rc;
+  if ((rc = check_bias(bias, batch, heads, n_query, n_ctx, impl)) != GA_OK) return rc;
+  if (bias != nullptr) {
+    impl = GA_IMPL_SIMT;
+    GA_CHECK_ARG(bias->pww_count == 0 || pww_partials != nullptr, "paint-with-words backward needs pww_partials");
+  }
   GA_CHECK_ARG(v != nullptr && lse != nullptr && d_o != nullptr && d_q != nullptr, "NULL operand");
   GA_CHECK_ALIGN(v, 16, "v");
   GA_CHECK_ALIGN(d_o, 16, "d_o");
@@ -114,15 +165,22 @@ extern "C" int ga_cross_attn_bwd(const void* q, const void* k, const void* v, co
                    head_dim, scale, dtype, force, st);
   }
   return simt::bwd(q, k, v, lse, d_o, d_acc, d_acc_batch_stride, d_acc_row_stride, d_q, d_k, d_v, batch, heads, n_query,
-                   n_ctx, head_dim, scale, dtype, st);
+                   n_ctx, head_dim, scale, dtype, bias, pww_partials, st);
 }
 
 extern "C" int ga_attn_probs(const void* q, const void* k, void* probs, int batch, int heads, int n_query, int n_ctx,
                              int head_dim, float scale, int dtype, ga_stream_t stream) {
+  return ga_attn_probs_ex(q, k, probs, nullptr, batch, heads, n_query, n_ctx, head_dim, scale, dtype, stream);
+}
+
+extern "C" int ga_attn_probs_ex(const void* q, const void* k, void* probs, const ga_score_bias_t* bias, int batch,
+                                int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
+                                ga_stream_t stream) {
   int rc = check_attn_args(q, k, batch, heads, n_query, n_ctx, head_dim, dtype);
   if (rc != GA_OK) return rc;
+  if ((rc = check_bias(bias, batch, heads, n_query, n_ctx, GA_IMPL_SIMT)) != GA_OK) return rc;
   GA_CHECK_ARG(probs != nullptr, "probs is NULL");
-  return simt::fwd(q, k, k, nullptr, nullptr, nullptr, probs, batch, heads, n_query, n_ctx, head_dim, scale, dtype,
+  return simt::fwd(q, k, k, nullptr, nullptr, nullptr, probs, batch, heads, n_query, n_ctx, head_dim, scale, dtype, bias,
                    static_cast<cudaStream_t>(stream));
 }
 

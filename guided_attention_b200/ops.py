@@ -114,9 +114,67 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 # ======================================================================================== K1 / K2 cross-attention
+class ScoreBias:
+    """Optional additive score bias of the cross-attention kernels (`ga_score_bias_t`).
+
+    mask      attention_mask of the processor call (reference utils/ptp_utils.py:135-136): fp32, broadcastable to
+              (B*H, N, T); kept as a stride-0 expanded view, never materialised.
+    pww_*     paint-with-words (reference utils/ptp_utils.py:113-138): `pww_masks` (n, N) uint8 = the BOX tokens' masks at
+              this layer's resolution, `pww_columns` their token indices, `pww_coef` a 1-element fp32 DEVICE tensor
+              holding w * 0.4 * ln(1 + sigma_t) (0 = off).  `smax` (1-element int64 device tensor) receives the packed
+              global score max from `ga_cross_attn_smax`; the backward reads the argmax from it."""
+
+    def __init__(self, mask=None, pww_masks=None, pww_columns=(), pww_coef=None):
+        self.mask, self.pww_masks, self.pww_columns, self.pww_coef = mask, pww_masks, list(pww_columns), pww_coef
+        self.smax = None
+
+    def struct(self, B, H, N, T, device):
+        sb = abi.GaScoreBias()
+        if self.mask is not None:
+            m = self.mask
+            if m.dtype != torch.float32:
+                m = m.float()
+            m = torch.broadcast_to(m, (B * H, N, T))         # raises like the reference's `scores + mask` would
+            if m.stride(2) != 1:
+                m = m.contiguous()
+            self._mask_view = m
+            sb.mask, sb.mask_stride_bh, sb.mask_stride_n = m.data_ptr(), m.stride(0), m.stride(1)
+        n = len(self.pww_columns)
+        if n:
+            if n > abi.GA_MAX_TOKENS:
+                raise ValueError(f"at most {abi.GA_MAX_TOKENS} paint-with-words tokens")
+            if self.pww_masks.shape != (n, N) or self.pww_masks.dtype != torch.uint8:
+                raise ValueError(f"pww_masks must be ({n}, {N}) uint8, got {tuple(self.pww_masks.shape)}")
+            if self.smax is None:
+                self.smax = torch.zeros(1, dtype=torch.int64, device=device)
+            sb.pww_masks, sb.pww_coef = self.pww_masks.data_ptr(), self.pww_coef.data_ptr()
+            sb.pww_smax, sb.pww_count = self.smax.data_ptr(), n
+            for i, c in enumerate(self.pww_columns):
+                sb.pww_column[i] = int(c)
+        return sb
+
+    @property
+    def has_pww(self):
+        return len(self.pww_columns) > 0
+
+
+def score_max(q, k, heads: int, scale: float, bias: "ScoreBias"):
+    """Launches `ga_cross_attn_smax` into `bias.smax` (paint-with-words pre-pass: the launch-wide max of the scores,
+    reference utils/ptp_utils.py:138 `attention_scores.max()`).  Returns the float value as a 0-dim tensor view."""
+    lib = abi.load()
+    B, N, Cdim = q.shape
+    T = k.shape[1]
+    sb = bias.struct(B, heads, N, T, q.device)
+    with torch.cuda.device(q.device):
+        abi.check(lib.ga_cross_attn_smax(_ptr(q), _ptr(k), _ptr(bias.smax), C.byref(sb), B, heads, N, T, Cdim // heads,
+                                         float(scale), _DTYPES[q.dtype], _stream(q)), "ga_cross_attn_smax")
+    _count("cross_attn_smax")
+    return bias.smax
+
+
 class _CrossAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, heads: int, scale: float, want_acc: bool, impl: int):
+    def forward(ctx, q, k, v, heads: int, scale: float, want_acc: bool, impl: int, bias=None):
         _need_cuda(q, k, v)
         lib = abi.load()
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -129,13 +187,24 @@ class _CrossAttnFn(torch.autograd.Function):
         lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
         acc = torch.empty((B, N, T), dtype=torch.float32, device=q.device) if want_acc else None
         nbytes = attn_fwd_bytes(B, heads, N, T, d, q.element_size(), want_acc)
-        with torch.cuda.device(q.device), _span("cross_attn_fwd", (B, heads, N, T, d, str(q.dtype), want_acc), nbytes,
-                                                q.device):
-            abi.check(lib.ga_cross_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(acc), B, heads, N, T, d,
-                                            float(scale), _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_fwd")
+        if bias is not None:
+            if bias.has_pww:
+                score_max(q, k, heads, scale, bias)
+            sb = bias.struct(B, heads, N, T, q.device)
+            with torch.cuda.device(q.device):
+                abi.check(lib.ga_cross_attn_fwd_ex(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(acc),
+                                                   C.byref(sb), B, heads, N, T, d, float(scale), _DTYPES[q.dtype],
+                                                   abi.GA_IMPL_AUTO, _stream(q)), "ga_cross_attn_fwd_ex")
+        else:
+            with torch.cuda.device(q.device), _span("cross_attn_fwd", (B, heads, N, T, d, str(q.dtype), want_acc),
+                                                    nbytes, q.device):
+                abi.check(lib.ga_cross_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(acc), B, heads, N, T,
+                                                d, float(scale), _DTYPES[q.dtype], impl, _stream(q)),
+                          "ga_cross_attn_fwd")
         _count("cross_attn_fwd")
         ctx.save_for_backward(q, k, v, lse)
         ctx.meta = (heads, float(scale), impl)
+        ctx.bias = bias
         # layers whose maps do not feed the loss (32^2 and 8^2 at attention_res 16) get d_acc = None, not a
         # materialised all-zero (B, N, 77) tensor that K2 would still read
         ctx.set_materialize_grads(False)
@@ -168,20 +237,34 @@ class _CrossAttnFn(torch.autograd.Function):
         d_k = torch.zeros(k.shape, dtype=torch.float32, device=q.device) if need_k else None
         d_v = torch.zeros(v.shape, dtype=torch.float32, device=q.device) if need_v else None
         nbytes = attn_bwd_bytes(B, heads, N, T, d, q.element_size(), d_acc is not None)
-        with torch.cuda.device(q.device), _span("cross_attn_bwd", (B, heads, N, T, d, str(q.dtype), d_acc is not None),
-                                                nbytes, q.device):
-            abi.check(lib.ga_cross_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(lse), _ptr(d_o), _ptr(d_acc), bstride,
-                                            rstride, _ptr(d_q), _ptr(d_k), _ptr(d_v), B, heads, N, T, d, scale,
-                                            _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_bwd")
+        bias = ctx.bias
+        if bias is not None:
+            sb = bias.struct(B, heads, N, T, q.device)
+            partials = torch.empty(B * heads * ((N + 63) // 64), dtype=torch.float32, device=q.device) \
+                if bias.has_pww else None
+            with torch.cuda.device(q.device):
+                abi.check(lib.ga_cross_attn_bwd_ex(_ptr(q), _ptr(k), _ptr(v), _ptr(lse), _ptr(d_o), _ptr(d_acc),
+                                                   bstride, rstride, _ptr(d_q), _ptr(d_k), _ptr(d_v), C.byref(sb),
+                                                   _ptr(partials), B, heads, N, T, d, scale, _DTYPES[q.dtype],
+                                                   abi.GA_IMPL_AUTO, _stream(q)), "ga_cross_attn_bwd_ex")
+        else:
+            with torch.cuda.device(q.device), _span("cross_attn_bwd",
+                                                    (B, heads, N, T, d, str(q.dtype), d_acc is not None), nbytes,
+                                                    q.device):
+                abi.check(lib.ga_cross_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(lse), _ptr(d_o), _ptr(d_acc), bstride,
+                                                rstride, _ptr(d_q), _ptr(d_k), _ptr(d_v), B, heads, N, T, d, scale,
+                                                _DTYPES[q.dtype], impl, _stream(q)), "ga_cross_attn_bwd")
         _count("cross_attn_bwd")
-        return (d_q, d_k.to(k.dtype) if need_k else None, d_v.to(v.dtype) if need_v else None, None, None, None, None)
+        return (d_q, d_k.to(k.dtype) if need_k else None, d_v.to(v.dtype) if need_v else None, None, None, None, None,
+                None)
 
 
-def cross_attention(q, k, v, heads: int, scale: float, want_acc: bool = False, impl: Optional[int] = None):
-    """O = softmax(scale Q K^T) V per head, q (B, N, H*d), k/v (B, T, H*d).  Returns (o, acc) with
+def cross_attention(q, k, v, heads: int, scale: float, want_acc: bool = False, impl: Optional[int] = None,
+                    bias: Optional[ScoreBias] = None):
+    """O = softmax(scale Q K^T [+ bias]) V per head, q (B, N, H*d), k/v (B, T, H*d).  Returns (o, acc) with
     acc (B, N, T) fp32 = sum over heads of the probabilities (None unless `want_acc`).  Differentiable in q (and k, v
-    when they require grad) through BOTH outputs."""
-    return _CrossAttnFn.apply(q, k, v, heads, scale, want_acc, default_impl if impl is None else impl)
+    when they require grad) through BOTH outputs; with a paint-with-words bias also through the global score max."""
+    return _CrossAttnFn.apply(q, k, v, heads, scale, want_acc, default_impl if impl is None else impl, bias)
 
 
 def self_attn_flops(B, H, N, d, direction="fwd"):
@@ -253,8 +336,15 @@ def attention_probs(q, k, heads: int, scale: float, bias=None):
     T = k.shape[1]
     p = torch.empty((B * heads, N, T), dtype=q.dtype, device=q.device)
     with torch.cuda.device(q.device):
-        abi.check(lib.ga_attn_probs(_ptr(q), _ptr(k), _ptr(p), B, heads, N, T, Cdim // heads, float(scale),
-                                    _DTYPES[q.dtype], _stream(q)), "ga_attn_probs")
+        if bias is not None:
+            if bias.has_pww and bias.smax is None:
+                score_max(q, k, heads, scale, bias)
+            sb = bias.struct(B, heads, N, T, q.device)
+            abi.check(lib.ga_attn_probs_ex(_ptr(q), _ptr(k), _ptr(p), C.byref(sb), B, heads, N, T, Cdim // heads,
+                                           float(scale), _DTYPES[q.dtype], _stream(q)), "ga_attn_probs_ex")
+        else:
+            abi.check(lib.ga_attn_probs(_ptr(q), _ptr(k), _ptr(p), B, heads, N, T, Cdim // heads, float(scale),
+                                        _DTYPES[q.dtype], _stream(q)), "ga_attn_probs")
     _count("attn_probs")
     return p
 

@@ -25,7 +25,8 @@ import torch
 from . import _cabi as abi
 from . import helpers, ops
 from . import shared_state as state
-from .ptp_utils import AttentionStore, HeadSummedMaps, TextKVCache, aggregate_attention, select_maps
+from .ptp_utils import (AttentionStore, HeadSummedMaps, PaintWithWords, TextKVCache, aggregate_attention,
+                        select_maps)
 from .substrate import DDIMScheduler, StableDiffusionPipelineBase, StableDiffusionPipelineOutput
 
 AT = helpers.AnnotationType
@@ -132,6 +133,9 @@ class _StepGraphs:
         """Copies the inputs into the static buffers and replays `name`; returns (static outputs, new latents | None).
         The static outputs are overwritten by the next replay of the same program."""
         self.store.text_kv = self.text_kv
+        pww = PaintWithWords.of(self.store)
+        if pww is not None:          # the step-dependent paint-with-words factor is data of the captured programs
+            pww.update(self.lat.device)
         g = self._graph(name)
         self.lat.copy_(latents)
         self.t.fill_(int(t))
@@ -700,6 +704,9 @@ class GuidedAttention(StableDiffusionPipelineBase):
         with step size 0 / are masked out of the result.  Returns the final latents (S, C, h, w).  Keyword losses are
         supported when they can be computed from the tail's statistics (the built-in toLeftOf); Python plug-ins that
         need the materialised maps are not."""
+        if (state.curHyperParams or {}).get("paint_with_words_stop", 0):
+            raise NotImplementedError("generate_batch does not support paint-with-words: the reference's bias uses the "
+                                      "max over the whole launch (utils/ptp_utils.py:138), which would couple the seeds")
         for _, (loss_obj, _args) in (getattr(state.config, "custom_loss", None) or {}).items():
             if not hasattr(loss_obj, "calc_loss_from_stats"):
                 raise NotImplementedError("generate_batch supports [CustomLoss:...] only for losses with a fused "
@@ -845,7 +852,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         state.always_save_iter = [0, 1, 2]
         self.scheduler = DDIMScheduler.from_config(self.scheduler.config)
         self.scheduler.set_timesteps(num_inference_steps, device=device)
-        state.sigmas = np.array(((1 - self.scheduler.alphas_cumprod) / self.scheduler.alphas_cumprod) ** 0.5)
+        state.sigmas = (((1 - self.scheduler.alphas_cumprod) / self.scheduler.alphas_cumprod) ** 0.5).numpy()
         timesteps = self.scheduler.timesteps
         state.timesteps = timesteps
 

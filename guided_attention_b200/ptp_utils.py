@@ -104,19 +104,13 @@ class AttendExciteCrossAttnProcessor:
         query = attn.to_q(hidden_states)
 
         if is_cross:
-            if attention_mask is not None:
-                raise NotImplementedError("fused cross-attention takes no attention_mask (the guided pipeline never "
-                                          "passes one, reference pipeline_guided_attention.py:946-947)")
-            stop = state.curHyperParams.get("paint_with_words_stop", 0) if state.curHyperParams else 0
-            if stop and state.cur_time_step_iter is not None and state.cur_time_step_iter < stop:
-                raise NotImplementedError("paint-with-words score bias (reference utils/ptp_utils.py:113-138) is not "
-                                          "implemented in the fused kernel yet (off by default in the reference)")
             key, value = self._text_kv(attn, encoder_hidden_states)
             keep = self.attnstore.wants_maps(sequence_length) if hasattr(self.attnstore, "wants_maps") \
                 else sequence_length <= 32 ** 2
-            out, acc = ops.cross_attention(query, key, value, attn.heads, attn.scale, want_acc=keep)
+            bias = self._score_bias(attention_mask, sequence_length, key.shape[1], query.device)
+            out, acc = ops.cross_attention(query, key, value, attn.heads, attn.scale, want_acc=keep, bias=bias)
             if keep:
-                maps = HeadSummedMaps(acc, attn.heads, query, key, attn.scale)
+                maps = HeadSummedMaps(acc, attn.heads, query, key, attn.scale, bias)
             else:
                 maps = _ShapeOnly(batch_size * attn.heads, sequence_length, key.shape[1])
             self.attnstore(maps, True, self.place_in_unet)
@@ -150,6 +144,93 @@ class AttendExciteCrossAttnProcessor:
         return hidden_states
 
 
+def _score_bias_method(self, attention_mask, n_query, n_ctx, device):
+    """The two optional additive score terms of the reference processor (utils/ptp_utils.py:113-138), handed to the
+    kernels as one `ops.ScoreBias`: the call's `attention_mask` (added as is, broadcast like `scores + mask`) and the
+    paint-with-words bias.  None when neither applies (the default: the tcgen05 kernels run)."""
+    pww = PaintWithWords.of(self.attnstore)
+    use_pww = pww is not None and n_ctx == 77 and pww.n_tokens() > 0
+    if attention_mask is None and not use_pww:
+        return None
+    if not use_pww:
+        return ops.ScoreBias(mask=attention_mask)
+    pww.update(device)
+    masks, columns = pww.masks_for(n_query, device)
+    return ops.ScoreBias(mask=attention_mask, pww_masks=masks, pww_columns=columns, pww_coef=pww.coef)
+
+
+class PaintWithWords:
+    """Host-side state of the paint-with-words bias (reference utils/ptp_utils.py:113-138), one per controller.
+
+    The reference switches the bias on while `cur_time_step_iter < paint_with_words_stop` and scales it with
+    ln(1 + sigma_t); both depend on the denoising step, which a captured CUDA graph cannot see.  So whenever the feature
+    is enabled (`paint_with_words_stop` > 0) every 77-key layer runs the biased kernels and the step-dependent factor
+    `w * 0.4 * ln(1 + sigma_t)` lives in a one-element DEVICE tensor (`coef`): 0 past `stop` (S + 0 * max(S) == S
+    exactly).  `update()` refreshes it from `shared_state`; the graph runner calls it before every replay."""
+
+    def __init__(self):
+        self.coef, self._value, self._masks = None, None, {}
+
+    @staticmethod
+    def of(controller):
+        hp = state.curHyperParams or {}
+        if not hp.get("paint_with_words_stop", 0):
+            return None
+        if getattr(controller, "pww", None) is None:
+            controller.pww = PaintWithWords()
+        return controller.pww
+
+    @staticmethod
+    def n_tokens():
+        from .helpers import AnnotationType
+        td = getattr(state.config, "token_dict", None) or {}
+        return sum(1 for v in td.values() if v['loss_type'] == AnnotationType.BOX)
+
+    @staticmethod
+    def current_coef() -> float:
+        import numpy as np
+        hp = state.curHyperParams
+        i = state.cur_time_step_iter
+        if i is None or not (i < hp.get("paint_with_words_stop", 0)):
+            return 0.0
+        return float(hp.get("paint_with_words_weight", 1.0) * .4 * np.log(1 + state.get_sigma()))
+
+    def update(self, device):
+        val = self.current_coef()
+        if self.coef is None or self.coef.device != torch.device(device):
+            self.coef = torch.zeros(1, dtype=torch.float32, device=device)
+            self._value = 0.0
+        if val != self._value:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("paint-with-words coefficient changed during CUDA-graph capture: call "
+                                   "PaintWithWords.update() before capturing / replaying")
+            self.coef.fill_(val)
+            self._value = val
+
+    def masks_for(self, n_query: int, device):
+        """((n_box, n_query) uint8 device masks at this layer's resolution, token-index column of each) -- rasterised
+        by K5 exactly like `helpers.inside_box(jj, ii, rect.of_size(hw))` (utils/ptp_utils.py:119-131), once per
+        (token table, resolution)."""
+        from .helpers import AnnotationType
+        hw = int(n_query ** .5)
+        shrink = float(state.curHyperParams["shrink_factor"])
+        boxes, columns = [], []
+        for idx, info in state.config.token_dict.items():
+            if info['loss_type'] == AnnotationType.BOX:
+                r = info['loss']
+                boxes.append((r.x / r.size, r.y / r.size, r.width / r.size, r.height / r.size)
+                             if r.size != 1 else (r.x, r.y, r.width, r.height))
+                columns.append(idx)
+        key = (tuple(boxes), tuple(columns), hw, n_query, shrink, str(device))
+        if key not in self._masks:
+            if len(self._masks) > 64:
+                self._masks.clear()
+            m = torch.zeros((len(boxes), n_query), dtype=torch.uint8, device=device)
+            m[:, :hw * hw] = ops.rasterize_boxes(boxes, hw, shrink, device).reshape(len(boxes), hw * hw)
+            self._masks[key] = m
+        return self._masks[key], columns
+
+
 def _text_kv_method(self, attn, encoder_hidden_states):
     """K and V of a cross-attention layer.  They depend on the text embeddings and the layer's weights only, yet the
     reference recomputes them in every one of the ~500 UNet passes of an image (utils/ptp_utils.py:72-75).  When the
@@ -164,6 +245,7 @@ def _text_kv_method(self, attn, encoder_hidden_states):
 
 
 AttendExciteCrossAttnProcessor._text_kv = _text_kv_method
+AttendExciteCrossAttnProcessor._score_bias = _score_bias_method
 
 
 class TextKVCache:

@@ -21,14 +21,26 @@ def init_distributed(backend: Optional[str] = None):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        n_dev = torch.cuda.device_count() if torch.cuda.is_available() else 0
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            # one process per GPU -> NCCL over NVLink.  More ranks than GPUs (several processes sharing a device, e.g.
+            # the 2-rank equality test on a 1-GPU box) cannot form an NCCL communicator: the final gather then goes
+            # through gloo on host copies (it is 32 KB per image and off the hot path either way).
+            backend = "nccl" if n_dev >= world else "gloo"
         kw = {}
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
             kw["device_id"] = torch.device("cuda", local_rank)
+        elif n_dev > 0:
+            torch.cuda.set_device(local_rank % n_dev)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local_rank
+
+
+def local_device(local_rank: int) -> torch.device:
+    """The CUDA device of this rank: its own GPU, or a shared one when there are more ranks than GPUs."""
+    n_dev = torch.cuda.device_count()
+    return torch.device("cuda", local_rank % n_dev) if n_dev > 0 else torch.device("cpu")
 
 
 def shard_seeds(seeds: Sequence[int], rank: int, world: int) -> List[int]:
@@ -41,6 +53,9 @@ def gather_results(local: torch.Tensor, n_total: int, rank: int, world: int) -> 
     One all_gather on equal-sized, zero-padded chunks."""
     if world == 1:
         return local
+    home = local.device
+    if dist.get_backend() == "gloo" and local.is_cuda:
+        local = local.cpu()
     per = (n_total + world - 1) // world
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
@@ -50,7 +65,7 @@ def gather_results(local: torch.Tensor, n_total: int, rank: int, world: int) -> 
     for r in range(world):
         idx = list(range(r, n_total, world))
         out[idx] = chunks[r][: len(idx)]
-    return out
+    return out.to(home)
 
 
 def _agree_on_template(local_template: Optional[torch.Tensor], rank: int, world: int, device=None):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 2
+#define GA_ABI_VERSION 3
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -124,6 +124,50 @@ int ga_cross_attn_bwd(const void* q, const void* k, const void* v, const float* 
                       float* d_v, int batch,
                       int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl,
                       ga_stream_t stream);
+
+/* ---- optional additive score bias of the cross-attention kernels ------------------------------------------------------
+ * Two independent parts, either may be absent; S' = scale*q.k + mask + pww, softmax and everything after it use S'.
+ *  - `mask`: the processor's `attention_mask` (utils/ptp_utils.py:135-136), fp32 DEVICE, already broadcast-indexable:
+ *    element (b*H + h, n, t) at mask[(b*H + h)*mask_stride_bh + n*mask_stride_n + t] (strides may be 0); NULL = none.
+ *  - paint-with-words (utils/ptp_utils.py:113-138, `paint_with_words_stop` > cur_time_step_iter, 77-key layers):
+ *    S'[bh, n, t] += w * 0.4 * max(S) * ln(1 + sigma_t) for every BOX token t whose box, rasterised at THIS layer's
+ *    resolution (`rect.of_size(hw)`, K5), contains pixel n.  `pww_masks` (pww_count, n_query) u8 DEVICE = those masks,
+ *    `pww_column[i]` = the token index (column of S) mask i biases, `pww_coef` = DEVICE scalar w*0.4*ln(1+sigma_t)
+ *    (device-resident so that a captured CUDA graph follows the denoising step; 0 switches the bias off),
+ *    `pww_smax` = DEVICE 8-byte word written by ga_cross_attn_smax: the global max of S (after `mask`) over
+ *    (b, h, n, t), taken in the same launch-wide sense as the reference's `attention_scores.max()`.
+ *    The max stays differentiable like in the reference: the backward adds  scale * coef * sum(mask o dS') * K[b*,t*,h*]
+ *    to dQ of the one query row (b*, n*, h*) that owns it.
+ * Only the SIMT variant implements the bias; GA_IMPL_AUTO selects it when `bias` is non-NULL. */
+typedef struct ga_score_bias {
+  const float* mask;
+  int64_t mask_stride_bh, mask_stride_n;
+  const uint8_t* pww_masks;
+  const float* pww_coef;
+  const unsigned long long* pww_smax;
+  int32_t pww_count;                 /* 0 = paint-with-words off; <= GA_MAX_TOKENS */
+  int32_t pww_column[GA_MAX_TOKENS];
+} ga_score_bias_t;
+
+/* max over (b, h, n, t) of scale*q.k (+ bias->mask when given; `bias` may be NULL) -> *smax (packed: order-preserving
+ * float bits << 32 | ~flat index, ties to the lowest index).  Zero-fills *smax on the stream first. */
+int ga_cross_attn_smax(const void* q, const void* k, unsigned long long* smax, const ga_score_bias_t* bias_host,
+                       int batch, int heads, int n_query, int n_ctx, int head_dim, float scale, int dtype,
+                       ga_stream_t stream);
+
+/* ga_cross_attn_fwd / ga_cross_attn_bwd / ga_attn_probs with the score bias (`bias_host` NULL = identical to the
+ * plain entry points).  `pww_partials`: caller-owned DEVICE workspace of batch*heads*ceil(n_query/64) floats, needed
+ * when bias_host->pww_count > 0 (per-CTA partial sums of the max gradient, reduced in a fixed order: deterministic).
+ * With paint-with-words d_k / d_v receive the softmax terms only (the max term's dK is not produced). */
+int ga_cross_attn_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, float* acc,
+                         const ga_score_bias_t* bias_host, int batch, int heads, int n_query, int n_ctx, int head_dim,
+                         float scale, int dtype, int impl, ga_stream_t stream);
+int ga_cross_attn_bwd_ex(const void* q, const void* k, const void* v, const float* lse, const void* d_o,
+                         const float* d_acc, int64_t d_acc_batch_stride, int d_acc_row_stride, void* d_q, float* d_k,
+                         float* d_v, const ga_score_bias_t* bias_host, float* pww_partials, int batch, int heads,
+                         int n_query, int n_ctx, int head_dim, float scale, int dtype, int impl, ga_stream_t stream);
+int ga_attn_probs_ex(const void* q, const void* k, void* probs, const ga_score_bias_t* bias_host, int batch, int heads,
+                     int n_query, int n_ctx, int head_dim, float scale, int dtype, ga_stream_t stream);
 
 /* Materialise P (B*H, N, T) in `dtype`, batch-major rows b*H+h, for API compatibility with code that reads the
  * reference's per-head maps (AttentionStore.get_average_attention, utils/ptp_utils.py:245-247).  Off the hot path. */

@@ -159,6 +159,24 @@ def make_processor_inputs(case):
     return attn, attn_self, x, ctx
 
 
+# paint-with-words (utils/ptp_utils.py:113-138): the reference processor on a 16x16 cross layer at denoising iteration
+# `iter` < `stop`, plus the gradient of a seeded linear functional of (output, stored probabilities) w.r.t. the
+# hidden states -- it exercises the gradient through the global max of the scores.
+PWW_CASE = dict(seed=321, query_dim=64, cross_dim=48, heads=4, dim_head=16, batch=2, n=256, T=77,
+                meta_prompt=DEFAULT_PROMPT, stop=3, iter=1, weight=1.5, steps=50, functional_seed=77)
+
+
+def pww_functional(case, y, probs):
+    """L = <y, R1> + <sum_h P[b, h], R2[b]> with seeded R1, R2: linear in the layer output and in the head-summed maps
+    (what the AttentionStore accumulators hold), so the product path can evaluate the same functional."""
+    g = torch.Generator("cpu").manual_seed(case["functional_seed"])
+    B, H = case["batch"], case["heads"]
+    r1 = torch.randn(y.shape, generator=g).to(y)
+    r2 = torch.randn((B,) + tuple(probs.shape[1:]), generator=g).to(probs)
+    head_sum = probs.reshape((B, H) + tuple(probs.shape[1:])).sum(1)
+    return (y * r1).sum() + (head_sum * r2).sum(), r1, r2
+
+
 # -------------------------------------------------------------------------------------------------- e2e case
 E2E_CASE = dict(meta_prompt=DEFAULT_PROMPT, unet_seed=0, embed_seed=1234, latent_seed=28, steps=5,
                 guidance_scale=7.5, embed_gain=4.0,

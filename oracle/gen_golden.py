@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
 from oracle.cases import (PARSE_CASES, MASK_CASES, LOSS_CASES, make_loss_inputs, PROCESSOR_CASE,  # noqa: E402
-                          make_processor_inputs, E2E_CASE, make_e2e_inputs)
+                          make_processor_inputs, E2E_CASE, make_e2e_inputs, PWW_CASE, pww_functional)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -170,6 +170,41 @@ def gen_processor(ref, arrays):
             "store_keys": {k: len(v) for k, v in store.attention_store.items()}, "cur_step": store.cur_step}
 
 
+def gen_pww(ref, arrays):
+    """The reference processor with paint-with-words active (utils/ptp_utils.py:113-138): output, stored
+    probabilities and d L / d hidden_states for a seeded linear functional L."""
+    from guided_attention_b200.substrate import DDIMScheduler
+    case = PWW_CASE
+    cfg, tok = _setup(ref, case["meta_prompt"], {"paint_with_words_stop": case["stop"],
+                                                 "paint_with_words_weight": case["weight"]})
+    sch = DDIMScheduler()
+    sch.set_timesteps(case["steps"])
+    ref.state.sigmas = (((1 - sch.alphas_cumprod) / sch.alphas_cumprod) ** 0.5).numpy()
+    ref.state.timesteps = sch.timesteps
+    ref.state.cur_time_step_iter = case["iter"]
+    attn, _, x, ctx = make_processor_inputs(case)
+    x.requires_grad_(True)
+    store = ref.ptp_utils.AttentionStore()
+    store.num_att_layers = 1
+    proc = ref.ptp_utils.AttendExciteCrossAttnProcessor(store, "down")
+    y = proc(attn, x, encoder_hidden_states=ctx)
+    P = store.attention_store["down_cross"][0]
+    L, _, _ = pww_functional(case, y, P)
+    (gx,) = torch.autograd.grad(L, x)
+    arrays["pww_out"] = y.detach().numpy()
+    arrays["pww_probs"] = P.detach().numpy()
+    arrays["pww_grad_x"] = gx.numpy()
+    # the same call one iteration past `stop`: the bias must be off
+    ref.state.cur_time_step_iter = case["stop"]
+    store2 = ref.ptp_utils.AttentionStore()
+    store2.num_att_layers = 1
+    y_off = ref.ptp_utils.AttendExciteCrossAttnProcessor(store2, "down")(attn, x.detach(), encoder_hidden_states=ctx)
+    arrays["pww_out_off"] = y_off.detach().numpy()
+    ref.state.cur_time_step_iter = 0
+    return {"sigma": float(ref.state.sigmas[int(sch.timesteps[case["iter"]])]), "functional": float(L),
+            "token_indices": list(cfg.token_dict.keys())}
+
+
 def gen_e2e(ref, arrays):
     """The reference's own `GuidedAttention.__call__` + patched UNet forward + refinement loop, on the tiny substrate
     UNet, CPU fp32."""
@@ -227,7 +262,7 @@ def main():
     arrays = {}
     doc = {"generator": "oracle/gen_golden.py", "torch": torch.__version__,
            "parse": gen_parse(ref), "masks": gen_masks(ref), "gaussian": gen_gaussian(ref),
-           "loss": gen_loss(ref, arrays), "processor": gen_processor(ref, arrays)}
+           "loss": gen_loss(ref, arrays), "processor": gen_processor(ref, arrays), "pww": gen_pww(ref, arrays)}
     with open(os.path.join(GOLDEN, "reference_kat.json"), "w") as f:
         json.dump(doc, f, indent=1)
     np.savez_compressed(os.path.join(GOLDEN, "reference_kat.npz"), **arrays)

@@ -50,14 +50,52 @@ class HyperParams:
 
 
 # --------------------------------------------------------------------------------------------- a1: attention
-def attention_probs(q: torch.Tensor, k: torch.Tensor, scale: float) -> torch.Tensor:
-    """softmax(scale * Q K^T) over keys; q (BH, N, d), k (BH, T, d).  reference utils/ptp_utils.py:103-109, 143-144."""
-    return torch.softmax(scale * torch.bmm(q, k.transpose(-1, -2)), dim=-1)
+@dataclass
+class PaintWithWords:
+    """State of the optional paint-with-words score bias (reference utils/ptp_utils.py:113-138): active for 77-key
+    layers while `cur_time_step_iter < paint_with_words_stop`.  `sigma` is `state.get_sigma()` =
+    sigmas[timesteps[cur_time_step_iter]] (utils/shared_state.py:26-27)."""
+    tokens: Sequence["TokenSpec"]
+    sigma: float
+    weight: float = 1.0           # curHyperParams["paint_with_words_weight"]
+    shrink_factor: float = .15    # inside_box reads curHyperParams["shrink_factor"] (utils/helpers.py:168-169)
 
 
-def cross_attention(q, k, v, scale):
+def pww_mask(pww: PaintWithWords, n_query: int, n_ctx: int = 77) -> torch.Tensor:
+    """(n_query, n_ctx) fp32: `weight` where pixel (ii, jj) of the hw x hw grid lies inside the (shrunk) box of a BOX
+    token, in that token's column.  reference utils/ptp_utils.py:119-133 (`rect.of_size(hw)`, `inside_box(jj, ii)`)."""
+    hw = int(n_query ** .5)
+    mask = torch.zeros((hw, hw, n_ctx))
+    for tok in pww.tokens:
+        if tok.kind == BOX:
+            m = inside_box_mask(rect_of_size(tuple(tok.payload), hw), hw, pww.shrink_factor)
+            mask[:, :, tok.index] = torch.from_numpy(m.astype(np.float32)) * pww.weight
+    return mask.reshape(n_query, n_ctx)
+
+
+def attention_scores(q: torch.Tensor, k: torch.Tensor, scale: float, attention_mask: Optional[torch.Tensor] = None,
+                     pww: Optional[PaintWithWords] = None) -> torch.Tensor:
+    """scale * Q K^T (+ attention_mask) (+ mask * 0.4 * max(scores) * ln(1 + sigma)); the max is over the whole
+    (B*H, N, T) tensor, taken after the attention_mask was added, and stays in the autograd graph.
+    reference utils/ptp_utils.py:103-138."""
+    s = scale * torch.bmm(q, k.transpose(-1, -2))
+    if attention_mask is not None:
+        s = s + attention_mask
+    if pww is not None and k.shape[1] == 77:
+        m = pww_mask(pww, q.shape[1], k.shape[1]).to(s.device)
+        s = s + m[None] * .4 * s.max() * float(np.log(1 + pww.sigma))
+    return s
+
+
+def attention_probs(q: torch.Tensor, k: torch.Tensor, scale: float, attention_mask: Optional[torch.Tensor] = None,
+                    pww: Optional[PaintWithWords] = None) -> torch.Tensor:
+    """softmax over keys; q (BH, N, d), k (BH, T, d).  reference utils/ptp_utils.py:103-109, 143-144."""
+    return torch.softmax(attention_scores(q, k, scale, attention_mask, pww), dim=-1)
+
+
+def cross_attention(q, k, v, scale, attention_mask=None, pww=None):
     """P and O = P V.  reference utils/ptp_utils.py:82-85."""
-    p = attention_probs(q, k, scale)
+    p = attention_probs(q, k, scale, attention_mask, pww)
     return p, torch.bmm(p, v)
 
 
@@ -73,11 +111,13 @@ def batch_to_head(t: torch.Tensor, heads: int) -> torch.Tensor:
 
 
 class OracleProcessor:
-    """Restates `AttendExciteCrossAttnProcessor.__call__` (utils/ptp_utils.py:66-93), paint-with-words off."""
+    """Restates `AttendExciteCrossAttnProcessor.__call__` (utils/ptp_utils.py:66-93).  `pww` is a callable returning the
+    current `PaintWithWords` state or None (off, the reference's default)."""
 
-    def __init__(self, store, place_in_unet):
+    def __init__(self, store, place_in_unet, pww=None):
         self.store = store
         self.place = place_in_unet
+        self.pww = pww
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
         is_cross = encoder_hidden_states is not None
@@ -85,7 +125,8 @@ class OracleProcessor:
         q = head_to_batch(attn.to_q(hidden_states), attn.heads)
         k = head_to_batch(attn.to_k(ctx), attn.heads)
         v = head_to_batch(attn.to_v(ctx), attn.heads)
-        p, o = cross_attention(q, k, v, attn.scale)
+        pww = self.pww() if (self.pww is not None and is_cross) else None
+        p, o = cross_attention(q, k, v, attn.scale, pww=pww)
         self.store(p, is_cross, self.place)
         return attn.to_out[1](attn.to_out[0](batch_to_head(o, attn.heads)))
 
@@ -117,7 +158,7 @@ class OracleStore:
             self.step_store = {k: [] for k in self.KEYS}
 
 
-def register(unet, store) -> int:
+def register(unet, store, pww=None) -> int:
     """Restates `register_attention_control` (utils/ptp_utils.py:149-175)."""
     procs, n = {}, 0
     for name in unet.attn_processors.keys():
@@ -130,7 +171,7 @@ def register(unet, store) -> int:
         else:
             continue
         n += 1
-        procs[name] = OracleProcessor(store, place)
+        procs[name] = OracleProcessor(store, place, pww)
     unet.set_attn_processor(procs)
     store.num_att_layers = n
     return n
@@ -392,14 +433,26 @@ class OraclePipeline:
     `_perform_iterative_refinement_step` (:475-581), with diagnostics off and `use_optimizer`=False."""
 
     def __init__(self, unet, scheduler, tokens: Sequence[TokenSpec], hp: HyperParams = HyperParams(),
-                 recurse_steps: int = 3, recurse_until: int = 14, custom_losses=()):
+                 recurse_steps: int = 3, recurse_until: int = 14, custom_losses=(), pww_stop: int = 0,
+                 pww_weight: float = 1.0):
         self.unet, self.scheduler = unet, scheduler
         self.tokens, self.hp = list(tokens), hp
         self.recurse_steps, self.recurse_until = max(recurse_steps, 1), recurse_until
         self.custom_losses = custom_losses
         self.store = OracleStore()
-        register(unet, self.store)
+        self.pww_stop, self.pww_weight, self._iter = pww_stop, pww_weight, 0
+        register(unet, self.store, self._pww_state if pww_stop > 0 else None)
         self.n_fwd = 0
+
+    def _pww_state(self):
+        """paint-with-words is on while cur_time_step_iter < paint_with_words_stop (utils/ptp_utils.py:113-114);
+        sigma = sigmas[timesteps[i]] with sigmas = sqrt((1 - a_bar) / a_bar) (pipeline :887-890, shared_state.py:26-27)."""
+        if self._iter >= self.pww_stop:
+            return None
+        ac = self.scheduler.alphas_cumprod
+        sigmas = (((1 - ac) / ac) ** 0.5).numpy()
+        return PaintWithWords(self.tokens, float(sigmas[int(self.scheduler.timesteps[self._iter])]), self.pww_weight,
+                              self.hp.shrink_factor)
 
     def _loss(self, attention_res, smooth_attentions, sigma, kernel_size, last_idx):
         abar = aggregate_attention(self.store.attention_store, attention_res)
@@ -452,6 +505,7 @@ class OraclePipeline:
                 break
             for recurse_step in range(self.recurse_steps):
                 updated = False
+                self._iter = i                      # state.cur_time_step_iter = i (:928)
                 with torch.enable_grad():
                     latents = latents.clone().detach().requires_grad_(True)
                     self._unet(latents, t, prompt_embeds[1][None])
@@ -481,7 +535,7 @@ class OraclePipeline:
                     if prev_t > 0:
                         bt = sch.alphas_cumprod[ti] / sch.alphas_cumprod[prev_t]
                         latents = bt.sqrt() * latents + (1 - bt).sqrt() * torch.randn(
-                            latents.shape, generator=renoise_gen)
+                            latents.shape, generator=renoise_gen).to(latents.device)
         trace.latents = latents.detach()
         trace.unet_forwards = self.n_fwd
         return trace

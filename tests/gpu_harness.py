@@ -95,6 +95,35 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def rms_rel_err(a, b):
+    """||a - b||_2 / ||b||_2: unlike `rel_err` (max-norm, dominated by the largest entries) this weighs every entry."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def tails_ok(a, b, rtol, atol=1e-7):
+    """Element-wise |a - b| <= atol + rtol |b|: a RELATIVE bound on every entry, so the small-probability tails of a
+    map are checked as strictly as its peaks.  Returns (ok, worst relative excess) for the assertion message."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    excess = np.abs(a - b) / (atol + rtol * np.abs(b))
+    return bool(excess.max() <= 1.0), float(excess.max())
+
+
+def record_metric(name, values):
+    """Appends measured parity numbers to gpurun_out/r02_parity_metrics.jsonl (brought back from the GPU box) so the
+    bounds asserted in the tests can be stated next to what was measured."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r02_parity_metrics.jsonl"), "a") as f:
+            f.write(json.dumps({"name": name, **values}) + "\n")
+    except OSError:
+        pass
+
+
 def run_microcase(res=16, heads=8, head_dim=40, layers=5, batch=1, dtype=torch.float16, seed=0, impl=None,
                   meta_prompt=DEFAULT_PROMPT, gain=1.0):
     cfg = setup_prompt(meta_prompt)

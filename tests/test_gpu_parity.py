@@ -12,7 +12,7 @@ from oracle import oracle as O
 from oracle.cases import (LOSS_CASES, MASK_CASES, PROCESSOR_CASE, E2E_CASE, make_loss_inputs, make_processor_inputs,
                           make_e2e_inputs)
 from tests.gpu_harness import (setup_prompt, oracle_tokens, oracle_hyper, make_layers, oracle_forward, cuda_forward,
-                               rel_err, run_microcase)
+                               rel_err, rms_rel_err, tails_ok, record_metric, run_microcase)
 
 pytestmark = pytest.mark.gpu
 
@@ -82,6 +82,10 @@ def test_cross_attention_forward(shape, dtype, rtol):
     assert rel_err(o.float().cpu().numpy(), want_o.numpy()) < rtol
     want_acc = P.reshape(B, H, N, T).sum(1)
     assert rel_err(acc.cpu().numpy(), want_acc.numpy()) < rtol
+    # the accumulator is fp32 whatever the operand dtype: every entry, tails included, to 1e-3 RELATIVE
+    assert rms_rel_err(acc.cpu().numpy(), want_acc.numpy()) < FP32_RTOL
+    assert tails_ok(acc.cpu().numpy(), want_acc.numpy(), FP32_RTOL)[0], tails_ok(acc.cpu().numpy(), want_acc.numpy(),
+                                                                                 FP32_RTOL)
     probs = ops.attention_probs(q.to(DEV), k.to(DEV), H, scale)
     assert probs.shape == (B * H, N, T)
     assert rel_err(probs.float().cpu().numpy(), P.numpy()) < rtol
@@ -122,6 +126,9 @@ def test_cross_attention_forward_tcgen05_vs_oracle_and_simt(shape, dtype, rtol, 
     if with_acc:
         assert rel_err(acc.cpu().numpy(), P.reshape(B, H, N, T).sum(1).numpy()) < 1e-3
         assert rel_err(acc.cpu().numpy(), acc_s.cpu().numpy()) < 1e-3
+        assert rms_rel_err(acc.cpu().numpy(), P.reshape(B, H, N, T).sum(1).numpy()) < 1e-3
+        ok, worst = tails_ok(acc.cpu().numpy(), P.reshape(B, H, N, T).sum(1).numpy(), 2e-3)   # ex2.approx in the tails
+        assert ok, worst
         o2, acc2 = ops.cross_attention(q.to(DEV), k.to(DEV), v.to(DEV), H, scale, want_acc=True,
                                        impl=TC)
         assert torch.equal(acc2, acc) and torch.equal(o2, o)        # deterministic cluster reduction
@@ -325,6 +332,16 @@ def test_tail_against_reference_golden(kat, kat_arrays, case):
     loss, losses, unscaled = pipe._compute_loss(ld)
     st = ld["_stats"].detach().cpu().numpy()
     assert ld["_spec"].token_indices == rec["token_indices"]
+    # the renormalised maps A = softmax(100 * Abar[:, :, 1:last]) entry by entry against the oracle (itself pinned to
+    # the reference by the statistics below): relative bound on every entry, not only on the peaks
+    with torch.no_grad():
+        abar = sum(P.sum(0) for P in Ps) / sum(P.shape[0] for P in Ps)
+        last = -1 if not case.get("normalize_eot") else len(cfg.stable.tokenizer(cfg.prompt)['input_ids']) - 1
+        want_A = O.renorm(abar.reshape(16, 16, -1), last).numpy()
+    got_A = ld["attention_for_text"].detach().cpu().numpy()
+    assert rms_rel_err(got_A, want_A) < FP32_RTOL
+    ok, worst = tails_ok(got_A, want_A, FP32_RTOL, atol=1e-9)
+    assert ok, worst
     np.testing.assert_allclose(st[:, abi.GA_STAT_MAX], rec["max"], rtol=FP32_RTOL)
     np.testing.assert_allclose(st[:, abi.GA_STAT_COL], rec["col"], rtol=FP32_RTOL)
     np.testing.assert_allclose(st[:, abi.GA_STAT_ROW], rec["row"], rtol=FP32_RTOL)
@@ -762,6 +779,11 @@ def test_seed_batching_with_keyword_loss_equals_separate_calls():
                             num_inference_steps=case["steps"], guidance_scale=7.5, thresholds=cfg.thresholds)
 
 
+# one guidance step, full size, fp16 vs the fp32 oracle: measured on B200 0.9995+ (gpurun_out/r02_parity_metrics.jsonl,
+# summarised in DESIGN.md section 4); asserted with margin
+SD14_ONE_STEP_MIN_GRAD_COSINE = 0.98
+
+
 def test_full_size_sd14_guidance_step_fp16():
     """BASELINE config 2 shapes: SD-1.4-shaped UNet, fp16, one guidance evaluation + latent gradient; compared with the
     fp32 CPU oracle driving the same UNet (loss within 2e-2, gradient cosine > 0.98)."""
@@ -796,7 +818,9 @@ def test_full_size_sd14_guidance_step_fp16():
     assert float(loss) == pytest.approx(float(r.loss), rel=FP16_RTOL)
     a, b = gd.float().cpu().flatten(), go.flatten()
     cos = float((a @ b) / (a.norm() * b.norm()))
-    assert cos > 0.98, cos
+    record_metric("sd14_one_step_fp16", {"loss": float(loss), "oracle_loss": float(r.loss), "grad_cosine": cos,
+                                         "grad_norm_ratio": float(a.norm() / b.norm())})
+    assert cos > SD14_ONE_STEP_MIN_GRAD_COSINE, cos
 
 
 def test_full_size_sd21_config4_guidance_step_fp16():
@@ -851,4 +875,76 @@ def test_full_size_sd21_config4_guidance_step_fp16():
     assert float(loss) == pytest.approx(ref_loss, rel=FP16_RTOL)
     a, b = gd.float().cpu().flatten(), go.flatten()
     cos = float((a @ b) / (a.norm() * b.norm()))
+    record_metric("sd21_config4_one_step_fp16", {"loss": float(loss), "oracle_loss": ref_loss, "grad_cosine": cos,
+                                                 "grad_norm_ratio": float(a.norm() / b.norm())})
     assert cos > 0.98, cos
+
+
+# ----------------------------------------------------------------- BASELINE config 2, multi-step latents (north_star)
+CONFIG2_HYPER = {"strict": False, "inside_loss_scale": .2, "outside_loss_scale": .2, "shrink_factor": .15,
+                 "thresholds": {0: .4, 2: .8, 4: .9, 8: .9}, "use_optimizer": False, "recurse_until": 14,
+                 "recurse_steps": 3}
+# Stated bound: after the first 10 DDIM steps of config 2 -- which contain ALL of its guidance
+# work: 4 threshold steps x 3 recursion rounds x (1 + 11 refinement forwards, 11 latent updates), re-noising between
+# rounds -- the fp16 product latents (CUDA graphs on) against the fp32 oracle driving the same weights:
+CONFIG2_MIN_COSINE = 0.995
+CONFIG2_MIN_PSNR_DB = 30.0
+
+
+class _StopDenoising(Exception):
+    pass
+
+
+def test_config2_ten_step_latents_fp16_vs_fp32_oracle():
+    """The configuration bench.py times (SD-1.4 shape, fp16, the bench's thresholds, CUDA graphs on) through the
+    product `__call__` for DDIM steps 0..9, against `OraclePipeline` (explicit-softmax attention, fp32, same weights,
+    on the device because the explicit (8, 4096, 4096) self-attention maps take minutes per pass on the host).
+    Same number of UNet passes; latents within the stated cosine / PSNR bound."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
+    from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, build_unet
+    from guided_attention_b200.run import synthetic_prompt_embeds
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n_steps = 10
+    cfg = setup_prompt(hyper=CONFIG2_HYPER)
+    cfg.thresholds = CONFIG2_HYPER["thresholds"]
+    embeds = synthetic_prompt_embeds(cfg.prompt, 768)
+    lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(28))
+    # oracle: fp32 on the device
+    unet = build_unet(UNetConfig.sd14(), seed=0, device=DEV)
+    opipe = O.OraclePipeline(unet, DDIMScheduler(), oracle_tokens(cfg), oracle_hyper(cfg), recurse_steps=3,
+                             recurse_until=14)
+    trace = opipe(embeds.to(DEV), lat.to(DEV), 28, num_inference_steps=50, guidance_scale=7.5,
+                  thresholds=CONFIG2_HYPER["thresholds"], max_steps=n_steps)
+    gold = trace.latents.float().cpu().numpy()
+    del unet, opipe
+    torch.cuda.empty_cache()
+    # product: fp16, fused kernels, CUDA graphs
+    unet_h = build_unet(UNetConfig.sd14(), seed=0, dtype=torch.float16, device=DEV)
+    pipe = GuidedAttention(unet=unet_h, scheduler=DDIMScheduler(), tokenizer=cfg.stable.tokenizer)
+    cfg.stable = pipe
+    pipe.use_cuda_graphs = True
+    store = AttentionStore()
+    register_attention_control(pipe, store)
+    seen = {}
+
+    def cb(i, t, latents):
+        if i >= n_steps:
+            raise _StopDenoising()
+        seen[i] = latents.detach().clone()
+    with pytest.raises(_StopDenoising):
+        pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5,
+             generator=torch.Generator("cpu").manual_seed(28), latents=lat.clone(), prompt_embeds=embeds[1:2],
+             negative_prompt_embeds=embeds[0:1], num_inference_steps=50, thresholds=cfg.thresholds,
+             output_type="latent", callback=cb, callback_steps=1)
+    got = seen[n_steps - 1].float().cpu().numpy()
+    passes = pipe.pass_counts["eval"] + pipe.pass_counts["update"] + pipe.pass_counts["cfg"] - 2   # step 10's eval + cfg
+    cos = float((got * gold).sum() / (np.linalg.norm(got) * np.linalg.norm(gold)))
+    psnr = _psnr(got, gold)
+    record_metric("config2_ten_step_latents", {"cosine": cos, "psnr_db": psnr, "unet_passes": passes,
+                                               "oracle_unet_passes": trace.unet_forwards,
+                                               "losses_first": trace.losses[:3], "losses_last": trace.losses[-3:]})
+    assert passes == trace.unet_forwards, (passes, trace.unet_forwards)
+    assert np.isfinite(got).all()
+    assert cos > CONFIG2_MIN_COSINE and psnr > CONFIG2_MIN_PSNR_DB, (cos, psnr)
