@@ -29,6 +29,10 @@ HYPER = {"strict": False, "inside_loss_scale": .2, "outside_loss_scale": .2, "sh
          "thresholds": {0: .4, 2: .8, 4: .9, 8: .9}, "use_optimizer": False, "recurse_until": 14, "recurse_steps": 3}
 BASE_SEED = 28
 EMBED_SEED = 1234
+# BASELINE config 5: the fixed 64-seed sweep.  Every timed image of every run takes its seed from this list
+# (`seed_idx % world_size == rank`, reference run.py:93-97 loops the same list sequentially), so the per-seed checksums
+# printed by runs at different N can be compared for EQUALITY.
+SWEEP_SEEDS = list(range(28, 92))
 
 
 def peaks():
@@ -109,42 +113,69 @@ def analytic_schedule(thresholds, n_steps, recurse_steps, recurse_until, max_ref
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def cpu_component_times(unet_kind, threads):
-    """One bounded sample of the reference's algorithm on the host cores (fp32, oracle port): a grad-enabled text-cond
-    UNet forward with explicit-softmax attention hooks, one loss evaluation, one backward to the latents, one CFG
-    forward (B=2)."""
-    from oracle import oracle as O
-    from tests.gpu_harness import setup_prompt, oracle_tokens, oracle_hyper
-    from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, build_unet
-    from guided_attention_b200.run import synthetic_prompt_embeds
-    torch.set_num_threads(threads)
-    cfg = setup_prompt(META_PROMPT, HYPER)
-    ucfg = UNetConfig.sd14() if unet_kind == "sd14" else UNetConfig.tiny()
-    unet = build_unet(ucfg, seed=0)
-    embeds = synthetic_prompt_embeds(cfg.prompt, ucfg.cross_attention_dim, seed=EMBED_SEED)
-    lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(BASE_SEED))
-    pipe = O.OraclePipeline(unet, DDIMScheduler(), oracle_tokens(cfg), oracle_hyper(cfg))
-    t = {}
-    with torch.enable_grad():
-        x = lat.clone().requires_grad_(True)
-        t0 = time.perf_counter()
-        unet(x, 981, encoder_hidden_states=embeds[1:2])
-        t["grad_fwd"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        r = pipe._loss(attention_res=16, smooth_attentions=True, sigma=0.5, kernel_size=3, last_idx=-1)
-        t["loss_eval"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        torch.autograd.grad(r.loss, x)
-        t["bwd"] = time.perf_counter() - t0
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        unet(torch.cat([lat] * 2), 981, encoder_hidden_states=embeds)
-        t["cfg_fwd"] = time.perf_counter() - t0
-    return t, float(r.loss)
+class _CpuRound:
+    """One recursion round of guided step 0 of config 2 on the host cores, through the oracle port's OWN loop code
+    (`OraclePipeline.__call__`, the restatement of reference pipeline_guided_attention.py:925-1053 and :475-581):
+    1 evaluation forward + R refinement iterations (grad-enabled forward with explicit-softmax hooks, loss, backward
+    to the latents, latent update) + the final evaluation forward with its threshold-step update + the CFG forward
+    (batch 2) + DDIM step.  R = 10 is the whole round the reference runs when no threshold is met (1 + 11 forwards,
+    11 backwards, 1 CFG); smaller R is a bounded sample of the same loop."""
+
+    def __init__(self, unet_kind, threads):
+        from oracle import oracle as O
+        from tests.gpu_harness import setup_prompt, oracle_tokens, oracle_hyper
+        from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, build_unet
+        from guided_attention_b200.run import synthetic_prompt_embeds
+        torch.set_num_threads(threads)
+        self.O = O
+        cfg = setup_prompt(META_PROMPT, HYPER)
+        ucfg = UNetConfig.sd14() if unet_kind == "sd14" else UNetConfig.tiny()
+        self.unet = build_unet(ucfg, seed=0)
+        self.embeds = synthetic_prompt_embeds(cfg.prompt, ucfg.cross_attention_dim, seed=EMBED_SEED)
+        self.pipe = O.OraclePipeline(self.unet, DDIMScheduler(), oracle_tokens(cfg), oracle_hyper(cfg), recurse_steps=1,
+                                     recurse_until=HYPER["recurse_until"])
+
+    def run(self, refine, seed=BASE_SEED, denoise_steps=50):
+        """Returns (seconds of the whole round, per-component seconds, pass counts)."""
+        O, pipe = self.O, self.pipe
+        sec = {"grad_fwd": 0.0, "cfg_fwd": 0.0, "loss_eval": 0.0, "bwd": 0.0}
+        cnt = {"grad_fwd": 0, "cfg_fwd": 0, "loss_eval": 0, "bwd": 0}
+        orig_unet, orig_loss, orig_update = pipe._unet, pipe._loss, O.update_latent
+
+        def timed(key, fn):
+            def wrapped(*a, **k):
+                t0 = time.perf_counter()
+                out = fn(*a, **k)
+                sec[key] += time.perf_counter() - t0
+                cnt[key] += 1
+                return out
+            return wrapped
+
+        def unet(x, t, emb):
+            return timed("cfg_fwd" if x.shape[0] == 2 else "grad_fwd", orig_unet)(x, t, emb)
+        pipe._unet, pipe._loss, O.update_latent = unet, timed("loss_eval", orig_loss), timed("bwd", orig_update)
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(seed))
+        try:
+            t0 = time.perf_counter()
+            trace = pipe(self.embeds, lat, seed, num_inference_steps=denoise_steps, guidance_scale=7.5,
+                         thresholds=HYPER["thresholds"], max_steps=1, max_refinement_steps=refine)
+            total = time.perf_counter() - t0
+        finally:
+            pipe._unet, pipe._loss, O.update_latent = orig_unet, orig_loss, orig_update
+        return total, sec, cnt, float(trace.losses[0][2])
 
 
-def cpu_images_per_s(times, schedule):
-    return 1.0 / sum(times[k] * schedule[k] for k in schedule)
+def cpu_images_per_s(per_pass_s, schedule):
+    return 1.0 / sum(per_pass_s[k] * schedule[k] for k in schedule)
+
+
+def _per_pass(samples):
+    """Average seconds per pass of each kind over the measured rounds."""
+    out = {}
+    for k in ("grad_fwd", "cfg_fwd", "loss_eval", "bwd"):
+        n = sum(c[k] for _, _, c in samples)
+        out[k] = sum(s[k] for _, s, _ in samples) / max(n, 1)
+    return out
 
 
 def run_reference(args):
@@ -153,23 +184,38 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     sched = analytic_schedule(HYPER["thresholds"], args.denoise_steps, HYPER["recurse_steps"], HYPER["recurse_until"])
-    vals = []
+    cpu = _CpuRound(args.unet, threads)
+    samples, wall = [], []
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        times, _ = cpu_component_times(args.unet, threads)
+        # the first timed step is the WHOLE round (10 refinement iterations); the others are bounded samples of the
+        # same loop so that `--steps K --warmup W` ends within minutes on 16 host cores
+        refine = args.ref_refine_first if i == args.warmup else args.ref_refine
+        total, sec, cnt, _ = cpu.run(refine, denoise_steps=args.denoise_steps)
         if i >= args.warmup:
-            vals.append((cpu_images_per_s(times, sched), time.perf_counter() - t0, times))
-    v = float(np.mean([x[0] for x in vals]))
-    sample = ("per step: 1 grad-enabled B=1 UNet forward with explicit-softmax hooks + 1 loss evaluation + 1 backward to "
-              "the latents + 1 CFG forward (B=2), fp32 on the host cores; extrapolated to one image with the "
-              f"analytic UNet-pass schedule {sched} (no threshold met)")
+            samples.append((total, sec, cnt))
+            wall.append(total)
+    per_pass = _per_pass(samples)
+    v = cpu_images_per_s(per_pass, sched)
+    measured_passes = {k: sum(c[k] for _, _, c in samples) for k in per_pass}
+    sample = (f"{args.steps} timed recursion rounds of guided step 0 through the oracle port's own loop "
+              f"(OraclePipeline.__call__, fp32, explicit-softmax hooks) on {threads} host threads: the first with "
+              f"{args.ref_refine_first} refinement iterations"
+              + (" (the WHOLE round the reference runs: 1 + 11 forwards, 11 backwards, 1 CFG forward)"
+                 if args.ref_refine_first == 10 else "") +
+              f", the others with {args.ref_refine}; measured passes {measured_passes} in "
+              f"{sum(wall):.1f} s; EXTRAPOLATED to one image with the analytic UNet-pass schedule {sched} "
+              "(no threshold met)")
     line = {"impl": "reference", "metric": "guided_images_per_s", "value": v, "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "extrapolated": True, "measured_s": sum(wall), "measured_s_per_step": wall,
             "config": workload_config(args, "f32"),
             "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample,
-                             "component_s": {k: float(np.mean([x[2][k] for x in vals])) for k in vals[0][2]}},
-            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                             "extrapolated": True, "measured_s": sum(wall), "measured_passes": measured_passes,
+                             "seconds_per_pass": per_pass, "schedule_per_image": sched},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "one host arm, whatever --gpus says: under torchrun rank 0 alone runs it.  A ratio against an "
+                    "N-GPU line compares N GPUs with ONE host and is not a per-device speed-up."}
     print(json.dumps(line))
     return 0
 
@@ -186,21 +232,17 @@ def workload_config(args, dtype):
 
 
 # ------------------------------------------------------------------------------------------------------ CUDA arm
-def run_ours(args):
-    from guided_attention_b200 import build as B
-    B.build()
-    from guided_attention_b200 import ops, run as R, shared_state as S, sweep
+def _sha(t):
+    """sha1 of the fp16 latents' bytes: the per-seed checksum compared across runs at different N (config 5)."""
+    import hashlib
+    return hashlib.sha1(t.detach().to(torch.float16).cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def build_pipeline(args, dev):
+    from guided_attention_b200 import run as R
     from guided_attention_b200.pipeline_guided_attention import GuidedAttention
     from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
     from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, WhitespaceTokenizer, build_unet
-    import torch.distributed as dist
-
-    rank, world, local_rank = sweep.init_distributed()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (CUDA arm) needs a GPU: the guidance path has no CPU fallback")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-
     cfg = setup_config(args.denoise_steps)
     ucfg = UNetConfig.sd14() if args.unet == "sd14" else UNetConfig.tiny()
     unet = build_unet(ucfg, seed=0, dtype=torch.float16, device=dev)
@@ -212,15 +254,22 @@ def run_ours(args):
     R.parseMetaPrompt(cfg)
     store = AttentionStore()
     register_attention_control(pipe, store)
-
     embeds_host = R.synthetic_prompt_embeds(cfg.prompt, ucfg.cross_attention_dim, seed=EMBED_SEED).pin_memory()
-    unet_calls = {"n": 0}
-    orig_forward = unet.forward
+    return cfg, pipe, store, embeds_host
 
-    def counted(*a, **k):
-        unet_calls["n"] += 1
-        return orig_forward(*a, **k)
-    unet.forward = counted
+
+def run_ours(args):
+    from guided_attention_b200 import build as B
+    B.build()
+    from guided_attention_b200 import ops, shared_state as S, sweep
+    import torch.distributed as dist
+
+    rank, world, local_rank = sweep.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (CUDA arm) needs a GPU: the guidance path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg, pipe, store, embeds_host = build_pipeline(args, dev)
 
     def host_latents(seed):
         g = torch.Generator("cpu").manual_seed(seed)
@@ -236,8 +285,11 @@ def run_ours(args):
                    output_type="latent")
         return out.images
 
-    def seed_of(phase, step):   # every rank and every timed image gets its own seed (weak scaling)
-        return BASE_SEED + phase * 1000 + step * world + rank
+    def seed_of(step):      # timed images: the config-5 sweep list, seed_idx % world == rank
+        return SWEEP_SEEDS[(step * world + rank) % len(SWEEP_SEEDS)]
+
+    def warm_seed(w):       # warm-up images come from the far end of the list
+        return SWEEP_SEEDS[-1 - ((w * world + rank) % len(SWEEP_SEEDS))]
 
     def barrier():
         if world > 1:
@@ -257,28 +309,31 @@ def run_ours(args):
             dist.barrier()
         return float(ms), res
 
+    if args.sweep64:
+        return run_sweep64(args, rank, world, dev, image, host_latents, embeds_host, timed, sweep, dist, pipe)
+
     embeds_dev = embeds_host.to(dev, non_blocking=True)
     for w in range(args.warmup):
-        image(seed_of(0, w), embeds_dev, host_latents(seed_of(0, w)).to(dev))
+        image(warm_seed(w), embeds_dev, host_latents(warm_seed(w)).to(dev))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     # (1) device-resident inputs: `value`
-    dev_lat = [host_latents(seed_of(1, i)).to(dev) for i in range(args.steps)]
+    dev_lat = [host_latents(seed_of(i)).to(dev) for i in range(args.steps)]
     ops.reset_launch_counts()
     pipe._count_pass("cfg", 0)
-    cfg_before = pipe.pass_counts["cfg"]
-    ms_value, _ = timed(lambda i: image(seed_of(1, i), embeds_dev, dev_lat[i]), args.steps)
+    before = dict(pipe.pass_counts)
+    ms_value, value_res = timed(lambda i: image(seed_of(i), embeds_dev, dev_lat[i]), args.steps)
     launches = ops.total_launches()
     counts = dict(ops.launch_counts)
-    cfg_passes = pipe.pass_counts["cfg"] - cfg_before
-    unet_passes = counts.get("guidance_tail_fwd", 0) + cfg_passes
+    passes = {k: pipe.pass_counts[k] - before[k] for k in before}
+    unet_passes = sum(passes.values())
     # (2) end to end: host buffers in, host buffer out, inside the timed region; final NCCL gather of the latents
-    host_lat = [host_latents(seed_of(1, i)) for i in range(args.steps)]
+    host_lat = [host_latents(seed_of(i)) for i in range(args.steps)]
     out_host = torch.empty(args.steps, 4, 64, 64, dtype=torch.float16).pin_memory()
 
     def e2e_step(i):
-        lat = image(seed_of(1, i), embeds_host.to(dev, non_blocking=True), host_lat[i].to(dev, non_blocking=True))
+        lat = image(seed_of(i), embeds_host.to(dev, non_blocking=True), host_lat[i].to(dev, non_blocking=True))
         out_host[i].copy_(lat[0], non_blocking=True)
         return lat
 
@@ -291,42 +346,77 @@ def run_ours(args):
     ms_e2e, e2e_res = timed(e2e_all, 1)
     clocks = sampler.stop()
 
+    # per-seed checksums (config 5 equality evidence): value leg == e2e leg in this process, and comparable across N
+    sums = {str(seed_of(i)): _sha(value_res[i]) for i in range(args.steps)}
+    same_legs = all(_sha(e2e_res[0][i]) == sums[str(seed_of(i))] for i in range(args.steps))
+    if world > 1:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (sums, same_legs))
+        sums = {k: v for d, _ in everyone for k, v in d.items()}
+        same_legs = all(ok for _, ok in everyone)
+
     # (3) roofline: one more image with per-launch CUDA events on the launching stream
     # (CUDA events cannot be recorded inside a graph replay: this pass runs the eager loop, same kernels)
     pipe.use_cuda_graphs = False
     ops.profiler = ops.LaunchProfiler()
-    image(seed_of(1, 0), embeds_dev, dev_lat[0])
+    image(seed_of(0), embeds_dev, dev_lat[0])
     prof = ops.profiler.summary()
     ops.profiler = None
     pipe.use_cuda_graphs = not args.no_graphs
-    roofline, kernel_table = roofline_from(prof)
+    tensor_roof, kernel_table = roofline_from(prof)
 
-    # (4) extension: S seeds per UNet pass (`generate_batch`), same per-seed semantics; reported next to the headline
+    # (4) extension: S seeds per UNet pass (`generate_batch`), same per-seed semantics; device-resident and end to end
     batched = None
     if args.seeds_per_batch > 1:
         Sb = args.seeds_per_batch
-        pipe.use_cuda_graphs = not args.no_graphs
         emb16 = embeds_dev.to(torch.float16)
 
-        def batch_step(i):
-            seeds = [seed_of(2, i * Sb + j) for j in range(Sb)]
-            return pipe.generate_batch(cfg.prompt, store, seeds, emb16[1:2], emb16[0:1], attention_res=16,
-                                       num_inference_steps=args.denoise_steps, guidance_scale=7.5,
-                                       thresholds=cfg.thresholds)
-        batch_step(0)                                   # warm-up: captures the batch-S graphs
-        ms_b, _ = timed(batch_step, 1)
-        batched = {"seeds_per_batch": Sb, "value": Sb * world / (ms_b / 1e3), "unit": "img/s",
-                   "ms_per_batch": ms_b, "note": "extension (SURVEY 8e): per-seed results equal the one-seed path "
-                   "(tests/test_gpu_parity.py::test_seed_batching_equals_separate_calls)"}
+        def batch_seeds(i):
+            return [SWEEP_SEEDS[((i * world + rank) * Sb + j) % len(SWEEP_SEEDS)] for j in range(Sb)]
 
-    # (5) the HBM-bound kernels at GPU-filling batch sizes (rank 0; last, because the tail timer re-installs the prompt)
-    saturated = None
-    if rank == 0 and not args.no_saturated:
+        def batch_lat(i):
+            return torch.cat([host_latents(sd) for sd in batch_seeds(i)]).pin_memory()
+
+        def batch_step(i, lat_dev=None, emb=None):
+            emb = emb16 if emb is None else emb
+            return pipe.generate_batch(cfg.prompt, store, batch_seeds(i), emb[1:2], emb[0:1], attention_res=16,
+                                       num_inference_steps=args.denoise_steps, guidance_scale=7.5,
+                                       thresholds=cfg.thresholds, latents=lat_dev)
+        batch_step(0, batch_lat(0).to(dev))                          # warm-up: captures the batch-S graphs
+        lat_b = batch_lat(0).to(dev)
+        ms_b, res_b = timed(lambda i: batch_step(0, lat_b), 1)
+        lat_bh = batch_lat(0)
+        out_bh = torch.empty(Sb, 4, 64, 64, dtype=torch.float16).pin_memory()
+
+        def batch_e2e(_):
+            r = batch_step(0, lat_bh.to(dev, non_blocking=True),
+                           embeds_host.to(dev, non_blocking=True).to(torch.float16))
+            out_bh.copy_(r, non_blocking=True)
+            torch.cuda.synchronize()
+            return r
+        ms_be, _ = timed(batch_e2e, 1)
+        batched = {"seeds_per_batch": Sb, "value": Sb * world / (ms_b / 1e3), "unit": "img/s", "ms_per_batch": ms_b,
+                   "e2e": {"value": Sb * world / (ms_be / 1e3), "unit": "img/s",
+                           "h2d_bytes_per_step": int(embeds_host.numel() * 4 + Sb * 4 * 64 * 64 * 4),
+                           "d2h_bytes_per_step": int(Sb * 4 * 64 * 64 * 2)},
+                   "seed_checksums": {str(sd): _sha(res_b[0][j:j + 1]) for j, sd in enumerate(batch_seeds(0))},
+                   "note": "extension (SURVEY 8e): S seeds advance through one UNet pass; per-seed results match the "
+                           "one-seed path within the bound tested in tests/test_gpu_parity.py (batched GEMM/conv "
+                           "shapes differ, so not bit-identical)"}
+
+    # (5) the metric's second half: HBM GB/s of the attention-map kernels, live, at GPU-filling batch sizes
+    # (rank 0; last, because the tail timer re-installs the prompt)
+    roofline, hbm_table = None, None
+    if not args.no_saturated:
         keep = (S.config, S.curHyperParams)
         torch.cuda.empty_cache()
-        saturated = saturated_rooflines(dev)
+        roofline, hbm_table = attn_map_roofline(dev, kernel_table)
         S.config, S.curHyperParams = keep
         torch.cuda.empty_cache()
+    if roofline is None:
+        roofline = tensor_roof
+    else:
+        roofline["tensor"] = tensor_roof
 
     n_img = args.steps * world
     value = n_img / (ms_value / 1e3)
@@ -338,21 +428,24 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(embeds_host.numel() * 4 + 4 * 64 * 64 * 4),
                     "d2h_bytes_per_step": int(4 * 64 * 64 * 2)},
             "gpu_launches": launches, "gpu_launches_by_kernel": counts, "unet_passes": unet_passes,
-            "clocks": clocks, "roofline": roofline, "kernels": kernel_table, "saturated_kernels": saturated,
-            "batched": batched}
+            "unet_passes_by_program": passes, "clocks": clocks, "roofline": roofline, "kernels": kernel_table,
+            "saturated_kernels": hbm_table, "batched": batched,
+            "seed_checksums": sums, "value_leg_equals_e2e_leg": same_legs}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times, _ = cpu_component_times(args.unet, threads)
-        per_image = {"grad_fwd": counts.get("guidance_tail_fwd", 0) / args.steps,
-                     "loss_eval": counts.get("guidance_tail_fwd", 0) / args.steps,
-                     "bwd": counts.get("guidance_tail_bwd", 0) / args.steps,
-                     "cfg_fwd": cfg_passes / args.steps}
+        total, sec, cnt, _ = _CpuRound(args.unet, threads).run(args.ref_refine_first, denoise_steps=args.denoise_steps)
+        per_pass = {k: sec[k] / max(cnt[k], 1) for k in sec}
+        n_eval = (passes["eval"] + passes["update"]) / args.steps
+        per_image = {"grad_fwd": n_eval, "loss_eval": n_eval, "bwd": passes["update"] / args.steps,
+                     "cfg_fwd": passes["cfg"] / args.steps}
         line["cpu_baseline"] = {
-            "value": cpu_images_per_s(times, per_image), "unit": "img/s", "cores": threads, "kind": "port",
-            "sample": "1 grad-enabled B=1 UNet forward with explicit-softmax hooks + 1 loss evaluation + 1 backward to "
-                      "the latents + 1 CFG forward (B=2), fp32 oracle port on the host cores, extrapolated with the "
-                      f"UNet-pass counts this run measured per image: {per_image}",
-            "component_s": times}
+            "value": cpu_images_per_s(per_pass, per_image), "unit": "img/s", "cores": threads, "kind": "port",
+            "extrapolated": True, "measured_s": total, "measured_passes": cnt, "seconds_per_pass": per_pass,
+            "sample": f"one WHOLE recursion round of guided step 0 ({cnt['grad_fwd']} grad-enabled B=1 forwards with "
+                      f"explicit-softmax hooks, {cnt['loss_eval']} loss evaluations, {cnt['bwd']} backwards to the "
+                      f"latents, {cnt['cfg_fwd']} CFG forward) through the oracle port's own loop, fp32, {threads} "
+                      f"host threads, {total:.1f} s measured; EXTRAPOLATED to one image with the UNet-pass counts "
+                      f"this run measured per image: {per_image}"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -361,43 +454,133 @@ def run_ours(args):
     return 0
 
 
-def saturated_rooflines(dev):
-    """The HBM-bound guidance kernels timed live at batch sizes that fill the GPU (the pipeline's own launches move
-    0.7-11 MB and are launch-latency bound by size): same timing method as the roofline leg (CUDA graph of back-to-back
-    launches between two CUDA events on the launching stream, rotating buffer sets larger than L2)."""
+def run_sweep64(args, rank, world, dev, image, host_latents, embeds_host, timed, sweep, dist, pipe):
+    """BASELINE config 5 as stated: the fixed seeds range(28, 92) through `sweep.run_seed_sweep` (static round-robin
+    `seed_idx % world`), host buffers in, ONE gather of the final latents at the end (NCCL over NVLink), strong scaling.
+    The line carries one checksum per seed: lines produced at different N must agree seed by seed."""
+    seeds = SWEEP_SEEDS[: args.sweep_seeds]
+    embeds_dev = embeds_host.to(dev)
+    for w in range(max(args.warmup, 1)):        # graph capture + warm-up outside the timed region
+        image(SWEEP_SEEDS[-1 - w], embeds_dev, host_latents(SWEEP_SEEDS[-1 - w]).to(dev))
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    box = {}
+
+    def job(_):
+        full, local, failures = sweep.run_seed_sweep(
+            lambda sd: image(sd, embeds_host.to(dev, non_blocking=True), host_latents(sd).to(dev, non_blocking=True))[0],
+            seeds, rank, world)
+        torch.cuda.synchronize()
+        box["full"], box["failures"] = full, failures
+        return full
+    ms, _ = timed(job, 1)
+    clocks = sampler.stop()
+    full = box["full"]
+    sums = {str(sd): _sha(full[i]) for i, sd in enumerate(seeds)}
+    import hashlib
+    line = {"metric": "guided_images_per_s", "mode": "sweep64", "value": len(seeds) / (ms / 1e3), "unit": "img/s",
+            "n_gpus": world, "steps": 1, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": dict(workload_config(args, "fp16"), seeds=f"range({seeds[0]}, {seeds[-1] + 1})",
+                           sharding="seed_idx % world_size == rank"),
+            "e2e": {"value": len(seeds) / (ms / 1e3), "unit": "img/s",
+                    "h2d_bytes_per_step": int(len(seeds) * (embeds_host.numel() * 4 + 4 * 64 * 64 * 4)),
+                    "d2h_bytes_per_step": 0},
+            "failures": box["failures"], "clocks": clocks, "seed_checksums": sums,
+            "checksum_of_checksums": hashlib.sha1("".join(sums[str(sd)] for sd in seeds).encode()).hexdigest()[:16]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+NOMINAL_HBM_GBS = 8000.0     # BASELINE.json metric: "attn-map kernel HBM GB/s vs 8 TB/s"
+
+# (kernel, N, d, maps) -> batch at which the launch fills the GPU; the pipeline's own launches (B = 1, 2) move
+# 0.7-11 MB and are launch-latency bound by size (SURVEY 8d "latency caveat")
+SATURATED_SHAPES = [("cross_attn", 1024, 80, True, 256), ("cross_attn", 256, 160, True, 512),
+                    ("cross_attn", 4096, 40, False, 128)]
+
+
+def ncu_traffic(kernel, shape_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summaries
+    (tools/ncu_all.sh -> tools/ncu_summary.py), newest round first.  Returns (bytes | None, source | None)."""
+    for name in ("r02_ncu_summary.json", "r01_ncu_final_summary.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(path):
+            continue
+        with open(path) as f:
+            rows = json.load(f)
+        for r in rows:
+            if r.get("bench_key") == [kernel, shape_key] and r.get("dram_traffic_bytes") is not None:
+                return float(r["dram_traffic_bytes"]), f"profiles/{name} (ncu --set full, same kernel and shape)"
+    return None, None
+
+
+def attn_map_roofline(dev, kernel_table):
+    """The HBM-bound guidance kernels timed LIVE in this run at GPU-filling batch sizes: CUDA graph of back-to-back
+    launches between two CUDA events on the launching stream, rotating buffer sets larger than L2
+    (`guided_attention_b200.microbench`).  Returns (`roofline` block for the dominant attention-map kernel, table).
+    Dominant = the attention-map kernel class (K1 with map accumulation, K2 with the injected map gradient, tail fwd /
+    bwd) with the largest summed device time inside one image of the pipeline (`kernel_table`)."""
     from guided_attention_b200 import microbench
-    peak = peaks()[0]
-    out = []
+    peak, _, how = peaks()
+    rows = []
+
+    def add(m, kernel, key, shape):
+        traffic, src = ncu_traffic(kernel, key)
+        rows.append({"kernel": kernel, "key": key, "shape": shape, "us": m["us"], "bytes": m["bytes"], "gbs": m["gbs"],
+                     "frac": m["gbs"] / peak, "frac_of_8tbs": m["gbs"] / NOMINAL_HBM_GBS, "traffic": traffic,
+                     "traffic_source": src})
     try:
         for direction in ("fwd", "bwd"):
-            m = microbench.time_cross_attn(128, 8, 4096, 77, 40, torch.float16, with_acc=False, direction=direction,
-                                           device=str(dev))
-            out.append({"kernel": m["kernel"], "shape": "B=128 H=8 N=4096 T=77 d=40 fp16", "us": m["us"],
-                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
-            m = microbench.time_cross_attn(256, 8, 1024, 77, 80, torch.float16, with_acc=True, direction=direction,
-                                           device=str(dev))
-            out.append({"kernel": m["kernel"], "shape": "B=256 H=8 N=1024 T=77 d=80 fp16 (maps)", "us": m["us"],
-                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
-            m = microbench.time_tail(16, 5, 2, n_samples=2048, direction=direction, device=str(dev))
-            out.append({"kernel": m["kernel"], "shape": "res 16, 5 layers x 2 slices, 2048 samples", "us": m["us"],
-                        "bytes": m["bytes"], "gbs": m["gbs"], "frac": m["gbs"] / peak})
+            for _, N, d, maps, B in SATURATED_SHAPES:
+                m = microbench.time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=maps, direction=direction,
+                                               device=str(dev))
+                add(m, f"cross_attn_{direction}", f"N{N}_d{d}_maps{maps}",
+                    f"B={B} H=8 N={N} T=77 d={d} fp16" + (" (maps)" if maps else ""))
+            for res in (16, 32):
+                m = microbench.time_tail(res, 5, 2, n_samples=2048 if res == 16 else 512, direction=direction,
+                                         device=str(dev))
+                add(m, f"guidance_tail_{direction}", f"res{res}",
+                    f"res {res}, 5 layers x 2 slices, {2048 if res == 16 else 512} samples")
     except Exception as e:   # never lose the headline line to an auxiliary measurement
-        out.append({"error": f"{type(e).__name__}: {e}"})
-    return out
+        rows.append({"error": f"{type(e).__name__}: {e}"})
+        return None, rows
 
-
-def ncu_traffic(kernel_prefix):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed `ncu --set full`
-    summary (profiles/r01_ncu_final_summary.json, captured with tools/ncu_all.sh at the shape the bench reports)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_final_summary.json")
-    if not os.path.isfile(path):
+    def key_of(row):     # in-pipeline class -> key of the saturated measurement
+        if row["kernel"].startswith("cross_attn"):
+            return f"N{row['shape'][2]}_d{row['shape'][4]}_maps{row['shape'][6]}"
+        if row["kernel"].startswith("guidance_tail"):
+            return f"res{row['shape'][0]}"
         return None
-    with open(path) as f:
-        rows = json.load(f)
-    tot = [r.get("dram_traffic_bytes") for r in rows if r["kernel"].split("::")[-1].replace("void ", "").startswith(kernel_prefix)
-           and r["report"].endswith("_b1.ncu-rep")]
-    tot = [t for t in tot if t is not None]
-    return float(sum(tot)) if tot else None
+    in_pipe = {}
+    for row in kernel_table:
+        k = key_of(row)
+        is_map = (row["kernel"].startswith("guidance_tail") or
+                  (row["kernel"].startswith("cross_attn") and row["shape"][6] == "True"))
+        if k is not None and is_map:
+            in_pipe[(row["kernel"], k)] = row
+    ranked = sorted(in_pipe.items(), key=lambda kv: -kv[1]["total_ms"])
+    top = next((r for (kern, k), _ in ranked for r in rows if r["kernel"] == kern and r["key"] == k), rows[0])
+    pipe_row = in_pipe.get((top["kernel"], top["key"]))
+    roof = {"bound": "hbm", "kernel": top["kernel"], "shape": top["shape"], "achieved": top["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": top["frac"], "frac_of_8tbs": top["frac_of_8tbs"], "traffic": top["traffic"],
+            "traffic_source": top["traffic_source"], "peak_source": how, "avg_launch_us": top["us"],
+            "algorithmic_bytes_per_launch": top["bytes"],
+            "how": "dominant attention-map kernel of the pipeline (largest summed device time among K1-with-maps, "
+                   "K2-with-map-gradient, tail fwd/bwd inside one image), timed live in this run at a GPU-filling "
+                   "batch: CUDA graph of back-to-back launches between CUDA events on the launching stream, rotating "
+                   "buffer sets larger than L2",
+            "in_pipeline_launch": None if pipe_row is None else {
+                "shape": pipe_row["shape"], "launches_per_image": pipe_row["launches"],
+                "kernel_us": pipe_row.get("kernel_us"), "gbs": pipe_row.get("gbs"),
+                "note": "the pipeline's own launch (B = 1 or 2) moves a few MB: launch-latency bound by size"},
+            "attn_map_kernels": [{k: r[k] for k in ("kernel", "shape", "us", "gbs", "frac", "frac_of_8tbs", "traffic")}
+                                 for r in rows]}
+    return roof, rows
 
 
 def roofline_from(prof):
@@ -438,7 +621,7 @@ def roofline_from(prof):
     if "tflops" in top:
         roof = {"bound": "tensor", "kernel": top["kernel"], "shape": top["shape"], "achieved": top["tflops"],
                 "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                "traffic": ncu_traffic(top["kernel"]) if top["shape"][:4] == ["1", "8", "4096", "40"] else None,
+                "traffic": ncu_traffic(top["kernel"], "B{}_H{}_N{}_d{}".format(*top["shape"][:4]))[0],
                 "peak_source": how, "avg_launch_us": top["kernel_us"],
                 "algorithmic_flops_per_launch": top["algorithmic_flops_per_launch"],
                 "issued_tflops": top["tflops_issued"],
@@ -469,6 +652,15 @@ def main():
     ap.add_argument("--no-saturated", action="store_true", help="skip the large-batch kernel rooflines")
     ap.add_argument("--seeds-per-batch", type=int, default=8,
                     help="also measure the seed-batched extension with this many seeds per UNet pass (0/1 = skip)")
+    ap.add_argument("--sweep64", action="store_true",
+                    help="BASELINE config 5: the fixed seeds range(28, 92) sharded seed_idx %% world, strong scaling, "
+                         "per-seed checksums in the line")
+    ap.add_argument("--sweep-seeds", type=int, default=64, help="with --sweep64: use the first n seeds of the list")
+    ap.add_argument("--ref-refine-first", type=int, default=10,
+                    help="reference arm / cpu_baseline: refinement iterations of the whole-round sample (10 = the "
+                         "reference's max_refinement_steps)")
+    ap.add_argument("--ref-refine", type=int, default=1,
+                    help="reference arm: refinement iterations of the bounded samples after the first timed step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

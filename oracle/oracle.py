@@ -491,7 +491,8 @@ class OraclePipeline:
                  num_inference_steps: int = 50, guidance_scale: float = 7.5, max_iter_to_alter: int = 25,
                  run_standard_sd: bool = False, thresholds: Dict[int, float] = None, scale_factor: int = 20,
                  scale_range=(1., .5), smooth_attentions=True, sigma=0.5, kernel_size=3, last_idx=-1,
-                 only_update_on_threshold_steps=True, max_steps: Optional[int] = None) -> PipelineTrace:
+                 only_update_on_threshold_steps=True, max_steps: Optional[int] = None,
+                 max_refinement_steps: int = 10) -> PipelineTrace:
         thresholds = {0: float("inf")} if not thresholds else thresholds
         sch = self.scheduler
         sch.set_timesteps(num_inference_steps)
@@ -516,7 +517,8 @@ class OraclePipeline:
                         step_size = scale_factor * np.sqrt(scale[i])
                         if not self._meets(i, thresholds, r):
                             updated = True
-                            r, latents = self._refine(latents, prompt_embeds, step_size, t, i, thresholds, lk, trace)
+                            r, latents = self._refine(latents, prompt_embeds, step_size, t, i, thresholds, lk, trace,
+                                                      max_refinement_steps)
                         if (not only_update_on_threshold_steps and i < max_iter_to_alter) or (i in thresholds):
                             if not self._meets(-1, thresholds, stale):
                                 updated = True

@@ -779,9 +779,9 @@ def test_seed_batching_with_keyword_loss_equals_separate_calls():
                             num_inference_steps=case["steps"], guidance_scale=7.5, thresholds=cfg.thresholds)
 
 
-# one guidance step, full size, fp16 vs the fp32 oracle: measured on B200 0.9995+ (gpurun_out/r02_parity_metrics.jsonl,
-# summarised in DESIGN.md section 4); asserted with margin
-SD14_ONE_STEP_MIN_GRAD_COSINE = 0.98
+# one guidance step, full size, fp16 vs the fp32 oracle: measured on B200 0.9971 (SD-1.4) / 0.9990 (SD-2.x, config 4)
+# (profiles/r02_parity_metrics.jsonl); asserted with margin
+SD14_ONE_STEP_MIN_GRAD_COSINE = 0.99
 
 
 def test_full_size_sd14_guidance_step_fp16():
@@ -877,7 +877,7 @@ def test_full_size_sd21_config4_guidance_step_fp16():
     cos = float((a @ b) / (a.norm() * b.norm()))
     record_metric("sd21_config4_one_step_fp16", {"loss": float(loss), "oracle_loss": ref_loss, "grad_cosine": cos,
                                                  "grad_norm_ratio": float(a.norm() / b.norm())})
-    assert cos > 0.98, cos
+    assert cos > 0.99, cos
 
 
 # ----------------------------------------------------------------- BASELINE config 2, multi-step latents (north_star)
@@ -887,8 +887,9 @@ CONFIG2_HYPER = {"strict": False, "inside_loss_scale": .2, "outside_loss_scale":
 # Stated bound: after the first 10 DDIM steps of config 2 -- which contain ALL of its guidance
 # work: 4 threshold steps x 3 recursion rounds x (1 + 11 refinement forwards, 11 latent updates), re-noising between
 # rounds -- the fp16 product latents (CUDA graphs on) against the fp32 oracle driving the same weights:
-CONFIG2_MIN_COSINE = 0.995
-CONFIG2_MIN_PSNR_DB = 30.0
+# measured on B200 (profiles/r02_parity_metrics.jsonl): cosine 0.999985, PSNR 57.5 dB, 168 = 168 UNet passes
+CONFIG2_MIN_COSINE = 0.9995
+CONFIG2_MIN_PSNR_DB = 45.0
 
 
 class _StopDenoising(Exception):

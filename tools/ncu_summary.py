@@ -25,6 +25,9 @@ def summarise(path):
     out = []
     for r in rows[2:]:
         d = {"report": path.split("/")[-1], "kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+        parts = d["report"].rsplit(".", 1)[0].split("__")     # <round>__<bench kernel>__<bench shape key>.ncu-rep
+        if len(parts) == 3:
+            d["bench_key"] = [parts[1], parts[2]]             # what bench.py's `ncu_traffic` looks up
         for k, name in KEYS.items():
             if k in hdr:
                 i = hdr.index(k)
