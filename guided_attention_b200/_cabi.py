@@ -21,7 +21,9 @@ GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
  GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER, GA_STAT_RAW_SUM,
  GA_STAT_RAW_COL, GA_STAT_RAW_ROW) = range(15)
 GA_STATS = 16
-GA_ABI_VERSION = 3
+GA_ABI_VERSION = 4
+GA_STEP_CTL_BYTES, GA_STEP_COUNTER_BASE = 256, 19
+(GA_STEP_N_EVAL, GA_STEP_N_UPDATE, GA_STEP_N_CFG, GA_STEP_N_REFINE, GA_STEP_N_ROUNDS, GA_STEP_N_RENOISE) = range(6)
 
 
 class GaToken(C.Structure):
@@ -41,6 +43,19 @@ class GaScoreBias(C.Structure):
     _fields_ = [("mask", C.c_void_p), ("mask_stride_bh", C.c_int64), ("mask_stride_n", C.c_int64),
                 ("pww_masks", C.c_void_p), ("pww_coef", C.c_void_p), ("pww_smax", C.c_void_p),
                 ("pww_count", C.c_int32), ("pww_column", C.c_int32 * GA_MAX_TOKENS)]
+
+
+class GaStepPrograms(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("eval", "update", "cfg", "advance", "renoise")]
+
+
+class GaStepParams(C.Structure):
+    _fields_ = [("thr_call", C.c_double), ("thr_cfg", C.c_double), ("thr_last", C.c_double),
+                ("has_thr_call", C.c_int32), ("has_thr_cfg", C.c_int32), ("has_thr_last", C.c_int32),
+                ("check", C.c_int32), ("update_cond", C.c_int32), ("recurse_ok", C.c_int32),
+                ("renoise_ok", C.c_int32), ("recurse_steps", C.c_int32), ("max_refine", C.c_int32),
+                ("timestep", C.c_int64), ("step_size", C.c_float), ("ddim", C.c_float * 4),
+                ("renoise", C.c_float * 2)]
 
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -67,6 +82,10 @@ PROTOTYPES = {
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ga_guidance_tail_bwd": (_i, [C.POINTER(GaTailParams), C.POINTER(GaToken), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i, _vp]),
+    "ga_step_driver_create": (_i, [C.POINTER(_vp), C.POINTER(GaStepPrograms), _vp, _vp, _vp, _vp, _vp,
+                                   C.POINTER(GaToken), _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ga_step_driver_run": (_i, [_vp, C.POINTER(GaStepParams), _vp]),
+    "ga_step_driver_destroy": (_i, [_vp]),
     "ga_smooth_fwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "ga_smooth_bwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "ga_box_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

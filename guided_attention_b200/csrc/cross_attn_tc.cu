@@ -1296,7 +1296,13 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
   {
     const int tiles = (N + kM - 1) / kM;
     const int units = acc != nullptr ? B * tiles : B * H * tiles;
-    bool use_pipe = d <= 160 && units >= (acc != nullptr ? sm_count() / 2 : 2 * sm_count());
+    // Crossovers measured on B200 (profiles/r02_crossover_sweep_before.jsonl).  With maps a pipelined CTA streams the H
+    // heads of one (b, tile) unit back to back, ~18 us per unit at d <= 80 and ~32 us at d = 160 however few units
+    // there are, while the single-shot cluster kernel costs ~9 us per wave of ~8 units: the pipelined kernel wins from
+    // 24 units (d <= 80: B = 3 at 32x32) / 40 units (d > 80: B = 20 at 16x16) on -- not from sm_count / 2 = 74 as in
+    // round 1, which left the seed-batched launches (B = 8, 16) on the slow side of the crossover.
+    const int min_units = acc != nullptr ? (d <= 80 ? 24 : 40) : 2 * sm_count();
+    bool use_pipe = d <= 160 && units >= min_units;
     if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
     if (force_variant == 0) use_pipe = false;
     if (force_variant == 1) {

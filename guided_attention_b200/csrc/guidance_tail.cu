@@ -544,6 +544,135 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   }
 }
 
+// Backward, fast path (no upstream gradient on attn_text -- every launch of the guided pipeline): the map gradient is
+// non-zero only in the tracked tokens' columns, so a row of d_abar is the attn_text row of the same pixel scaled by one
+// per-pixel scalar (-k * sum_t a[col_t] dA_t), with n_tokens entries patched.  The kernel is therefore a shifted,
+// scaled row copy (75-float rows in, 80-float padded rows out) and is laid out for instruction count, which is what
+// bounded the previous version (ncu: issue slots 81 %, DRAM 36 %): one CTA owns `tile` pixels of one sample
+// (the whole 16x16 map, or 256 row-major pixels of a larger one plus a halo of one row + one pixel on each side for
+// the 3x3 filter adjoint); the per-token gradients dA_t are computed once per CTA, one thread per pixel; the streaming
+// phase gives every thread whole float4 chunks of the output (4 scalar loads, 4 multiplies, one 128-bit store).
+__global__ void __launch_bounds__(kThreads)
+tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
+                       const float* __restrict__ weights, const float* __restrict__ attn_text,
+                       const float* __restrict__ smoothed, const float* __restrict__ stats,
+                       const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
+                       const float* __restrict__ g_stats, float* __restrict__ d_abar, int d_abar_rstride, int tile) {
+  extern __shared__ float sds[];            // [token][tile + 2 halo] d loss / d smoothed | [token][tile] dA | [tile] dot
+  __shared__ TokenGrad tg[GA_MAX_TOKENS];
+  const int res = p.res, npix = res * res, tp = p.last - p.first, nt = p.n_tokens;
+  const int smp = blockIdx.y;
+  attn_text += (int64_t)smp * npix * tp;
+  smoothed += (int64_t)smp * nt * npix;
+  stats += (int64_t)smp * nt * GA_STATS;
+  argmax += (int64_t)smp * nt;
+  d_abar += (int64_t)smp * npix * d_abar_rstride;
+  if ((int)threadIdx.x < nt) {
+    const int t = threadIdx.x;
+    tg[t] = make_token_grad(p, toks.t[t], stats + (int64_t)t * GA_STATS, argmax[t],
+                            g_total != nullptr ? g_total[smp] : 0.f,
+                            g_stats != nullptr ? g_stats + ((int64_t)smp * nt + t) * GA_STATS : nullptr);
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * tile;
+  const int halo = p.smooth ? res + 1 : 0;
+  const int lo = max(p0 - halo, 0), hi = min(p0 + tile + halo, npix), span = tile + 2 * halo;
+  const int n_own = min(tile, npix - p0);
+  const float inv_res = 1.f / (float)res;
+  float* sdi = sds + nt * span;
+  float* sdot = sdi + nt * tile;
+  // phase 1: d loss / d smoothed over tile + halo, one thread per pixel, tokens in the inner loop
+  for (int i = threadIdx.x; i < hi - lo; i += kThreads) {
+    const int q = lo + i;
+    const int y = (int)(((float)q + 0.5f) * inv_res), x = q - y * res;
+    for (int t = 0; t < nt; ++t)
+      sds[t * span + i] = dsmoothed_at(tg[t], q, y, x, res, masks, weights, smoothed + (int64_t)t * npix);
+  }
+  __syncthreads();
+  // phase 2: adjoint of the reflect-padded 3x3 filter (+ raw-map statistics) -> dA_t for the tile's own pixels, and
+  // the per-pixel dot product sum_t a[col_t] dA_t in token order (same fma chain as the general kernel)
+  for (int px = threadIdx.x; px < n_own; px += kThreads) {
+    const int pix = p0 + px;
+    const int y = (int)(((float)pix + 0.5f) * inv_res), x = pix - y * res;
+    float wy[3], wx[3];
+#pragma unroll
+    for (int dd = -1; dd <= 1; ++dd) {
+      wy[dd + 1] = p.w1d[1 - dd] + ((y == 1 && dd == -1) ? p.w1d[0] : 0.f) + ((y == res - 2 && dd == 1) ? p.w1d[2] : 0.f);
+      wx[dd + 1] = p.w1d[1 - dd] + ((x == 1 && dd == -1) ? p.w1d[0] : 0.f) + ((x == res - 2 && dd == 1) ? p.w1d[2] : 0.f);
+    }
+    float dot = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const float* ds = sds + t * span - lo;
+      float dimg = 0.f;
+      if (p.smooth) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= res) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= res) continue;
+            dimg = fmaf(wy[dy + 1] * wx[dx + 1], ds[yy * res + xx], dimg);
+          }
+        }
+      } else {
+        dimg = ds[pix];
+      }
+      const TokenGrad& g = tg[t];
+      if (g.r_gcol != 0.f || g.r_grow != 0.f || g.r_gsum != 0.f)
+        dimg += g.r_gsum + (g.r_gcol * (((float)x + 0.5f) - g.r_col) + g.r_grow * (((float)y + 0.5f) - g.r_row)) * g.r_inv_sum;
+      sdi[t * tile + px] = dimg;
+      dot = fmaf(__ldg(attn_text + (int64_t)pix * tp + g.column), dimg, dot);
+    }
+    sdot[px] = dot;
+  }
+  __syncthreads();
+  // phase 3: the rows -- a shifted, scaled copy.  One warp per pixel, lanes over the padded output row (three
+  // slots: columns lane, lane + 32, lane + 64): every load and store instruction of a warp covers one contiguous
+  // 128-byte span; four pixels per iteration keep 12 loads per lane in flight.
+  const float k = p.temperature * p.inv_count;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t hit[3];          // bit t: tracked token t owns the column of this lane's slot
+#pragma unroll
+  for (int sl = 0; sl < 3; ++sl) {
+    hit[sl] = 0u;
+    for (int t = 0; t < nt; ++t)
+      if (tg[t].column + p.first == lane + 32 * sl) hit[sl] |= 1u << t;
+  }
+  constexpr int kPix = 4;
+  for (int px0 = warp * kPix; px0 < n_own; px0 += kWarps * kPix) {
+    float x[kPix][3];
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const float* arow = attn_text + (int64_t)(p0 + px0 + u) * tp - p.first;
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        const int j = lane + 32 * sl;
+        x[u][sl] = (px0 + u < n_own && j >= p.first && j < p.last) ? __ldg(arow + j) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const int px = px0 + u;
+      if (px >= n_own) break;
+      const float dot = sdot[px], nk = -k * dot;
+      float* orow = d_abar + (int64_t)(p0 + px) * d_abar_rstride;
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        const int j = lane + 32 * sl;
+        float val = nk * x[u][sl];
+        if (hit[sl] != 0u) {                 // a tracked column: k a (dA - dot); tokens sharing a column add up
+          float da = 0.f;
+          for (uint32_t m = hit[sl]; m != 0u; m &= m - 1u) da += sdi[(__ffs(m) - 1) * tile + px];
+          val = k * x[u][sl] * (da - dot);
+        }
+        if (j < d_abar_rstride) orow[j] = val;
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------- stand-alone stages
 __global__ void smooth_fwd_kernel(const float* __restrict__ maps, float* __restrict__ out, int n, int res, float w0,
                                   float w1, float w2) {
@@ -752,7 +881,30 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   GA_CHECK_ARG(npix % 4 == 0, "res*res must be a multiple of 4 (res %d)", p.res);
   GA_CHECK_ALIGN(attn_text, 16, "attn_text");
   if ((d_abar_row_stride & 3) == 0) GA_CHECK_ALIGN(d_abar, 16, "d_abar");
-  // small launches: one 4-pixel group per warp (latency); large ones: 4 groups per warp (amortise the halo staging)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_attn_text == nullptr && (d_abar_row_stride & 3) == 0) {
+    // the pipeline's case: sparse map gradient.  Large launches give a CTA 256 pixels (a whole 16x16 map: no halo at
+    // all); small ones 64, so that a single evaluation still spreads over a few SMs.
+    const int tile = 256;
+    const int nt = p.n_tokens > 0 ? p.n_tokens : 1;
+    const size_t smem = ((size_t)nt * (2 * tile + 2 * (p.res + 1)) + tile) * sizeof(float);
+    // (small launches -- the pipeline's own single evaluation, small seed batches -- are latency-bound and stay on the
+    // general kernel below, which spreads its 4-pixel groups over more CTAs: 4.4 vs 10 us at 1 sample, 6.2 vs 13.5 us
+    // at 64; the crossover measured on B200 is ~400 samples at res 16: profiles/r02_microbench_tail_bwd.jsonl)
+    if (smem <= 48 * 1024 && (int64_t)p.n_samples * npix >= 96 * 1024) {
+      static bool carve_set = false;
+      if (!carve_set) {     // several CTAs per SM: ask for enough shared memory for 8 of them, keep the rest as L1
+        cudaFuncSetAttribute(tail::tail_bwd_sparse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+        carve_set = true;
+      }
+      const dim3 grid((npix + tile - 1) / tile, p.n_samples);
+      tail::tail_bwd_sparse_kernel<<<grid, tail::kThreads, smem, st>>>(p, toks, masks, weights, attn_text, smoothed,
+                                                                      stats, argmax, g_total, g_stats, d_abar,
+                                                                      d_abar_row_stride, tile);
+      return check_launch("guidance_tail_bwd_sparse");
+    }
+  }
+  // general path (upstream gradient on attn_text: Python custom-loss plug-ins)
   int groups_per_warp = ((int64_t)p.n_samples * npix >= 128 * 1024) ? 4 : 1;
   auto halo_bytes = [&](int gpw) {
     // staged d loss / d smoothed (tile + halo) and d loss / d raw map (tile), per token
@@ -763,7 +915,7 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   const dim3 grid((npix + ppc - 1) / ppc, p.n_samples);
   const size_t smem = halo_bytes(groups_per_warp);
   if (smem > 14 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d x %d tokens too large for the tail backward", p.res, p.n_tokens);
-  tail::tail_bwd_kernel<<<grid, tail::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  tail::tail_bwd_kernel<<<grid, tail::kThreads, smem, st>>>(
       p, toks, masks, weights, attn_text, smoothed, stats, argmax, g_total, g_stats, g_attn_text, d_abar,
       d_abar_row_stride, groups_per_warp);
   return check_launch("guidance_tail_bwd");

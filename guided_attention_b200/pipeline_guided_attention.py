@@ -68,6 +68,16 @@ class _StepGraphs:
         self.pool = None
         # text K/V projections are computed once per embedding buffer instead of once per UNet pass (ptp_utils.TextKVCache)
         self.text_kv = TextKVCache()
+        # device-side step driver (csrc/step_driver.cu): re-noise coefficients, the pre-drawn re-noise
+        # tensors of one image with their draw counter, the control block, and the driver handle
+        hp = state.curHyperParams or {}
+        n_steps = int(pipe.scheduler.num_inference_steps or 0)
+        self.max_draws = max(1, n_steps * max(int(hp.get("recurse_steps", 1)) - 1, 0))
+        self.bt = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.noise = torch.zeros((self.max_draws,) + tuple(latents_like.shape), dtype=torch.float32, device=dev)
+        self.n_draws = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ctl = torch.zeros(abi.GA_STEP_CTL_BYTES // 4, dtype=torch.int32, device=dev)
+        self._driver = None
 
     def set_embeds(self, prompt_embeds):
         self.embeds.copy_(prompt_embeds)
@@ -104,6 +114,62 @@ class _StepGraphs:
             self.lat_out.copy_(out.prev_sample)
         return {}
 
+    def _prog_advance(self):
+        with torch.no_grad():
+            self.lat.copy_(self.lat_out)
+        return {}
+
+    def _prog_renoise(self):
+        """Back to the previous noise level before a recursion round (reference :1046-1050), with the next of the
+        image's pre-drawn noise tensors: same fp32 arithmetic as `GuidedAttention._renoise`."""
+        with torch.no_grad():
+            # (clamped: the warm-up passes before capture advance the counter past a one-entry buffer)
+            noise = self.noise.index_select(0, self.n_draws.clamp(max=self.max_draws - 1))[0]
+            self.lat.copy_((self.bt[0] * self.lat.float() + self.bt[1] * noise).to(self.lat.dtype))
+            self.n_draws.add_(1)
+        return {}
+
+    def driver(self):
+        """The step driver for these programs (`ga_step_driver_create`), built on first use: captures all five
+        programs, hands their raw cudaGraph_t handles plus the static `stats` buffers to the library."""
+        if self._driver is not None:
+            return self._driver
+        self.store.text_kv = self.text_kv
+        for name in ("eval", "update", "cfg", "advance", "renoise"):
+            self._graph(name)
+        lib = abi.load()
+        progs = abi.GaStepPrograms(*[int(self.graphs[n].raw_cuda_graph())
+                                     for n in ("eval", "update", "cfg", "advance", "renoise")])
+
+        def custom_of(out):
+            if out["losses"] and out["losses"][-1][0] is None and torch.is_tensor(out["losses"][-1][1]):
+                c = out["losses"][-1][1]
+                if c.dtype != torch.float32 or not c.is_cuda:
+                    raise RuntimeError("custom loss term must be a float32 CUDA tensor")
+                return c
+            return None
+        spec = self.pipe._tail_spec_cache[1]
+        self._custom = (custom_of(self.outputs["eval"]), custom_of(self.outputs["update"]))
+        handle = C.c_void_p()
+        abi.check(lib.ga_step_driver_create(
+            C.byref(handle), C.byref(progs), C.c_void_p(self.ctl.data_ptr()),
+            C.c_void_p(self.outputs["eval"]["stats"].data_ptr()), C.c_void_p(self.outputs["update"]["stats"].data_ptr()),
+            C.c_void_p(self._custom[0].data_ptr() if self._custom[0] is not None else 0),
+            C.c_void_p(self._custom[1].data_ptr() if self._custom[1] is not None else 0),
+            spec.tokens, len(spec.token_indices), int(spec.params.n_groups),
+            int(bool(getattr(state.config, "sub_prompt_avg_within", False))),
+            C.c_void_p(self.t.data_ptr()), C.c_void_p(self.step.data_ptr()), C.c_void_p(self.coef.data_ptr()),
+            C.c_void_p(self.bt.data_ptr())), "ga_step_driver_create")
+        self._driver = handle
+        return handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_driver", None) is not None:
+                abi.load().ga_step_driver_destroy(self._driver)
+        except Exception:
+            pass
+
     def _graph(self, name):
         if name in self.graphs:
             return self.graphs[name]
@@ -117,7 +183,9 @@ class _StepGraphs:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         snap = dict(ops.launch_counts)
-        g = torch.cuda.CUDAGraph()
+        # keep_graph: the raw cudaGraph_t stays available for the step driver (csrc/step_driver.cu clones it into its
+        # conditional graph); `replay()` instantiates on first use
+        g = torch.cuda.CUDAGraph(keep_graph=True)
         with torch.cuda.graph(g, pool=self.pool):
             self.outputs[name] = prog()
         if self.pool is None:
@@ -663,6 +731,82 @@ class GuidedAttention(StableDiffusionPipelineBase):
                     latents = self._renoise(latents, t, renoise_gen)
         return latents
 
+    # ------------------------------------------------------------------------------- device-side control (f3)
+    device_side_control = True    # with CUDA graphs: refinement / recursion / threshold tests run inside one graph launch
+    control_mode = None           # what the last `__call__` used: "device", "host-graphs" or "eager"
+
+    def _denoise_device(self, G, latents, timesteps, thresholds, scale_range, scale_factor, recurse_steps,
+                        recurse_until, max_iter_to_alter, renoise_gen):
+        """The guided loop of `__call__` (reference :925-1053) with the per-step control flow ON THE DEVICE
+        (`csrc/step_driver.cu`): one graph launch per denoising step, no loss is read back, the host only feeds the
+        step's scalars (timestep, step size, DDIM / re-noise coefficients, thresholds).  Same UNet passes in the same
+        order and the same latents as `_denoise_graphed`.  The image's re-noise tensors are drawn up front from the
+        same CPU generator stream, in the same order the host loop would draw them."""
+        cfg = state.config
+        lib = abi.load()
+        drv = G.driver()
+        dev = G.lat.device
+        n_train = self.scheduler.config.num_train_timesteps
+        ratio = n_train // self.scheduler.num_inference_steps
+
+        def update_cond(i):
+            return (not cfg.only_update_on_threshold_steps and i < max_iter_to_alter) or (i in cfg.thresholds)
+        n_draws = 0
+        for i, t in enumerate(timesteps):
+            if ((i in thresholds) or update_cond(i)) and not (i > recurse_until) and int(t) - ratio > 0:
+                n_draws += recurse_steps - 1
+        if n_draws > G.max_draws:
+            raise RuntimeError(f"{n_draws} re-noise draws exceed the captured capacity {G.max_draws}")
+        if n_draws:
+            noise = torch.stack([torch.randn(latents.shape, generator=renoise_gen, dtype=torch.float32)
+                                 for _ in range(n_draws)]).pin_memory()
+            G.noise[:n_draws].copy_(noise, non_blocking=True)
+        G.n_draws.zero_()
+        G.lat.copy_(latents)
+        before = G.ctl.clone()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        last_cfg = list(cfg.thresholds.values())[-1] if len(cfg.thresholds) else 0.0
+        pww = PaintWithWords.of(G.store)
+        for i, t in enumerate(timesteps):
+            t = int(t)
+            state.cur_time_step_iter = i
+            if pww is not None:
+                pww.update(dev)
+            p = abi.GaStepParams()
+            p.has_thr_call = int(i in thresholds and len(thresholds) > 0)
+            p.thr_call = float(thresholds[i]) if p.has_thr_call else 0.0
+            p.has_thr_cfg = int(i in cfg.thresholds and len(cfg.thresholds) > 0)
+            p.thr_cfg = float(cfg.thresholds[i]) if p.has_thr_cfg else 0.0
+            p.has_thr_last, p.thr_last = int(len(cfg.thresholds) > 0), float(last_cfg)
+            p.update_cond = int(update_cond(i))
+            p.check = int((i in thresholds) or bool(p.update_cond))
+            p.recurse_ok = int(not (i > recurse_until))
+            prev_t = t - ratio
+            p.renoise_ok = int(prev_t > 0)
+            p.recurse_steps, p.max_refine = int(recurse_steps), 10
+            p.timestep = t
+            p.step_size = float(scale_factor * np.sqrt(scale_range[i]))
+            for n, c in enumerate(self.scheduler.coefficients(t)):
+                p.ddim[n] = float(c)
+            if prev_t > 0:
+                Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_t])
+                p.renoise[0], p.renoise[1] = Bt ** 0.5, (1 - Bt) ** 0.5
+            with torch.cuda.device(dev):
+                abi.check(lib.ga_step_driver_run(drv, C.byref(p), stream), "ga_step_driver_run")
+        out = G.lat.clone()
+        # bookkeeping after the fact: one small read together with the image (the caller reads the latents anyway)
+        base = abi.GA_STEP_COUNTER_BASE
+        d = (G.ctl - before)[base:base + 6].cpu().tolist()
+        n_prog = {"eval": d[abi.GA_STEP_N_EVAL], "update": d[abi.GA_STEP_N_UPDATE], "cfg": d[abi.GA_STEP_N_CFG]}
+        self.last_step_counters = {"eval": d[0], "update": d[1], "cfg": d[2], "refine_iterations": d[3],
+                                   "rounds": d[4], "renoise": d[5]}
+        for name, n in n_prog.items():
+            self._count_pass(name, n)
+            G.replays[name] = G.replays.get(name, 0) + n
+            for k, v in G.launches[name].items():
+                ops._count(k, v * n)
+        return out
+
     def _renoise(self, latents, t, renoise_gen):
         """Back to the previous noise level before a recursion (reference :1046-1050)."""
         prev_timestep = t - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
@@ -879,11 +1023,20 @@ class GuidedAttention(StableDiffusionPipelineBase):
                    and do_classifier_free_guidance and latents.shape[0] == 1
                    and not state.curHyperParams.get("use_optimizer", False) and cross_attention_kwargs is None)
         attention_store.text_kv = None      # the eager loop does not own the embedding buffers: no K/V caching
+        self.control_mode = "eager"
         if graphed:
             G = self._step_graphs(attention_store, loss_kw, prompt_embeds, guidance_scale, latents)
-            latents = self._denoise_graphed(G, latents, timesteps, thresholds, scale_range, scale_factor,
-                                            recurse_steps, recurse_until, max_iter_to_alter, run_standard_sd,
-                                            renoise_gen, callback, callback_steps)
+            if self.device_side_control and callback is None and not run_standard_sd:
+                self.control_mode = "device"
+                if renoise_gen is None:
+                    renoise_gen = torch.Generator("cpu").manual_seed(0)      # recurse_steps == 1: never drawn from
+                latents = self._denoise_device(G, latents, timesteps, thresholds, scale_range, scale_factor,
+                                               recurse_steps, recurse_until, max_iter_to_alter, renoise_gen)
+            else:
+                self.control_mode = "host-graphs"
+                latents = self._denoise_graphed(G, latents, timesteps, thresholds, scale_range, scale_factor,
+                                                recurse_steps, recurse_until, max_iter_to_alter, run_standard_sd,
+                                                renoise_gen, callback, callback_steps)
             timesteps = []      # the eager loop below has nothing left to do
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 3
+#define GA_ABI_VERSION 4
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -219,6 +219,55 @@ int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* 
                          const float* weights, const float* attn_text, const float* smoothed, const float* stats,
                          const int32_t* argmax, const float* g_total, const float* g_stats, const float* g_attn_text,
                          float* d_abar, int d_abar_row_stride, ga_stream_t stream);
+
+/* ---- device-side driver of one denoising step -----------------------------------------------------------
+ * Replaces the HOST control flow of one denoising step of reference pipeline_guided_attention.py:925-1053 -- recursion
+ * rounds, `_perform_iterative_refinement_step` (:475-581), the threshold tests `meets_threshold` (:1074-1088) on the
+ * sub-prompt-grouped unscaled losses (:358-387) and the re-noising (:1046-1050) -- by ONE CUDA graph with conditional
+ * (WHILE / IF) nodes built from five device programs the caller captured (raw `cudaGraph_t` handles; cloned into the
+ * driver's graph, the caller keeps ownership and must keep the memory they reference alive):
+ *     eval, update, cfg : the three programs of the guided loop (reads `latents`, update/cfg write `latents_out`)
+ *     advance           : latents <- latents_out
+ *     renoise           : latents <- sqrt(Bt) latents + sqrt(1 - Bt) noise[n_draws++]
+ * The tail kernel's `stats` of the eval / update programs (static buffers, (n_tokens, GA_STATS) fp32) and the optional
+ * custom-loss scalars are read by the driver's decision kernels; the same UNet passes run, in the same order, as in the
+ * host-driven loop, and no value is read back to the host. */
+#define GA_STEP_CTL_BYTES 256
+typedef struct ga_step_programs {
+  void *eval, *update, *cfg, *advance, *renoise; /* cudaGraph_t */
+} ga_step_programs_t;
+
+typedef struct ga_step_params {     /* everything that changes from one denoising step to the next */
+  double thr_call;        /* thresholds[i] of the __call__ argument (used for the first test of a round, :963)         */
+  double thr_cfg;         /* state.config.thresholds[i] (refinement loop, :501)                                          */
+  double thr_last;        /* last value of state.config.thresholds (the `-1` test of :1001)                              */
+  int32_t has_thr_call, has_thr_cfg, has_thr_last; /* key present / dict non-empty                                       */
+  int32_t check;          /* (i in thresholds) or update_cond: the round's first evaluation is tested at all            */
+  int32_t update_cond;    /* (not only_update_on_threshold_steps and i < max_iter_to_alter) or i in config.thresholds   */
+  int32_t recurse_ok;     /* not (i > recurse_until)                                                                      */
+  int32_t renoise_ok;     /* prev_timestep > 0 (:1047)                                                                    */
+  int32_t recurse_steps;  /* >= 1                                                                                          */
+  int32_t max_refine;     /* max_refinement_steps (10)                                                                    */
+  int64_t timestep;       /* -> *t_dev                                                                                     */
+  float step_size;        /* scale_factor * sqrt(scale_range[i]) -> *step_dev                                             */
+  float ddim[4];          /* DDIM coefficients of the step -> ddim_dev[0..3]                                              */
+  float renoise[2];       /* sqrt(Bt), sqrt(1 - Bt) -> renoise_dev[0..1]                                                  */
+} ga_step_params_t;
+
+/* ctl_dev: GA_STEP_CTL_BYTES of zero-initialised DEVICE memory (state + lifetime counters, see ga_step_counters).
+ * tokens_host: the tail's token table (group ids and kinds are used); n_groups, avg_within as in the tail spec.
+ * t_dev (int64), step_dev (float), ddim_dev (float[4]), renoise_dev (float[2]): the DEVICE scalars the captured programs
+ * read; ga_step_driver_run fills them from `params_host` on the stream before launching the graph. */
+int ga_step_driver_create(void** driver_out, const ga_step_programs_t* programs, void* ctl_dev,
+                          const float* stats_eval, const float* stats_update, const float* custom_eval,
+                          const float* custom_update, const ga_token_t* tokens_host, int n_tokens, int n_groups,
+                          int avg_within, int64_t* t_dev, float* step_dev, float* ddim_dev, float* renoise_dev);
+int ga_step_driver_run(void* driver, const ga_step_params_t* params_host, ga_stream_t stream);
+int ga_step_driver_destroy(void* driver);
+/* int32 offsets into ctl_dev of the lifetime counters (UNet passes by program, refinement iterations, rounds, re-noise) */
+enum ga_step_counter { GA_STEP_N_EVAL = 0, GA_STEP_N_UPDATE = 1, GA_STEP_N_CFG = 2, GA_STEP_N_REFINE = 3,
+                       GA_STEP_N_ROUNDS = 4, GA_STEP_N_RENOISE = 5 };
+#define GA_STEP_COUNTER_BASE 19 /* counters start at ((int32_t*)ctl_dev)[GA_STEP_COUNTER_BASE] */
 
 /* ---- stand-alone stages (same device code as the tail), for the module-level API -----------------------------------
  * GaussianSmoothing.forward on reflect-padded maps (utils/gaussian_smoothing.py:63-71 + pipeline :253):

@@ -949,3 +949,46 @@ def test_config2_ten_step_latents_fp16_vs_fp32_oracle():
     assert passes == trace.unet_forwards, (passes, trace.unet_forwards)
     assert np.isfinite(got).all()
     assert cos > CONFIG2_MIN_COSINE and psnr > CONFIG2_MIN_PSNR_DB, (cos, psnr)
+
+
+# measured on B200 (profiles/r02_parity_metrics.jsonl); asserted with margin
+BATCH_FP16_MIN_COSINE = 0.999
+BATCH_FP16_MIN_PSNR_DB = 35.0
+
+
+def test_seed_batching_full_size_fp16_matches_separate_calls():
+    """`generate_batch` on the configuration the bench's `batched` figure is measured on (SD-1.4 shape, fp16, CUDA
+    graphs, the bench's thresholds, 50 steps, 4 seeds per UNet pass) against separate `__call__`s of the same seeds.
+    Batched convolutions / GEMMs pick other algorithms than batch-1 ones, so the bound is PSNR / cosine, not equality."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200.ptp_utils import AttentionStore, register_attention_control
+    from guided_attention_b200.substrate import DDIMScheduler, UNetConfig, build_unet
+    from guided_attention_b200.run import synthetic_prompt_embeds
+    cfg = setup_prompt(hyper=CONFIG2_HYPER)
+    cfg.thresholds = CONFIG2_HYPER["thresholds"]
+    unet = build_unet(UNetConfig.sd14(), seed=0, dtype=torch.float16, device=DEV)
+    pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=cfg.stable.tokenizer)
+    cfg.stable = pipe
+    pipe.use_cuda_graphs = True
+    store = AttentionStore()
+    register_attention_control(pipe, store)
+    embeds = synthetic_prompt_embeds(cfg.prompt, 768).to(DEV, torch.float16)
+    seeds = [28, 29, 30, 31]
+    singles = []
+    for sd in seeds:
+        lat = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(sd))
+        out = pipe(prompt=cfg.prompt, attention_store=store, attention_res=16, guidance_scale=7.5,
+                   generator=torch.Generator("cpu").manual_seed(sd), latents=lat, prompt_embeds=embeds[1:2],
+                   negative_prompt_embeds=embeds[0:1], num_inference_steps=50, thresholds=cfg.thresholds,
+                   output_type="latent")
+        singles.append(out.images.float().cpu().numpy())
+    batch = pipe.generate_batch(cfg.prompt, store, seeds, embeds[1:2], embeds[0:1], attention_res=16,
+                                num_inference_steps=50, guidance_scale=7.5, thresholds=cfg.thresholds)
+    batch = batch.float().cpu().numpy()
+    worst = {"cosine": 1.0, "psnr_db": 1e9}
+    for n, single in enumerate(singles):
+        b = batch[n:n + 1]
+        cos = float((b * single).sum() / (np.linalg.norm(b) * np.linalg.norm(single)))
+        worst = {"cosine": min(worst["cosine"], cos), "psnr_db": min(worst["psnr_db"], _psnr(b, single))}
+    record_metric("seed_batching_full_size_fp16", worst)
+    assert worst["cosine"] > BATCH_FP16_MIN_COSINE and worst["psnr_db"] > BATCH_FP16_MIN_PSNR_DB, worst
