@@ -46,7 +46,7 @@ class GaScoreBias(C.Structure):
 
 
 class GaStepPrograms(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("eval", "update", "cfg", "advance", "renoise")]
+    _fields_ = [(n, C.c_void_p) for n in ("eval", "update", "cfg", "advance", "renoise", "refine_update")]
 
 
 class GaStepParams(C.Structure):
@@ -82,7 +82,7 @@ PROTOTYPES = {
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ga_guidance_tail_bwd": (_i, [C.POINTER(GaTailParams), C.POINTER(GaToken), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i, _vp]),
-    "ga_step_driver_create": (_i, [C.POINTER(_vp), C.POINTER(GaStepPrograms), _vp, _vp, _vp, _vp, _vp,
+    "ga_step_driver_create": (_i, [C.POINTER(_vp), C.POINTER(GaStepPrograms), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    C.POINTER(GaToken), _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ga_step_driver_run": (_i, [_vp, C.POINTER(GaStepParams), _vp]),
     "ga_step_driver_destroy": (_i, [_vp]),

@@ -301,6 +301,248 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
+// ================================================================================ forward, single pass (default)
+// One pass over the keys with an online softmax, so QK^T is issued once (2 GEMMs per key block instead of 3) and the
+// scores cross TMEM -> registers once.  Each compute group keeps its OWN output accumulator in TMEM (O_0 for the even
+// key blocks, O_1 for the odd ones) together with its own running row maximum and row sum, so the groups never have
+// to agree on a maximum while the blocks stream; the epilogue merges the two partial results
+//     m = max(m_0, m_1),  l = l_0 2^(m_0 - m) + l_1 2^(m_1 - m),  O = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / l.
+// The running maximum is LAZY: a group keeps exponentiating against a stale maximum as long as the block maximum
+// exceeds it by less than 2^kLazyBits (P <= 256: harmless for the 16-bit P operand and the fp32 sums), and only when a
+// row jumps further does its warp rescale its O accumulator in TMEM (tcgen05.ld -> multiply -> tcgen05.st, after the
+// group's previous PV GEMM has completed).  After the first block of a group that is rare, so the common path of a
+// block is: tcgen05.ld S -> max -> exp2 -> sum -> pack -> tcgen05.st P -> arrive.
+//
+//   TMEM:  3 score buffers of `bk` columns | O_0 (npv) | O_1 (npv)      (d = 160: 192 + 320 = 512 columns)
+//   roles as in the two-pass kernel below: warp 0 TMA producer, warp 1 issuer of S = Q K_j^T, warp 2 issuer of
+//   O_g += P_j V_j (its commit frees the K/V stage and the score buffer), warps 4-7 / 8-11 compute groups.
+constexpr float kLazyBits = 8.f;
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+self_attn_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                      const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // q_full, o_ready, kv_full[4], kv_free[4], s_ready[3], p_ready[3], p_free[3]
+  __shared__ __align__(8) uint64_t bars[19];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float xm[2][kM], xl[2][kM];   // running maxima / sums of the two compute groups
+
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = tile * kM;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kv_block_bytes = (uint32_t)BK * 128u;
+  const uint32_t k_bytes = (uint32_t)p.nblk * kv_block_bytes;
+  const uint32_t stage_bytes = 2u * k_bytes;
+  const uint32_t sQ = base;
+  const uint32_t sKV = sQ + (uint32_t)p.nblk * kQBlockBytes;
+  auto Q_FULL = [&]() { return smem_u32(&bars[0]); };
+  auto O_READY = [&]() { return smem_u32(&bars[1]); };
+  auto KV_FULL = [&](int s) { return smem_u32(&bars[2 + s]); };
+  auto KV_FREE = [&](int s) { return smem_u32(&bars[6 + s]); };
+  auto S_READY = [&](int i) { return smem_u32(&bars[10 + i]); };
+  auto P_READY = [&](int i) { return smem_u32(&bars[13 + i]); };
+  auto P_FREE = [&](int i) { return smem_u32(&bars[16 + i]); };
+  constexpr uint32_t colO = (uint32_t)(kSBuf * BK);
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(Q_FULL(), 1);
+    mbar_init(O_READY(), 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
+    for (int i = 0; i < kSBuf; ++i) {
+      mbar_init(S_READY(i), 1);
+      mbar_init(P_READY(i), kGroupThreads);
+      mbar_init(P_FREE(i), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
+  const int nb = p.nb, NS = p.stages;
+  const int ksteps = (p.d + 15) >> 4;
+  const int fmt = p.bf16 ? 1 : 0;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      // ------------------------------------------------------------------------------------------- producer
+      if (elect_one()) {
+        mbar_expect_tx(Q_FULL(), (uint32_t)p.nblk * kQBlockBytes);
+        for (int blk = 0; blk < p.nblk; ++blk)
+          tma_load_4d(sQ + blk * kQBlockBytes, &map_q, Q_FULL(), blk * kBlockCols, h, row0, b);
+      }
+      RingPos st = {0, 0};
+      for (int it = 0; it < nb; ++it) {
+        if (it >= NS) mbar_wait(KV_FREE(st.idx), st.par ^ 1u);
+        if (elect_one()) {
+          const uint32_t sK = sKV + st.idx * stage_bytes, sV = sK + k_bytes;
+          mbar_expect_tx(KV_FULL(st.idx), stage_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk) {
+            tma_load_4d(sK + blk * kv_block_bytes, &map_k, KV_FULL(st.idx), blk * kBlockCols, h, it * BK, b);
+            tma_load_4d(sV + blk * kv_block_bytes, &map_v, KV_FULL(st.idx), blk * kBlockCols, h, it * BK, b);
+          }
+        }
+        __syncwarp();
+        st.advance(NS);
+      }
+    } else if (warp == 1) {
+      // ----------------------------------------------------------------------------- MMA issuer 1: S = Q K^T
+      const uint32_t idesc_qk = make_idesc(fmt, 0, BK, kM);
+      const uint64_t dQ0 = smem_desc_sw128(sQ, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(sKV, 16, 1024);                          // stage 0, K-major
+      mbar_wait(Q_FULL(), 0);
+      RingPos st = {0, 0}, sb = {0, 0};
+      for (int it = 0; it < nb; ++it) {
+        // the buffer's previous item (it - 3): its P has been consumed by its PV GEMM
+        if (it >= kSBuf) mbar_wait(P_FREE(sb.idx), sb.par ^ 1u);
+        mbar_wait(KV_FULL(st.idx), st.par);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_kmajor_gemm(tmem + (uint32_t)(sb.idx * BK), dQ0, kQBlockBytes, desc_advance(dK0, st.idx * stage_bytes),
+                            kv_block_bytes, ksteps, idesc_qk);
+          tc_commit(S_READY(sb.idx));
+        }
+        __syncwarp();
+        st.advance(NS);
+        sb.advance(kSBuf);
+      }
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------- MMA issuer 2: O_(it & 1) += P V
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dV0 = smem_desc_sw128(sKV + k_bytes, kv_block_bytes, 1024);    // stage 0, MN-major
+      RingPos st = {0, 0}, sb = {0, 0};
+      for (int it = 0; it < nb; ++it) {
+        mbar_wait(P_READY(sb.idx), sb.par);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + colO + (uint32_t)((it & 1) * p.npv), tmem + (uint32_t)(sb.idx * BK),
+                          desc_advance(dV0, st.idx * stage_bytes), BK / 16, idesc_pv, it >= 2);
+          tc_commit(KV_FREE(st.idx));
+          tc_commit(P_FREE(sb.idx));
+        }
+        __syncwarp();
+        st.advance(NS);
+        sb.advance(kSBuf);
+      }
+      if (elect_one()) tc_commit(O_READY());
+      __syncwarp();
+    }
+  } else {
+    reg_alloc<232>();
+    // --------------------------------------------------------------------------------------- compute groups
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const int row = row0 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t colOg = colO + (uint32_t)(g * p.npv);
+    const float sc = p.scale * 1.4426950408889634f;
+    const bool bf16 = p.bf16 != 0;
+    const float lazy = kLazyBits / sc;               // the lazy-maximum slack in raw score units
+
+    float m_used = -INFINITY;                        // the maximum this row's exponentials are taken against (raw units)
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = g; it < nb; it += 2) {
+      const int buf = it % kSBuf;
+      const uint32_t colS = (uint32_t)(buf * BK);
+      mbar_wait(S_READY(buf), (uint32_t)(it / kSBuf) & 1u);
+      tc_fence_after();
+      float s[BK];
+#pragma unroll
+      for (int c = 0; c < BK / 16; ++c) tmem_ld16(lane_base + colS + c * 16, s + c * 16);
+      tmem_ld_wait();
+      const int key0 = it * BK;
+      if (key0 + BK > p.N) {
+#pragma unroll
+        for (int j = 0; j < BK; ++j)
+          if (key0 + j >= p.N) s[j] = -INFINITY;
+      }
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < BK; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+      const float bm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const bool jump = bm > m_used + lazy;          // first block: m_used = -inf
+      if (__any_sync(0xffffffffu, jump)) {
+        if (it >= 2) {
+          // rescale this group's accumulator: its previous PV GEMM (item it - 2) must have completed
+          const int pit = it - 2;
+          mbar_wait(P_FREE(pit % kSBuf), (uint32_t)(pit / kSBuf) & 1u);
+          tc_fence_after();
+          const float f = jump ? ex2_approx((m_used - bm) * sc) : 1.f;
+          for (int cc = 0; cc < p.npv / 16; ++cc) {
+            float ov[16];
+            tmem_ld16(lane_base + colOg + cc * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] *= f;
+            tmem_st16(lane_base + colOg + cc * 16, ov);
+          }
+          tmem_st_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) l4[i] *= f;
+        }
+        if (jump) m_used = bm;
+      }
+      const float mo = m_used * sc;
+#pragma unroll
+      for (int j = 0; j < BK; ++j) { s[j] = ex2_approx(fmaf(s[j], sc, -mo)); l4[j & 3] += s[j]; }
+      // P (packed 16-bit, BK / 2 columns) over the head of the score buffer: every score is in registers by now
+#pragma unroll
+      for (int c = 0; c < BK / 16; ++c) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) packed[i] = pack16(s[c * 16 + 2 * i], s[c * 16 + 2 * i + 1], bf16);
+        tmem_st8(lane_base + colS + c * 8, packed);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(P_READY(buf));
+    }
+    // ---- merge the two groups' partial softmax states
+    xm[g][r] = m_used;
+    xl[g][r] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    named_bar_sync(1, 2 * kGroupThreads);
+    const bool has1 = nb >= 2;                       // group 1 saw no key block otherwise: O_1 is unwritten TMEM
+    const float m0 = xm[0][r], m1 = has1 ? xm[1][r] : -INFINITY;
+    const float m = fmaxf(m0, m1);
+    const float f0 = ex2_approx((m0 - m) * sc), f1 = has1 ? ex2_approx((m1 - m) * sc) : 0.f;
+    const float l = xl[0][r] * f0 + (has1 ? xl[1][r] * f1 : 0.f);
+    const float inv = 1.f / l;
+    if (g == 0 && row < p.N) p.lse[((int64_t)b * p.H + h) * p.N + row] = m * p.scale + logf(l);
+    const float w0 = f0 * inv, w1 = f1 * inv;
+
+    // ---- epilogue: the two groups take alternate 16-column chunks of O = w0 O_0 + w1 O_1
+    mbar_wait(O_READY(), 0);
+    tc_fence_after();
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+    for (int cc = g; cc < p.npv / 16; cc += 2) {
+      float oa[16], ob[16];
+      tmem_ld16(lane_base + colO + cc * 16, oa);
+      if (has1) tmem_ld16(lane_base + colO + (uint32_t)p.npv + cc * 16, ob);
+      tmem_ld_wait();
+      if (row < p.N) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = has1 ? fmaf(ob[2 * i], w1, oa[2 * i] * w0) : oa[2 * i] * w0;
+          const float a1 = has1 ? fmaf(ob[2 * i + 1], w1, oa[2 * i + 1] * w0) : oa[2 * i + 1] * w0;
+          w[i] = pack16(a0, a1, bf16);
+        }
+        const int col = cc * 16;
+        if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // ------------------------------------------------------------------------------------------------------ host
 bool supports(int dtype, int head_dim) {
   return (dtype == GA_F16 || dtype == GA_BF16) && head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 160;
@@ -327,9 +569,25 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B,
   if ((rc = make_map(&mq, q, dtype, B, N, H, d, kM)) != GA_OK) return rc;
   if ((rc = make_map(&mk, k, dtype, B, N, H, d, p.bk)) != GA_OK) return rc;
   if ((rc = make_map(&mv, v, dtype, B, N, H, d, p.bk)) != GA_OK) return rc;
+  dim3 grid((N + kM - 1) / kM, H, B);
+  // GA_SA_TWO_PASS=1 selects the round-1 two-pass kernel (A/B measurements); the single-pass kernel needs two output
+  // accumulators behind the three score buffers: 3 bk + 2 npv <= 512 TMEM columns (true for every head_dim <= 160)
+  static int two_pass = -1;
+  if (two_pass < 0) {
+    const char* e2 = getenv("GA_SA_TWO_PASS");
+    two_pass = (e2 != nullptr && e2[0] == '1') ? 1 : 0;
+  }
+  if (two_pass == 0 && kSBuf * p.bk + 2 * p.npv <= 512) {
+    const void* kern = p.bk == 128 ? reinterpret_cast<const void*>(self_attn_fwd1_kernel<128>)
+                                   : reinterpret_cast<const void*>(self_attn_fwd1_kernel<64>);
+    cudaError_t e1 = ensure_smem(kern, p.bk == 128 ? 4 : 5, smem);
+    if (e1 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1));
+    if (p.bk == 128) self_attn_fwd1_kernel<128><<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+    else self_attn_fwd1_kernel<64><<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+    return check_launch("self_attn_fwd1");
+  }
   cudaError_t e = ensure_smem(reinterpret_cast<const void*>(self_attn_fwd_kernel), 0, smem);
   if (e != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  dim3 grid((N + kM - 1) / kM, H, B);
   self_attn_fwd_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
   return check_launch("self_attn_fwd");
 }

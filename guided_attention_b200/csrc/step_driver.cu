@@ -91,8 +91,9 @@ __global__ void init_kernel(Ctl* ctl) {
 // after the round's first evaluation (reference :946-1004; host mirror: pipeline `_denoise_graphed`)
 __global__ void decide_round_kernel(Ctl* ctl, const float* stats, const float* custom, Tokens tk,
                                     cudaGraphConditionalHandle h_refine, cudaGraphConditionalHandle h_final_update,
-                                    cudaGraphConditionalHandle h_final_eval) {
+                                    cudaGraphConditionalHandle h_final_eval, float* refine_first) {
   if (threadIdx.x != 0) return;
+  if (refine_first != nullptr) *refine_first = 1.f;   // a refinement that starts now starts with fresh optimizer state
   ctl->n_eval += 1;
   ctl->n_rounds += 1;
   bool met = true, do_update = false;
@@ -113,8 +114,9 @@ __global__ void decide_round_kernel(Ctl* ctl, const float* stats, const float* c
 
 // after every refinement iteration (reference :501-557: the loop re-tests the losses it computed BEFORE the update)
 __global__ void decide_refine_kernel(Ctl* ctl, const float* stats, const float* custom, Tokens tk,
-                                     cudaGraphConditionalHandle h_refine) {
+                                     cudaGraphConditionalHandle h_refine, float* refine_first) {
   if (threadIdx.x != 0) return;
+  if (refine_first != nullptr) *refine_first = 0.f;
   ctl->iteration += 1;
   ctl->n_update += 1;
   ctl->n_refine += 1;
@@ -188,9 +190,11 @@ static int add_cond(cudaGraph_t g, cudaGraphNode_t* tail, cudaGraphConditionalHa
 }
 
 static int build(Driver* d, const ga_step_programs_t* pr, const float* stats_eval, const float* stats_update,
-                 const float* custom_eval, const float* custom_update, const Tokens& tk) {
+                 const float* custom_eval, const float* custom_update, const float* stats_refine,
+                 const float* custom_refine, float* refine_first, const Tokens& tk) {
   cudaGraph_t ev = (cudaGraph_t)pr->eval, up = (cudaGraph_t)pr->update, cf = (cudaGraph_t)pr->cfg,
               adv = (cudaGraph_t)pr->advance, rn = (cudaGraph_t)pr->renoise;
+  cudaGraph_t rup = pr->refine_update != nullptr ? (cudaGraph_t)pr->refine_update : up;
   GA_CUDA(cudaGraphCreate(&d->graph, 0));
   cudaGraph_t G = d->graph;
   int rc;
@@ -215,17 +219,17 @@ static int build(Driver* d, const ga_step_programs_t* pr, const float* stats_eva
   if ((rc = add_child(R, &rt, ev)) != GA_OK) return rc;
   {
     Tokens t = tk;
-    void* a[] = {&ctl, (void*)&stats_eval, (void*)&custom_eval, &t, &h_refine, &h_fu, &h_fe};
+    void* a[] = {&ctl, (void*)&stats_eval, (void*)&custom_eval, &t, &h_refine, &h_fu, &h_fe, &refine_first};
     if ((rc = add_kernel(R, &rt, (void*)decide_round_kernel, a)) != GA_OK) return rc;
   }
   {   // WHILE (refine) { update; advance; decide_refine }
     cudaGraph_t F;
     if ((rc = add_cond(R, &rt, h_refine, cudaGraphCondTypeWhile, &F)) != GA_OK) return rc;
     cudaGraphNode_t ft = nullptr;
-    if ((rc = add_child(F, &ft, up)) != GA_OK) return rc;
+    if ((rc = add_child(F, &ft, rup)) != GA_OK) return rc;
     if ((rc = add_child(F, &ft, adv)) != GA_OK) return rc;
     Tokens t = tk;
-    void* a[] = {&ctl, (void*)&stats_update, (void*)&custom_update, &t, &h_refine};
+    void* a[] = {&ctl, (void*)&stats_refine, (void*)&custom_refine, &t, &h_refine, &refine_first};
     if ((rc = add_kernel(F, &ft, (void*)decide_refine_kernel, a)) != GA_OK) return rc;
   }
   {   // IF (final_update) { update; advance }
@@ -264,13 +268,18 @@ using namespace ga;
 
 extern "C" int ga_step_driver_create(void** driver_out, const ga_step_programs_t* programs, void* ctl_dev,
                                      const float* stats_eval, const float* stats_update, const float* custom_eval,
-                                     const float* custom_update, const ga_token_t* tokens_host, int n_tokens,
+                                     const float* custom_update, const float* stats_refine,
+                                     const float* custom_refine, float* refine_first_dev,
+                                     const ga_token_t* tokens_host, int n_tokens,
                                      int n_groups, int avg_within, int64_t* t_dev, float* step_dev, float* ddim_dev,
                                      float* renoise_dev) {
   GA_CHECK_ARG(driver_out != nullptr && programs != nullptr && ctl_dev != nullptr, "NULL argument");
   GA_CHECK_ARG(programs->eval && programs->update && programs->cfg && programs->advance && programs->renoise,
                "all five device programs are required");
   GA_CHECK_ARG(stats_eval != nullptr && stats_update != nullptr, "stats pointers are required");
+  GA_CHECK_ARG(programs->refine_update == nullptr || stats_refine != nullptr,
+               "a separate refinement program needs its own stats buffer");
+  if (programs->refine_update == nullptr) { stats_refine = stats_update; custom_refine = custom_update; }
   GA_CHECK_ARG(n_tokens >= 0 && n_tokens <= GA_MAX_TOKENS && (n_tokens == 0 || tokens_host != nullptr),
                "n_tokens %d out of range", n_tokens);
   GA_CHECK_ARG(t_dev && step_dev && ddim_dev && renoise_dev, "per-step scalar buffers are required");
@@ -289,7 +298,8 @@ extern "C" int ga_step_driver_create(void** driver_out, const ga_step_programs_t
   d->step_dev = step_dev;
   d->ddim_dev = ddim_dev;
   d->renoise_dev = renoise_dev;
-  int rc = step::build(d, programs, stats_eval, stats_update, custom_eval, custom_update, tk);
+  int rc = step::build(d, programs, stats_eval, stats_update, custom_eval, custom_update, stats_refine, custom_refine,
+                       refine_first_dev, tk);
   if (rc != GA_OK) {
     if (d->exec) cudaGraphExecDestroy(d->exec);
     if (d->graph) cudaGraphDestroy(d->graph);

@@ -78,6 +78,11 @@ class _StepGraphs:
         self.n_draws = torch.zeros(1, dtype=torch.int64, device=dev)
         self.ctl = torch.zeros(abi.GA_STEP_CTL_BYTES // 4, dtype=torch.int32, device=dev)
         self._driver = None
+        # `use_optimizer` (reference :495-497, :545-547): the refinement loop steps the latents with SGD + momentum 0.8;
+        # `mom` is the momentum buffer, `first` = 1 on the first iteration of a refinement (fresh optimizer state)
+        self.use_optimizer = bool(hp.get("use_optimizer", False))
+        self.mom = torch.zeros_like(latents_like)
+        self.first = torch.ones((), dtype=torch.float32, device=dev)
 
     def set_embeds(self, prompt_embeds):
         self.embeds.copy_(prompt_embeds)
@@ -100,6 +105,24 @@ class _StepGraphs:
             (g,) = torch.autograd.grad(loss, [lat])
         with torch.no_grad():
             self.lat_out.copy_((lat.detach().float() - self.step * g.float()).to(lat.dtype))
+        return {"loss": loss.detach(), "losses": [(i, v.detach()) for i, v in losses],
+                "unscaled": [(i, v.detach()) for i, v in unscaled], "stats": ld["_stats"].detach()}
+
+    def _prog_update_mom(self):
+        """One refinement iteration under `use_optimizer`: torch.optim.SGD(lr = step_size / 2.5, momentum = 0.8) on the
+        latents (reference :495-497: a fresh optimizer per refinement; :545-547: loss.backward(); optim.step()), i.e.
+        buf <- 0.8 buf + grad (buf = grad on the first iteration), latents <- latents - lr buf, in the latents' dtype."""
+        with torch.enable_grad():
+            lat = self.lat.detach().clone().requires_grad_(True)
+            self.pipe.unet(lat, self.t, encoder_hidden_states=self.embeds[1:2])
+            ld = self.pipe._aggregate_and_get_max_attention_per_token(**self.loss_kw)
+            loss, losses, unscaled = self.pipe._compute_loss(ld)
+            (g,) = torch.autograd.grad(loss, [lat])
+        with torch.no_grad():
+            keep = (0.8 * (1.0 - self.first)).to(self.mom.dtype)
+            self.mom.mul_(keep).add_(g)
+            lr = self.step / 2.5
+            self.lat_out.copy_((lat.detach().float() - lr * self.mom.float()).to(lat.dtype))
         return {"loss": loss.detach(), "losses": [(i, v.detach()) for i, v in losses],
                 "unscaled": [(i, v.detach()) for i, v in unscaled], "stats": ld["_stats"].detach()}
 
@@ -135,11 +158,11 @@ class _StepGraphs:
         if self._driver is not None:
             return self._driver
         self.store.text_kv = self.text_kv
-        for name in ("eval", "update", "cfg", "advance", "renoise"):
+        names = ("eval", "update", "cfg", "advance", "renoise") + (("update_mom",) if self.use_optimizer else ())
+        for name in names:
             self._graph(name)
         lib = abi.load()
-        progs = abi.GaStepPrograms(*[int(self.graphs[n].raw_cuda_graph())
-                                     for n in ("eval", "update", "cfg", "advance", "renoise")])
+        progs = abi.GaStepPrograms(*[int(self.graphs[n].raw_cuda_graph()) for n in names])
 
         def custom_of(out):
             if out["losses"] and out["losses"][-1][0] is None and torch.is_tensor(out["losses"][-1][1]):
@@ -149,13 +172,17 @@ class _StepGraphs:
                 return c
             return None
         spec = self.pipe._tail_spec_cache[1]
-        self._custom = (custom_of(self.outputs["eval"]), custom_of(self.outputs["update"]))
+        refine = self.outputs["update_mom"] if self.use_optimizer else None
+        self._custom = (custom_of(self.outputs["eval"]), custom_of(self.outputs["update"]),
+                        custom_of(refine) if refine is not None else None)
+
+        def ptr(t):
+            return C.c_void_p(t.data_ptr() if t is not None else 0)
         handle = C.c_void_p()
         abi.check(lib.ga_step_driver_create(
-            C.byref(handle), C.byref(progs), C.c_void_p(self.ctl.data_ptr()),
-            C.c_void_p(self.outputs["eval"]["stats"].data_ptr()), C.c_void_p(self.outputs["update"]["stats"].data_ptr()),
-            C.c_void_p(self._custom[0].data_ptr() if self._custom[0] is not None else 0),
-            C.c_void_p(self._custom[1].data_ptr() if self._custom[1] is not None else 0),
+            C.byref(handle), C.byref(progs), ptr(self.ctl), ptr(self.outputs["eval"]["stats"]),
+            ptr(self.outputs["update"]["stats"]), ptr(self._custom[0]), ptr(self._custom[1]),
+            ptr(refine["stats"] if refine is not None else None), ptr(self._custom[2]), ptr(self.first),
             spec.tokens, len(spec.token_indices), int(spec.params.n_groups),
             int(bool(getattr(state.config, "sub_prompt_avg_within", False))),
             C.c_void_p(self.t.data_ptr()), C.c_void_p(self.step.data_ptr()), C.c_void_p(self.coef.data_ptr()),
@@ -214,7 +241,7 @@ class _StepGraphs:
                 self.coef[n].fill_(float(c))
         g.replay()
         self.replays[name] = self.replays.get(name, 0) + 1
-        self.pipe._count_pass(name)
+        self.pipe._count_pass("update" if name == "update_mom" else name)
         for k, v in self.launches[name].items():
             ops._count(k, v)
         return self.outputs[name], (self.lat_out.clone() if name != "eval" else None)
@@ -705,10 +732,13 @@ class GuidedAttention(StableDiffusionPipelineBase):
                         did_we_update = True
                         iteration, u = 0, None
                         state.sub_iteration = 0
+                        refine_prog = "update_mom" if G.use_optimizer else "update"
+                        G.first.fill_(1.0)
                         while u is None or not self.meets_threshold(i, cfg.thresholds, u):
                             iteration += 1
                             state.sub_iteration = iteration
-                            o, latents = G.run("update", latents, t, step_size=step_size)
+                            o, latents = G.run(refine_prog, latents, t, step_size=step_size)
+                            G.first.fill_(0.0)
                             u = self._host_values(o["unscaled"])
                             if iteration >= 10:
                                 helpers.log('\t Exceeded max number of iterations (10)! ', True)
@@ -802,6 +832,10 @@ class GuidedAttention(StableDiffusionPipelineBase):
                                    "rounds": d[4], "renoise": d[5]}
         for name, n in n_prog.items():
             self._count_pass(name, n)
+        if G.use_optimizer:      # the refinement iterations ran the momentum program
+            n_prog["update_mom"] = d[abi.GA_STEP_N_REFINE]
+            n_prog["update"] -= d[abi.GA_STEP_N_REFINE]
+        for name, n in n_prog.items():
             G.replays[name] = G.replays.get(name, 0) + n
             for k, v in G.launches[name].items():
                 ops._count(k, v * n)
@@ -1020,8 +1054,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
                        smooth_attentions=smooth_attentions, sigma=sigma, kernel_size=kernel_size, normalize_eot=sd_2_1)
         num_warmup_steps = len(timesteps) - num_inference_steps * self.scheduler.order
         graphed = (self.use_cuda_graphs and latents.is_cuda and state.config.diagnostic_level == 0
-                   and do_classifier_free_guidance and latents.shape[0] == 1
-                   and not state.curHyperParams.get("use_optimizer", False) and cross_attention_kwargs is None)
+                   and do_classifier_free_guidance and latents.shape[0] == 1 and cross_attention_kwargs is None)
         attention_store.text_kv = None      # the eager loop does not own the embedding buffers: no K/V caching
         self.control_mode = "eager"
         if graphed:

@@ -235,6 +235,8 @@ int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const ga_token_t* 
 #define GA_STEP_CTL_BYTES 256
 typedef struct ga_step_programs {
   void *eval, *update, *cfg, *advance, *renoise; /* cudaGraph_t */
+  void* refine_update; /* cudaGraph_t or NULL: the update program of the refinement loop when it differs from `update`
+                          (`use_optimizer`: SGD with momentum, reference :495-497, :545-547); NULL = `update` */
 } ga_step_programs_t;
 
 typedef struct ga_step_params {     /* everything that changes from one denoising step to the next */
@@ -257,10 +259,14 @@ typedef struct ga_step_params {     /* everything that changes from one denoisin
 /* ctl_dev: GA_STEP_CTL_BYTES of zero-initialised DEVICE memory (state + lifetime counters, see ga_step_counters).
  * tokens_host: the tail's token table (group ids and kinds are used); n_groups, avg_within as in the tail spec.
  * t_dev (int64), step_dev (float), ddim_dev (float[4]), renoise_dev (float[2]): the DEVICE scalars the captured programs
- * read; ga_step_driver_run fills them from `params_host` on the stream before launching the graph. */
+ * read; ga_step_driver_run fills them from `params_host` on the stream before launching the graph.
+ * stats_refine / custom_refine: outputs of `programs->refine_update` (ignored when that is NULL).
+ * refine_first_dev: optional DEVICE float the driver sets to 1 when a refinement is about to start and to 0 after each
+ * of its iterations (the momentum program uses it to start from a fresh optimizer state); may be NULL. */
 int ga_step_driver_create(void** driver_out, const ga_step_programs_t* programs, void* ctl_dev,
                           const float* stats_eval, const float* stats_update, const float* custom_eval,
-                          const float* custom_update, const ga_token_t* tokens_host, int n_tokens, int n_groups,
+                          const float* custom_update, const float* stats_refine, const float* custom_refine,
+                          float* refine_first_dev, const ga_token_t* tokens_host, int n_tokens, int n_groups,
                           int avg_within, int64_t* t_dev, float* step_dev, float* ddim_dev, float* renoise_dev);
 int ga_step_driver_run(void* driver, const ga_step_params_t* params_host, ga_stream_t stream);
 int ga_step_driver_destroy(void* driver);

@@ -147,3 +147,28 @@ def test_device_driver_full_size_config2_fp16():
     assert n_dev == n_host == {"eval": 58, "update": 132, "cfg": 58}, (n_dev, n_host)
     assert torch.isfinite(dev.float()).all()
     assert torch.equal(dev, host)
+
+
+def test_use_optimizer_graphed_paths_match_the_eager_optimizer_loop():
+    """`use_optimizer` (reference :495-497, :545-547: the refinement loop steps the latents with
+    torch.optim.SGD(lr = step_size / 2.5, momentum = 0.8), a fresh optimizer per refinement): the eager loop runs the
+    real torch optimizer; the graphed host loop and the device driver run the captured momentum program.  fp16:
+    device == host-graphs bit for bit; both against eager within the graph-vs-eager bound."""
+    hyper = {"use_optimizer": True, "thresholds": {0: 0.01, 2: 0.01}, "recurse_steps": 2, "recurse_until": 1}
+    pipe, store, cfg, embeds, case = _pipe(torch.float16, None, hyper)
+    pipe.use_cuda_graphs = False
+    eager, n_eager, _, mode_e = _run(pipe, store, cfg, embeds, case, 28, False)
+    pipe.use_cuda_graphs = True
+    host, n_host, _, mode_h = _run(pipe, store, cfg, embeds, case, 28, False)
+    dev, n_dev, _, mode_d = _run(pipe, store, cfg, embeds, case, 28, True)
+    assert (mode_e, mode_h, mode_d) == ("eager", "host-graphs", "device")
+    assert n_dev == n_host
+    assert n_eager["eval"] + n_eager["cfg"] == sum(n_host.values())      # eager counts every UNet forward as eval / cfg
+    assert torch.equal(dev, host)
+    a, b = host.float().cpu().numpy(), eager.float().cpu().numpy()
+    cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.9999 and _psnr(a, b) > 45, (cos, _psnr(a, b))
+    # momentum matters: the plain-SGD image of the same seed is a different image
+    pipe2, store2, cfg2, embeds2, case2 = _pipe(torch.float16, None, dict(hyper, use_optimizer=False))
+    plain, _, _, _ = _run(pipe2, store2, cfg2, embeds2, case2, 28, True)
+    assert _psnr(plain.float().cpu().numpy(), a) < 40
