@@ -702,6 +702,269 @@ cross_attn_fwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
+// ================================================================ K1, persistent STREAMING variant (maps kept, d > 64)
+// With maps a CTA streams the H heads of one (b, tile) unit, every item with its own K and V, so the pipelined kernel
+// above must keep K/V inside the ring stage: 72 KB per stage at d = 80 and 108 KB at d = 160 next to the 41 KB
+// head-sum staging tile, i.e. TWO stages / ONE stage -- the kernel is ring-latency bound (18 / 32 us per unit whatever
+// the unit count, profiles/r02_crossover_sweep_before.jsonl).  Like the streaming K2 below, this variant rings
+// 64-channel BLOCKS: a stage is (Q block, K block) = 26 KB, S is accumulated over the blocks as they land and a stage
+// is released by the commit that follows its own k-steps; the item's V (needed only by the second GEMM) waits in a
+// small ring of V slots; O rows leave from registers.  Softmax groups, head-sum accumulation and TMEM layout are
+// those of the pipelined kernel (NG = 2).
+struct FwdStreamParams {
+  PipeParams b;
+  int ring_stages;   // (Q block, K block) stages, 2 .. kMaxStages
+  int v_slots;       // 2 .. 4
+};
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                                const __grid_constant__ CUtensorMap map_v, const FwdStreamParams sp) {
+  const PipeParams& p = sp.b;
+  extern __shared__ uint8_t smem_raw[];
+  // ring_full[6], ring_free[6], v_full[4], v_free[4], s_ready[4], p_ready[4], p_free[4], o_ready[4], tmem_free[4]
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 28];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_inv[8][kM];
+
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  constexpr uint32_t ring_stage_bytes = kQBlockBytes + kKVBlockBytes;
+  const int R = sp.ring_stages, NV = sp.v_slots;
+  const uint32_t v_slot_bytes = (uint32_t)p.nblk * kKVBlockBytes;
+  const uint32_t v_base = base + (uint32_t)R * ring_stage_bytes;
+  float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)R * ring_stage_bytes + (size_t)NV * v_slot_bytes);
+  auto RING_FULL = [&](int s) { return smem_u32(&bars[s]); };
+  auto RING_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  auto V_FULL = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
+  auto V_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
+  auto S_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 8 + s]); };
+  auto P_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 12 + s]); };
+  auto P_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 16 + s]); };
+  auto O_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 20 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 24 + s]); };
+  const int nS = p.n_sbuf, nO = p.n_obuf;
+  const int sMask = nS - 1, oMask = nO - 1, sShift = nS == 4 ? 2 : 1, oShift = nO == 4 ? 2 : 1;
+  auto sIdx = [&](int k) { return k & sMask; };
+  auto oIdx = [&](int k) { return k & oMask; };
+  auto colS = [&](int k) { return (uint32_t)((k & sMask) * kTpad); };
+  auto colO = [&](int k) { return (uint32_t)(nS * kTpad + (k & oMask) * p.npv); };
+  auto sPar = [&](int k) { return (uint32_t)(k >> sShift) & 1u; };
+  auto oPar = [&](int k) { return (uint32_t)(k >> oShift) & 1u; };
+  const int my_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_units * p.H;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(RING_FULL(s), 1); mbar_init(RING_FREE(s), 1); }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(V_FULL(s), 1);
+      mbar_init(V_FREE(s), 1);
+      mbar_init(S_READY(s), 1);
+      mbar_init(P_READY(s), kGroupThreads);
+      mbar_init(P_FREE(s), 1);
+      mbar_init(O_READY(s), 1);
+      mbar_init(TMEM_FREE(s), kGroupThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
+  const int fmt = p.bf16 ? 1 : 0;
+  const int ksteps = (p.d + 15) >> 4;
+  const bool bf16 = p.bf16 != 0;
+
+  if (warp >= 12) {
+    reg_dealloc<56>();
+    if (warp == 12) {
+      // ------------------------------------------------------------------------------------- TMA producer
+      ItemIter it;
+      it.init(p);
+      int rs = 0, ring_fills = 0, vs = 0;
+      uint32_t rpar = 0, vpar = 0;
+      for (int k = 0; k < n_items; ++k) {
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          if (ring_fills >= R) mbar_wait(RING_FREE(rs), rpar ^ 1u);
+          if (elect_one()) {
+            const uint32_t sQ = base + rs * ring_stage_bytes, sK = sQ + kQBlockBytes;
+            mbar_expect_tx(RING_FULL(rs), ring_stage_bytes);
+            tma_load_4d(sQ, &map_q, RING_FULL(rs), blk * kBlockCols, it.h, it.tile * kM, it.b);
+            tma_load_4d(sK, &map_k, RING_FULL(rs), blk * kBlockCols, it.h, 0, it.b);
+          }
+          __syncwarp();
+          ++ring_fills;
+          if (++rs == R) { rs = 0; rpar ^= 1u; }
+        }
+        if (k >= NV) mbar_wait(V_FREE(vs), vpar ^ 1u);
+        if (elect_one()) {
+          const uint32_t sV = v_base + vs * v_slot_bytes;
+          mbar_expect_tx(V_FULL(vs), v_slot_bytes);
+          for (int blk = 0; blk < p.nblk; ++blk)
+            tma_load_4d(sV + blk * kKVBlockBytes, &map_v, V_FULL(vs), blk * kBlockCols, it.h, 0, it.b);
+        }
+        __syncwarp();
+        if (++vs == NV) { vs = 0; vpar ^= 1u; }
+        it.next(p);
+      }
+    } else if (warp == 13) {
+      // ------------------------------------------------------------- MMA issuer 1: S += Q_blk K_blk^T per block
+      const uint32_t idesc_qk = make_idesc(fmt, 0, kTpad, kM);
+      const uint64_t dQ0 = smem_desc_sw128(base, 16, 1024), dK0 = smem_desc_sw128(base + kQBlockBytes, 16, 1024);
+      int rs = 0;
+      uint32_t rpar = 0;
+      for (int k = 0; k < n_items; ++k) {
+        if (k >= nS) mbar_wait(P_FREE(sIdx(k)), sPar(k) ^ 1u);
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          mbar_wait(RING_FULL(rs), rpar);
+          tc_fence_after();
+          if (elect_one()) {
+            const int nks = min(4, ksteps - 4 * blk);
+            const uint32_t roff = (uint32_t)rs * ring_stage_bytes;
+            for (int ks = 0; ks < nks; ++ks)
+              mma_ss(tmem + colS(k), desc_advance(dQ0, roff + ks * 32u), desc_advance(dK0, roff + ks * 32u), idesc_qk,
+                     (blk > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(RING_FREE(rs));
+            if (blk == p.nblk - 1) tc_commit(S_READY(sIdx(k)));
+          }
+          __syncwarp();
+          if (++rs == R) { rs = 0; rpar ^= 1u; }
+        }
+      }
+    } else if (warp == 14) {
+      // ------------------------------------------------------------------------------ MMA issuer 2: O = P V
+      const uint32_t idesc_pv = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dV0 = smem_desc_sw128(v_base, kKVBlockBytes, 1024);
+      int vs = 0;
+      uint32_t vpar = 0;
+      for (int k = 0; k < n_items; ++k) {
+        mbar_wait(P_READY(sIdx(k)), sPar(k));
+        if (k >= nO) mbar_wait(TMEM_FREE(oIdx(k)), oPar(k) ^ 1u);
+        mbar_wait(V_FULL(vs), vpar);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + colO(k), tmem + colS(k), desc_advance(dV0, (uint32_t)vs * v_slot_bytes), kTpad / 16,
+                          idesc_pv, false);
+          tc_commit(O_READY(oIdx(k)));
+          tc_commit(P_FREE(sIdx(k)));
+          tc_commit(V_FREE(vs));
+        }
+        __syncwarp();
+        if (++vs == NV) { vs = 0; vpar ^= 1u; }
+      }
+    }
+  } else if (warp < 4) {
+    reg_dealloc<88>();
+    // ---------------------------------------------------------------------------------------- epilogue
+    const int r = (warp << 5) + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    ItemIter it;
+    it.init(p);
+    for (int k = 0; k < n_items; ++k) {
+      const int ob = oIdx(k);
+      mbar_wait(O_READY(ob), oPar(k));
+      tc_fence_after();
+      const float inv = s_inv[k & 7][r];
+      const int row = it.tile * kM + r;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)it.b * p.N + row) * p.H + it.h) * (int64_t)p.d * 2;
+      for (int c0 = 0; c0 < p.npv / 16; c0 += 2) {
+        float ov[32];
+        tmem_ld16(lane_base + colO(k) + c0 * 16, ov);
+        if (c0 + 1 < p.npv / 16) tmem_ld16(lane_base + colO(k) + (c0 + 1) * 16, ov + 16);
+        tmem_ld_wait();
+        if (row < p.N) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (c0 + u >= p.npv / 16) break;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[u * 16 + 2 * i] * inv, ov[u * 16 + 2 * i + 1] * inv, bf16);
+            const int col = (c0 + u) * 16;
+            if (col < p.d) *reinterpret_cast<uint4*>(orow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (col + 8 < p.d) *reinterpret_cast<uint4*>(orow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(ob));
+      it.next(p);
+    }
+  } else {
+    reg_alloc<184>();
+    // ------------------------------------------------------------------------------------ softmax groups
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;
+    float pacc[kTpad];
+#pragma unroll
+    for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+    int k = 0;
+    for (int u = 0; u < my_units; ++u) {
+      const int unit = blockIdx.x + u * gridDim.x;
+      const int b = unit / p.tiles, tile = unit - b * p.tiles;
+      const int row = tile * kM + r;
+      for (int h = 0; h < p.H; ++h, ++k) {
+        if ((k & 1) != g) continue;
+        const uint32_t lane_addr = lane_base + colS(k);
+        mbar_wait(S_READY(sIdx(k)), sPar(k));
+        tc_fence_after();
+        float s[kTpad];
+#pragma unroll
+        for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + cc * 16, s + cc * 16);
+        tmem_ld_wait();
+        float m, sum;
+        row_softmax_ilp(s, p.T, sc, m, sum);
+#pragma unroll
+        for (int cc = 0; cc < kTpad / 16; ++cc) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) packed[i] = pack16(s[cc * 16 + 2 * i], s[cc * 16 + 2 * i + 1], bf16);
+          tmem_st8(lane_addr + cc * 8, packed);
+        }
+        const float inv = __fdividef(1.f, sum);
+        s_inv[k & 7][r] = inv;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(P_READY(sIdx(k)));
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) pacc[j] = fmaf(s[j], inv, pacc[j]);
+        if (row < p.N)
+          p.lse[((int64_t)b * p.H + h) * p.N + row] = (m * sc + lg2_approx(sum)) * 0.6931471805599453f;
+      }
+      // ---- end of the (b, tile) unit: combine the two groups' head sums, write the accumulator rows coalesced
+      if (g == 1) {
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] = pacc[j];
+      }
+      named_bar_sync(1, 2 * kGroupThreads);
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] += pacc[j];
+      }
+      named_bar_sync(2, 2 * kGroupThreads);
+      for (int i = warp - 4; i < kM; i += 8) {
+        const int gr = tile * kM + i;
+        if (gr >= p.N) break;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int j = lane + 32 * kk;
+          if (j < p.T) p.acc[((int64_t)b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
+        }
+      }
+      named_bar_sync(3, 2 * kGroupThreads);
+#pragma unroll
+      for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // ============================================================================================== K2 (backward)
 //   S  = Q K^T, dP = dO V^T                two K-major GEMMs into two TMEM regions
 //   P  = exp(scale S - lse);  dP += d_acc[row]  (the attention-map gradient injected by the guidance tail)
@@ -1176,6 +1439,303 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
   if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
+// ====================================================================== K2, persistent STREAMING variant (d > 64)
+// The pipelined kernel above keeps whole items (Q, dO, K, V of one 128-row tile) in its shared-memory ring: 104 KB per
+// stage at d = 80 and 156 KB at d = 160, i.e. two stages / one stage, and a stage is only handed back when the item's
+// LAST GEMM has retired.  ncu on that kernel (profiles/r02_ncu_summary.json): DRAM 25-34 %, issue slots 12-19 %,
+// tensor pipe 8-9 % -- nothing is busy, the SM simply has too few bytes in flight.  This variant changes what the ring
+// holds:
+//   * K and V of the current (batch element, head) live in two dedicated slots (the next element's K/V are fetched
+//     into the other slot while the current one is in use); a CTA's items are consecutive row tiles of one head, so
+//     they change rarely;
+//   * the ring holds 64-channel BLOCKS of Q and dO (32 KB per stage: 4 stages at d = 80, 3 at d = 160).  S and dP
+//     are accumulated over the blocks as they arrive, and a stage is released by the tcgen05.commit that follows
+//     ITS OWN k-steps -- the producer streams Q / dO at HBM rate instead of waiting for epilogues;
+//   * dQ rows leave from registers (the dead-Q-tile staging of the pipelined kernel no longer exists).
+// Compute groups, TMEM stages and the epilogue are those of the pipelined kernel.
+struct BwdStreamParams {
+  BwdPipeParams b;
+  int ring_stages;   // 2 .. kMaxStages
+};
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                                const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                                const BwdStreamParams sp) {
+  const BwdPipeParams& p = sp.b;
+  extern __shared__ uint8_t smem_raw[];
+  // ring_full[6], ring_free[6], kv_full[2], kv_free[2], then sd_ready / ds_ready / dq_ready / tmem_free x 3
+  __shared__ __align__(8) uint64_t bars[28];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_half = (uint32_t)p.nblk * kKVBlockBytes;       // K (or V) of one head: nblk blocks
+  const uint32_t kv_slot_bytes = 2u * kv_half;
+  const uint32_t ring_base = base + 2u * kv_slot_bytes;
+  constexpr uint32_t ring_stage_bytes = 2u * kQBlockBytes;         // one block of Q + one block of dO
+  const int R = sp.ring_stages;
+  auto RING_FULL = [&](int s) { return smem_u32(&bars[s]); };
+  auto RING_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
+  auto KV_FULL = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
+  auto KV_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 2 + s]); };
+  auto SD_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 4 + s]); };
+  auto DS_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 7 + s]); };
+  auto DQ_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 10 + s]); };
+  auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 13 + s]); };
+  const int nT = p.tstages;
+  const uint32_t stage_cols = nT == 3 ? 160u : (uint32_t)kStageCols;
+  auto tIdx = [&](int k) { return nT == 3 ? k % 3 : (k & 1); };
+  auto tPar = [&](int k) { return (uint32_t)(nT == 3 ? k / 3 : k >> 1) & 1u; };
+  const int teams = gridDim.x / p.H, team = blockIdx.x / p.H, my_h = blockIdx.x % p.H;
+  const int rt0 = (int)(((int64_t)p.units * team) / teams);
+  const int n_items = (int)(((int64_t)p.units * (team + 1)) / teams) - rt0;
+  const bool dq_aliased = p.col_dq == kColDP;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(RING_FULL(s), 1); mbar_init(RING_FREE(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(SD_READY(s), 1);
+      mbar_init(DS_READY(s), kGroupThreads);
+      mbar_init(DQ_READY(s), 1);
+      mbar_init(TMEM_FREE(s), kGroupThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(tmem_base_slot);
+  const int fmt = p.bf16 ? 1 : 0;
+  const int ksteps = (p.d + 15) >> 4;
+  const bool bf16 = p.bf16 != 0;
+
+  auto batch_of = [&](int k) { return (rt0 + k) / p.tiles; };
+  auto coords = [&](int k, int& b, int& h, int& tile) {
+    const int rt = rt0 + k;
+    h = my_h;
+    b = rt / p.tiles;
+    tile = rt - b * p.tiles;
+  };
+
+  if (warp >= 12) {
+    reg_dealloc<56>();
+    if (warp == 12) {
+      // ------------------------------------------------------------------------------------------ TMA producer
+      int cur_b = -1, kv_fills = 0, ring_fills = 0, rs = 0;
+      uint32_t rpar = 0;
+      for (int k = 0; k < n_items; ++k) {
+        int b, h, tile;
+        coords(k, b, h, tile);
+        if (b != cur_b) {
+          const int slot = kv_fills & 1;
+          if (kv_fills >= 2) mbar_wait(KV_FREE(slot), (uint32_t)((kv_fills >> 1) - 1) & 1u);
+          if (elect_one()) {
+            const uint32_t sK = base + slot * kv_slot_bytes, sV = sK + kv_half;
+            mbar_expect_tx(KV_FULL(slot), kv_slot_bytes);
+            for (int blk = 0; blk < p.nblk; ++blk) {
+              tma_load_4d(sK + blk * kKVBlockBytes, &map_k, KV_FULL(slot), blk * kBlockCols, h, 0, b);
+              tma_load_4d(sV + blk * kKVBlockBytes, &map_v, KV_FULL(slot), blk * kBlockCols, h, 0, b);
+            }
+          }
+          __syncwarp();
+          ++kv_fills;
+          cur_b = b;
+        }
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          if (ring_fills >= R) mbar_wait(RING_FREE(rs), rpar ^ 1u);
+          if (elect_one()) {
+            const uint32_t sQ = ring_base + rs * ring_stage_bytes, sG = sQ + kQBlockBytes;
+            mbar_expect_tx(RING_FULL(rs), ring_stage_bytes);
+            tma_load_4d(sQ, &map_q, RING_FULL(rs), blk * kBlockCols, h, tile * kM, b);
+            tma_load_4d(sG, &map_do, RING_FULL(rs), blk * kBlockCols, h, tile * kM, b);
+          }
+          __syncwarp();
+          ++ring_fills;
+          if (++rs == R) { rs = 0; rpar ^= 1u; }
+        }
+      }
+    } else if (warp == 13) {
+      // --------------------------------------------- MMA issuer 1: S += Q_blk K_blk^T, dP += dO_blk V_blk^T per block
+      const uint32_t idesc_nt = make_idesc(fmt, 0, kTpad, kM);
+      const uint64_t dQ0 = smem_desc_sw128(ring_base, 16, 1024), dG0 = smem_desc_sw128(ring_base + kQBlockBytes, 16, 1024);
+      const uint64_t dK0 = smem_desc_sw128(base, 16, 1024), dV0 = smem_desc_sw128(base + kv_half, 16, 1024);
+      int cur_b = -1, kv_uses = 0, rs = 0;
+      uint32_t rpar = 0;
+      for (int k = 0; k < n_items; ++k) {
+        const int ts = tIdx(k);
+        const uint32_t ph = tPar(k);
+        if (k >= nT) {
+          mbar_wait(DQ_READY(ts), ph ^ 1u);
+          if (dq_aliased) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
+        }
+        const int b = batch_of(k);
+        if (b != cur_b) {
+          ++kv_uses;
+          cur_b = b;
+          mbar_wait(KV_FULL((kv_uses - 1) & 1), (uint32_t)((kv_uses - 1) >> 1) & 1u);
+        }
+        const uint32_t kv_off = (uint32_t)((kv_uses - 1) & 1) * kv_slot_bytes;
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          mbar_wait(RING_FULL(rs), rpar);
+          tc_fence_after();
+          if (elect_one()) {
+            const int nks = min(4, ksteps - 4 * blk);
+            const uint32_t roff = (uint32_t)rs * ring_stage_bytes, koff = kv_off + (uint32_t)blk * kKVBlockBytes;
+            for (int ks = 0; ks < nks; ++ks)
+              mma_ss(tmem + ts * stage_cols + kColS, desc_advance(dQ0, roff + ks * 32u), desc_advance(dK0, koff + ks * 32u),
+                     idesc_nt, (blk > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < nks; ++ks)
+              mma_ss(tmem + ts * stage_cols + kColDP, desc_advance(dG0, roff + ks * 32u), desc_advance(dV0, koff + ks * 32u),
+                     idesc_nt, (blk > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(RING_FREE(rs));            // this block's Q / dO are dead once these k-steps have retired
+            if (blk == p.nblk - 1) tc_commit(SD_READY(ts));
+          }
+          __syncwarp();
+          if (++rs == R) { rs = 0; rpar ^= 1u; }
+        }
+      }
+    } else if (warp == 14) {
+      // ------------------------------------------------------------------------------ MMA issuer 2: dQ = dS K
+      const uint32_t idesc_dq = make_idesc(fmt, 1, p.npv, kM);
+      const uint64_t dKmn0 = smem_desc_sw128(base, kKVBlockBytes, 1024);
+      int cur_b = -1, kv_uses = 0;
+      for (int k = 0; k < n_items; ++k) {
+        const int ts = tIdx(k);
+        const uint32_t ph = tPar(k);
+        const int b = batch_of(k);
+        if (b != cur_b) { ++kv_uses; cur_b = b; }
+        const int slot = (kv_uses - 1) & 1;
+        mbar_wait(DS_READY(ts), ph);
+        if (!dq_aliased && k >= nT) mbar_wait(TMEM_FREE(ts), ph ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tmem_gemm(tmem + ts * stage_cols + p.col_dq, tmem + ts * stage_cols + kColP,
+                          desc_advance(dKmn0, (uint32_t)slot * kv_slot_bytes), kTpad / 16, idesc_dq, false);
+          tc_commit(DQ_READY(ts));
+          // last item of this batch element on this CTA: its K/V slot may be refilled once this GEMM has retired
+          if (k == n_items - 1 || batch_of(k + 1) != b) tc_commit(KV_FREE(slot));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 4) {
+    reg_dealloc<88>();
+    // ---------------------------------------------------------------------------------------- epilogue (dQ)
+    const int r = (warp << 5) + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k = 0; k < n_items; ++k) {
+      const int ts = tIdx(k);
+      mbar_wait(DQ_READY(ts), tPar(k));
+      tc_fence_after();
+      int b, h, tile;
+      coords(k, b, h, tile);
+      const int row = tile * kM + r;
+      uint8_t* grow = reinterpret_cast<uint8_t*>(p.d_q) + (((int64_t)b * p.N + row) * p.H + h) * (int64_t)p.d * 2;
+      for (int c0 = 0; c0 < p.npv / 16; c0 += 2) {
+        float ov[32];
+        tmem_ld16(lane_base + ts * stage_cols + p.col_dq + c0 * 16, ov);
+        if (c0 + 1 < p.npv / 16) tmem_ld16(lane_base + ts * stage_cols + p.col_dq + (c0 + 1) * 16, ov + 16);
+        tmem_ld_wait();
+        if (row < p.N) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (c0 + u >= p.npv / 16) break;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack16(ov[u * 16 + 2 * i], ov[u * 16 + 2 * i + 1], bf16);
+            const int col = (c0 + u) * 16;
+            if (col < p.d) *reinterpret_cast<uint4*>(grow + col * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (col + 8 < p.d) *reinterpret_cast<uint4*>(grow + col * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TMEM_FREE(ts));
+    }
+  } else {
+    reg_alloc<184>();
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp & 3) << 5) + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;
+    for (int k = g; k < n_items; k += 2) {
+      int b, h, tile;
+      coords(k, b, h, tile);
+      const int row = tile * kM + r;
+      const bool live = row < p.N;
+      const int ts = tIdx(k);
+      const uint32_t ph = tPar(k);
+      const uint32_t lane_addr = lane_base + ts * stage_cols;
+      const float l2 = live ? __ldg(p.lse + ((int64_t)b * p.H + h) * p.N + row) * 1.4426950408889634f : 0.f;
+      const float* dacc = (p.d_acc != nullptr && live)
+                              ? p.d_acc + (int64_t)b * p.d_acc_bstride + (int64_t)row * p.d_acc_rstride : nullptr;
+      // the row of the injected map gradient is fetched BEFORE waiting for the GEMMs (it is an L2 hit, shared by all
+      // heads and batch elements, but 20 row-strided 16-byte loads per thread are ~0.5 us of exposed latency otherwise);
+      // its registers are dead again before the scores are loaded
+      float dp[kTpad];
+      const bool vec_acc = (p.d_acc_rstride & 3) == 0;
+      if (dacc != nullptr) {
+        if (vec_acc) {
+#pragma unroll
+          for (int j = 0; j < kTpad; j += 4) {
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + 3 < p.d_acc_rstride) v4 = __ldg(reinterpret_cast<const float4*>(dacc + j));
+            dp[j] = v4.x; dp[j + 1] = v4.y; dp[j + 2] = v4.z; dp[j + 3] = v4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j) dp[j] = j < p.T ? __ldg(dacc + j) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTpad; ++j) dp[j] = 0.f;
+      }
+      mbar_wait(SD_READY(ts), ph);
+      tc_fence_after();
+      float s[kTpad];
+#pragma unroll
+      for (int cc = 0; cc < kTpad / 16; ++cc) {
+        tmem_ld16(lane_addr + kColDP + cc * 16, s + cc * 16);      // dP through the registers the scores will use
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < kTpad; ++j) dp[j] += s[j];
+#pragma unroll
+      for (int cc = 0; cc < kTpad / 16; ++cc) tmem_ld16(lane_addr + kColS + cc * 16, s + cc * 16);
+      tmem_ld_wait();
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < kTpad; ++j) {
+        const bool ok = live && (j < kTpad - 16 || j < p.T);
+        const float pr = ok ? ex2_approx(fmaf(s[j], sc, -l2)) : 0.f;
+        s[j] = pr;
+        d4[j & 3] = fmaf(pr, dp[j], d4[j & 3]);
+      }
+      const float dsum = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+#pragma unroll
+      for (int cc = 0; cc < kTpad / 16; ++cc) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = cc * 16 + 2 * i;
+          packed[i] = pack16(s[j] * (dp[j] - dsum) * p.scale, s[j + 1] * (dp[j + 1] - dsum) * p.scale, bf16);
+        }
+        tmem_st8(lane_addr + kColP + cc * 8, packed);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(DS_READY(ts));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // --------------------------------------------------------------------------------------------------- host side
 static int heads_per_cta_for(int H) {
   for (int hpc = 1; hpc <= H; ++hpc)
@@ -1221,6 +1781,31 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     p.ablate = e != nullptr ? atoi(e) : 0;
   }
 #endif
+  // maps kept and more than one 64-channel block: the streaming variant (GA_K1_STREAM=0 keeps the whole-item ring,
+  // =1 streams d <= 64 as well)
+  static int stream_mode = -2;
+  if (stream_mode == -2) {
+    const char* es = getenv("GA_K1_STREAM");
+    stream_mode = es == nullptr ? -1 : atoi(es);
+  }
+  if (p.grouped && ((stream_mode == -1 && p.nblk >= 2) || stream_mode == 1)) {
+    FwdStreamParams sp;
+    sp.b = p;
+    const size_t acc_bytes = (size_t)kM * kAccStride * sizeof(float), ring = (size_t)kQBlockBytes + kKVBlockBytes;
+    const size_t vslot = (size_t)p.nblk * kKVBlockBytes;
+    sp.v_slots = 3;
+    sp.ring_stages = 0;
+    for (int n = kMaxStages; n >= 2; --n)
+      if (1024 + acc_bytes + sp.v_slots * vslot + n * ring <= 226 * 1024) { sp.ring_stages = n; break; }
+    if (sp.ring_stages >= p.nblk) {
+      const size_t smem_s = 1024 + acc_bytes + sp.v_slots * vslot + sp.ring_stages * ring;
+      cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_stream_kernel), 6, smem_s);
+      if (es2 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(es2));
+      const int grid_s = p.units < sm_count() ? p.units : sm_count();
+      cross_attn_fwd_tc_stream_kernel<<<grid_s, kPipeThreads, smem_s, st>>>(mq, mk, mv, sp);
+      return check_launch("cross_attn_fwd_tc_stream");
+    }
+  }
   CUtensorMap mo;
   int rc;
   if ((rc = make_map(&mo, f.o, dtype, f.B, f.N, f.H, f.d, 32)) != GA_OK) return rc;   // one store per epilogue warp
@@ -1296,12 +1881,12 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
   {
     const int tiles = (N + kM - 1) / kM;
     const int units = acc != nullptr ? B * tiles : B * H * tiles;
-    // Crossovers measured on B200 (profiles/r02_crossover_sweep_before.jsonl).  With maps a pipelined CTA streams the H
-    // heads of one (b, tile) unit back to back, ~18 us per unit at d <= 80 and ~32 us at d = 160 however few units
-    // there are, while the single-shot cluster kernel costs ~9 us per wave of ~8 units: the pipelined kernel wins from
-    // 24 units (d <= 80: B = 3 at 32x32) / 40 units (d > 80: B = 20 at 16x16) on -- not from sm_count / 2 = 74 as in
-    // round 1, which left the seed-batched launches (B = 8, 16) on the slow side of the crossover.
-    const int min_units = acc != nullptr ? (d <= 80 ? 24 : 40) : 2 * sm_count();
+    // Crossovers measured on B200 (profiles/r02_crossover_sweep_before.jsonl, r02_crossover_sweep.jsonl).  With maps a
+    // persistent CTA streams the H heads of one (b, tile) unit back to back: ~17 us per unit at d = 80 and ~19-26 us
+    // at d = 160 (streaming variant) however few units there are, while the single-shot cluster kernel costs ~9 us per
+    // wave of ~8 units: the persistent kernel wins from ~24 units on (B = 3 at 32x32, B = 12 at 16x16) -- not from
+    // sm_count / 2 = 74 as in round 1, which left the seed-batched launches (B = 8, 16) on the slow side.
+    const int min_units = acc != nullptr ? 24 : 2 * sm_count();
     bool use_pipe = d <= 160 && units >= min_units;
     if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
     if (force_variant == 0) use_pipe = false;
@@ -1361,6 +1946,32 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
     p.tstages = npv <= kTpad ? 3 : 2;
     p.col_dq = p.tstages == 3 ? kColDP : ((2 * kTpad + npv <= kStageCols) ? 2 * kTpad : kColDP);
     const size_t stage = (size_t)nblk * 2 * (kQBlockBytes + kKVBlockBytes);
+    // the streaming variant -- K/V slots + a ring of Q/dO blocks -- measured faster than the whole-item ring at every
+    // head dim (B200, profiles/r02_microbench_k2_stream.jsonl: d = 80: 386 vs 490 us, d = 160: 347 vs 419 us,
+    // d = 40: 304 vs 320 us); GA_K2_STREAM=0 keeps the whole-item ring for A/B runs
+    static int stream_mode = -2;
+    if (stream_mode == -2) {
+      const char* es = getenv("GA_K2_STREAM");
+      stream_mode = es == nullptr ? -1 : atoi(es);
+    }
+    if (stream_mode != 0) {
+      BwdStreamParams sp;
+      sp.b = p;
+      const size_t kv = (size_t)2 * 2 * nblk * kKVBlockBytes, ring = (size_t)2 * kQBlockBytes;
+      sp.ring_stages = 0;
+      for (int n = kMaxStages; n >= 2; --n)
+        if (1024 + kv + n * ring <= 226 * 1024) { sp.ring_stages = n; break; }
+      if (sp.ring_stages >= 2) {
+        const size_t smem_s = 1024 + kv + sp.ring_stages * ring;
+        cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_stream_kernel), 5, smem_s);
+        if (es2 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(es2));
+        if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);
+        int teams_s = sm_count() / H;
+        if (teams_s > p.units) teams_s = p.units;
+        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, sp);
+        return check_launch("cross_attn_bwd_tc_stream");
+      }
+    }
     p.smem_stages = 1;
     for (int n = kMaxStages; n >= 2; --n)
       if (n * stage + 1024 <= 224 * 1024) { p.smem_stages = n; break; }

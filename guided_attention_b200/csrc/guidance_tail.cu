@@ -581,6 +581,10 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
   const float inv_res = 1.f / (float)res;
   float* sdi = sds + nt * span;
   float* sdot = sdi + nt * tile;
+  bool has_dup = false;
+  for (int t = 1; t < nt; ++t)
+    for (int t2 = 0; t2 < t; ++t2) has_dup |= tg[t].column == tg[t2].column;
+  float* sda = has_dup ? sdot + tile : sdi;       // per-column sums of dA; the launcher sizes the extra [token][tile]
   // phase 1: d loss / d smoothed over tile + halo, one thread per pixel, tokens in the inner loop
   for (int i = threadIdx.x; i < hi - lo; i += kThreads) {
     const int q = lo + i;
@@ -626,48 +630,57 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
       dot = fmaf(__ldg(attn_text + (int64_t)pix * tp + g.column), dimg, dot);
     }
     sdot[px] = dot;
+    if (has_dup) {          // tokens that share a column (never in practice): their gradients add up
+      for (int t = 0; t < nt; ++t) {
+        float da = 0.f;
+        for (int t2 = 0; t2 < nt; ++t2)
+          if (tg[t2].column == tg[t].column) da += sdi[t2 * tile + px];
+        sda[t * tile + px] = da;
+      }
+    }
   }
   __syncthreads();
   // phase 3: the rows -- a shifted, scaled copy.  One warp per pixel, lanes over the padded output row (three
   // slots: columns lane, lane + 32, lane + 64): every load and store instruction of a warp covers one contiguous
-  // 128-byte span; four pixels per iteration keep 12 loads per lane in flight.
+  // 128-byte span; four pixels per iteration keep 12 loads per lane in flight.  Everything that does not depend on
+  // the pixel (slot predicates, the token that owns a slot's column, 32-bit offsets) is hoisted out of the loop.
   const float k = p.temperature * p.inv_count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t hit[3];          // bit t: tracked token t owns the column of this lane's slot
+  bool rd[3], wr[3];
+  int tok[3];               // tracked token that owns the column of this lane's slot (-1: none)
 #pragma unroll
   for (int sl = 0; sl < 3; ++sl) {
-    hit[sl] = 0u;
-    for (int t = 0; t < nt; ++t)
-      if (tg[t].column + p.first == lane + 32 * sl) hit[sl] |= 1u << t;
+    const int j = lane + 32 * sl;
+    rd[sl] = j >= p.first && j < p.last;
+    wr[sl] = j < d_abar_rstride;
+    tok[sl] = -1;
+    for (int t = nt - 1; t >= 0; --t)
+      if (tg[t].column + p.first == j) tok[sl] = t;
   }
+  const float* a0 = attn_text + (int64_t)p0 * tp - p.first + lane;        // element (px, slot) = a0[px * tp + 32 * slot]
+  float* o0 = d_abar + (int64_t)p0 * d_abar_rstride + lane;
   constexpr int kPix = 4;
   for (int px0 = warp * kPix; px0 < n_own; px0 += kWarps * kPix) {
     float x[kPix][3];
 #pragma unroll
     for (int u = 0; u < kPix; ++u) {
-      const float* arow = attn_text + (int64_t)(p0 + px0 + u) * tp - p.first;
+      const float* ar = a0 + (px0 + u) * tp;
+      const bool live = px0 + u < n_own;
 #pragma unroll
-      for (int sl = 0; sl < 3; ++sl) {
-        const int j = lane + 32 * sl;
-        x[u][sl] = (px0 + u < n_own && j >= p.first && j < p.last) ? __ldg(arow + j) : 0.f;
-      }
+      for (int sl = 0; sl < 3; ++sl) x[u][sl] = (live && rd[sl]) ? __ldg(ar + 32 * sl) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < kPix; ++u) {
       const int px = px0 + u;
-      if (px >= n_own) break;
-      const float dot = sdot[px], nk = -k * dot;
-      float* orow = d_abar + (int64_t)(p0 + px) * d_abar_rstride;
+      if (px < n_own) {
+        const float dot = sdot[px], nk = -k * dot;
+        float* orow = o0 + px * d_abar_rstride;
 #pragma unroll
-      for (int sl = 0; sl < 3; ++sl) {
-        const int j = lane + 32 * sl;
-        float val = nk * x[u][sl];
-        if (hit[sl] != 0u) {                 // a tracked column: k a (dA - dot); tokens sharing a column add up
-          float da = 0.f;
-          for (uint32_t m = hit[sl]; m != 0u; m &= m - 1u) da += sdi[(__ffs(m) - 1) * tile + px];
-          val = k * x[u][sl] * (da - dot);
+        for (int sl = 0; sl < 3; ++sl) {
+          float val = nk * x[u][sl];
+          if (tok[sl] >= 0) val = k * x[u][sl] * (sda[tok[sl] * tile + px] - dot);   // k a (dA - dot)
+          if (wr[sl]) orow[32 * sl] = val;
         }
-        if (j < d_abar_rstride) orow[j] = val;
       }
     }
   }
@@ -887,7 +900,7 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
     // all); small ones 64, so that a single evaluation still spreads over a few SMs.
     const int tile = 256;
     const int nt = p.n_tokens > 0 ? p.n_tokens : 1;
-    const size_t smem = ((size_t)nt * (2 * tile + 2 * (p.res + 1)) + tile) * sizeof(float);
+    const size_t smem = ((size_t)nt * (3 * tile + 2 * (p.res + 1)) + tile) * sizeof(float);
     // (small launches -- the pipeline's own single evaluation, small seed batches -- are latency-bound and stay on the
     // general kernel below, which spreads its 4-pixel groups over more CTAs: 4.4 vs 10 us at 1 sample, 6.2 vs 13.5 us
     // at 64; the crossover measured on B200 is ~400 samples at res 16: profiles/r02_microbench_tail_bwd.jsonl)

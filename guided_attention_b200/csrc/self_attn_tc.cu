@@ -317,6 +317,10 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 //   roles as in the two-pass kernel below: warp 0 TMA producer, warp 1 issuer of S = Q K_j^T, warp 2 issuer of
 //   O_g += P_j V_j (its commit frees the K/V stage and the score buffer), warps 4-7 / 8-11 compute groups.
 constexpr float kLazyBits = 8.f;
+#ifndef GA_SA_POLY_EVERY
+#define GA_SA_POLY_EVERY 6
+#endif
+constexpr int kPolyEvery = GA_SA_POLY_EVERY;   // every 6th exponential on the FMA pipe (0 = all on the SFU)
 
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -489,7 +493,11 @@ self_attn_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       const float mo = m_used * sc;
 #pragma unroll
-      for (int j = 0; j < BK; ++j) { s[j] = ex2_approx(fmaf(s[j], sc, -mo)); l4[j & 3] += s[j]; }
+      for (int j = 0; j < BK; ++j) {
+        const float x = fmaf(s[j], sc, -mo);
+        s[j] = (kPolyEvery > 0 && (j % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ex2_poly3(x) : ex2_approx(x);
+        l4[j & 3] += s[j];
+      }
       // P (packed 16-bit, BK / 2 columns) over the head of the score buffer: every score is in registers by now
 #pragma unroll
       for (int c = 0; c < BK / 16; ++c) {

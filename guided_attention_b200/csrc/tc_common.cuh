@@ -143,6 +143,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5 -- below the 2^-11 rounding of the 16-bit P operand it feeds), n added to the exponent
+// bits.  9 FMA/ALU-pipe instructions, i.e. the same issue cost as one MUFU.EX2 at the SM's 16/clk SFU rate: the softmax
+// loops of the self-attention kernels, whose top unit is the SFU (ncu: XU 64 %), hand every kPolyEvery-th exponential
+// to this path.  x <= ~8 here; x below -126 (masked keys: -inf) gives 2^-126 ~ 0.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                    // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.f);
+  float pl = fmaf(0.055171169340610504f, f, 0.24261002242565155f);
+  pl = fmaf(pl, f, 0.6932609677314758f);
+  pl = fmaf(pl, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
 // ---- warp-uniform role helpers ----------------------------------------------------------------------------------
 // The TMA-producer and MMA-issuer roles run as WHOLE warps in warp-uniform control flow and pick one lane with
 // elect.sync for the asynchronous instructions.  A role entered through a divergent `lane == 0` branch makes the
