@@ -317,10 +317,14 @@ self_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 //   roles as in the two-pass kernel below: warp 0 TMA producer, warp 1 issuer of S = Q K_j^T, warp 2 issuer of
 //   O_g += P_j V_j (its commit frees the K/V stage and the score buffer), warps 4-7 / 8-11 compute groups.
 constexpr float kLazyBits = 8.f;
+// Every kPolyEvery-th exponential can be handed to the FMA pipe (tc::ex2_poly3, the FA-4 trick).  Measured on B200 at
+// N = 4096, d = 40 (profiles/r02_microbench_self_attn_poly_ab.txt): 58.0 us with every exponential on the SFU, 59.3-59.8 us
+// with every 4th / 6th / 8th on the FMA pipe -- the kernel is not SFU-bound enough (XU 64 %, issue slots 42 %) for the
+// nine extra issue slots per polynomial to pay, so the default is off.
 #ifndef GA_SA_POLY_EVERY
-#define GA_SA_POLY_EVERY 6
+#define GA_SA_POLY_EVERY 0
 #endif
-constexpr int kPolyEvery = GA_SA_POLY_EVERY;   // every 6th exponential on the FMA pipe (0 = all on the SFU)
+constexpr int kPolyEvery = GA_SA_POLY_EVERY;
 
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)

@@ -145,9 +145,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
 // (max relative error 7.5e-5 -- below the 2^-11 rounding of the 16-bit P operand it feeds), n added to the exponent
-// bits.  9 FMA/ALU-pipe instructions, i.e. the same issue cost as one MUFU.EX2 at the SM's 16/clk SFU rate: the softmax
-// loops of the self-attention kernels, whose top unit is the SFU (ncu: XU 64 %), hand every kPolyEvery-th exponential
-// to this path.  x <= ~8 here; x below -126 (masked keys: -inf) gives 2^-126 ~ 0.
+// bits.  9 FMA/ALU-pipe instructions, i.e. the same issue cost as one MUFU.EX2 at the SM's 16/clk SFU rate; an A/B
+// option of the self-attention forward (GA_SA_POLY_EVERY, off by default: measured slower, see self_attn_tc.cu).  x <= ~8 here; x below -126 (masked keys: -inf) gives 2^-126 ~ 0.
 __device__ __forceinline__ float ex2_poly3(float x) {
   x = fmaxf(x, -126.f);
   const float t = x + 12582912.f;                    // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
@@ -268,6 +267,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 template <int kRegs> __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
