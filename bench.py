@@ -227,6 +227,10 @@ def workload_config(args, dtype):
                         "recurse_steps 3, attention_res 16" + ("" if args.unet == "sd14" else " [TINY UNET: NOT THE BASELINE CONFIG]"),
             "unet": args.unet, "denoise_steps": args.denoise_steps, "images_per_step_per_gpu": 1,
             "cuda_graphs": not getattr(args, "no_graphs", False),
+            "control_flow": ("eager host loop" if getattr(args, "no_graphs", False) else
+                             "host loop replaying graphs (one D2H read per loss evaluation)"
+                             if getattr(args, "host_control", False) else
+                             "device-side step driver (CUDA conditional graph nodes, no loss read back)"),
             "l2_policy": "inputs larger than L2: every UNet pass streams 1.7 GB of fp16 weights (L2 is 126 MB)",
             "parallelism": f"seed-sharded, {args.gpus} process(es), no hot-path collective"}
 
@@ -249,6 +253,7 @@ def build_pipeline(args, dev):
     pipe = GuidedAttention(unet=unet, scheduler=DDIMScheduler(), tokenizer=WhitespaceTokenizer())
     cfg.stable = pipe
     pipe.use_cuda_graphs = not args.no_graphs
+    pipe.device_side_control = not getattr(args, "host_control", False)
     R.register_custom_loss("toLeftOf", R.ToLeftOf())
     R.overrideConfig(cfg)
     R.parseMetaPrompt(cfg)
@@ -650,6 +655,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-saturated", action="store_true", help="skip the large-batch kernel rooflines")
+    ap.add_argument("--host-control", action="store_true",
+                    help="A/B: drive refinement / recursion from the host (graph replays + one D2H read per evaluation) "
+                         "instead of the device-side step driver")
     ap.add_argument("--seeds-per-batch", type=int, default=8,
                     help="also measure the seed-batched extension with this many seeds per UNet pass (0/1 = skip)")
     ap.add_argument("--sweep64", action="store_true",

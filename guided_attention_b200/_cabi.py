@@ -21,7 +21,7 @@ GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
  GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER, GA_STAT_RAW_SUM,
  GA_STAT_RAW_COL, GA_STAT_RAW_ROW) = range(15)
 GA_STATS = 16
-GA_ABI_VERSION = 4
+GA_ABI_VERSION = 5
 GA_STEP_CTL_BYTES, GA_STEP_COUNTER_BASE = 256, 19
 (GA_STEP_N_EVAL, GA_STEP_N_UPDATE, GA_STEP_N_CFG, GA_STEP_N_REFINE, GA_STEP_N_ROUNDS, GA_STEP_N_RENOISE) = range(6)
 
@@ -85,6 +85,7 @@ PROTOTYPES = {
     "ga_step_driver_create": (_i, [C.POINTER(_vp), C.POINTER(GaStepPrograms), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    C.POINTER(GaToken), _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ga_step_driver_run": (_i, [_vp, C.POINTER(GaStepParams), _vp]),
+    "ga_step_driver_set_params": (_i, [_vp, C.POINTER(GaStepParams), _vp]),
     "ga_step_driver_destroy": (_i, [_vp]),
     "ga_smooth_fwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "ga_smooth_bwd": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float), _vp]),

@@ -323,6 +323,14 @@ extern "C" int ga_step_driver_run(void* driver, const ga_step_params_t* params_h
   return GA_OK;
 }
 
+extern "C" int ga_step_driver_set_params(void* driver, const ga_step_params_t* params_host, ga_stream_t stream) {
+  GA_CHECK_ARG(driver != nullptr && params_host != nullptr, "NULL argument");
+  step::Driver* d = static_cast<step::Driver*>(driver);
+  step::set_params_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(d->ctl, *params_host, d->t_dev, d->step_dev,
+                                                                             d->ddim_dev, d->renoise_dev);
+  return check_launch("step set_params");
+}
+
 extern "C" int ga_step_driver_destroy(void* driver) {
   if (driver == nullptr) return GA_OK;
   step::Driver* d = static_cast<step::Driver*>(driver);

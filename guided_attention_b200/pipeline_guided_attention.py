@@ -797,6 +797,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         last_cfg = list(cfg.thresholds.values())[-1] if len(cfg.thresholds) else 0.0
         pww = PaintWithWords.of(G.store)
+        plain_steps = 0
         for i, t in enumerate(timesteps):
             t = int(t)
             state.cur_time_step_iter = i
@@ -822,14 +823,27 @@ class GuidedAttention(StableDiffusionPipelineBase):
                 Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_t])
                 p.renoise[0], p.renoise[1] = Bt ** 0.5, (1 - Bt) ** 0.5
             with torch.cuda.device(dev):
-                abi.check(lib.ga_step_driver_run(drv, C.byref(p), stream), "ga_step_driver_run")
+                if p.check:
+                    abi.check(lib.ga_step_driver_run(drv, C.byref(p), stream), "ga_step_driver_run")
+                else:
+                    # nothing to decide on this step (no threshold, no update): the reference still runs its
+                    # text-conditioned forward and the CFG step (:946-947, :1008-1029) -- replay them directly, still
+                    # without any read-back (a conditional node costs ~50 us per executed body)
+                    abi.check(lib.ga_step_driver_set_params(drv, C.byref(p), stream), "ga_step_driver_set_params")
+                    G.graphs["eval"].replay()
+                    G.graphs["cfg"].replay()
+                    G.graphs["advance"].replay()
+                    plain_steps += 1
         out = G.lat.clone()
         # bookkeeping after the fact: one small read together with the image (the caller reads the latents anyway)
         base = abi.GA_STEP_COUNTER_BASE
         d = (G.ctl - before)[base:base + 6].cpu().tolist()
+        d[abi.GA_STEP_N_EVAL] += plain_steps
+        d[abi.GA_STEP_N_CFG] += plain_steps
+        d[abi.GA_STEP_N_ROUNDS] += plain_steps
         n_prog = {"eval": d[abi.GA_STEP_N_EVAL], "update": d[abi.GA_STEP_N_UPDATE], "cfg": d[abi.GA_STEP_N_CFG]}
         self.last_step_counters = {"eval": d[0], "update": d[1], "cfg": d[2], "refine_iterations": d[3],
-                                   "rounds": d[4], "renoise": d[5]}
+                                   "rounds": d[4], "renoise": d[5], "steps_without_decisions": plain_steps}
         for name, n in n_prog.items():
             self._count_pass(name, n)
         if G.use_optimizer:      # the refinement iterations ran the momentum program

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 4
+#define GA_ABI_VERSION 5
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -269,6 +269,10 @@ int ga_step_driver_create(void** driver_out, const ga_step_programs_t* programs,
                           float* refine_first_dev, const ga_token_t* tokens_host, int n_tokens, int n_groups,
                           int avg_within, int64_t* t_dev, float* step_dev, float* ddim_dev, float* renoise_dev);
 int ga_step_driver_run(void* driver, const ga_step_params_t* params_host, ga_stream_t stream);
+/* Only the parameter kernel of ga_step_driver_run (fills *t_dev, *step_dev, ddim_dev, renoise_dev and the control block):
+ * for denoising steps that test no threshold the caller can replay `eval`, `cfg` and `advance` itself -- there is nothing
+ * to decide, and a conditional node costs ~50 us per executed body (measured, tools/diag_cond_graph.py). */
+int ga_step_driver_set_params(void* driver, const ga_step_params_t* params_host, ga_stream_t stream);
 int ga_step_driver_destroy(void* driver);
 /* int32 offsets into ctl_dev of the lifetime counters (UNet passes by program, refinement iterations, rounds, re-noise) */
 enum ga_step_counter { GA_STEP_N_EVAL = 0, GA_STEP_N_UPDATE = 1, GA_STEP_N_CFG = 2, GA_STEP_N_REFINE = 3,
