@@ -167,24 +167,11 @@ __device__ void token_stage(const ga_tail_params_t& p, const ga_token_t& tk, int
 }
 
 // --------------------------------------------------------------------------------------------------- forward
-// grid = ceil(res^2 / 8) CTAs x 256 threads.  Phase R: one warp per pixel.  The last CTA to finish runs phase S.
-__global__ void __launch_bounds__(kThreads)
-tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
-                const float* __restrict__ weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
-                float* total, unsigned int* ticket) {
-  extern __shared__ float simg[];  // kWarps * res*res floats (phase S only)
-  __shared__ __align__(16) float srow[kWarps][4 * GA_MAX_CTX];   // phase R: 4 pixels x T tokens per warp
-  __shared__ bool is_last;
+// Phase R (per pixel): mean over the accumulator slices, x100, softmax over the text tokens -> attn_text rows.
+__device__ __forceinline__ void tail_phase_r(const AccArgs& acc, const ga_tail_params_t& p, float* attn_text, int smp,
+                                             float (*srow)[4 * GA_MAX_CTX]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npix = p.res * p.res, T = p.n_ctx, tp = p.last - p.first;
-  const int smp = blockIdx.y;                       // independent sample
-  attn_text += (int64_t)smp * npix * tp;
-  smoothed += (int64_t)smp * p.n_tokens * npix;
-  stats += (int64_t)smp * p.n_tokens * GA_STATS;
-  argmax += (int64_t)smp * p.n_tokens;
-  total += smp;
-  ticket += smp;
-
   // Phase R.  A warp owns 4 consecutive pixels = 4*T contiguous floats of every slice = T aligned float4 chunks
   // (npix % 4 == 0 is guaranteed by the host wrapper): 128-bit coalesced loads, lanes over chunks, slices summed in a
   // fixed order; the sums are re-distributed through shared memory so that lanes become text tokens for the softmax.
@@ -245,17 +232,14 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
     }
   }
 
-  // ---- hand-over to phase S: the last CTA to take a ticket sees every other CTA's attn_text
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int tkt = atomicAdd(ticket, 1u);
-    is_last = (tkt == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+}
 
+// Phase S (per tracked token) + the total, for one sample; `simg` holds min(kWarps, n_tokens) maps of res*res floats.
+__device__ __forceinline__ void tail_phase_s(const ga_tail_params_t& p, const TokArgs& toks, const uint8_t* masks,
+                                             const float* weights, const float* attn_text, float* smoothed, float* stats,
+                                             int32_t* argmax, float* total, unsigned int* ticket, float* simg) {
+  const int warp = threadIdx.x >> 5;
+  const int npix = p.res * p.res;
   for (int t0 = 0; t0 < p.n_tokens; t0 += kWarps) {
     const int t = t0 + warp;
     if (t < p.n_tokens)
@@ -268,6 +252,61 @@ tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __
     total[0] = tot;
     *ticket = 0u;  // leave the workspace zero for the next launch
   }
+}
+
+// Small launches: ONE launch.  grid = (ceil(res^2 / 32), n_samples) CTAs x 256 threads; phase R in every CTA, the last
+// CTA of a sample to finish (ticket counter) runs phase S.
+__global__ void __launch_bounds__(kThreads)
+tail_fwd_kernel(AccArgs acc, ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
+                const float* __restrict__ weights, float* attn_text, float* smoothed, float* stats, int32_t* argmax,
+                float* total, unsigned int* ticket) {
+  extern __shared__ float simg[];  // min(kWarps, n_tokens) * res*res floats (phase S only)
+  __shared__ __align__(16) float srow[kWarps][4 * GA_MAX_CTX];   // phase R: 4 pixels x T tokens per warp
+  __shared__ bool is_last;
+  const int npix = p.res * p.res, tp = p.last - p.first;
+  const int smp = blockIdx.y;                       // independent sample
+  attn_text += (int64_t)smp * npix * tp;
+  smoothed += (int64_t)smp * p.n_tokens * npix;
+  stats += (int64_t)smp * p.n_tokens * GA_STATS;
+  argmax += (int64_t)smp * p.n_tokens;
+  total += smp;
+  ticket += smp;
+  tail_phase_r(acc, p, attn_text, smp, srow);
+  // ---- hand-over to phase S: the last CTA to take a ticket sees every other CTA's attn_text
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tkt = atomicAdd(ticket, 1u);
+    is_last = (tkt == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  tail_phase_s(p, toks, masks, weights, attn_text, smoothed, stats, argmax, total, ticket, simg);
+}
+
+// Large launches (many samples): two launches.  Fused, the kernel needs 64 registers and the phase-S staging of every
+// CTA although one CTA per sample uses it: 4 CTAs per SM, ncu warps-active 49 %, DRAM 48-58 %.  The per-pixel phase on
+// its own is a lean streaming kernel (6 CTAs per SM), the per-token phase one CTA per sample.  Same device code, same
+// bits as the fused kernel.
+__global__ void __launch_bounds__(kThreads, 6)
+tail_fwd_r_kernel(AccArgs acc, ga_tail_params_t p, float* attn_text) {
+  __shared__ __align__(16) float srow[kWarps][4 * GA_MAX_CTX];
+  const int smp = blockIdx.y;
+  attn_text += (int64_t)smp * p.res * p.res * (p.last - p.first);
+  tail_phase_r(acc, p, attn_text, smp, srow);
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_fwd_s_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks, const float* __restrict__ weights,
+                  const float* attn_text, float* smoothed, float* stats, int32_t* argmax, float* total) {
+  extern __shared__ float simg[];
+  const int npix = p.res * p.res, tp = p.last - p.first;
+  const int smp = blockIdx.x;
+  unsigned int dummy_ticket = 0u;
+  tail_phase_s(p, toks, masks, weights, attn_text + (int64_t)smp * npix * tp, smoothed + (int64_t)smp * p.n_tokens * npix,
+               stats + (int64_t)smp * p.n_tokens * GA_STATS, argmax + (int64_t)smp * p.n_tokens, total + smp,
+               &dummy_ticket, simg);
 }
 
 // -------------------------------------------------------------------------------------------------- backward
@@ -552,7 +591,10 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
 // (the whole 16x16 map, or 256 row-major pixels of a larger one plus a halo of one row + one pixel on each side for
 // the 3x3 filter adjoint); the per-token gradients dA_t are computed once per CTA, one thread per pixel; the streaming
 // phase gives every thread whole float4 chunks of the output (4 scalar loads, 4 multiplies, one 128-bit store).
-__global__ void __launch_bounds__(kThreads)
+#ifndef GA_TAIL_BWD_MIN_CTAS
+#define GA_TAIL_BWD_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(kThreads, GA_TAIL_BWD_MIN_CTAS)
 tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
                        const float* __restrict__ weights, const float* __restrict__ attn_text,
                        const float* __restrict__ smoothed, const float* __restrict__ stats,
@@ -855,7 +897,8 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
   }
   GA_CHECK_ARG(ticket != nullptr, "ticket workspace is NULL");
   const int npix = p.res * p.res;
-  const size_t smem = (size_t)tail::kWarps * npix * sizeof(float);
+  const int n_maps = p.n_tokens < tail::kWarps ? (p.n_tokens > 0 ? p.n_tokens : 1) : tail::kWarps;
+  const size_t smem = (size_t)n_maps * npix * sizeof(float);     // phase S: one staged map per concurrently processed token
   if (smem > 200 * 1024) return fail(GA_ERR_UNSUPPORTED, "res %d too large for the fused tail", p.res);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (smem > 24 * 1024) {   // static (phase R rows) + dynamic (phase S maps) can pass the 48 KB default from res 32 up
@@ -871,6 +914,15 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
   GA_CHECK_ARG(npix % 4 == 0, "res*res must be a multiple of 4 (res %d)", p.res);
   for (int i = 0; i < n_acc; ++i) GA_CHECK_ALIGN(acc_host[i], 16, "accumulator");
   const dim3 grid((npix / 4 + tail::kWarps - 1) / tail::kWarps, p.n_samples);
+  if ((int64_t)p.n_samples * npix >= 96 * 1024 && smem <= 48 * 1024) {
+    // many samples: lean per-pixel kernel + one CTA per sample for the per-token phase (see the kernels' comment)
+    tail::tail_fwd_r_kernel<<<grid, tail::kThreads, 0, st>>>(acc, p, attn_text);
+    int rc2 = check_launch("guidance_tail_fwd_r");
+    if (rc2 != GA_OK) return rc2;
+    tail::tail_fwd_s_kernel<<<p.n_samples, tail::kThreads, smem, st>>>(p, toks, masks, weights, attn_text, smoothed,
+                                                                      stats, argmax, total);
+    return check_launch("guidance_tail_fwd_s");
+  }
   tail::tail_fwd_kernel<<<grid, tail::kThreads, smem, st>>>(acc, p, toks, masks, weights, attn_text, smoothed, stats,
                                                             argmax, total, reinterpret_cast<unsigned int*>(ticket));
   return check_launch("guidance_tail_fwd");

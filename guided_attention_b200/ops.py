@@ -448,6 +448,9 @@ class _GuidanceTailFn(torch.autograd.Function):
         ctx.save_for_backward(attn_text, smoothed, stats, argmax)
         ctx.spec, ctx.params, ctx.batches = spec, p, [a.shape[0] for a in accs]
         ctx.mark_non_differentiable(smoothed, argmax)
+        # outputs that do not feed the loss hand back None, not zeros: with g_attn_text = NULL the backward takes the
+        # sparse fast path (the built-in losses never differentiate attn_text directly)
+        ctx.set_materialize_grads(False)
         return attn_text, smoothed, stats, argmax, total
 
     @staticmethod

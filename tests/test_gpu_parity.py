@@ -473,6 +473,37 @@ def test_tail_sample_batching_equals_separate_evaluations():
             assert torch.equal(a, b_[s_ * B:(s_ + 1) * B])
 
 
+@pytest.mark.parametrize("res,S", [(16, 400), (32, 100)])
+def test_tail_large_launch_variants_equal_small_launch_kernels(res, S):
+    """Launches with >= 96K pixels take other kernels (forward: lean per-pixel kernel + one CTA per sample for the
+    per-token phase; backward: the 256-pixel-tile sparse kernel).  Same arithmetic in the same order: every output,
+    gradients included, must be bit-identical to the small-launch kernels run on quarters of the batch."""
+    from guided_attention_b200.pipeline_guided_attention import GuidedAttention
+    from guided_attention_b200 import ops
+    cfg = setup_prompt()
+    pipe = GuidedAttention(unet=None, tokenizer=cfg.stable.tokenizer)
+    pipe.prompt = cfg.prompt
+    L, B, T = 3, 1, 77
+    assert S * res * res >= 96 * 1024 > (S // 4) * res * res
+    g = torch.Generator(DEV).manual_seed(33)
+    layers = [torch.softmax(3 * torch.randn(S * B, res * res, T, generator=g, device=DEV), -1) for _ in range(L)]
+    spec = pipe._tail_spec(res, T, True, 0.5, 3, False, torch.device(DEV))
+    w = torch.randn(S, generator=g, device=DEV)
+    big = [a.clone().requires_grad_(True) for a in layers]
+    out_b = ops.guidance_tail(spec, big, L * B, n_samples=S)
+    gb = torch.autograd.grad((out_b[4] * w).sum(), big)
+    q = S // 4
+    for c in range(4):
+        sl = slice(c * q * B, (c + 1) * q * B)
+        small = [a[sl].clone().requires_grad_(True) for a in layers]
+        out_s = ops.guidance_tail(spec, small, L * B, n_samples=q)
+        for a, b_ in zip(out_s, out_b):
+            assert torch.equal(a, b_[c * q:(c + 1) * q])
+        gs = torch.autograd.grad((out_s[4] * w[c * q:(c + 1) * q]).sum(), small)
+        for a, b_ in zip(gs, gb):
+            assert torch.equal(a, b_[sl])
+
+
 def test_box_without_inside_pixel_raises_like_reference():
     from guided_attention_b200.pipeline_guided_attention import GuidedAttention
     cfg = setup_prompt('a [dot:.5,.5,.02,.02] here')
