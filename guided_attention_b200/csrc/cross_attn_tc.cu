@@ -1456,16 +1456,29 @@ cross_attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap map_q, const _
 struct BwdStreamParams {
   BwdPipeParams b;
   int ring_stages;   // 2 .. kMaxStages
+  int g_slots;       // 0: the map-gradient rows are read with per-thread loads; 1: TMA-staged 128-row tiles (see below)
+  int g_batched;     // 1: the map gradient has a batch stride (coordinate b), 0: one (N, rstride) matrix for every b
 };
+
+// The injected map gradient (round 2, second pass).  A compute thread needs ITS row of d_abar (80 floats): read with
+// per-thread 128-bit loads, every load instruction of a warp touches 32 different 128-byte lines (rows are 320 bytes
+// apart), i.e. 32 L1 tag cycles per instruction, 20 instructions per thread, 8 warps: ~1.2 us of LSU time per item --
+// measured: d = 80, B = 256: 351 us with the map gradient, 214 us without.  With `g_slots` the otherwise idle fourth
+// warp of the producer warpgroup streams the item's 128 x 80 fp32 tile into shared memory with three TMA boxes
+// (32 columns x 128 rows, 128-byte swizzle: a thread reading its own row chunk by chunk is bank-conflict free), and
+// the compute threads pick their row up with 20 shared-memory loads.
+constexpr uint32_t kGPieceBytes = kM * 128;          // 32 fp32 columns x 128 rows
+constexpr uint32_t kGSlotBytes = 3 * kGPieceBytes;   // columns 0..95 (80..95 are out of range: zero-filled)
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                                const BwdStreamParams sp) {
+                                const __grid_constant__ CUtensorMap map_g, const BwdStreamParams sp) {
   const BwdPipeParams& p = sp.b;
   extern __shared__ uint8_t smem_raw[];
-  // ring_full[6], ring_free[6], kv_full[2], kv_free[2], then sd_ready / ds_ready / dq_ready / tmem_free x 3
-  __shared__ __align__(8) uint64_t bars[28];
+  // ring_full[6], ring_free[6], kv_full[2], kv_free[2], then sd_ready / ds_ready / dq_ready / tmem_free x 3,
+  // g_full[2] (one per compute group: a waiter must see every phase of its barrier), g_free
+  __shared__ __align__(8) uint64_t bars[31];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -1483,6 +1496,10 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
   auto DS_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 7 + s]); };
   auto DQ_READY = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 10 + s]); };
   auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 13 + s]); };
+  auto G_FULL = [&](int g) { return smem_u32(&bars[2 * kMaxStages + 16 + g]); };
+  const uint32_t G_FREE = smem_u32(&bars[2 * kMaxStages + 18]);
+  const bool g_staged = sp.g_slots > 0 && p.d_acc != nullptr;
+  const uint32_t g_base = ring_base + (uint32_t)R * ring_stage_bytes;
   const int nT = p.tstages;
   const uint32_t stage_cols = nT == 3 ? 160u : (uint32_t)kStageCols;
   auto tIdx = [&](int k) { return nT == 3 ? k % 3 : (k & 1); };
@@ -1494,6 +1511,10 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    if (g_staged) prefetch_tmap(&map_g);
+    mbar_init(G_FULL(0), 1);
+    mbar_init(G_FULL(1), 1);
+    mbar_init(G_FREE, kGroupThreads);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(RING_FULL(s), 1); mbar_init(RING_FREE(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(KV_FULL(s), 1); mbar_init(KV_FREE(s), 1); }
     for (int s = 0; s < 3; ++s) {
@@ -1621,6 +1642,19 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
         }
         __syncwarp();
       }
+    } else if (g_staged) {
+      // ------------------------------------------------- map-gradient producer: one 128 x 80 fp32 tile per item
+      for (int k = 0; k < n_items; ++k) {
+        int b, h, tile;
+        coords(k, b, h, tile);
+        if (k >= 1) mbar_wait(G_FREE, (uint32_t)(k - 1) & 1u);
+        if (elect_one()) {
+          mbar_expect_tx(G_FULL(k & 1), kGSlotBytes);
+          for (int pc = 0; pc < 3; ++pc)
+            tma_load_3d(g_base + pc * kGPieceBytes, &map_g, G_FULL(k & 1), pc * 32, tile * kM, sp.g_batched ? b : 0);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp < 4) {
     reg_dealloc<88>();
@@ -1678,7 +1712,18 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
       // its registers are dead again before the scores are loaded
       float dp[kTpad];
       const bool vec_acc = (p.d_acc_rstride & 3) == 0;
-      if (dacc != nullptr) {
+      if (g_staged) {
+        // this thread's row of the TMA-staged tile: piece (32 columns) / 128-byte row / 16-byte chunk ^ (row & 7)
+        mbar_wait(G_FULL(g), (uint32_t)(k >> 1) & 1u);
+        const uint32_t grow = g_base + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < kTpad; j += 4) {
+          const uint32_t a = grow + (uint32_t)(j >> 5) * kGPieceBytes + ((uint32_t)(((j >> 2) & 7) ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(dp[j]), "=f"(dp[j + 1]), "=f"(dp[j + 2]), "=f"(dp[j + 3]) : "r"(a) : "memory");
+        }
+        mbar_arrive(G_FREE);                  // (release: the loads above are performed before the arrival)
+      } else if (dacc != nullptr) {
         if (vec_acc) {
 #pragma unroll
           for (int j = 0; j < kTpad; j += 4) {
@@ -1958,17 +2003,39 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
       BwdStreamParams sp;
       sp.b = p;
       const size_t kv = (size_t)2 * 2 * nblk * kKVBlockBytes, ring = (size_t)2 * kQBlockBytes;
-      sp.ring_stages = 0;
-      for (int n = kMaxStages; n >= 2; --n)
-        if (1024 + kv + n * ring <= 226 * 1024) { sp.ring_stages = n; break; }
+      auto stages_for = [&](size_t extra) {
+        for (int n = kMaxStages; n >= 2; --n)
+          if (1024 + kv + extra + n * ring <= 226 * 1024) return n;
+        return 0;
+      };
+      // TMA-staged map-gradient tile: when its 48 KB leave at least three ring stages (d <= 128) and the rows can be
+      // described to the TMA (16-byte aligned base and strides, at most 96 columns); GA_K2_GSTAGE=0/1 forces it
+      static int g_mode = -2;
+      if (g_mode == -2) {
+        const char* eg = getenv("GA_K2_GSTAGE");
+        g_mode = eg == nullptr ? -1 : atoi(eg);
+      }
+      sp.g_slots = 0;
+      sp.g_batched = d_acc_bstride != 0 ? 1 : 0;
+      CUtensorMap mgr = mq;      // placeholder when the staged path is off (never dereferenced)
+      const bool g_ok = d_acc != nullptr && (d_acc_rstride & 3) == 0 && d_acc_rstride <= 96 && (d_acc_bstride & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(d_acc) & 15) == 0;
+      if (g_ok && g_mode != 0 && stages_for(kGSlotBytes) >= (g_mode == 1 ? 2 : 3)) {
+        if ((rc = make_map_rows_f32(&mgr, d_acc, d_acc_rstride, N, sp.g_batched ? B : 1,
+                                    sp.g_batched ? d_acc_bstride : (int64_t)N * d_acc_rstride, kM)) != GA_OK)
+          return rc;
+        sp.g_slots = 1;
+      }
+      const size_t g_bytes = sp.g_slots ? (size_t)kGSlotBytes : 0;
+      sp.ring_stages = stages_for(g_bytes);
       if (sp.ring_stages >= 2) {
-        const size_t smem_s = 1024 + kv + sp.ring_stages * ring;
+        const size_t smem_s = 1024 + kv + sp.ring_stages * ring + g_bytes;
         cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_stream_kernel), 5, smem_s);
         if (es2 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(es2));
         if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);
         int teams_s = sm_count() / H;
         if (teams_s > p.units) teams_s = p.units;
-        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, sp);
+        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, mgr, sp);
         return check_launch("cross_attn_bwd_tc_stream");
       }
     }

@@ -50,6 +50,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // Pull a tile into L2 without touching shared memory: lets a producer keep far more HBM requests in flight than its
 // shared-memory ring has stages (the later cp.async.bulk.tensor of the same tile then hits L2).
 __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
@@ -318,6 +324,27 @@ static inline int make_map(CUtensorMap* map, const void* ptr, int dtype, int B, 
            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GA_OK;
+}
+
+// (cols, rows, batches) view of fp32 rows with a row pitch of `cols` floats and a batch stride of `bstride` floats;
+// box = 32 columns x box_rows rows; 128-byte swizzle; out-of-range columns / rows are filled with zeros.
+static inline int make_map_rows_f32(CUtensorMap* map, const void* ptr, int cols, int rows, int batches, int64_t bstride,
+                                    int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)bstride * 4};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = CUDA_ERROR_INVALID_CONTEXT;
+  for (int attempt = 0; attempt < 2 && r == CUDA_ERROR_INVALID_CONTEXT; ++attempt) {
+    if (attempt == 1) cudaFree(nullptr);      // bind the primary context (see make_map)
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 rows) failed (%d)", (int)r);
   return GA_OK;
 }
 

@@ -305,6 +305,32 @@ def test_cross_attention_backward_tcgen05(shape, dtype, rtol, with_dacc, variant
     assert rel_err(res[TCB], res[abi.GA_IMPL_SIMT]) < rtol
 
 
+@pytest.mark.parametrize("shape", [(8, 80, 1024, 77, 3), (8, 40, 192, 77, 7), (8, 160, 256, 77, 4)])
+def test_cross_attention_backward_tcgen05_per_sample_map_gradient(shape):
+    """Seed batching hands K2 one map-gradient matrix PER batch element (batch stride != 0, padded 80-float rows): the
+    persistent kernel's TMA-staged tile path must pick the right element's rows."""
+    from guided_attention_b200 import ops, _cabi as abi
+    H, d, N, T, B = shape
+    q, k, v = _attn_case(H, d, N, T, B, torch.float16, seed=31)
+    scale = d ** -0.5
+    g = torch.Generator("cpu").manual_seed(32)
+    d_o = torch.randn(B, N, H * d, generator=g).half()
+    padded = torch.zeros(B, N, 80)
+    padded[:, :, :T] = 3.0 * torch.randn(B, N, T, generator=g)
+    res = {}
+    for impl in (abi.GA_IMPL_TCGEN05_PIPE, abi.GA_IMPL_SIMT):
+        ops.default_bwd_impl = impl
+        try:
+            qd = q.to(DEV).requires_grad_(True)
+            o, acc = ops.cross_attention(qd, k.to(DEV), v.to(DEV), H, scale, want_acc=True, impl=impl)
+            (dq,) = torch.autograd.grad([o, acc], (qd,), [d_o.to(DEV), padded.to(DEV)[:, :, :T]])   # strides (N*80, 80, 1)
+            torch.cuda.synchronize()
+            res[impl] = dq.float().cpu().numpy()
+        finally:
+            ops.default_bwd_impl = abi.GA_IMPL_AUTO
+    assert rel_err(res[abi.GA_IMPL_TCGEN05_PIPE], res[abi.GA_IMPL_SIMT]) < FP16_RTOL
+
+
 # ------------------------------------------------------------------------------------------------ guidance tail
 def _tail_inputs_from_case(case, kat):
     cfg = setup_prompt(case["meta_prompt"], case.get("hyper"), case.get("cfg"))
