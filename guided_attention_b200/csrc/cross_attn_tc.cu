@@ -1465,15 +1465,16 @@ struct BwdStreamParams {
 // apart), i.e. 32 L1 tag cycles per instruction, 20 instructions per thread, 8 warps: ~1.2 us of LSU time per item --
 // measured: d = 80, B = 256: 351 us with the map gradient, 214 us without.  With `g_slots` the otherwise idle fourth
 // warp of the producer warpgroup streams the item's 128 x 80 fp32 tile into shared memory with three TMA boxes
-// (32 columns x 128 rows, 128-byte swizzle: a thread reading its own row chunk by chunk is bank-conflict free), and
-// the compute threads pick their row up with 20 shared-memory loads.
-constexpr uint32_t kGPieceBytes = kM * 128;          // 32 fp32 columns x 128 rows
-constexpr uint32_t kGSlotBytes = 3 * kGPieceBytes;   // columns 0..95 (80..95 are out of range: zero-filled)
+// (32 + 32 + 16 columns x 128 rows, 128- / 64-byte swizzle: a thread reading its own row chunk by chunk is
+// bank-conflict free), and the compute threads pick their row up with 20 shared-memory loads.
+constexpr uint32_t kGPieceBytes = kM * 128;                  // 32 fp32 columns x 128 rows
+constexpr uint32_t kGSlotBytes = 2 * kGPieceBytes + kM * 64; // columns 0..31 | 32..63 | 64..79 (64-byte rows)
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                                const __grid_constant__ CUtensorMap map_g, const BwdStreamParams sp) {
+                                const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_g16,
+                                const BwdStreamParams sp) {
   const BwdPipeParams& p = sp.b;
   extern __shared__ uint8_t smem_raw[];
   // ring_full[6], ring_free[6], kv_full[2], kv_free[2], then sd_ready / ds_ready / dq_ready / tmem_free x 3,
@@ -1511,7 +1512,7 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_do); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
-    if (g_staged) prefetch_tmap(&map_g);
+    if (g_staged) { prefetch_tmap(&map_g); prefetch_tmap(&map_g16); }
     mbar_init(G_FULL(0), 1);
     mbar_init(G_FULL(1), 1);
     mbar_init(G_FREE, kGroupThreads);
@@ -1650,8 +1651,10 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
         if (k >= 1) mbar_wait(G_FREE, (uint32_t)(k - 1) & 1u);
         if (elect_one()) {
           mbar_expect_tx(G_FULL(k & 1), kGSlotBytes);
-          for (int pc = 0; pc < 3; ++pc)
-            tma_load_3d(g_base + pc * kGPieceBytes, &map_g, G_FULL(k & 1), pc * 32, tile * kM, sp.g_batched ? b : 0);
+          const int gb = sp.g_batched ? b : 0;
+          tma_load_3d(g_base, &map_g, G_FULL(k & 1), 0, tile * kM, gb);
+          tma_load_3d(g_base + kGPieceBytes, &map_g, G_FULL(k & 1), 32, tile * kM, gb);
+          tma_load_3d(g_base + 2 * kGPieceBytes, &map_g16, G_FULL(k & 1), 64, tile * kM, gb);
         }
         __syncwarp();
       }
@@ -1713,12 +1716,20 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
       float dp[kTpad];
       const bool vec_acc = (p.d_acc_rstride & 3) == 0;
       if (g_staged) {
-        // this thread's row of the TMA-staged tile: piece (32 columns) / 128-byte row / 16-byte chunk ^ (row & 7)
+        // this thread's row of the TMA-staged tile.  32-column pieces (128-byte rows, 128-byte swizzle): chunk c of
+        // row r sits at chunk c ^ (r & 7); 16-column piece (64-byte rows, 64-byte swizzle): at chunk c ^ ((r >> 1) & 3).
         mbar_wait(G_FULL(g), (uint32_t)(k >> 1) & 1u);
         const uint32_t grow = g_base + (uint32_t)r * 128u;
 #pragma unroll
-        for (int j = 0; j < kTpad; j += 4) {
+        for (int j = 0; j < 64; j += 4) {
           const uint32_t a = grow + (uint32_t)(j >> 5) * kGPieceBytes + ((uint32_t)(((j >> 2) & 7) ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(dp[j]), "=f"(dp[j + 1]), "=f"(dp[j + 2]), "=f"(dp[j + 3]) : "r"(a) : "memory");
+        }
+#pragma unroll
+        for (int j = 64; j < kTpad; j += 4) {
+          const uint32_t a = g_base + 2 * kGPieceBytes + (uint32_t)r * 64u +
+                             ((uint32_t)(((j - 64) >> 2) ^ ((r >> 1) & 3)) << 4);
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(dp[j]), "=f"(dp[j + 1]), "=f"(dp[j + 2]), "=f"(dp[j + 3]) : "r"(a) : "memory");
         }
@@ -2008,8 +2019,9 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
           if (1024 + kv + extra + n * ring <= 226 * 1024) return n;
         return 0;
       };
-      // TMA-staged map-gradient tile: when its 48 KB leave at least three ring stages (d <= 128) and the rows can be
-      // described to the TMA (16-byte aligned base and strides, at most 96 columns); GA_K2_GSTAGE=0/1 forces it
+      // TMA-staged map-gradient tile (40 KB) whenever the rows can be described to the TMA (16-byte aligned base and
+      // strides, at most 80 columns) and two ring stages remain: d = 160 runs 242 us with two stages + the staged tile
+      // vs 278 us with three stages + per-thread loads (B = 512, N = 256); GA_K2_GSTAGE=0 turns it off for A/B runs
       static int g_mode = -2;
       if (g_mode == -2) {
         const char* eg = getenv("GA_K2_GSTAGE");
@@ -2017,13 +2029,14 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
       }
       sp.g_slots = 0;
       sp.g_batched = d_acc_bstride != 0 ? 1 : 0;
-      CUtensorMap mgr = mq;      // placeholder when the staged path is off (never dereferenced)
-      const bool g_ok = d_acc != nullptr && (d_acc_rstride & 3) == 0 && d_acc_rstride <= 96 && (d_acc_bstride & 3) == 0 &&
+      CUtensorMap mgr = mq, mgr16 = mq;      // placeholders when the staged path is off (never dereferenced)
+      const bool g_ok = d_acc != nullptr && (d_acc_rstride & 3) == 0 && d_acc_rstride <= kTpad && (d_acc_bstride & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(d_acc) & 15) == 0;
-      if (g_ok && g_mode != 0 && stages_for(kGSlotBytes) >= (g_mode == 1 ? 2 : 3)) {
-        if ((rc = make_map_rows_f32(&mgr, d_acc, d_acc_rstride, N, sp.g_batched ? B : 1,
-                                    sp.g_batched ? d_acc_bstride : (int64_t)N * d_acc_rstride, kM)) != GA_OK)
-          return rc;
+      if (g_ok && g_mode != 0 && stages_for(kGSlotBytes) >= 2) {
+        const int nb = sp.g_batched ? B : 1;
+        const int64_t bs = sp.g_batched ? d_acc_bstride : (int64_t)N * d_acc_rstride;
+        if ((rc = make_map_rows_f32(&mgr, d_acc, d_acc_rstride, N, nb, bs, 32, kM, CU_TENSOR_MAP_SWIZZLE_128B)) != GA_OK) return rc;
+        if ((rc = make_map_rows_f32(&mgr16, d_acc, d_acc_rstride, N, nb, bs, 16, kM, CU_TENSOR_MAP_SWIZZLE_64B)) != GA_OK) return rc;
         sp.g_slots = 1;
       }
       const size_t g_bytes = sp.g_slots ? (size_t)kGSlotBytes : 0;
@@ -2035,7 +2048,7 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
         if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);
         int teams_s = sm_count() / H;
         if (teams_s > p.units) teams_s = p.units;
-        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, mgr, sp);
+        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, mgr, mgr16, sp);
         return check_launch("cross_attn_bwd_tc_stream");
       }
     }

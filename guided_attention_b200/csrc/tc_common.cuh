@@ -328,20 +328,21 @@ static inline int make_map(CUtensorMap* map, const void* ptr, int dtype, int B, 
 }
 
 // (cols, rows, batches) view of fp32 rows with a row pitch of `cols` floats and a batch stride of `bstride` floats;
-// box = 32 columns x box_rows rows; 128-byte swizzle; out-of-range columns / rows are filled with zeros.
+// box = box_cols columns (box_cols * 4 bytes = the swizzle span) x box_rows rows; out-of-range columns / rows are
+// filled with zeros.
 static inline int make_map_rows_f32(CUtensorMap* map, const void* ptr, int cols, int rows, int batches, int64_t bstride,
-                                    int box_rows) {
+                                    int box_cols, int box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)bstride * 4};
-  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = CUDA_ERROR_INVALID_CONTEXT;
   for (int attempt = 0; attempt < 2 && r == CUDA_ERROR_INVALID_CONTEXT; ++attempt) {
     if (attempt == 1) cudaFree(nullptr);      // bind the primary context (see make_map)
     r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return fail(GA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 rows) failed (%d)", (int)r);
