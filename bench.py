@@ -518,9 +518,11 @@ def ncu_traffic(kernel, shape_key):
             continue
         with open(path) as f:
             rows = json.load(f)
-        for r in rows:
-            if r.get("bench_key") == [kernel, shape_key] and r.get("dram_traffic_bytes") is not None:
-                return float(r["dram_traffic_bytes"]), f"profiles/{name} (ncu --set full, same kernel and shape)"
+        # an op that is two kernels (large-launch tail forward, self-attention backward) has one row per kernel
+        hit = [float(r["dram_traffic_bytes"]) for r in rows
+               if r.get("bench_key") == [kernel, shape_key] and r.get("dram_traffic_bytes") is not None]
+        if hit:
+            return sum(hit), f"profiles/{name} (ncu --set full, same kernel and shape)"
     return None, None
 
 

@@ -1470,6 +1470,7 @@ struct BwdStreamParams {
 constexpr uint32_t kGPieceBytes = kM * 128;                  // 32 fp32 columns x 128 rows
 constexpr uint32_t kGSlotBytes = 2 * kGPieceBytes + kM * 64; // columns 0..31 | 32..63 | 64..79 (64-byte rows)
 
+template <bool kGStaged>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -1499,7 +1500,7 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
   auto TMEM_FREE = [&](int s) { return smem_u32(&bars[2 * kMaxStages + 13 + s]); };
   auto G_FULL = [&](int g) { return smem_u32(&bars[2 * kMaxStages + 16 + g]); };
   const uint32_t G_FREE = smem_u32(&bars[2 * kMaxStages + 18]);
-  const bool g_staged = sp.g_slots > 0 && p.d_acc != nullptr;
+  constexpr bool g_staged = kGStaged;       // (the host instantiates the staged kernel only with a map gradient)
   const uint32_t g_base = ring_base + (uint32_t)R * ring_stage_bytes;
   const int nT = p.tstages;
   const uint32_t stage_cols = nT == 3 ? 160u : (uint32_t)kStageCols;
@@ -1643,7 +1644,7 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
         }
         __syncwarp();
       }
-    } else if (g_staged) {
+    } else if (g_staged && warp == 15) {
       // ------------------------------------------------- map-gradient producer: one 128 x 80 fp32 tile per item
       for (int k = 0; k < n_items; ++k) {
         int b, h, tile;
@@ -1715,7 +1716,7 @@ cross_attn_bwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
       // its registers are dead again before the scores are loaded
       float dp[kTpad];
       const bool vec_acc = (p.d_acc_rstride & 3) == 0;
-      if (g_staged) {
+      if constexpr (g_staged) {
         // this thread's row of the TMA-staged tile.  32-column pieces (128-byte rows, 128-byte swizzle): chunk c of
         // row r sits at chunk c ^ (r & 7); 16-column piece (64-byte rows, 64-byte swizzle): at chunk c ^ ((r >> 1) & 3).
         mbar_wait(G_FULL(g), (uint32_t)(k >> 1) & 1u);
@@ -1986,7 +1987,11 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
   if ((rc = make_map(&mv, v, dtype, B, T, H, d, kTpad)) != GA_OK) return rc;
   const int nblk = (d + kBlockCols - 1) / kBlockCols, npv = (d + 15) & ~15;
   const int tiles = (N + kM - 1) / kM, units = B * H * tiles;
-  bool use_pipe = d <= 160 && units >= 2 * sm_count() && H <= sm_count();
+  // crossover measured on B200 (profiles/r02b_crossover_sweep.jsonl): without a map gradient the persistent kernel wins
+  // from ~2 items per SM; with one (TMA-staged tile vs per-thread row loads in the single-shot kernel) already at 256
+  // items (N = 1024 d = 80: 10.9 vs 12.3 us, N = 256 d = 160: 15.0 vs 21.3 us), a tie at 128
+  const int min_items = d_acc != nullptr ? (5 * sm_count()) / 4 : 2 * sm_count();
+  bool use_pipe = d <= 160 && units >= min_items && H <= sm_count();
   if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
   if (force_variant == 0) use_pipe = false;
   if (force_variant == 1) {
@@ -2043,12 +2048,13 @@ int bwd(const void* q, const void* k, const void* v, const float* lse, const voi
       sp.ring_stages = stages_for(g_bytes);
       if (sp.ring_stages >= 2) {
         const size_t smem_s = 1024 + kv + sp.ring_stages * ring + g_bytes;
-        cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_bwd_tc_stream_kernel), 5, smem_s);
+        auto kern = sp.g_slots ? cross_attn_bwd_tc_stream_kernel<true> : cross_attn_bwd_tc_stream_kernel<false>;
+        cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(kern), sp.g_slots ? 7 : 5, smem_s);
         if (es2 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(es2));
         if (H > sm_count()) return fail(GA_ERR_UNSUPPORTED, "pipelined cross-attention backward: %d heads", H);
         int teams_s = sm_count() / H;
         if (teams_s > p.units) teams_s = p.units;
-        cross_attn_bwd_tc_stream_kernel<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, mgr, mgr16, sp);
+        kern<<<teams_s * H, kPipeThreads, smem_s, st>>>(mq, mg, mk, mv, mgr, mgr16, sp);
         return check_launch("cross_attn_bwd_tc_stream");
       }
     }
