@@ -583,6 +583,47 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
   }
 }
 
+// Rows of the sparse backward: out[px][j] = -k dot[px] a[px][j - first] for the text columns, 0 elsewhere.  One warp per
+// pixel row, lanes over the padded output row (three slots: columns lane, lane + 32, lane + 64): every load and store
+// instruction of a warp covers one contiguous 128-byte span; four pixels per iteration keep 12 loads per lane in flight.
+// With compile-time row lengths (TP, RS, FIRST != 0: the Stable Diffusion shape) every access of an iteration is an
+// immediate offset from two base pointers: 13 warp-instructions per pixel instead of the 68 of the first version
+// (64-bit address arithmetic per access, per-slot token tests; ncu: 75 % of the kernel's instructions, issue slots 64 %).
+template <int TP, int RS, int FIRST>
+__device__ __forceinline__ void tail_bwd_rows(const float* a0, float* __restrict__ o0,
+                                              const float* __restrict__ sdot, float k, int n_own, int tp_rt, int rs_rt,
+                                              int first_rt) {
+  const int tp = TP ? TP : tp_rt, rs = RS ? RS : rs_rt, first = TP ? FIRST : first_rt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool rd[3], wr[3];
+#pragma unroll
+  for (int sl = 0; sl < 3; ++sl) {
+    const int j = lane + 32 * sl;
+    rd[sl] = j >= first && j < first + tp;
+    wr[sl] = j < rs;
+  }
+  constexpr int kPix = 4;
+  for (int px0 = warp * kPix; px0 < n_own; px0 += kWarps * kPix) {
+    const float* ar = a0 + px0 * tp + (lane - first);
+    float* orow = o0 + px0 * rs + lane;
+    float x[kPix][3];
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const bool live = TP ? true : (px0 + u < n_own);       // (the fixed-shape path is only taken with n_own % 4 == 0)
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) x[u][sl] = (live && rd[sl]) ? ar[u * tp + 32 * sl] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      if (!TP && px0 + u >= n_own) break;
+      const float nk = -k * sdot[px0 + u];
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl)
+        if (wr[sl]) orow[u * rs + 32 * sl] = nk * x[u][sl];
+    }
+  }
+}
+
 // Backward, fast path (no upstream gradient on attn_text -- every launch of the guided pipeline): the map gradient is
 // non-zero only in the tracked tokens' columns, so a row of d_abar is the attn_text row of the same pixel scaled by one
 // per-pixel scalar (-k * sum_t a[col_t] dA_t), with n_tokens entries patched.  The kernel is therefore a shifted,
@@ -592,16 +633,22 @@ tail_bwd_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ ma
 // the 3x3 filter adjoint); the per-token gradients dA_t are computed once per CTA, one thread per pixel; the streaming
 // phase gives every thread whole float4 chunks of the output (4 scalar loads, 4 multiplies, one 128-bit store).
 #ifndef GA_TAIL_BWD_MIN_CTAS
-#define GA_TAIL_BWD_MIN_CTAS 6
+#define GA_TAIL_BWD_MIN_CTAS 4
 #endif
+// (round 2, second pass) The tile's attn_text rows -- tile x 75 contiguous floats -- are fetched by ONE bulk copy
+// (cp.async.bulk global -> shared, mbarrier complete_tx) issued before anything else, so the stream is in flight while
+// phases 1-2 chase their small dependent loads; phase 2 and the row phase then read shared memory.  Before, a CTA's
+// global row loads only started after two __syncthreads (ncu: 40 % of the stall samples sat in phases 1-2 with the
+// memory pipe idle).
 __global__ void __launch_bounds__(kThreads, GA_TAIL_BWD_MIN_CTAS)
 tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restrict__ masks,
                        const float* __restrict__ weights, const float* __restrict__ attn_text,
                        const float* __restrict__ smoothed, const float* __restrict__ stats,
                        const int32_t* __restrict__ argmax, const float* __restrict__ g_total,
                        const float* __restrict__ g_stats, float* __restrict__ d_abar, int d_abar_rstride, int tile) {
-  extern __shared__ float sds[];            // [token][tile + 2 halo] d loss / d smoothed | [token][tile] dA | [tile] dot
+  extern __shared__ __align__(16) float srows[];   // [tile][tp] attn_text rows | sds (see below)
   __shared__ TokenGrad tg[GA_MAX_TOKENS];
+  __shared__ __align__(8) uint64_t rows_bar;
   const int res = p.res, npix = res * res, tp = p.last - p.first, nt = p.n_tokens;
   const int smp = blockIdx.y;
   attn_text += (int64_t)smp * npix * tp;
@@ -609,6 +656,20 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
   stats += (int64_t)smp * nt * GA_STATS;
   argmax += (int64_t)smp * nt;
   d_abar += (int64_t)smp * npix * d_abar_rstride;
+  float* sds = srows + tile * tp;           // [token][tile + 2 halo] d loss / d smoothed | [token][tile] dA | [tile] dot
+  {
+    const int p0b = blockIdx.x * tile, n_ownb = min(tile, npix - p0b);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&rows_bar);
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)n_ownb * tp * 4u;     // multiple of 16: npix % 4 == 0, tile % 4 == 0
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(srows)), "l"(attn_text + (int64_t)p0b * tp), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+  }
   if ((int)threadIdx.x < nt) {
     const int t = threadIdx.x;
     tg[t] = make_token_grad(p, toks.t[t], stats + (int64_t)t * GA_STATS, argmax[t],
@@ -635,6 +696,16 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
       sds[t * span + i] = dsmoothed_at(tg[t], q, y, x, res, masks, weights, smoothed + (int64_t)t * npix);
   }
   __syncthreads();
+  // the tile's rows have landed? (init + copy were issued by thread 0 before the first __syncthreads)
+  {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&rows_bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+      if (spin > (1u << 24)) __trap();       // a lost copy must fail the launch, not hang the GPU
+    }
+  }
   // phase 2: adjoint of the reflect-padded 3x3 filter (+ raw-map statistics) -> dA_t for the tile's own pixels, and
   // the per-pixel dot product sum_t a[col_t] dA_t in token order (same fma chain as the general kernel)
   for (int px = threadIdx.x; px < n_own; px += kThreads) {
@@ -669,7 +740,7 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
       if (g.r_gcol != 0.f || g.r_grow != 0.f || g.r_gsum != 0.f)
         dimg += g.r_gsum + (g.r_gcol * (((float)x + 0.5f) - g.r_col) + g.r_grow * (((float)y + 0.5f) - g.r_row)) * g.r_inv_sum;
       sdi[t * tile + px] = dimg;
-      dot = fmaf(__ldg(attn_text + (int64_t)pix * tp + g.column), dimg, dot);
+      dot = fmaf(srows[px * tp + g.column], dimg, dot);
     }
     sdot[px] = dot;
     if (has_dup) {          // tokens that share a column (never in practice): their gradients add up
@@ -682,48 +753,22 @@ tail_bwd_sparse_kernel(ga_tail_params_t p, TokArgs toks, const uint8_t* __restri
     }
   }
   __syncthreads();
-  // phase 3: the rows -- a shifted, scaled copy.  One warp per pixel, lanes over the padded output row (three
-  // slots: columns lane, lane + 32, lane + 64): every load and store instruction of a warp covers one contiguous
-  // 128-byte span; four pixels per iteration keep 12 loads per lane in flight.  Everything that does not depend on
-  // the pixel (slot predicates, the token that owns a slot's column, 32-bit offsets) is hoisted out of the loop.
+  // phase 3: the rows -- a shifted, scaled copy (see tail_bwd_rows) -- then the nt patched entries of every row
   const float k = p.temperature * p.inv_count;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  bool rd[3], wr[3];
-  int tok[3];               // tracked token that owns the column of this lane's slot (-1: none)
-#pragma unroll
-  for (int sl = 0; sl < 3; ++sl) {
-    const int j = lane + 32 * sl;
-    rd[sl] = j >= p.first && j < p.last;
-    wr[sl] = j < d_abar_rstride;
-    tok[sl] = -1;
-    for (int t = nt - 1; t >= 0; --t)
-      if (tg[t].column + p.first == j) tok[sl] = t;
-  }
-  const float* a0 = attn_text + (int64_t)p0 * tp - p.first + lane;        // element (px, slot) = a0[px * tp + 32 * slot]
-  float* o0 = d_abar + (int64_t)p0 * d_abar_rstride + lane;
-  constexpr int kPix = 4;
-  for (int px0 = warp * kPix; px0 < n_own; px0 += kWarps * kPix) {
-    float x[kPix][3];
-#pragma unroll
-    for (int u = 0; u < kPix; ++u) {
-      const float* ar = a0 + (px0 + u) * tp;
-      const bool live = px0 + u < n_own;
-#pragma unroll
-      for (int sl = 0; sl < 3; ++sl) x[u][sl] = (live && rd[sl]) ? __ldg(ar + 32 * sl) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < kPix; ++u) {
-      const int px = px0 + u;
-      if (px < n_own) {
-        const float dot = sdot[px], nk = -k * dot;
-        float* orow = o0 + px * d_abar_rstride;
-#pragma unroll
-        for (int sl = 0; sl < 3; ++sl) {
-          float val = nk * x[u][sl];
-          if (tok[sl] >= 0) val = k * x[u][sl] * (sda[tok[sl] * tile + px] - dot);   // k a (dA - dot)
-          if (wr[sl]) orow[32 * sl] = val;
-        }
-      }
+  const float* a0 = srows;
+  float* o0 = d_abar + (int64_t)p0 * d_abar_rstride;
+  if (tp == 75 && d_abar_rstride == 80 && p.first == 1 && (n_own & 3) == 0)
+    tail_bwd_rows<75, 80, 1>(a0, o0, sdot, k, n_own, tp, d_abar_rstride, p.first);      // SD: 77 tokens, text = [1, 76)
+  else
+    tail_bwd_rows<0, 0, 0>(a0, o0, sdot, k, n_own, tp, d_abar_rstride, p.first);
+  __syncthreads();          // the copy wrote (a scaled value into) the tracked columns too: order the patch after it
+  for (int px = threadIdx.x; px < n_own; px += kThreads) {
+    const float dot = sdot[px];
+    const float* arow = a0 + px * tp;
+    float* orow = o0 + (int64_t)px * d_abar_rstride + p.first;
+    for (int t = 0; t < nt; ++t) {
+      const int col = tg[t].column;
+      orow[col] = k * arow[col] * (sda[t * tile + px] - dot);                              // k a (dA - dot)
     }
   }
 }
@@ -950,17 +995,24 @@ extern "C" int ga_guidance_tail_bwd(const ga_tail_params_t* params_host, const g
   if (g_attn_text == nullptr && (d_abar_row_stride & 3) == 0) {
     // the pipeline's case: sparse map gradient.  Large launches give a CTA 256 pixels (a whole 16x16 map: no halo at
     // all); small ones 64, so that a single evaluation still spreads over a few SMs.
-    const int tile = 256;
+    static int tile_env = -1;
+    if (tile_env < 0) {
+      const char* e = getenv("GA_TAIL_BWD_TILE");
+      tile_env = e != nullptr ? atoi(e) : 0;
+    }
+    const int tile = tile_env > 0 ? (tile_env & ~3) : 128;
     const int nt = p.n_tokens > 0 ? p.n_tokens : 1;
-    const size_t smem = ((size_t)nt * (3 * tile + 2 * (p.res + 1)) + tile) * sizeof(float);
+    const int tp = p.last - p.first;
+    const size_t smem = ((size_t)tile * tp + (size_t)nt * (3 * tile + 2 * (p.res + 1)) + tile) * sizeof(float);
     // (small launches -- the pipeline's own single evaluation, small seed batches -- are latency-bound and stay on the
     // general kernel below, which spreads its 4-pixel groups over more CTAs: 4.4 vs 10 us at 1 sample, 6.2 vs 13.5 us
     // at 64; the crossover measured on B200 is ~400 samples at res 16: profiles/r02_microbench_tail_bwd.jsonl)
-    if (smem <= 48 * 1024 && (int64_t)p.n_samples * npix >= 96 * 1024) {
-      static bool carve_set = false;
-      if (!carve_set) {     // several CTAs per SM: ask for enough shared memory for 8 of them, keep the rest as L1
-        cudaFuncSetAttribute(tail::tail_bwd_sparse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
-        carve_set = true;
+    if (smem <= 100 * 1024 && (int64_t)p.n_samples * npix >= 96 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(tail::tail_bwd_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(tail::tail_bwd_sparse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr_set = true;
       }
       const dim3 grid((npix + tile - 1) / tile, p.n_samples);
       tail::tail_bwd_sparse_kernel<<<grid, tail::kThreads, smem, st>>>(p, toks, masks, weights, attn_text, smoothed,
