@@ -512,7 +512,7 @@ SATURATED_SHAPES = [("cross_attn", 1024, 80, True, 256), ("cross_attn", 256, 160
 def ncu_traffic(kernel, shape_key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summaries
     (tools/ncu_all.sh -> tools/ncu_summary.py), newest round first.  Returns (bytes | None, source | None)."""
-    for name in ("r02_ncu_summary.json", "r01_ncu_final_summary.json"):
+    for name in ("r02b_ncu_summary.json", "r02_ncu_summary.json", "r01_ncu_final_summary.json"):
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.isfile(path):
             continue

@@ -964,8 +964,10 @@ extern "C" int ga_guidance_tail_fwd(const float* const* acc_host, const int32_t*
     tail::tail_fwd_r_kernel<<<grid, tail::kThreads, 0, st>>>(acc, p, attn_text);
     int rc2 = check_launch("guidance_tail_fwd_r");
     if (rc2 != GA_OK) return rc2;
-    tail::tail_fwd_s_kernel<<<p.n_samples, tail::kThreads, smem, st>>>(p, toks, masks, weights, attn_text, smoothed,
-                                                                      stats, argmax, total);
+    // one warp per tracked token: a block of n_maps warps (3 for the usual prompts) keeps ~3x more samples resident
+    // per SM than 8-warp blocks with 5 idle warps (the per-token phase is latency-bound: strided column gathers)
+    tail::tail_fwd_s_kernel<<<p.n_samples, 32 * n_maps, smem, st>>>(p, toks, masks, weights, attn_text, smoothed,
+                                                                   stats, argmax, total);
     return check_launch("guidance_tail_fwd_s");
   }
   tail::tail_fwd_kernel<<<grid, tail::kThreads, smem, st>>>(acc, p, toks, masks, weights, attn_text, smoothed, stats,
