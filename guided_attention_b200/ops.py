@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -76,9 +77,49 @@ class _NoSpan:
 profiler: Optional[LaunchProfiler] = None
 _NOSPAN = _NoSpan()
 
+# NVTX ranges (tracing): with GA_NVTX=1 every launch made through this module sits in a range named
+# "ga::<kernel> <shape key>", and the pipeline adds "ga::denoise_step i" / "ga::image" ranges around them, so
+# `ncu --nvtx --nvtx-include "ga::cross_attn_fwd*/"` (or any NVTX-aware tool) can select one kernel or one denoising step
+# of a whole image.  Off by default: a range push/pop per launch is host time the eager path would pay for nothing.
+nvtx_enabled = os.environ.get("GA_NVTX", "0") == "1"
+
+
+class _NvtxSpan:
+    def __init__(self, label, inner):
+        self.label, self.inner = label, inner
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.label)
+        self.inner.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.inner.__exit__(*exc)
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx_range(label):
+    """Context manager: an NVTX range when GA_NVTX=1, nothing otherwise (used by the pipeline around steps / images)."""
+    return _NvtxSpan("ga::" + label, _NOSPAN) if nvtx_enabled else _NOSPAN
+
+
+def nvtx_push(label):
+    if nvtx_enabled:
+        torch.cuda.nvtx.range_push("ga::" + label)
+
+
+def nvtx_pop():
+    if nvtx_enabled:
+        torch.cuda.nvtx.range_pop()
+
 
 def _span(name, key, nbytes, device):
-    return profiler.span(name, key, nbytes, device) if profiler is not None else _NOSPAN
+    inner = profiler.span(name, key, nbytes, device) if profiler is not None else _NOSPAN
+    if nvtx_enabled:
+        return _NvtxSpan("ga::%s %s" % (name, "x".join(str(k) for k in key) if isinstance(key, (tuple, list)) else key),
+                         inner)
+    return inner
 
 
 def attn_fwd_bytes(B, H, N, T, d, esize, with_acc):

@@ -715,6 +715,9 @@ class GuidedAttention(StableDiffusionPipelineBase):
         cfg = state.config
         for i, t in enumerate(timesteps):
             t = int(t)
+            if i:
+                ops.nvtx_pop()
+            ops.nvtx_push("denoise_step %d (host-driven graphs)" % i)
             for recurse_step in range(0, recurse_steps):
                 did_we_update = False
                 state.cur_time_step_iter = i
@@ -759,6 +762,8 @@ class GuidedAttention(StableDiffusionPipelineBase):
                     break
                 if recurse_step != (recurse_steps - 1):
                     latents = self._renoise(latents, t, renoise_gen)
+        if len(timesteps):
+            ops.nvtx_pop()
         return latents
 
     # ------------------------------------------------------------------------------- device-side control (f3)
@@ -822,7 +827,7 @@ class GuidedAttention(StableDiffusionPipelineBase):
             if prev_t > 0:
                 Bt = float(self.scheduler.alphas_cumprod[t] / self.scheduler.alphas_cumprod[prev_t])
                 p.renoise[0], p.renoise[1] = Bt ** 0.5, (1 - Bt) ** 0.5
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), ops.nvtx_range("denoise_step %d (device control)" % i):
                 if p.check:
                     abi.check(lib.ga_step_driver_run(drv, C.byref(p), stream), "ga_step_driver_run")
                 else:
@@ -1088,6 +1093,9 @@ class GuidedAttention(StableDiffusionPipelineBase):
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 t = int(t)
+                if i:
+                    ops.nvtx_pop()
+                ops.nvtx_push("denoise_step %d (eager)" % i)
                 for recurse_step in range(0, recurse_steps):
                     did_we_update = False
                     state.cur_time_step_iter = i
@@ -1139,6 +1147,8 @@ class GuidedAttention(StableDiffusionPipelineBase):
                         break
                     if recurse_step != (recurse_steps - 1):
                         latents = self._renoise(latents, t, renoise_gen)
+            if len(timesteps):
+                ops.nvtx_pop()
 
         latents = latents.detach()
         has_nsfw_concept = False
