@@ -1,0 +1,481 @@
+// Fused GroupNorm (+ SiLU) forward / backward for channels-last 16-bit activations (sm_100a).
+//
+// Why it is here: the guidance path differentiates the loss with respect to the LATENTS, so every guided step runs the
+// UNet forward AND backward (reference pipeline_guided_attention.py:455-470 `_update_latent`, :583-743 the UNet forward
+// the pipeline drives).  In the launch list of a guided image (profiles/r02b_ncu_launches_summary.txt) the GroupNorm
+// of the ResNet / transformer blocks is the largest non-GEMM item: PyTorch runs it as RowwiseMoments (one CTA per
+// (sample, group): 32 CTAs on 148 SMs at batch 1, 26 us) + ComputeFusedParams + an elementwise kernel + a separate
+// SiLU, and five more kernels in the backward -- 27 % of the device time of an image.  Here one GroupNorm(+SiLU) is two
+// launches per direction, each spread over the whole GPU, HBM/L2-bound byte work:
+//
+//   stats kernel   grid (pixel chunks, channel slices, samples).  A thread owns one 8-channel vector (128-bit loads,
+//                  coalesced along the channel axis of the NHWC tensor) and walks the pixels of its chunk, per-channel
+//                  sums in registers; per-group partials are combined in a FIXED order through shared memory and written
+//                  as (mean, M2) of the chunk.
+//   apply kernel   same decomposition.  Prologue: every CTA merges the <= 128 chunk partials of the groups of ITS slice
+//                  with Chan's parallel-variance update, one warp per group, all loads issued before the first merge,
+//                  fixed order: bit-stable run to run (the repo's multi-GPU sweep is an equality test), no atomics, no
+//                  grid-wide hand-off (a first version let the last CTA of the stats kernel merge everything: its
+//                  serial tail grew with the batch, 85 us at 8 samples).  Then y = silu(x * a + b) with
+//                  a = rstd * gamma, b = beta - mean * a per channel.
+//   backward       the same two-launch shape: partial sums of  dxh = dz * gamma  and  dxh * xhat  per (sample, group)
+//                  (dz = dy * silu'(z), z recomputed from x), then
+//                  dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)).
+// The second launch of each direction re-reads x (and dy) from L2 (the largest activation of an SD UNet is 7.9 MB).
+// Statistics are fp32; the affine parameters are read in the activation dtype.  d gamma / d beta are not produced (the
+// UNet is frozen on the guidance path: ptp_utils.register_attention_control).
+#include "ga_common.cuh"
+
+namespace ga {
+namespace gn {
+
+constexpr int kThreads = 256;
+
+struct Params {
+  const void* x;
+  const void* dy;
+  const void* gamma;
+  const void* beta;
+  void* out;              // y (forward) or dx (backward)
+  float* stats;           // [n][groups][2] = mean, rstd
+  float* ws;              // chunk partials [n][P][groups][2]: (mean, M2) forward, (sum dxh, sum dxh * xhat) backward
+  int n, hw, c, groups, cpg;
+  int cs;                 // channel slices per pixel (grid.y); a slice holds whole groups
+  int vs;                 // 8-channel vectors per slice (<= kThreads)
+  int pl;                 // pixel lanes = kThreads / vs
+  int chunk;              // pixels per CTA
+  int P;                  // chunks (grid.x)
+  float eps;
+};
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& w, float* f) {
+  const float2 a = Word<T>::unpack(w.x), b = Word<T>::unpack(w.y), c = Word<T>::unpack(w.z), d = Word<T>::unpack(w.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+template <typename T> __device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(Word<T>::pack(f[0], f[1]), Word<T>::pack(f[2], f[3]), Word<T>::pack(f[4], f[5]),
+                    Word<T>::pack(f[6], f[7]));
+}
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
+// A thread's coordinates: which 8-channel vector of which slice, which pixel lane.
+struct Coord {
+  int n, c0, pl, p0, p1;
+  bool active;
+  __device__ __forceinline__ void init(const Params& p) {
+    const int tid = threadIdx.x;
+    pl = tid / p.vs;
+    const int v = tid - pl * p.vs;
+    active = pl < p.pl;
+    n = blockIdx.z;
+    c0 = ((int)blockIdx.y * p.vs + v) * 8;
+    p0 = (int)blockIdx.x * p.chunk;
+    p1 = min(p0 + p.chunk, p.hw);
+  }
+};
+
+// Per-channel sums of a thread -> per-group sums of the CTA's slice, fixed order.  A vector touches at most two groups
+// (checked on the host): the first `k` elements belong to group c0 / cpg, the rest to the next one.
+__device__ __forceinline__ void group_partials(const Params& p, const Coord& t, const float* s, const float* q,
+                                               float4* part, float& S, float& Q, int& g_out, bool& owner) {
+  const int g0 = t.c0 / p.cpg;
+  const int k = min(8, (g0 + 1) * p.cpg - t.c0);
+  float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e < k) { sA += s[e]; qA += q[e]; } else { sB += s[e]; qB += q[e]; }
+  }
+  part[threadIdx.x] = t.active ? make_float4(sA, qA, sB, qB) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int gps = p.groups / p.cs;
+  owner = (int)threadIdx.x < gps;
+  S = 0.f; Q = 0.f; g_out = 0;
+  if (owner) {
+    const int slice_c0 = (int)blockIdx.y * p.vs * 8;
+    const int g = (int)blockIdx.y * gps + (int)threadIdx.x;
+    const int v_lo = (g * p.cpg - slice_c0) >> 3, v_hi = ((g + 1) * p.cpg - 1 - slice_c0) >> 3;
+    for (int l = 0; l < p.pl; ++l)
+      for (int v = v_lo; v <= v_hi; ++v) {
+        const int gv = (slice_c0 + v * 8) / p.cpg;
+        const float4 w = part[l * p.vs + v];
+        if (gv == g) { S += w.x; Q += w.y; } else if (gv + 1 == g) { S += w.z; Q += w.w; }
+      }
+    g_out = g;
+  }
+}
+
+constexpr int kMaxChunks = 128;       // chunk partials per (sample, group): four per lane of the merging warp
+constexpr int kMaxSliceGroups = 256;  // groups one CTA's slice may hold
+
+// Prologue of the apply kernels: (mean, rstd) of every group of this CTA's slice from the chunk partials (mean, M2).
+__device__ __forceinline__ void merge_stats(const Params& p, float2* sst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gps = p.groups / p.cs, n = blockIdx.z;
+  for (int gl = warp; gl < gps; gl += kThreads / 32) {
+    const int g = (int)blockIdx.y * gps + gl;
+    float2 w[kMaxChunks / 32];
+#pragma unroll
+    for (int i = 0; i < kMaxChunks / 32; ++i) {
+      const int ch = lane + 32 * i;
+      w[i] = ch < p.P ? __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g)
+                      : make_float2(0.f, 0.f);
+    }
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks / 32; ++i) {
+      const int ch = lane + 32 * i;
+      if (ch < p.P) {
+        const float cb = (float)((min((ch + 1) * p.chunk, p.hw) - ch * p.chunk) * p.cpg);
+        const float tot = cnt + cb, delta = w[i].x - mean, f = cb / tot;
+        mean = fmaf(delta, f, mean);
+        m2 += w[i].y + delta * delta * cnt * f;
+        cnt = tot;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float cb = __shfl_down_sync(0xffffffffu, cnt, off);
+      const float mb = __shfl_down_sync(0xffffffffu, mean, off);
+      const float qb = __shfl_down_sync(0xffffffffu, m2, off);
+      if (cb > 0.f) {
+        const float tot = cnt + cb, delta = mb - mean, f = cb / tot;
+        mean = fmaf(delta, f, mean);
+        m2 += qb + delta * delta * cnt * f;
+        cnt = tot;
+      }
+    }
+    if (lane == 0) {
+      const float2 st = make_float2(mean, rsqrtf(m2 / cnt + p.eps));
+      sst[gl] = st;
+      if (blockIdx.x == 0) reinterpret_cast<float2*>(p.stats)[n * p.groups + g] = st;   // kept for the backward
+    }
+  }
+  __syncthreads();
+}
+
+// Prologue of the backward apply kernel: mean(dxh), mean(dxh * xhat) of every group of the slice (plain sums).
+__device__ __forceinline__ void merge_sums(const Params& p, float2* scf) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gps = p.groups / p.cs, n = blockIdx.z;
+  const float inv_m = 1.f / ((float)p.hw * (float)p.cpg);
+  for (int gl = warp; gl < gps; gl += kThreads / 32) {
+    const int g = (int)blockIdx.y * gps + gl;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks / 32; ++i) {
+      const int ch = lane + 32 * i;
+      if (ch < p.P) {
+        const float2 w = __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g);
+        s1 += w.x;
+        s2 += w.y;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s1 += __shfl_down_sync(0xffffffffu, s1, off);
+      s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) scf[gl] = make_float2(s1 * inv_m, s2 * inv_m);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------- forward: stats
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const Params p) {
+  __shared__ float4 part[kThreads];
+  Coord t;
+  t.init(p);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  if (t.active) {
+    const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + ((int64_t)t.n * p.hw) * p.c + t.c0);
+    const int64_t stride = (int64_t)p.c / 8;
+#pragma unroll 4
+    for (int px = t.p0 + t.pl; px < t.p1; px += p.pl) {
+      float f[8];
+      unpack8<T>(__ldg(xp + px * stride), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
+  }
+  float S, Q;
+  int g;
+  bool owner;
+  group_partials(p, t, s, q, part, S, Q, g, owner);
+  if (owner) {
+    const float cnt = (float)((t.p1 - t.p0) * p.cpg);
+    const float mean = cnt > 0.f ? S / cnt : 0.f;
+    const float m2 = fmaxf(Q - S * mean, 0.f);
+    float* w = p.ws + (((int64_t)t.n * p.P + blockIdx.x) * p.groups + g) * 2;
+    w[0] = mean;
+    w[1] = m2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- forward: apply
+template <typename T, bool kSilu>
+__global__ void __launch_bounds__(kThreads) gn_apply_kernel(const Params p) {
+  __shared__ float2 sst[kMaxSliceGroups];
+  Coord t;
+  t.init(p);
+  merge_stats(p, sst);
+  if (!t.active) return;
+  float a[8], b[8];
+  {
+    float gm[8], bt[8];
+    const int g_first = (int)blockIdx.y * (p.groups / p.cs);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 st = sst[(t.c0 + e) / p.cpg - g_first];
+      a[e] = st.y * gm[e];
+      b[e] = fmaf(-st.x, a[e], bt[e]);
+    }
+  }
+  const int64_t base = ((int64_t)t.n * p.hw) * p.c + t.c0;
+  const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + base);
+  uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + base);
+  const int64_t stride = (int64_t)p.c / 8;
+#pragma unroll 4
+  for (int px = t.p0 + t.pl; px < t.p1; px += p.pl) {
+    float f[8];
+    unpack8<T>(__ldg(xp + px * stride), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float z = fmaf(f[e], a[e], b[e]);
+      f[e] = kSilu ? z * sigmoidf_fast(z) : z;
+    }
+    yp[px * stride] = pack8<T>(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: sums
+template <typename T, bool kSilu>
+__global__ void __launch_bounds__(kThreads) gn_bwd_sums_kernel(const Params p) {
+  __shared__ float4 part[kThreads];
+  Coord t;
+  t.init(p);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  if (t.active) {
+    float a[8], b[8], gm[8], r[8], mr[8];
+    {
+      float bt[8];
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = (t.c0 + e) / p.cpg;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + t.n * p.groups + g);
+        r[e] = st.y;
+        mr[e] = st.x * st.y;
+        a[e] = st.y * gm[e];
+        b[e] = fmaf(-st.x, a[e], bt[e]);
+      }
+    }
+    const int64_t base = ((int64_t)t.n * p.hw) * p.c + t.c0;
+    const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + base);
+    const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dy) + base);
+    const int64_t stride = (int64_t)p.c / 8;
+#pragma unroll 2
+    for (int px = t.p0 + t.pl; px < t.p1; px += p.pl) {
+      float f[8], d[8];
+      unpack8<T>(__ldg(xp + px * stride), f);
+      unpack8<T>(__ldg(gp + px * stride), d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float dz = d[e];
+        if (kSilu) {
+          const float z = fmaf(f[e], a[e], b[e]);
+          const float sg = sigmoidf_fast(z);
+          dz *= sg * fmaf(z, 1.f - sg, 1.f);
+        }
+        const float dxh = dz * gm[e];
+        const float xh = fmaf(f[e], r[e], -mr[e]);
+        s[e] += dxh;
+        q[e] = fmaf(dxh, xh, q[e]);
+      }
+    }
+  }
+  float S, Q;
+  int g;
+  bool owner;
+  group_partials(p, t, s, q, part, S, Q, g, owner);
+  if (owner) {
+    float* w = p.ws + (((int64_t)t.n * p.P + blockIdx.x) * p.groups + g) * 2;
+    w[0] = S;
+    w[1] = Q;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- backward: apply
+template <typename T, bool kSilu>
+__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const Params p) {
+  __shared__ float2 scf[kMaxSliceGroups];
+  Coord t;
+  t.init(p);
+  merge_sums(p, scf);
+  if (!t.active) return;
+  float a[8], b[8], gr[8], r[8], mr[8], k1[8], k2[8];
+  {
+    float gm[8], bt[8];
+    const int g_first = (int)blockIdx.y * (p.groups / p.cs);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (t.c0 + e) / p.cpg;
+      const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + t.n * p.groups + g);
+      const float2 cf = scf[g - g_first];
+      r[e] = st.y;
+      mr[e] = st.x * st.y;
+      a[e] = st.y * gm[e];
+      b[e] = fmaf(-st.x, a[e], bt[e]);
+      gr[e] = gm[e] * st.y;
+      k1[e] = cf.x * st.y;
+      k2[e] = cf.y * st.y;
+    }
+  }
+  const int64_t base = ((int64_t)t.n * p.hw) * p.c + t.c0;
+  const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + base);
+  const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dy) + base);
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + base);
+  const int64_t stride = (int64_t)p.c / 8;
+#pragma unroll 2
+  for (int px = t.p0 + t.pl; px < t.p1; px += p.pl) {
+    float f[8], d[8];
+    unpack8<T>(__ldg(xp + px * stride), f);
+    unpack8<T>(__ldg(gp + px * stride), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = d[e];
+      if (kSilu) {
+        const float z = fmaf(f[e], a[e], b[e]);
+        const float sg = sigmoidf_fast(z);
+        dz *= sg * fmaf(z, 1.f - sg, 1.f);
+      }
+      const float xh = fmaf(f[e], r[e], -mr[e]);
+      f[e] = fmaf(dz, gr[e], -k1[e]) - xh * k2[e];
+    }
+    op[px * stride] = pack8<T>(f);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------- host
+// Decomposition of one (n, hw, c) tensor with `groups` groups; false when the shape is outside what the kernels assume.
+static bool plan(Params& p, int n, int hw, int c, int groups) {
+  if (n < 1 || hw < 1 || c < 8 || groups < 1 || c % groups != 0 || c % 8 != 0) return false;
+  if ((int64_t)n * groups > (1 << 20)) return false;
+  p.n = n; p.hw = hw; p.c = c; p.groups = groups; p.cpg = c / groups;
+  const int V = c / 8;
+  int cs = (V + kThreads - 1) / kThreads;
+  while (cs <= groups && (groups % cs != 0 || V % cs != 0 || ((V / cs) * 8) % p.cpg != 0 || V / cs > kThreads)) ++cs;
+  if (cs > groups) return false;
+  p.cs = cs;
+  p.vs = V / cs;
+  p.pl = kThreads / p.vs;
+  for (int v = 0; v < V; ++v)                      // a vector may touch at most two groups
+    if ((v * 8 + 7) / p.cpg - (v * 8) / p.cpg > 1) return false;
+  int chunk = (hw + 127) / 128;
+  if (chunk < p.pl) chunk = p.pl;
+  if (chunk > hw) chunk = hw;
+  p.chunk = chunk;
+  p.P = (hw + chunk - 1) / chunk;
+  if (p.P > kMaxChunks || groups / cs > kMaxSliceGroups || n > 65535 || cs > 65535) return false;
+  return true;
+}
+
+int64_t ws_bytes(int n, int hw, int c, int groups) {
+  Params p;
+  if (!plan(p, n, hw, c, groups)) return -1;
+  return (int64_t)n * p.P * groups * 2 * (int64_t)sizeof(float);
+}
+
+template <typename T>
+static void launch_fwd(const Params& p, bool silu, cudaStream_t st) {
+  const dim3 grid(p.P, p.cs, p.n);
+  gn_stats_kernel<T><<<grid, kThreads, 0, st>>>(p);
+  if (silu) gn_apply_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
+  else gn_apply_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
+}
+template <typename T>
+static void launch_bwd(const Params& p, bool silu, cudaStream_t st) {
+  const dim3 grid(p.P, p.cs, p.n);
+  if (silu) {
+    gn_bwd_sums_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
+    gn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
+  } else {
+    gn_bwd_sums_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
+    gn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
+  }
+}
+
+int fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
+        int hw, int c, int groups, float eps, int silu, int dtype, cudaStream_t st) {
+  Params p;
+  if (!plan(p, n, hw, c, groups))
+    return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
+  p.x = x; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.out = y; p.stats = stats; p.ws = ws;
+  p.eps = eps;
+  if (dtype == GA_F16) launch_fwd<__half>(p, silu != 0, st);
+  else launch_fwd<__nv_bfloat16>(p, silu != 0, st);
+  return check_launch("group_norm_fwd");
+}
+
+int bwd(const void* x, const void* dy, const void* gamma, const void* beta, const float* stats, void* dx, float* ws,
+        int n, int hw, int c, int groups, int silu, int dtype, cudaStream_t st) {
+  Params p;
+  if (!plan(p, n, hw, c, groups))
+    return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
+  p.x = x; p.dy = dy; p.gamma = gamma; p.beta = beta; p.out = dx; p.stats = const_cast<float*>(stats); p.ws = ws;
+  p.eps = 0.f;
+  if (dtype == GA_F16) launch_bwd<__half>(p, silu != 0, st);
+  else launch_bwd<__nv_bfloat16>(p, silu != 0, st);
+  return check_launch("group_norm_bwd");
+}
+
+}  // namespace gn
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int64_t ga_group_norm_ws_bytes(int n, int hw, int channels, int groups) {
+  return gn::ws_bytes(n, hw, channels, groups);
+}
+
+static int check_gn_args(const void* x, const void* gamma, const void* beta, const void* out, const void* stats,
+                         const void* ws, int dtype) {
+  GA_CHECK_ARG(x && gamma && beta && out && stats && ws, "NULL operand");
+  GA_CHECK_ARG(dtype == GA_F16 || dtype == GA_BF16, "group norm: 16-bit activations only (dtype %d)", dtype);
+  GA_CHECK_ALIGN(x, 16, "x");
+  GA_CHECK_ALIGN(out, 16, "output");
+  GA_CHECK_ALIGN(gamma, 16, "gamma");
+  GA_CHECK_ALIGN(beta, 16, "beta");
+  GA_CHECK_ALIGN(stats, 8, "stats");
+  GA_CHECK_ALIGN(ws, 8, "ws");
+  return GA_OK;
+}
+
+extern "C" int ga_group_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, float* ws,
+                                 int n, int hw, int channels, int groups, float eps, int silu,
+                                 int dtype, ga_stream_t stream) {
+  int rc = check_gn_args(x, gamma, beta, y, stats, ws, dtype);
+  if (rc != GA_OK) return rc;
+  return gn::fwd(x, gamma, beta, y, stats, ws, n, hw, channels, groups, eps, silu, dtype,
+                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ga_group_norm_bwd(const void* x, const void* d_y, const void* gamma, const void* beta, const float* stats,
+                                 void* d_x, float* ws, int n, int hw, int channels, int groups,
+                                 int silu, int dtype, ga_stream_t stream) {
+  int rc = check_gn_args(x, gamma, beta, d_x, stats, ws, dtype);
+  if (rc != GA_OK) return rc;
+  GA_CHECK_ARG(d_y != nullptr, "NULL operand");
+  GA_CHECK_ALIGN(d_y, 16, "d_y");
+  return gn::bwd(x, d_y, gamma, beta, stats, d_x, ws, n, hw, channels, groups, silu, dtype,
+                 static_cast<cudaStream_t>(stream));
+}

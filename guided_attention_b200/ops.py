@@ -393,6 +393,75 @@ def attention_probs(q, k, heads: int, scale: float, bias=None):
     return p
 
 
+# ================================================================================= GroupNorm (+ SiLU) of the UNet
+_gn_plan_cache = {}   # (n, hw, c, groups) -> workspace bytes (-1: unsupported shape)
+
+
+def group_norm_ws_bytes(n: int, hw: int, c: int, groups: int) -> int:
+    key = (n, hw, c, groups)
+    if key not in _gn_plan_cache:
+        _gn_plan_cache[key] = int(abi.load().ga_group_norm_ws_bytes(n, hw, c, groups))
+    return _gn_plan_cache[key]
+
+
+def group_norm_supported(x: torch.Tensor, weight, bias, groups: int) -> bool:
+    """The fused kernels take channels-last-able 4-D CUDA activations in fp16 / bf16 with frozen affine parameters."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16)):
+        return False
+    if weight is None or bias is None or weight.requires_grad or bias.requires_grad:
+        return False
+    n, c, h, w = x.shape
+    return group_norm_ws_bytes(n, h * w, c, groups) >= 0
+
+
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups: int, eps: float, silu: bool):
+        _need_cuda(x, weight, bias)
+        lib = abi.load()
+        x = x.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        if weight.dtype != x.dtype:
+            weight, bias = weight.to(x.dtype), bias.to(x.dtype)
+        weight, bias = weight.contiguous(), bias.contiguous()
+        y = torch.empty_like(x)                       # keeps the channels-last strides
+        stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+        ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
+        nbytes = 3 * x.numel() * x.element_size()     # x read twice (the second time from L2), y written
+        with torch.cuda.device(x.device), _span("group_norm_fwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
+            abi.check(lib.ga_group_norm_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats), _ptr(ws),
+                                            n, h * w, c, groups, float(eps), int(silu),
+                                            _DTYPES[x.dtype], _stream(x)), "ga_group_norm_fwd")
+        _count("group_norm_fwd", 2)
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.meta = (groups, bool(silu))
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, weight, bias, stats = ctx.saved_tensors
+        groups, silu = ctx.meta
+        lib = abi.load()
+        n, c, h, w = x.shape
+        d_y = d_y.contiguous(memory_format=torch.channels_last)
+        d_x = torch.empty_like(x)
+        ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
+        nbytes = 5 * x.numel() * x.element_size()
+        with torch.cuda.device(x.device), _span("group_norm_bwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
+            abi.check(lib.ga_group_norm_bwd(_ptr(x), _ptr(d_y), _ptr(weight), _ptr(bias), _ptr(stats), _ptr(d_x),
+                                            _ptr(ws), n, h * w, c, groups, int(silu),
+                                            _DTYPES[x.dtype], _stream(x)), "ga_group_norm_bwd")
+        _count("group_norm_bwd", 2)
+        return d_x, None, None, None, None, None
+
+
+def group_norm(x, weight, bias, groups: int, eps: float = 1e-5, silu: bool = False):
+    """`silu(GroupNorm(x))` (or plain GroupNorm) on a (n, C, h, w) fp16 / bf16 CUDA tensor, computed on its channels-last
+    layout (a channels-first input is converted once): two launches forward, two backward, differentiable in x only.
+    Replaces `torch.nn.GroupNorm` (+ `F.silu`) inside the UNet the guidance path runs forward and backward."""
+    return _GroupNormFn.apply(x, weight, bias, int(groups), float(eps), bool(silu))
+
+
 # ============================================================================================== K5 rasteriser
 def rasterize_boxes(boxes: Sequence[Sequence[float]], res: int, shrink: float, device) -> torch.Tensor:
     """(n, res, res) uint8 masks of `helpers.inside_box` for unit-square boxes (x, y, w, h); bit-exact vs the host."""

@@ -20,6 +20,7 @@ Same public names, signatures and bookkeeping (`register_attention_control`, `At
 from __future__ import annotations
 
 import abc
+import os
 from typing import List
 
 import torch
@@ -302,6 +303,41 @@ def register_attention_control(model, controller):
     # be bypassed.  Freezing the weights does not change any value the reference computes.
     if hasattr(model.unet, "requires_grad_"):
         model.unet.requires_grad_(False)
+    register_fused_norms(model.unet)
+
+
+def _fused_silu_norm(norm, x):
+    if ops.group_norm_supported(x, norm.weight, norm.bias, norm.num_groups):
+        return ops.group_norm(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=True)
+    return torch.nn.functional.silu(norm(x))
+
+
+def register_fused_norms(unet) -> int:
+    """Routes the UNet's `nn.GroupNorm` layers (ResNet blocks, transformer wrappers, `conv_norm_out`) through the fused
+    channels-last kernels of `ops.group_norm` whenever the activation is a 16-bit CUDA tensor and the affine parameters
+    are frozen; anything else (fp32, CPU, trainable norms) keeps PyTorch's own op.  Blocks that expose a
+    `fused_norm_act` hook (the substrate's ResnetBlock2D: norm -> SiLU -> conv) get the SiLU folded into the same
+    launch.  The guided loop runs the UNet forward and backward ~250 times per image and these norms were the largest
+    non-GEMM item of its launch list (csrc/group_norm.cu).  Idempotent; `GA_FUSED_NORM=0` leaves the UNet untouched
+    (A/B measurements).  Returns the number of norm layers now routed."""
+    if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
+        return 0
+    n = 0
+    for m in unet.modules():
+        if isinstance(m, torch.nn.GroupNorm):
+            if not getattr(m, "_ga_fused", False):
+                stock = m.forward
+
+                def forward(x, _m=m, _stock=stock):
+                    if ops.group_norm_supported(x, _m.weight, _m.bias, _m.num_groups):
+                        return ops.group_norm(x, _m.weight, _m.bias, _m.num_groups, _m.eps, silu=False)
+                    return _stock(x)
+                m.forward = forward
+                m._ga_fused = True
+            n += 1
+        elif hasattr(m, "fused_norm_act"):
+            m.fused_norm_act = _fused_silu_norm
+    return n
 
 
 class AttentionControl(abc.ABC):

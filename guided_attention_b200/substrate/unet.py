@@ -220,11 +220,19 @@ class ResnetBlock2D(nn.Module):
         self.norm2 = nn.GroupNorm(groups, out_ch, eps=1e-5)
         self.conv2 = nn.Conv2d(out_ch, out_ch, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(in_ch, out_ch, 1) if in_ch != out_ch else None
+        # hook for a fused `silu(norm(x))` (callable(norm_module, x) -> tensor); None = the two stock ops.  Installed by
+        # the product path (`ptp_utils.register_fused_norms`), never by the oracle.
+        self.fused_norm_act = None
+
+    def _norm_act(self, norm, x):
+        if self.fused_norm_act is not None:
+            return self.fused_norm_act(norm, x)
+        return F.silu(norm(x))
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv1(self._norm_act(self.norm1, x))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv2(self._norm_act(self.norm2, h))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 5
+#define GA_ABI_VERSION 6
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -291,6 +291,25 @@ int ga_box_loss_fwd(const float* p, const uint8_t* mask, const float* weights, i
                     ga_stream_t stream);
 int ga_box_loss_bwd(const float* p, const uint8_t* mask, const float* weights, int res, int strict,
                     const float* g_out2, float* g_p, ga_stream_t stream);
+
+/* ---- the caller either side of the attention layers: GroupNorm (+ SiLU) of the UNet blocks -------------------------
+ * The guidance path runs the UNet forward AND backward on every guided step (pipeline_guided_attention.py:455-470
+ * `_update_latent`; the UNet forward the pipeline drives: :583-743); the norms of its ResNet / transformer blocks
+ * (diffusers `ResnetBlock2D`: norm1 -> SiLU -> conv1, norm2 -> SiLU -> conv2; `Transformer2DModel.norm`) are
+ * `torch.nn.GroupNorm(32, C)` on (n, C, h, w) activations.  These entry points replace that op pair for CHANNELS-LAST
+ * 16-bit activations: x, y, d_y, d_x are (n, hw, channels) dense (NHWC memory), gamma / beta (channels) in the same
+ * dtype, `stats` (n, groups, 2) fp32 = (mean, rstd) written by the forward and read by the backward.
+ *   y = act(GroupNorm(x)),  act = SiLU when `silu` != 0, identity otherwise;   d_x = d loss / d x  (no d gamma / d beta:
+ *   the UNet is frozen on the guidance path).
+ * `ws`: scratch of ga_group_norm_ws_bytes() bytes (contents irrelevant on entry, per call in flight).  Two launches per
+ * call, no atomics: results are bit-stable run to run.
+ * ga_group_norm_ws_bytes returns -1 when the shape is not supported (channels % 8, channels % groups, a group
+ * narrower than the kernels' 8-channel vectors allow). */
+int64_t ga_group_norm_ws_bytes(int n, int hw, int channels, int groups);
+int ga_group_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
+                      int hw, int channels, int groups, float eps, int silu, int dtype, ga_stream_t stream);
+int ga_group_norm_bwd(const void* x, const void* d_y, const void* gamma, const void* beta, const float* stats, void* d_x,
+                      float* ws, int n, int hw, int channels, int groups, int silu, int dtype, ga_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -158,7 +158,7 @@ def test_meets_threshold_truth_table(kat):
 def test_library_exports_every_declared_symbol():
     """No compute calls here (no GPU): the library loads and exports exactly what include/guided_attn.h declares."""
     header = open(os.path.join(ROOT, "include", "guided_attn.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(ga_\w+)\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(ga_\w+)\(", header, flags=re.M))
     assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
     lib = _cabi.load()
     for name in declared:
