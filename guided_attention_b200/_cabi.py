@@ -92,8 +92,9 @@ PROTOTYPES = {
     "ga_box_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ga_box_loss_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ga_group_norm_ws_bytes": (_i64, [_i, _i, _i, _i]),
-    "ga_group_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
-    "ga_group_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ga_group_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_group_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ga_add_bias_residual": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
 }
 
 _lib = None

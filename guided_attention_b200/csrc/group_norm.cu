@@ -13,7 +13,7 @@
 //                  sums in registers; per-group partials are combined in a FIXED order through shared memory and written
 //                  as (mean, M2) of the chunk.
 //   apply kernel   same decomposition.  Prologue: every CTA merges the <= 128 chunk partials of the groups of ITS slice
-//                  with Chan's parallel-variance update, one warp per group, all loads issued before the first merge,
+//                  with Chan's parallel-variance update, 8-32 threads per group, all loads issued before the first merge,
 //                  fixed order: bit-stable run to run (the repo's multi-GPU sweep is an equality test), no atomics, no
 //                  grid-wide hand-off (a first version let the last CTA of the stats kernel merge everything: its
 //                  serial tail grew with the batch, 85 us at 8 samples).  Then y = silu(x * a + b) with
@@ -36,6 +36,7 @@ struct Params {
   const void* dy;
   const void* gamma;
   const void* beta;
+  const void* shift;      // optional (n, c): the kernels normalise x + shift[n, c] (a conv bias + time embedding folded in)
   void* out;              // y (forward) or dx (backward)
   float* stats;           // [n][groups][2] = mean, rstd
   float* ws;              // chunk partials [n][P][groups][2]: (mean, M2) forward, (sum dxh, sum dxh * xhat) backward
@@ -74,6 +75,15 @@ struct Coord {
   }
 };
 
+template <typename T> __device__ __forceinline__ void load_shift(const Params& p, const Coord& t, float* sh) {
+  if (p.shift != nullptr) {
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.shift) + (int64_t)t.n * p.c + t.c0)), sh);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh[e] = 0.f;
+  }
+}
+
 // Per-channel sums of a thread -> per-group sums of the CTA's slice, fixed order.  A vector touches at most two groups
 // (checked on the host): the first `k` elements belong to group c0 / cpg, the rest to the next one.
 __device__ __forceinline__ void group_partials(const Params& p, const Coord& t, const float* s, const float* q,
@@ -87,95 +97,124 @@ __device__ __forceinline__ void group_partials(const Params& p, const Coord& t, 
   }
   part[threadIdx.x] = t.active ? make_float4(sA, qA, sB, qB) : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
+  // `sub` threads per group (a power of two inside one warp): sub-lane j sums the pixel lanes j, j + sub, ... of the
+  // vectors that overlap its group, then a shuffle tree in a fixed order
   const int gps = p.groups / p.cs;
-  owner = (int)threadIdx.x < gps;
-  S = 0.f; Q = 0.f; g_out = 0;
-  if (owner) {
-    const int slice_c0 = (int)blockIdx.y * p.vs * 8;
-    const int g = (int)blockIdx.y * gps + (int)threadIdx.x;
+  const int sub = gps * 8 <= kThreads ? 8 : 1;
+  const int gl = (int)threadIdx.x / sub, j = (int)threadIdx.x - gl * sub;
+  const bool live = gl < gps;
+  const int slice_c0 = (int)blockIdx.y * p.vs * 8;
+  const int g = (int)blockIdx.y * gps + gl;
+  S = 0.f; Q = 0.f;
+  if (live) {
     const int v_lo = (g * p.cpg - slice_c0) >> 3, v_hi = ((g + 1) * p.cpg - 1 - slice_c0) >> 3;
-    for (int l = 0; l < p.pl; ++l)
+    for (int l = j; l < p.pl; l += sub)
       for (int v = v_lo; v <= v_hi; ++v) {
-        const int gv = (slice_c0 + v * 8) / p.cpg;
         const float4 w = part[l * p.vs + v];
-        if (gv == g) { S += w.x; Q += w.y; } else if (gv + 1 == g) { S += w.z; Q += w.w; }
+        // a vector that starts inside the group contributes its first part, one that starts before it its second part
+        if (slice_c0 + v * 8 >= g * p.cpg) { S += w.x; Q += w.y; } else { S += w.z; Q += w.w; }
       }
-    g_out = g;
   }
+  if (sub == 8) {
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      S += __shfl_down_sync(0xffffffffu, S, off, 8);
+      Q += __shfl_down_sync(0xffffffffu, Q, off, 8);
+    }
+  }
+  owner = live && j == 0;
+  g_out = g;
 }
 
-constexpr int kMaxChunks = 128;       // chunk partials per (sample, group): four per lane of the merging warp
-constexpr int kMaxSliceGroups = 256;  // groups one CTA's slice may hold
+constexpr int kMaxChunks = 128;       // chunk partials per (sample, group)
+constexpr int kMaxSliceGroups = 32;   // groups one CTA's slice may hold (SD: 32 groups, one or two slices)
+constexpr int kMergeLoads = 16;       // partials one thread of the merging prologue holds: kMaxChunks / 8
 
-// Prologue of the apply kernels: (mean, rstd) of every group of this CTA's slice from the chunk partials (mean, M2).
+// Layout of the merging prologues: `tpg` = 8, 16 or 32 threads per group (all inside one warp), so that the whole CTA
+// merges all groups of its slice at once and every thread has ALL its partials in flight before the first merge (one
+// L2 round trip instead of one per group).
+__device__ __forceinline__ int merge_tpg(int gps) {
+  int tpg = 8;
+  while (tpg < 32 && tpg * 2 * gps <= kThreads) tpg *= 2;
+  return tpg;
+}
+
+// Prologue of the apply kernels: (mean, rstd) of every group of this CTA's slice from the chunk partials (mean, M2),
+// Chan's parallel update in a fixed order (thread-sequential over its chunks, then a shuffle tree).
 __device__ __forceinline__ void merge_stats(const Params& p, float2* sst) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gps = p.groups / p.cs, n = blockIdx.z;
-  for (int gl = warp; gl < gps; gl += kThreads / 32) {
-    const int g = (int)blockIdx.y * gps + gl;
-    float2 w[kMaxChunks / 32];
+  const int tpg = merge_tpg(gps);
+  const int gl = (int)threadIdx.x / tpg, j = (int)threadIdx.x - gl * tpg;
+  const bool live = gl < gps;
+  const int g = (int)blockIdx.y * gps + gl;
+  float2 w[kMergeLoads];
 #pragma unroll
-    for (int i = 0; i < kMaxChunks / 32; ++i) {
-      const int ch = lane + 32 * i;
-      w[i] = ch < p.P ? __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g)
-                      : make_float2(0.f, 0.f);
+  for (int i = 0; i < kMergeLoads; ++i) {
+    const int ch = j + tpg * i;
+    w[i] = (live && ch < p.P) ? __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g)
+                              : make_float2(0.f, 0.f);
+  }
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMergeLoads; ++i) {
+    const int ch = j + tpg * i;
+    if (live && ch < p.P) {
+      const float cb = (float)((min((ch + 1) * p.chunk, p.hw) - ch * p.chunk) * p.cpg);
+      const float tot = cnt + cb, delta = w[i].x - mean, f = __fdividef(cb, tot);
+      mean = fmaf(delta, f, mean);
+      m2 += w[i].y + delta * delta * cnt * f;
+      cnt = tot;
     }
-    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  }
 #pragma unroll
-    for (int i = 0; i < kMaxChunks / 32; ++i) {
-      const int ch = lane + 32 * i;
-      if (ch < p.P) {
-        const float cb = (float)((min((ch + 1) * p.chunk, p.hw) - ch * p.chunk) * p.cpg);
-        const float tot = cnt + cb, delta = w[i].x - mean, f = cb / tot;
-        mean = fmaf(delta, f, mean);
-        m2 += w[i].y + delta * delta * cnt * f;
-        cnt = tot;
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float cb = __shfl_down_sync(0xffffffffu, cnt, off);
-      const float mb = __shfl_down_sync(0xffffffffu, mean, off);
-      const float qb = __shfl_down_sync(0xffffffffu, m2, off);
-      if (cb > 0.f) {
-        const float tot = cnt + cb, delta = mb - mean, f = cb / tot;
+  for (int off = 16; off > 0; off >>= 1) {
+    if (off < tpg) {
+      const float cb = __shfl_down_sync(0xffffffffu, cnt, off, 32);
+      const float mb = __shfl_down_sync(0xffffffffu, mean, off, 32);
+      const float qb = __shfl_down_sync(0xffffffffu, m2, off, 32);
+      if (cb > 0.f && j + off < tpg) {
+        const float tot = cnt + cb, delta = mb - mean, f = __fdividef(cb, tot);
         mean = fmaf(delta, f, mean);
         m2 += qb + delta * delta * cnt * f;
         cnt = tot;
       }
     }
-    if (lane == 0) {
-      const float2 st = make_float2(mean, rsqrtf(m2 / cnt + p.eps));
-      sst[gl] = st;
-      if (blockIdx.x == 0) reinterpret_cast<float2*>(p.stats)[n * p.groups + g] = st;   // kept for the backward
-    }
+  }
+  if (live && j == 0) {
+    const float2 st = make_float2(mean, rsqrtf(m2 / cnt + p.eps));
+    sst[gl] = st;
+    if (blockIdx.x == 0) reinterpret_cast<float2*>(p.stats)[n * p.groups + g] = st;   // kept for the backward
   }
   __syncthreads();
 }
 
 // Prologue of the backward apply kernel: mean(dxh), mean(dxh * xhat) of every group of the slice (plain sums).
 __device__ __forceinline__ void merge_sums(const Params& p, float2* scf) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gps = p.groups / p.cs, n = blockIdx.z;
-  const float inv_m = 1.f / ((float)p.hw * (float)p.cpg);
-  for (int gl = warp; gl < gps; gl += kThreads / 32) {
-    const int g = (int)blockIdx.y * gps + gl;
-    float s1 = 0.f, s2 = 0.f;
+  const int tpg = merge_tpg(gps);
+  const int gl = (int)threadIdx.x / tpg, j = (int)threadIdx.x - gl * tpg;
+  const bool live = gl < gps;
+  const int g = (int)blockIdx.y * gps + gl;
+  float2 w[kMergeLoads];
 #pragma unroll
-    for (int i = 0; i < kMaxChunks / 32; ++i) {
-      const int ch = lane + 32 * i;
-      if (ch < p.P) {
-        const float2 w = __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g);
-        s1 += w.x;
-        s2 += w.y;
-      }
-    }
+  for (int i = 0; i < kMergeLoads; ++i) {
+    const int ch = j + tpg * i;
+    w[i] = (live && ch < p.P) ? __ldg(reinterpret_cast<const float2*>(p.ws) + ((int64_t)n * p.P + ch) * p.groups + g)
+                              : make_float2(0.f, 0.f);
+  }
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s1 += __shfl_down_sync(0xffffffffu, s1, off);
-      s2 += __shfl_down_sync(0xffffffffu, s2, off);
+  for (int i = 0; i < kMergeLoads; ++i) { s1 += w[i].x; s2 += w[i].y; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if (off < tpg) {
+      const float a1 = __shfl_down_sync(0xffffffffu, s1, off, 32), a2 = __shfl_down_sync(0xffffffffu, s2, off, 32);
+      if (j + off < tpg) { s1 += a1; s2 += a2; }
     }
-    if (lane == 0) scf[gl] = make_float2(s1 * inv_m, s2 * inv_m);
+  }
+  if (live && j == 0) {
+    const float inv_m = 1.f / ((float)p.hw * (float)p.cpg);
+    scf[gl] = make_float2(s1 * inv_m, s2 * inv_m);
   }
   __syncthreads();
 }
@@ -192,12 +231,18 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const Params p) {
   if (t.active) {
     const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + ((int64_t)t.n * p.hw) * p.c + t.c0);
     const int64_t stride = (int64_t)p.c / 8;
+    float sh[8];
+    load_shift<T>(p, t, sh);
 #pragma unroll 4
     for (int px = t.p0 + t.pl; px < t.p1; px += p.pl) {
       float f[8];
       unpack8<T>(__ldg(xp + px * stride), f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+      for (int e = 0; e < 8; ++e) {
+        const float v = f[e] + sh[e];
+        s[e] += v;
+        q[e] = fmaf(v, v, q[e]);
+      }
     }
   }
   float S, Q;
@@ -228,11 +273,13 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const Params p) {
     const int g_first = (int)blockIdx.y * (p.groups / p.cs);
     unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
     unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+    float sh[8];
+    load_shift<T>(p, t, sh);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float2 st = sst[(t.c0 + e) / p.cpg - g_first];
       a[e] = st.y * gm[e];
-      b[e] = fmaf(-st.x, a[e], bt[e]);
+      b[e] = fmaf(sh[e] - st.x, a[e], bt[e]);        // (x + shift - mean) * rstd * gamma + beta
     }
   }
   const int64_t base = ((int64_t)t.n * p.hw) * p.c + t.c0;
@@ -267,14 +314,17 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_sums_kernel(const Params p) {
       float bt[8];
       unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
       unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+      float sh[8];
+      load_shift<T>(p, t, sh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int g = (t.c0 + e) / p.cpg;
         const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + t.n * p.groups + g);
+        const float mu = st.x - sh[e];               // everything below is a function of x + shift
         r[e] = st.y;
-        mr[e] = st.x * st.y;
+        mr[e] = mu * st.y;
         a[e] = st.y * gm[e];
-        b[e] = fmaf(-st.x, a[e], bt[e]);
+        b[e] = fmaf(-mu, a[e], bt[e]);
       }
     }
     const int64_t base = ((int64_t)t.n * p.hw) * p.c + t.c0;
@@ -326,15 +376,18 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const Params p) 
     const int g_first = (int)blockIdx.y * (p.groups / p.cs);
     unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + t.c0)), gm);
     unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + t.c0)), bt);
+    float sh[8];
+    load_shift<T>(p, t, sh);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int g = (t.c0 + e) / p.cpg;
       const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + t.n * p.groups + g);
       const float2 cf = scf[g - g_first];
+      const float mu = st.x - sh[e];
       r[e] = st.y;
-      mr[e] = st.x * st.y;
+      mr[e] = mu * st.y;
       a[e] = st.y * gm[e];
-      b[e] = fmaf(-st.x, a[e], bt[e]);
+      b[e] = fmaf(-mu, a[e], bt[e]);
       gr[e] = gm[e] * st.y;
       k1[e] = cf.x * st.y;
       k2[e] = cf.y * st.y;
@@ -414,34 +467,85 @@ static void launch_bwd(const Params& p, bool silu, cudaStream_t st) {
   }
 }
 
-int fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
+int fwd(const void* x, const void* shift, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
         int hw, int c, int groups, float eps, int silu, int dtype, cudaStream_t st) {
   Params p;
   if (!plan(p, n, hw, c, groups))
     return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
-  p.x = x; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.out = y; p.stats = stats; p.ws = ws;
+  p.x = x; p.shift = shift; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.out = y; p.stats = stats; p.ws = ws;
   p.eps = eps;
   if (dtype == GA_F16) launch_fwd<__half>(p, silu != 0, st);
   else launch_fwd<__nv_bfloat16>(p, silu != 0, st);
   return check_launch("group_norm_fwd");
 }
 
-int bwd(const void* x, const void* dy, const void* gamma, const void* beta, const float* stats, void* dx, float* ws,
-        int n, int hw, int c, int groups, int silu, int dtype, cudaStream_t st) {
+int bwd(const void* x, const void* shift, const void* dy, const void* gamma, const void* beta, const float* stats,
+        void* dx, float* ws, int n, int hw, int c, int groups, int silu, int dtype, cudaStream_t st) {
   Params p;
   if (!plan(p, n, hw, c, groups))
     return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
-  p.x = x; p.dy = dy; p.gamma = gamma; p.beta = beta; p.out = dx; p.stats = const_cast<float*>(stats); p.ws = ws;
+  p.x = x; p.shift = shift; p.dy = dy; p.gamma = gamma; p.beta = beta; p.out = dx; p.stats = const_cast<float*>(stats); p.ws = ws;
   p.eps = 0.f;
   if (dtype == GA_F16) launch_bwd<__half>(p, silu != 0, st);
   else launch_bwd<__nv_bfloat16>(p, silu != 0, st);
   return check_launch("group_norm_bwd");
 }
 
+// ---------------------------------------------------------------------------- bias (+ residual) epilogue of a conv
+// out = a + bias[c] (+ b): PyTorch adds a convolution's bias with a broadcast `add_` (a non-vectorised elementwise
+// kernel, ~5 us per convolution) and the block's residual with another launch; on the channels-last tensor the bias
+// index is the fastest dimension, so both fit one 128-bit-vectorised pass.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) add_bias_residual_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                                     const uint4* __restrict__ bias, uint4* __restrict__ out,
+                                                                     int64_t n_vec, int vec_per_pixel) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * kThreads) {
+    float fa[8], fb[8], fc[8];
+    unpack8<T>(__ldg(a + i), fa);
+    unpack8<T>(__ldg(bias + (int)(i % vec_per_pixel)), fc);
+    if (b != nullptr) {
+      unpack8<T>(__ldg(b + i), fb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fa[e] += fb[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fa[e] += fc[e];
+    out[i] = pack8<T>(fa);
+  }
+}
+
+int add_bias_residual(const void* a, const void* b, const void* bias, void* out, int64_t n_pixels, int c, int dtype,
+                      cudaStream_t st) {
+  const int64_t n_vec = n_pixels * (c / 8);
+  if (n_vec == 0) return GA_OK;
+  int64_t blocks = (n_vec + kThreads - 1) / kThreads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const uint4 *pa = static_cast<const uint4*>(a), *pb = static_cast<const uint4*>(b), *pc = static_cast<const uint4*>(bias);
+  if (dtype == GA_F16)
+    add_bias_residual_kernel<__half><<<(int)blocks, kThreads, 0, st>>>(pa, pb, pc, static_cast<uint4*>(out), n_vec, c / 8);
+  else
+    add_bias_residual_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, st>>>(pa, pb, pc, static_cast<uint4*>(out), n_vec,
+                                                                             c / 8);
+  return check_launch("add_bias_residual");
+}
+
 }  // namespace gn
 }  // namespace ga
 
 using namespace ga;
+
+extern "C" int ga_add_bias_residual(const void* a, const void* b, const void* bias, void* out, int64_t n_pixels,
+                                    int channels, int dtype, ga_stream_t stream) {
+  GA_CHECK_ARG(a && bias && out, "NULL operand");
+  GA_CHECK_ARG(dtype == GA_F16 || dtype == GA_BF16, "add_bias_residual: 16-bit activations only (dtype %d)", dtype);
+  GA_CHECK_ARG(n_pixels >= 0 && channels >= 8 && channels % 8 == 0, "add_bias_residual: channels %d must be a multiple of 8",
+               channels);
+  GA_CHECK_ALIGN(a, 16, "a");
+  GA_CHECK_ALIGN(out, 16, "out");
+  GA_CHECK_ALIGN(bias, 16, "bias");
+  if (b != nullptr) GA_CHECK_ALIGN(b, 16, "b");
+  return gn::add_bias_residual(a, b, bias, out, n_pixels, channels, dtype, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int64_t ga_group_norm_ws_bytes(int n, int hw, int channels, int groups) {
   return gn::ws_bytes(n, hw, channels, groups);
@@ -460,22 +564,24 @@ static int check_gn_args(const void* x, const void* gamma, const void* beta, con
   return GA_OK;
 }
 
-extern "C" int ga_group_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, float* ws,
-                                 int n, int hw, int channels, int groups, float eps, int silu,
+extern "C" int ga_group_norm_fwd(const void* x, const void* shift, const void* gamma, const void* beta, void* y,
+                                 float* stats, float* ws, int n, int hw, int channels, int groups, float eps, int silu,
                                  int dtype, ga_stream_t stream) {
   int rc = check_gn_args(x, gamma, beta, y, stats, ws, dtype);
   if (rc != GA_OK) return rc;
-  return gn::fwd(x, gamma, beta, y, stats, ws, n, hw, channels, groups, eps, silu, dtype,
+  if (shift != nullptr) GA_CHECK_ALIGN(shift, 16, "shift");
+  return gn::fwd(x, shift, gamma, beta, y, stats, ws, n, hw, channels, groups, eps, silu, dtype,
                  static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ga_group_norm_bwd(const void* x, const void* d_y, const void* gamma, const void* beta, const float* stats,
-                                 void* d_x, float* ws, int n, int hw, int channels, int groups,
+extern "C" int ga_group_norm_bwd(const void* x, const void* shift, const void* d_y, const void* gamma, const void* beta,
+                                 const float* stats, void* d_x, float* ws, int n, int hw, int channels, int groups,
                                  int silu, int dtype, ga_stream_t stream) {
   int rc = check_gn_args(x, gamma, beta, d_x, stats, ws, dtype);
   if (rc != GA_OK) return rc;
   GA_CHECK_ARG(d_y != nullptr, "NULL operand");
   GA_CHECK_ALIGN(d_y, 16, "d_y");
-  return gn::bwd(x, d_y, gamma, beta, stats, d_x, ws, n, hw, channels, groups, silu, dtype,
+  if (shift != nullptr) GA_CHECK_ALIGN(shift, 16, "shift");
+  return gn::bwd(x, shift, d_y, gamma, beta, stats, d_x, ws, n, hw, channels, groups, silu, dtype,
                  static_cast<cudaStream_t>(stream));
 }

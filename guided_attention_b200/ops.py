@@ -416,30 +416,32 @@ def group_norm_supported(x: torch.Tensor, weight, bias, groups: int) -> bool:
 
 class _GroupNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, groups: int, eps: float, silu: bool):
-        _need_cuda(x, weight, bias)
+    def forward(ctx, x, weight, bias, shift, groups: int, eps: float, silu: bool):
+        _need_cuda(x, weight, bias, shift)
         lib = abi.load()
         x = x.contiguous(memory_format=torch.channels_last)
         n, c, h, w = x.shape
         if weight.dtype != x.dtype:
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
         weight, bias = weight.contiguous(), bias.contiguous()
+        if shift is not None:
+            shift = shift.to(x.dtype).reshape(n, c).contiguous()
         y = torch.empty_like(x)                       # keeps the channels-last strides
         stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
         ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
         nbytes = 3 * x.numel() * x.element_size()     # x read twice (the second time from L2), y written
         with torch.cuda.device(x.device), _span("group_norm_fwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
-            abi.check(lib.ga_group_norm_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats), _ptr(ws),
-                                            n, h * w, c, groups, float(eps), int(silu),
-                                            _DTYPES[x.dtype], _stream(x)), "ga_group_norm_fwd")
+            abi.check(lib.ga_group_norm_fwd(_ptr(x), _ptr(shift), _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats),
+                                            _ptr(ws), n, h * w, c, groups, float(eps), int(silu), _DTYPES[x.dtype],
+                                            _stream(x)), "ga_group_norm_fwd")
         _count("group_norm_fwd", 2)
-        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.save_for_backward(x, weight, bias, stats, shift)
         ctx.meta = (groups, bool(silu))
         return y
 
     @staticmethod
     def backward(ctx, d_y):
-        x, weight, bias, stats = ctx.saved_tensors
+        x, weight, bias, stats, shift = ctx.saved_tensors
         groups, silu = ctx.meta
         lib = abi.load()
         n, c, h, w = x.shape
@@ -448,18 +450,58 @@ class _GroupNormFn(torch.autograd.Function):
         ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
         nbytes = 5 * x.numel() * x.element_size()
         with torch.cuda.device(x.device), _span("group_norm_bwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
-            abi.check(lib.ga_group_norm_bwd(_ptr(x), _ptr(d_y), _ptr(weight), _ptr(bias), _ptr(stats), _ptr(d_x),
-                                            _ptr(ws), n, h * w, c, groups, int(silu),
-                                            _DTYPES[x.dtype], _stream(x)), "ga_group_norm_bwd")
+            abi.check(lib.ga_group_norm_bwd(_ptr(x), _ptr(shift), _ptr(d_y), _ptr(weight), _ptr(bias), _ptr(stats),
+                                            _ptr(d_x), _ptr(ws), n, h * w, c, groups, int(silu), _DTYPES[x.dtype],
+                                            _stream(x)), "ga_group_norm_bwd")
         _count("group_norm_bwd", 2)
-        return d_x, None, None, None, None, None
+        return d_x, None, None, None, None, None, None
 
 
-def group_norm(x, weight, bias, groups: int, eps: float = 1e-5, silu: bool = False):
-    """`silu(GroupNorm(x))` (or plain GroupNorm) on a (n, C, h, w) fp16 / bf16 CUDA tensor, computed on its channels-last
-    layout (a channels-first input is converted once): two launches forward, two backward, differentiable in x only.
-    Replaces `torch.nn.GroupNorm` (+ `F.silu`) inside the UNet the guidance path runs forward and backward."""
-    return _GroupNormFn.apply(x, weight, bias, int(groups), float(eps), bool(silu))
+def group_norm(x, weight, bias, groups: int, eps: float = 1e-5, silu: bool = False, shift=None):
+    """`silu(GroupNorm(x + shift))` (SiLU and the per-(sample, channel) `shift` optional) on a (n, C, h, w) fp16 / bf16
+    CUDA tensor, computed on its channels-last layout (a channels-first input is converted once): two launches forward,
+    two backward, differentiable in x only (`shift` -- a conv bias plus the time-embedding projection -- does not depend
+    on the latents).  Replaces `torch.nn.GroupNorm` (+ `F.silu`, + the broadcast adds in front of it) inside the UNet
+    the guidance path runs forward and backward."""
+    if shift is not None and shift.requires_grad:
+        raise ValueError("group_norm: `shift` must not require a gradient (only x is differentiated)")
+    return _GroupNormFn.apply(x, weight, bias, shift, int(groups), float(eps), bool(silu))
+
+
+class _AddBiasResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, bias, b):
+        _need_cuda(a, bias, b)
+        lib = abi.load()
+        a = a.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = a.shape
+        if b is not None:
+            b = b.contiguous(memory_format=torch.channels_last)
+        bias = bias.to(a.dtype).contiguous()
+        out = torch.empty_like(a)
+        nbytes = (3 if b is not None else 2) * a.numel() * a.element_size()
+        with torch.cuda.device(a.device), _span("add_bias_residual", (n, h * w, c, int(b is not None)), nbytes, a.device):
+            abi.check(lib.ga_add_bias_residual(_ptr(a), _ptr(b), _ptr(bias), _ptr(out), n * h * w, c, _DTYPES[a.dtype],
+                                               _stream(a)), "ga_add_bias_residual")
+        _count("add_bias_residual")
+        ctx.has_b = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, (g if ctx.has_b else None)
+
+
+def add_bias_residual(a, bias, b=None):
+    """`a + bias[None, :, None, None] (+ b)` on (n, C, h, w) fp16 / bf16 CUDA tensors in one vectorised channels-last
+    pass: a convolution's bias and, with `b`, the block's residual connection.  Differentiable in a and b."""
+    if bias.requires_grad:
+        raise ValueError("add_bias_residual: `bias` must not require a gradient")
+    return _AddBiasResidualFn.apply(a, bias, b)
+
+
+def fused_unet_ops_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
 
 
 # ============================================================================================== K5 rasteriser

@@ -24,6 +24,7 @@ import os
 from typing import List
 
 import torch
+import torch.nn.functional as F
 
 from . import ops
 from . import shared_state as state
@@ -309,17 +310,77 @@ def register_attention_control(model, controller):
 def _fused_silu_norm(norm, x):
     if ops.group_norm_supported(x, norm.weight, norm.bias, norm.num_groups):
         return ops.group_norm(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=True)
-    return torch.nn.functional.silu(norm(x))
+    return F.silu(norm(x))
+
+
+def _plain_conv(conv) -> bool:
+    return (conv.bias is not None and not conv.weight.requires_grad and not conv.bias.requires_grad and conv.groups == 1
+            and tuple(conv.dilation) == (1, 1) and conv.padding_mode == "zeros" and not isinstance(conv.padding, str))
+
+
+def _shift_bias(block):
+    """conv1.bias + time_emb_proj.bias of a ResNet block (both frozen), cached until either tensor is modified."""
+    tb, cb = block.time_emb_proj.bias, block.conv1.bias
+    key = (tb.data_ptr(), tb._version, cb.data_ptr(), cb._version, tb.dtype)
+    hit = getattr(block, "_ga_shift_bias", None)
+    if hit is None or hit[0] != key:
+        hit = (key, (tb.detach() + cb.detach()))
+        block._ga_shift_bias = hit
+    return hit[1]
+
+
+def _fused_resnet_forward(block, x, temb):
+    """ResnetBlock2D with its elementwise work folded away (same mathematics as the stock forward):
+        h   = conv1_nobias(silu(norm1(x)))
+        h   = conv2_nobias(silu(norm2(h + shift)))       shift[n, c] = conv1.bias + time_emb_proj(silu(temb))
+        out = h + conv2.bias + shortcut(x)               one vectorised pass
+    i.e. 4 broadcast / residual add launches fewer per block and direction than PyTorch issues."""
+    n1, n2, c1, c2 = block.norm1, block.norm2, block.conv1, block.conv2
+    if not (ops.group_norm_supported(x, n1.weight, n1.bias, n1.num_groups) and _plain_conv(c1) and _plain_conv(c2)
+            and c2.out_channels % 8 == 0 and not temb.requires_grad and not block.time_emb_proj.weight.requires_grad):
+        return None
+    h = F.conv2d(ops.group_norm(x, n1.weight, n1.bias, n1.num_groups, n1.eps, silu=True), c1.weight, None, c1.stride,
+                 c1.padding)
+    if not ops.group_norm_supported(h, n2.weight, n2.bias, n2.num_groups):
+        return None
+    shift = F.linear(F.silu(temb), block.time_emb_proj.weight, _shift_bias(block))
+    if shift.shape[0] != h.shape[0]:
+        shift = shift.expand(h.shape[0], -1)
+    h = F.conv2d(ops.group_norm(h, n2.weight, n2.bias, n2.num_groups, n2.eps, silu=True, shift=shift), c2.weight, None,
+                 c2.stride, c2.padding)
+    xs = x if block.conv_shortcut is None else block.conv_shortcut(x)
+    return ops.add_bias_residual(h, c2.bias, xs)
+
+
+def _patch_conv(m):
+    stock = m.forward
+
+    def forward(x, _m=m, _stock=stock):
+        if (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and _plain_conv(_m)
+                and _m.weight.dtype == x.dtype):
+            if tuple(_m.kernel_size) == (1, 1) and tuple(_m.stride) == (1, 1) and tuple(_m.padding) == (0, 0):
+                # a 1x1 convolution on a channels-last tensor IS a linear layer over (pixels, channels): cuBLAS adds
+                # the bias in the GEMM epilogue; the result is again a channels-last (n, C, h, w) view
+                y = F.linear(x.permute(0, 2, 3, 1), _m.weight.view(_m.out_channels, _m.in_channels), _m.bias)
+                return y.permute(0, 3, 1, 2)
+            if _m.out_channels % 8 == 0:
+                return ops.add_bias_residual(F.conv2d(x, _m.weight, None, _m.stride, _m.padding), _m.bias)
+        return _stock(x)
+    m.forward = forward
 
 
 def register_fused_norms(unet) -> int:
-    """Routes the UNet's `nn.GroupNorm` layers (ResNet blocks, transformer wrappers, `conv_norm_out`) through the fused
-    channels-last kernels of `ops.group_norm` whenever the activation is a 16-bit CUDA tensor and the affine parameters
-    are frozen; anything else (fp32, CPU, trainable norms) keeps PyTorch's own op.  Blocks that expose a
-    `fused_norm_act` hook (the substrate's ResnetBlock2D: norm -> SiLU -> conv) get the SiLU folded into the same
-    launch.  The guided loop runs the UNet forward and backward ~250 times per image and these norms were the largest
-    non-GEMM item of its launch list (csrc/group_norm.cu).  Idempotent; `GA_FUSED_NORM=0` leaves the UNet untouched
-    (A/B measurements).  Returns the number of norm layers now routed."""
+    """Routes the elementwise work of the UNet around the attention layers through the fused channels-last kernels of
+    `csrc/group_norm.cu` whenever the activation is a 16-bit CUDA tensor and the parameters are frozen; anything else
+    (fp32, CPU, trainable layers) keeps PyTorch's own ops:
+      * every `nn.GroupNorm` (ResNet blocks, transformer wrappers, `conv_norm_out`) -> `ops.group_norm`;
+      * blocks that expose the `fused_norm_act` / `fused_forward` hooks (the substrate's ResnetBlock2D) get SiLU, the
+        conv1 bias, the time-embedding add, the conv2 bias and the residual add folded in (`_fused_resnet_forward`);
+      * every biased `nn.Conv2d`: 1x1 -> `F.linear` on the channels-last view (bias in the GEMM epilogue), others ->
+        bias-free cuDNN convolution + one vectorised bias pass instead of PyTorch's broadcast `add_`.
+    The guided loop runs the UNet forward and backward ~250 times per image and these ops were the largest non-GEMM
+    items of its launch list (csrc/group_norm.cu, profiles/r02c_profile_ops.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
+    the UNet untouched (A/B measurements).  Returns the number of norm layers now routed."""
     if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
         return 0
     n = 0
@@ -335,8 +396,15 @@ def register_fused_norms(unet) -> int:
                 m.forward = forward
                 m._ga_fused = True
             n += 1
-        elif hasattr(m, "fused_norm_act"):
-            m.fused_norm_act = _fused_silu_norm
+        elif isinstance(m, torch.nn.Conv2d):
+            if not getattr(m, "_ga_fused", False):
+                _patch_conv(m)
+                m._ga_fused = True
+        else:
+            if hasattr(m, "fused_norm_act"):
+                m.fused_norm_act = _fused_silu_norm
+            if hasattr(m, "fused_forward"):
+                m.fused_forward = _fused_resnet_forward
     return n
 
 

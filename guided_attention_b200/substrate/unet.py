@@ -223,6 +223,9 @@ class ResnetBlock2D(nn.Module):
         # hook for a fused `silu(norm(x))` (callable(norm_module, x) -> tensor); None = the two stock ops.  Installed by
         # the product path (`ptp_utils.register_fused_norms`), never by the oracle.
         self.fused_norm_act = None
+        # hook for the whole block (callable(block, x, temb) -> tensor, or None to decline): same mathematics with the
+        # conv biases / time-embedding add / residual add folded into neighbouring kernels
+        self.fused_forward = None
 
     def _norm_act(self, norm, x):
         if self.fused_norm_act is not None:
@@ -230,6 +233,10 @@ class ResnetBlock2D(nn.Module):
         return F.silu(norm(x))
 
     def forward(self, x, temb):
+        if self.fused_forward is not None:
+            out = self.fused_forward(self, x, temb)
+            if out is not None:
+                return out
         h = self.conv1(self._norm_act(self.norm1, x))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(self._norm_act(self.norm2, h))

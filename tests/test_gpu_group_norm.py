@@ -123,3 +123,84 @@ def test_unet_with_fused_norms_matches_stock_unet():
     rel_o = float((res[0][0] - res[1][0]).abs().max() / res[0][0].abs().max())
     assert cos_o > 0.9999 and cos_g > 0.999 and rel_o < 2e-2, (cos_o, cos_g, rel_o)
     assert np.isfinite(res[1][1].cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 320, 64, 64, 32), (2, 1280, 16, 16, 32), (1, 640, 24, 24, 32), (2, 96, 8, 8, 8)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_group_norm_with_shift_matches_torch(shape, dtype):
+    """`shift` (n, C): the conv bias + time-embedding projection the ResNet block adds in front of norm2."""
+    from guided_attention_b200 import ops
+    n, c, h, w, groups = shape
+    x, wgt, b, dy = _inputs(n, c, h, w, dtype, seed=11)
+    shift = (0.7 * torch.randn(n, c, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))).to(dtype)
+    xq = x.detach().requires_grad_(True)
+    y = ops.group_norm(xq, wgt, b, groups, 1e-5, silu=True, shift=shift)
+    (dx,) = torch.autograd.grad(y, xq, dy)
+    xr = x.float().detach().requires_grad_(True)
+    y_ref = F.silu(F.group_norm(xr + shift.float()[:, :, None, None], groups, wgt.float(), b.float(), 1e-5))
+    (dx_ref,) = torch.autograd.grad(y_ref, xr, dy.float())
+    rtol, atol = TOL[dtype]
+    assert torch.allclose(y.float(), y_ref, rtol=rtol, atol=atol), float((y.float() - y_ref).abs().max())
+    err = float((dx.float() - dx_ref).abs().max() / dx_ref.abs().max())
+    assert err < (4e-3 if dtype == torch.float16 else 3e-2), err
+
+
+@pytest.mark.parametrize("with_b", [False, True])
+def test_add_bias_residual_is_exactly_the_rounded_sum(with_b):
+    from guided_attention_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(4)
+    a = torch.randn(2, 640, 17, 9, device=DEV, generator=g).half().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(2, 640, 17, 9, device=DEV, generator=g).half() if with_b else None     # channels-first on purpose
+    bias = torch.randn(640, device=DEV, generator=g).half()
+    aq = a.detach().requires_grad_(True)
+    bq = b.detach().requires_grad_(True) if with_b else None
+    out = ops.add_bias_residual(aq, bias, bq)
+    ref = a.float() + bias.float()[None, :, None, None] + (b.float() if with_b else 0.0)
+    assert torch.equal(out, ref.half())                       # one rounding of the fp32 sum
+    gout = torch.randn_like(out)
+    grads = torch.autograd.grad(out, [aq] + ([bq] if with_b else []), gout)
+    assert all(torch.equal(gr, gout) for gr in grads)
+
+
+def test_patched_convolutions_match_cudnn_with_bias():
+    """1x1 convolutions run as `F.linear` on the channels-last view, the others as bias-free cuDNN + one bias pass."""
+    from guided_attention_b200 import ptp_utils
+    torch.manual_seed(0)
+    for (cin, cout, k, stride) in ((320, 320, 1, 1), (640, 320, 1, 1), (320, 640, 3, 1), (320, 320, 3, 2), (4, 320, 3, 1)):
+        conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2).to(DEV).half().requires_grad_(False)
+        conv = conv.to(memory_format=torch.channels_last)
+        x = torch.randn(2, cin, 32, 32, device=DEV).half().contiguous(memory_format=torch.channels_last)
+        xq = x.clone().requires_grad_(True)
+        ref = conv(xq)
+        (gref,) = torch.autograd.grad(ref.float().square().sum(), xq)
+        holder = torch.nn.Sequential(conv)
+        ptp_utils.register_fused_norms(holder)
+        xq2 = x.clone().requires_grad_(True)
+        got = conv(xq2)
+        (ggot,) = torch.autograd.grad(got.float().square().sum(), xq2)
+        assert got.shape == ref.shape
+        assert float((got.float() - ref.float()).abs().max() / ref.float().abs().max()) < 4e-3, (cin, cout, k)
+        assert float((ggot.float() - gref.float()).abs().max() / gref.float().abs().max()) < 1e-2, (cin, cout, k)
+
+
+def test_fused_resnet_block_matches_stock_block():
+    from guided_attention_b200 import ptp_utils
+    from guided_attention_b200.substrate.unet import ResnetBlock2D
+    for (cin, cout) in ((320, 320), (960, 640)):
+        torch.manual_seed(1)
+        stock = ResnetBlock2D(cin, cout, 1280, 32).to(DEV).half().requires_grad_(False).to(memory_format=torch.channels_last)
+        fused = ResnetBlock2D(cin, cout, 1280, 32).to(DEV).half().requires_grad_(False).to(memory_format=torch.channels_last)
+        fused.load_state_dict(stock.state_dict())
+        ptp_utils.register_fused_norms(fused)
+        assert fused.fused_forward is not None
+        x = torch.randn(2, cin, 32, 32, device=DEV).half().contiguous(memory_format=torch.channels_last)
+        temb = torch.randn(2, 1280, device=DEV).half()
+        res = []
+        for blk in (stock, fused):
+            xq = x.clone().requires_grad_(True)
+            out = blk(xq, temb)
+            (gx,) = torch.autograd.grad(out.float().square().sum(), xq)
+            res.append((out.float(), gx.float()))
+        assert float((res[0][0] - res[1][0]).abs().max() / res[0][0].abs().max()) < 5e-3
+        assert float(F.cosine_similarity(res[0][1].flatten(), res[1][1].flatten(), dim=0)) > 0.9999
