@@ -25,6 +25,7 @@
 // Statistics are fp32; the affine parameters are read in the activation dtype.  d gamma / d beta are not produced (the
 // UNet is frozen on the guidance path: ptp_utils.register_attention_control).
 #include "ga_common.cuh"
+#include <stdlib.h>
 
 namespace ga {
 namespace gn {
@@ -58,6 +59,10 @@ template <typename T> __device__ __forceinline__ uint4 pack8(const float* f) {
                     Word<T>::pack(f[6], f[7]));
 }
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+// Programmatic dependent launch: the second kernel of a pair is launched while the first still runs (its CTAs are
+// scheduled as the first one's retire) and waits here until the first has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // A thread's coordinates: which 8-channel vector of which slice, which pixel lane.
 struct Coord {
@@ -142,6 +147,7 @@ __device__ __forceinline__ int merge_tpg(int gps) {
 // Prologue of the apply kernels: (mean, rstd) of every group of this CTA's slice from the chunk partials (mean, M2),
 // Chan's parallel update in a fixed order (thread-sequential over its chunks, then a shuffle tree).
 __device__ __forceinline__ void merge_stats(const Params& p, float2* sst) {
+  pdl_wait();
   const int gps = p.groups / p.cs, n = blockIdx.z;
   const int tpg = merge_tpg(gps);
   const int gl = (int)threadIdx.x / tpg, j = (int)threadIdx.x - gl * tpg;
@@ -190,6 +196,7 @@ __device__ __forceinline__ void merge_stats(const Params& p, float2* sst) {
 
 // Prologue of the backward apply kernel: mean(dxh), mean(dxh * xhat) of every group of the slice (plain sums).
 __device__ __forceinline__ void merge_sums(const Params& p, float2* scf) {
+  pdl_wait();
   const int gps = p.groups / p.cs, n = blockIdx.z;
   const int tpg = merge_tpg(gps);
   const int gl = (int)threadIdx.x / tpg, j = (int)threadIdx.x - gl * tpg;
@@ -223,6 +230,7 @@ __device__ __forceinline__ void merge_sums(const Params& p, float2* scf) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const Params p) {
   __shared__ float4 part[kThreads];
+  pdl_launch_dependents();
   Coord t;
   t.init(p);
   float s[8], q[8];
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const Params p) {
 template <typename T, bool kSilu>
 __global__ void __launch_bounds__(kThreads) gn_bwd_sums_kernel(const Params p) {
   __shared__ float4 part[kThreads];
+  pdl_launch_dependents();
   Coord t;
   t.init(p);
   float s[8], q[8];
@@ -448,22 +457,47 @@ int64_t ws_bytes(int n, int hw, int c, int groups) {
   return (int64_t)n * p.P * groups * 2 * (int64_t)sizeof(float);
 }
 
+// GA_GN_PDL=0 launches the second kernel of a pair as an ordinary stream-ordered launch (A/B measurements).
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GA_GN_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename K>
+static void launch_second(K kernel, const dim3& grid, const Params& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 template <typename T>
 static void launch_fwd(const Params& p, bool silu, cudaStream_t st) {
   const dim3 grid(p.P, p.cs, p.n);
   gn_stats_kernel<T><<<grid, kThreads, 0, st>>>(p);
-  if (silu) gn_apply_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
-  else gn_apply_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
+  if (silu) launch_second(gn_apply_kernel<T, true>, grid, p, st);
+  else launch_second(gn_apply_kernel<T, false>, grid, p, st);
 }
 template <typename T>
 static void launch_bwd(const Params& p, bool silu, cudaStream_t st) {
   const dim3 grid(p.P, p.cs, p.n);
   if (silu) {
     gn_bwd_sums_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
-    gn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, st>>>(p);
+    launch_second(gn_bwd_apply_kernel<T, true>, grid, p, st);
   } else {
     gn_bwd_sums_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
-    gn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, st>>>(p);
+    launch_second(gn_bwd_apply_kernel<T, false>, grid, p, st);
   }
 }
 
@@ -529,10 +563,97 @@ int add_bias_residual(const void* a, const void* b, const void* bias, void* out,
   return check_launch("add_bias_residual");
 }
 
+// ------------------------------------------------------------------------------------------------------- GEGLU
+// The transformer blocks' feed-forward gate (diffusers `GEGLU.forward`: `h, gate = proj(x).chunk(2, -1); h * gelu(gate)`)
+// on the projection output p (rows, 2 * inner): PyTorch runs gelu and the product as two NON-vectorised elementwise
+// kernels (the chunks are strided views) and the backward as gelu_backward + two products + a concatenating copy.
+//   forward   out[r, j] = p[r, j] * gelu(p[r, inner + j])                         (exact erf GELU)
+//   backward  d_p[r, j] = d_out * gelu(g),  d_p[r, inner + j] = d_out * h * gelu'(g)
+__device__ __forceinline__ float gelu_f(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float g) {
+  return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) geglu_fwd_kernel(const uint4* __restrict__ p, uint4* __restrict__ out,
+                                                             int64_t n_vec, int vec_per_row) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = i / vec_per_row;
+    const int v = (int)(i - r * vec_per_row);
+    float h[8], g[8];
+    unpack8<T>(__ldg(p + r * 2 * vec_per_row + v), h);
+    unpack8<T>(__ldg(p + r * 2 * vec_per_row + vec_per_row + v), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] *= gelu_f(g[e]);
+    out[i] = pack8<T>(h);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) geglu_bwd_kernel(const uint4* __restrict__ p, const uint4* __restrict__ d_out,
+                                                             uint4* __restrict__ d_p, int64_t n_vec, int vec_per_row) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = i / vec_per_row;
+    const int v = (int)(i - r * vec_per_row);
+    float h[8], g[8], d[8], dh[8], dg[8];
+    unpack8<T>(__ldg(p + r * 2 * vec_per_row + v), h);
+    unpack8<T>(__ldg(p + r * 2 * vec_per_row + vec_per_row + v), g);
+    unpack8<T>(__ldg(d_out + i), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      dh[e] = d[e] * gelu_f(g[e]);
+      dg[e] = d[e] * h[e] * gelu_grad_f(g[e]);
+    }
+    d_p[r * 2 * vec_per_row + v] = pack8<T>(dh);
+    d_p[r * 2 * vec_per_row + vec_per_row + v] = pack8<T>(dg);
+  }
+}
+
+int geglu(const void* p, const void* d_out, void* out, int64_t rows, int inner, int dtype, bool backward, cudaStream_t st) {
+  const int64_t n_vec = rows * (inner / 8);
+  if (n_vec == 0) return GA_OK;
+  int64_t blocks = (n_vec + kThreads - 1) / kThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const uint4* pp = static_cast<const uint4*>(p);
+  if (!backward) {
+    if (dtype == GA_F16) geglu_fwd_kernel<__half><<<(int)blocks, kThreads, 0, st>>>(pp, static_cast<uint4*>(out), n_vec, inner / 8);
+    else geglu_fwd_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, st>>>(pp, static_cast<uint4*>(out), n_vec, inner / 8);
+  } else {
+    const uint4* pd = static_cast<const uint4*>(d_out);
+    if (dtype == GA_F16) geglu_bwd_kernel<__half><<<(int)blocks, kThreads, 0, st>>>(pp, pd, static_cast<uint4*>(out), n_vec, inner / 8);
+    else geglu_bwd_kernel<__nv_bfloat16><<<(int)blocks, kThreads, 0, st>>>(pp, pd, static_cast<uint4*>(out), n_vec, inner / 8);
+  }
+  return check_launch(backward ? "geglu_bwd" : "geglu_fwd");
+}
+
 }  // namespace gn
 }  // namespace ga
 
 using namespace ga;
+
+static int check_geglu_args(const void* p, const void* out, int64_t rows, int inner, int dtype) {
+  GA_CHECK_ARG(p && out, "NULL operand");
+  GA_CHECK_ARG(dtype == GA_F16 || dtype == GA_BF16, "geglu: 16-bit activations only (dtype %d)", dtype);
+  GA_CHECK_ARG(rows >= 0 && inner >= 8 && inner % 8 == 0, "geglu: inner width %d must be a multiple of 8", inner);
+  GA_CHECK_ALIGN(p, 16, "proj");
+  GA_CHECK_ALIGN(out, 16, "output");
+  return GA_OK;
+}
+
+extern "C" int ga_geglu_fwd(const void* proj, void* out, int64_t rows, int inner, int dtype, ga_stream_t stream) {
+  int rc = check_geglu_args(proj, out, rows, inner, dtype);
+  if (rc != GA_OK) return rc;
+  return gn::geglu(proj, nullptr, out, rows, inner, dtype, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ga_geglu_bwd(const void* proj, const void* d_out, void* d_proj, int64_t rows, int inner, int dtype,
+                            ga_stream_t stream) {
+  int rc = check_geglu_args(proj, d_proj, rows, inner, dtype);
+  if (rc != GA_OK) return rc;
+  GA_CHECK_ARG(d_out != nullptr, "NULL operand");
+  GA_CHECK_ALIGN(d_out, 16, "d_out");
+  return gn::geglu(proj, d_out, d_proj, rows, inner, dtype, true, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int ga_add_bias_residual(const void* a, const void* b, const void* bias, void* out, int64_t n_pixels,
                                     int channels, int dtype, ga_stream_t stream) {

@@ -204,6 +204,33 @@ def time_group_norm(n, c, h, w, groups=32, silu=True, direction="fwd", impl="fus
             "bytes": nbytes, "gbs": nbytes / us / 1e3, "buffer_sets": n_sets}
 
 
+def time_geglu(rows, inner, direction="fwd", impl="fused", dtype=torch.float16, device="cuda:0"):
+    """The feed-forward gate `h * gelu(gate)` on a (1, rows, 2 * inner) projection: fused kernel vs PyTorch's ops."""
+    import torch.nn.functional as F
+    nbytes = rows * inner * 2 * (3 if direction == "fwd" else 8)
+    n_sets = max(2, min(32, (2 * L2_BYTES) // max(rows * inner * 2 * 3, 1) + 1))
+    g = torch.Generator(device=device).manual_seed(0)
+    ps = [torch.randn(1, rows, 2 * inner, device=device, generator=g).to(dtype) for _ in range(n_sets)]
+    d_out = torch.randn(1, rows, inner, device=device, generator=g).to(dtype)
+
+    def run(p):
+        if impl == "fused":
+            return ops.geglu(p)
+        h, gate = p.chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+    def launch(i):
+        if direction == "fwd":
+            with torch.no_grad():
+                run(ps[i])
+        else:
+            p = ps[i].detach().requires_grad_(True)
+            torch.autograd.grad(run(p), p, d_out)
+    us = _time_graph(launch, n_sets)
+    return {"kernel": f"geglu_{direction}", "impl": impl, "rows": rows, "inner": inner, "us": us, "bytes": nbytes,
+            "gbs": nbytes / us / 1e3, "buffer_sets": n_sets}
+
+
 def sweep_group_norm(device="cuda:0"):
     """The GroupNorm shapes of one SD-1.4 UNet pass at batch 1 / 2, and at the seed-batched 8."""
     for n in (1, 2, 8):
@@ -244,6 +271,12 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--single-self":
         a = sys.argv[2:]
         print(json.dumps(time_self_attn(int(a[1]), 8, int(a[2]), int(a[3]), torch.float16, a[0])))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--geglu":
+        for rows, inner in ((4096, 1280), (1024, 2560), (256, 5120), (64, 5120), (8192, 1280)):
+            for direction in ("fwd", "fwdbwd"):
+                for impl in ("torch", "fused"):
+                    print(json.dumps(time_geglu(rows, inner, direction, impl)))
+                    sys.stdout.flush()
     elif len(sys.argv) > 1 and sys.argv[1] == "--group-norm":
         for r in sweep_group_norm():
             print(json.dumps(r))

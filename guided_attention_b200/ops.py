@@ -500,6 +500,50 @@ def add_bias_residual(a, bias, b=None):
     return _AddBiasResidualFn.apply(a, bias, b)
 
 
+class _GegluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proj):
+        _need_cuda(proj)
+        lib = abi.load()
+        proj = proj.contiguous()
+        inner = proj.shape[-1] // 2
+        rows = proj.numel() // (2 * inner)
+        out = torch.empty(proj.shape[:-1] + (inner,), dtype=proj.dtype, device=proj.device)
+        with torch.cuda.device(proj.device), _span("geglu_fwd", (rows, inner), 3 * rows * inner * proj.element_size(),
+                                                   proj.device):
+            abi.check(lib.ga_geglu_fwd(_ptr(proj), _ptr(out), rows, inner, _DTYPES[proj.dtype], _stream(proj)),
+                      "ga_geglu_fwd")
+        _count("geglu_fwd")
+        ctx.save_for_backward(proj)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (proj,) = ctx.saved_tensors
+        lib = abi.load()
+        inner = proj.shape[-1] // 2
+        rows = proj.numel() // (2 * inner)
+        d_out = d_out.contiguous()
+        d_proj = torch.empty_like(proj)
+        with torch.cuda.device(proj.device), _span("geglu_bwd", (rows, inner), 5 * rows * inner * proj.element_size(),
+                                                   proj.device):
+            abi.check(lib.ga_geglu_bwd(_ptr(proj), _ptr(d_out), _ptr(d_proj), rows, inner, _DTYPES[proj.dtype],
+                                       _stream(proj)), "ga_geglu_bwd")
+        _count("geglu_bwd")
+        return d_proj
+
+
+def geglu(proj: torch.Tensor) -> torch.Tensor:
+    """`h * gelu(gate)` with `h, gate = proj.chunk(2, dim=-1)` (exact erf GELU) on a 16-bit CUDA tensor (..., 2 * inner):
+    one vectorised launch per direction.  The gate of the transformer blocks' feed-forward (diffusers `GEGLU`)."""
+    return _GegluFn.apply(proj)
+
+
+def geglu_supported(proj: torch.Tensor) -> bool:
+    return (proj.is_cuda and proj.dtype in (torch.float16, torch.bfloat16) and proj.shape[-1] % 16 == 0
+            and proj.numel() > 0)
+
+
 def fused_unet_ops_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
 

@@ -377,12 +377,14 @@ def register_fused_norms(unet) -> int:
       * blocks that expose the `fused_norm_act` / `fused_forward` hooks (the substrate's ResnetBlock2D) get SiLU, the
         conv1 bias, the time-embedding add, the conv2 bias and the residual add folded in (`_fused_resnet_forward`);
       * every biased `nn.Conv2d`: 1x1 -> `F.linear` on the channels-last view (bias in the GEMM epilogue), others ->
-        bias-free cuDNN convolution + one vectorised bias pass instead of PyTorch's broadcast `add_`.
+        bias-free cuDNN convolution + one vectorised bias pass instead of PyTorch's broadcast `add_`;
+      * every `GEGLU` feed-forward gate -> `ops.geglu` (one vectorised launch per direction).
     The guided loop runs the UNet forward and backward ~250 times per image and these ops were the largest non-GEMM
     items of its launch list (csrc/group_norm.cu, profiles/r02c_profile_ops.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
-    the UNet untouched (A/B measurements).  Returns the number of norm layers now routed."""
+    the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
     if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
         return 0
+    off = set(filter(None, os.environ.get("GA_FUSED_DISABLE", "").split(",")))   # A/B: any of conv, resnet, geglu
     n = 0
     for m in unet.modules():
         if isinstance(m, torch.nn.GroupNorm):
@@ -397,13 +399,27 @@ def register_fused_norms(unet) -> int:
                 m._ga_fused = True
             n += 1
         elif isinstance(m, torch.nn.Conv2d):
-            if not getattr(m, "_ga_fused", False):
+            if not getattr(m, "_ga_fused", False) and "conv" not in off:
                 _patch_conv(m)
+                m._ga_fused = True
+        elif type(m).__name__ == "GEGLU" and isinstance(getattr(m, "proj", None), torch.nn.Linear):
+            if not getattr(m, "_ga_fused", False) and "geglu" not in off:
+                stock = m.forward
+
+                def forward(x, *a, _m=m, _stock=stock, **kw):
+                    if not a and not kw and not _m.proj.weight.requires_grad:
+                        proj = _m.proj(x)
+                        if ops.geglu_supported(proj):
+                            return ops.geglu(proj)
+                        h, gate = proj.chunk(2, dim=-1)
+                        return h * F.gelu(gate)
+                    return _stock(x, *a, **kw)
+                m.forward = forward
                 m._ga_fused = True
         else:
             if hasattr(m, "fused_norm_act"):
                 m.fused_norm_act = _fused_silu_norm
-            if hasattr(m, "fused_forward"):
+            if hasattr(m, "fused_forward") and "resnet" not in off:
                 m.fused_forward = _fused_resnet_forward
     return n
 

@@ -320,6 +320,15 @@ int ga_group_norm_bwd(const void* x, const void* shift, const void* d_y, const v
 int ga_add_bias_residual(const void* a, const void* b, const void* bias, void* out, int64_t n_pixels, int channels,
                          int dtype, ga_stream_t stream);
 
+/* The gate of the transformer blocks' feed-forward (diffusers `GEGLU.forward`: `h, gate = proj(x).chunk(2, dim=-1);
+ * return h * gelu(gate)`, exact erf GELU) on the projection output `proj` (rows, 2 * inner), dense 16-bit:
+ *   out (rows, inner) = proj[:, :inner] * gelu(proj[:, inner:]);   d_proj (rows, 2 * inner) from d_out (rows, inner).
+ * One vectorised launch per direction instead of PyTorch's strided gelu + product (+ gelu_backward, two products and a
+ * concatenating copy in the backward). */
+int ga_geglu_fwd(const void* proj, void* out, int64_t rows, int inner, int dtype, ga_stream_t stream);
+int ga_geglu_bwd(const void* proj, const void* d_out, void* d_proj, int64_t rows, int inner, int dtype,
+                 ga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

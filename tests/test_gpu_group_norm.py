@@ -204,3 +204,27 @@ def test_fused_resnet_block_matches_stock_block():
             res.append((out.float(), gx.float()))
         assert float((res[0][0] - res[1][0]).abs().max() / res[0][0].abs().max()) < 5e-3
         assert float(F.cosine_similarity(res[0][1].flatten(), res[1][1].flatten(), dim=0)) > 0.9999
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 4096, 1280), (2, 1024, 2560), (1, 256, 5120), (3, 7, 64)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_geglu_matches_torch(shape, dtype):
+    """`h * gelu(gate)` of the feed-forward (exact erf GELU) and its gradient vs PyTorch in fp32 on the same inputs."""
+    from guided_attention_b200 import ops
+    b, n, inner = shape
+    g = torch.Generator(device=DEV).manual_seed(inner)
+    proj = (1.5 * torch.randn(b, n, 2 * inner, device=DEV, generator=g)).to(dtype)
+    d_out = torch.randn(b, n, inner, device=DEV, generator=g).to(dtype)
+    assert ops.geglu_supported(proj)
+    pq = proj.detach().requires_grad_(True)
+    out = ops.geglu(pq)
+    (dp,) = torch.autograd.grad(out, pq, d_out)
+    pr = proj.float().detach().requires_grad_(True)
+    h, gate = pr.chunk(2, dim=-1)
+    ref = h * F.gelu(gate)
+    (dp_ref,) = torch.autograd.grad(ref, pr, d_out.float())
+    rtol, atol = TOL[dtype]
+    assert out.shape == ref.shape and out.dtype == dtype
+    assert torch.allclose(out.float(), ref, rtol=rtol, atol=atol), float((out.float() - ref).abs().max())
+    assert torch.allclose(dp.float(), dp_ref, rtol=rtol, atol=4 * atol), float((dp.float() - dp_ref).abs().max())
