@@ -231,6 +231,10 @@ def workload_config(args, dtype):
                              "host loop replaying graphs (one D2H read per loss evaluation)"
                              if getattr(args, "host_control", False) else
                              "device-side step driver (CUDA conditional graph nodes, no loss read back)"),
+            "unet_elementwise": ("PyTorch ops (GA_FUSED_NORM=0)" if os.environ.get("GA_FUSED_NORM", "1") == "0" else
+                                 "fused channels-last kernels of this repo: GroupNorm(+SiLU, +conv bias / time-embedding "
+                                 "shift), conv bias + residual, GEGLU" +
+                                 (" [off: %s]" % os.environ["GA_FUSED_DISABLE"] if os.environ.get("GA_FUSED_DISABLE") else "")),
             "l2_policy": "inputs larger than L2: every UNet pass streams 1.7 GB of fp16 weights (L2 is 126 MB)",
             "parallelism": f"seed-sharded, {args.gpus} process(es), no hot-path collective"}
 
@@ -612,7 +616,28 @@ def roofline_from(prof):
     if not table:
         return None, table
     dts = {"torch.float16": torch.float16, "torch.bfloat16": torch.bfloat16, "torch.float32": torch.float32}
-    for row in table[:8]:
+    n_attn = n_unet = 0
+    for row in table:
+        is_attn = row["kernel"].startswith(("cross_attn", "self_attn"))
+        if (is_attn and n_attn >= 8) or (not is_attn and n_unet >= 6):
+            continue
+        n_attn, n_unet = n_attn + int(is_attn), n_unet + int(not is_attn)
+        if row["kernel"].startswith("group_norm"):
+            # UNet-side fused kernels (the callers either side of the attention layers): kernel-only time of the same
+            # call, next to PyTorch's own ops for that call on the same tensors
+            n, hw, c, groups, silu = (int(x) for x in row["shape"][:5])
+            direction = "fwd" if row["kernel"].endswith("fwd") else "fwdbwd"
+            m = microbench.time_group_norm(n, c, hw, 1, groups, bool(silu), direction, "fused", device=dev)
+            t = microbench.time_group_norm(n, c, hw, 1, groups, bool(silu), direction, "torch", device=dev)
+            row["kernel_us" if direction == "fwd" else "fwd_plus_bwd_us"] = m["us"]
+            row["gbs"], row["torch_ops_us"] = m["gbs"], t["us"]
+        elif row["kernel"].startswith("geglu"):
+            rows_, inner = (int(x) for x in row["shape"][:2])
+            direction = "fwd" if row["kernel"].endswith("fwd") else "fwdbwd"
+            m = microbench.time_geglu(rows_, inner, direction, "fused", device=dev)
+            t = microbench.time_geglu(rows_, inner, direction, "torch", device=dev)
+            row["kernel_us" if direction == "fwd" else "fwd_plus_bwd_us"] = m["us"]
+            row["gbs"], row["torch_ops_us"] = m["gbs"], t["us"]
         if row["kernel"].startswith("cross_attn"):
             B, H, N, T, dd = (int(x) for x in row["shape"][:5])
             m = microbench.time_cross_attn(B, H, N, T, dd, dts[row["shape"][5]], with_acc=row["shape"][6] == "True",
@@ -624,7 +649,7 @@ def roofline_from(prof):
                                           device=dev)
             row["kernel_us"], row["tflops"], row["tflops_issued"] = m["us"], m["tflops_algorithmic"], m["tflops_issued"]
             row["algorithmic_flops_per_launch"] = m["tflops_algorithmic"] * m["us"] * 1e6
-    top = next((r for r in table if "kernel_us" in r), table[0])
+    top = next((r for r in table if "kernel_us" in r and r["kernel"].startswith(("self_attn", "cross_attn"))), table[0])
     if "tflops" in top:
         roof = {"bound": "tensor", "kernel": top["kernel"], "shape": top["shape"], "achieved": top["tflops"],
                 "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
@@ -643,7 +668,7 @@ def roofline_from(prof):
                 "note": "one launch at the pipeline's batch (B=1 text-cond pass, B=2 CFG pass) moves 0.7-11 MB: launch-"
                         "latency bound by size; profiles/ holds the batch sweep where the same kernels run "
                         "bandwidth-bound"}
-    return roof, table[:10]
+    return roof, [r for r in table if "kernel_us" in r or "fwd_plus_bwd_us" in r][:14]
 
 
 def main():

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "ga_group_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "ga_group_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ga_add_bias_residual": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "ga_layer_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
     "ga_geglu_fwd": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "ga_geglu_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
 }

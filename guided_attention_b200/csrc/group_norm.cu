@@ -626,10 +626,97 @@ int geglu(const void* p, const void* d_out, void* out, int64_t rows, int inner, 
   return check_launch(backward ? "geglu_bwd" : "geglu_fwd");
 }
 
+// --------------------------------------------------------------------------------------------------- LayerNorm
+// The three LayerNorms of every transformer block (diffusers `BasicTransformerBlock.norm1/2/3`) on (rows, C) tokens,
+// C = 320 / 640 / 1280: one WARP per row, the row held in registers (<= 8 vectors of 8 channels per lane), exact two-pass
+// mean / variance with warp shuffles, 128-bit loads and stores.  mean / rstd are saved for the backward.
+constexpr int kLnMaxVec = 8;   // vectors per lane: C <= 32 * 8 * 8 = 2048
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) layer_norm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gamma,
+                                                                  const uint4* __restrict__ beta, uint4* __restrict__ y,
+                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                  int64_t rows, int V, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* xr = x + row * V;
+  float f[kLnMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      unpack8<T>(__ldg(xr + v), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[i][e];
+    }
+  }
+  const float inv_c = 1.f / (float)(V * 8);
+  const float mean = warp_sum(sum) * inv_c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (lane + 32 * i < V) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[i][e] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  uint4* yr = y + row * V;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      float g[8], b[8];
+      unpack8<T>(__ldg(gamma + v), g);
+      unpack8<T>(__ldg(beta + v), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[i][e] = fmaf((f[i][e] - mean) * rstd, g[e], b[e]);
+      yr[v] = pack8<T>(f[i]);
+    }
+  }
+}
+
+int layer_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int64_t rows,
+                   int c, float eps, int dtype, cudaStream_t st) {
+  if (rows == 0) return GA_OK;
+  const int V = c / 8;
+  const int64_t blocks = (rows + kThreads / 32 - 1) / (kThreads / 32);
+  const uint4 *px = static_cast<const uint4*>(x), *pg = static_cast<const uint4*>(gamma), *pb = static_cast<const uint4*>(beta);
+  if (dtype == GA_F16)
+    layer_norm_fwd_kernel<__half><<<(unsigned)blocks, kThreads, 0, st>>>(px, pg, pb, static_cast<uint4*>(y), mean, rstd, rows, V, eps);
+  else
+    layer_norm_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, st>>>(px, pg, pb, static_cast<uint4*>(y), mean, rstd, rows,
+                                                                                V, eps);
+  return check_launch("layer_norm_fwd");
+}
+
 }  // namespace gn
 }  // namespace ga
 
 using namespace ga;
+
+extern "C" int ga_layer_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                                 int64_t rows, int channels, float eps, int dtype, ga_stream_t stream) {
+  GA_CHECK_ARG(x && gamma && beta && y && mean && rstd, "NULL operand");
+  GA_CHECK_ARG(dtype == GA_F16 || dtype == GA_BF16, "layer norm: 16-bit activations only (dtype %d)", dtype);
+  GA_CHECK_ARG(rows >= 0 && rows < ((int64_t)1 << 34) && channels >= 8 && channels % 8 == 0 &&
+                   channels <= 32 * 8 * gn::kLnMaxVec,
+               "layer norm: channels %d must be a multiple of 8 in [8, %d]", channels, 32 * 8 * gn::kLnMaxVec);
+  GA_CHECK_ALIGN(x, 16, "x");
+  GA_CHECK_ALIGN(y, 16, "y");
+  GA_CHECK_ALIGN(gamma, 16, "gamma");
+  GA_CHECK_ALIGN(beta, 16, "beta");
+  return gn::layer_norm_fwd(x, gamma, beta, y, mean, rstd, rows, channels, eps, dtype, static_cast<cudaStream_t>(stream));
+}
 
 static int check_geglu_args(const void* p, const void* out, int64_t rows, int inner, int dtype) {
   GA_CHECK_ARG(p && out, "NULL operand");

@@ -544,6 +544,49 @@ def geglu_supported(proj: torch.Tensor) -> bool:
             and proj.numel() > 0)
 
 
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float):
+        _need_cuda(x, weight, bias)
+        lib = abi.load()
+        x = x.contiguous()
+        c = x.shape[-1]
+        rows = x.numel() // c
+        if weight.dtype != x.dtype:
+            weight, bias = weight.to(x.dtype), bias.to(x.dtype)
+        weight, bias = weight.contiguous(), bias.contiguous()
+        y = torch.empty_like(x)
+        stat_shape = x.shape[:-1] + (1,)
+        mean = torch.empty(stat_shape, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(stat_shape, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), _span("layer_norm_fwd", (rows, c), 2 * x.numel() * x.element_size(), x.device):
+            abi.check(lib.ga_layer_norm_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), rows, c,
+                                            float(eps), _DTYPES[x.dtype], _stream(x)), "ga_layer_norm_fwd")
+        _count("layer_norm_fwd")
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        # the input gradient stays PyTorch's kernel (one launch, already vectorised); gamma / beta are frozen
+        d_x = torch.ops.aten.native_layer_norm_backward(d_y.contiguous(), x, [x.shape[-1]], mean, rstd, weight, bias,
+                                                        [True, False, False])[0]
+        return d_x, None, None, None
+
+
+def layer_norm(x, weight, bias, eps: float = 1e-5):
+    """`F.layer_norm(x, (C,), weight, bias, eps)` over the last dimension of a 16-bit CUDA tensor: one warp per row, the
+    row in registers (forward).  The three norms of every transformer block."""
+    return _LayerNormFn.apply(x, weight, bias, float(eps))
+
+
+def layer_norm_supported(x, weight, bias) -> bool:
+    return (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight is not None and bias is not None
+            and not weight.requires_grad and not bias.requires_grad and x.shape[-1] % 8 == 0 and 8 <= x.shape[-1] <= 2048
+            and x.numel() > 0)
+
+
 def fused_unet_ops_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
 

@@ -378,13 +378,14 @@ def register_fused_norms(unet) -> int:
         conv1 bias, the time-embedding add, the conv2 bias and the residual add folded in (`_fused_resnet_forward`);
       * every biased `nn.Conv2d`: 1x1 -> `F.linear` on the channels-last view (bias in the GEMM epilogue), others ->
         bias-free cuDNN convolution + one vectorised bias pass instead of PyTorch's broadcast `add_`;
-      * every `GEGLU` feed-forward gate -> `ops.geglu` (one vectorised launch per direction).
+      * every `GEGLU` feed-forward gate -> `ops.geglu` (one vectorised launch per direction);
+      * every `nn.LayerNorm` over the channel dimension -> `ops.layer_norm` (warp-per-row forward).
     The guided loop runs the UNet forward and backward ~250 times per image and these ops were the largest non-GEMM
     items of its launch list (csrc/group_norm.cu, profiles/r02c_profile_ops.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
-    the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
+    the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu,layernorm` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
     if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
         return 0
-    off = set(filter(None, os.environ.get("GA_FUSED_DISABLE", "").split(",")))   # A/B: any of conv, resnet, geglu
+    off = set(filter(None, os.environ.get("GA_FUSED_DISABLE", "").split(",")))   # A/B: any of conv, resnet, geglu, layernorm
     n = 0
     for m in unet.modules():
         if isinstance(m, torch.nn.GroupNorm):
@@ -401,6 +402,16 @@ def register_fused_norms(unet) -> int:
         elif isinstance(m, torch.nn.Conv2d):
             if not getattr(m, "_ga_fused", False) and "conv" not in off:
                 _patch_conv(m)
+                m._ga_fused = True
+        elif isinstance(m, torch.nn.LayerNorm):
+            if not getattr(m, "_ga_fused", False) and "layernorm" not in off and len(m.normalized_shape) == 1:
+                stock = m.forward
+
+                def forward(x, _m=m, _stock=stock):
+                    if ops.layer_norm_supported(x, _m.weight, _m.bias):
+                        return ops.layer_norm(x, _m.weight, _m.bias, _m.eps)
+                    return _stock(x)
+                m.forward = forward
                 m._ga_fused = True
         elif type(m).__name__ == "GEGLU" and isinstance(getattr(m, "proj", None), torch.nn.Linear):
             if not getattr(m, "_ga_fused", False) and "geglu" not in off:

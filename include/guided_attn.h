@@ -329,6 +329,12 @@ int ga_geglu_fwd(const void* proj, void* out, int64_t rows, int inner, int dtype
 int ga_geglu_bwd(const void* proj, const void* d_out, void* d_proj, int64_t rows, int inner, int dtype,
                  ga_stream_t stream);
 
+/* LayerNorm forward of the transformer blocks (diffusers `BasicTransformerBlock.norm1/2/3`: `torch.nn.LayerNorm(C)`) on
+ * dense 16-bit tokens x (rows, channels): y = (x - mean) * rstd * gamma + beta, one warp per row; `mean`, `rstd` (rows)
+ * fp32 are written for the backward (which stays PyTorch's `native_layer_norm_backward`). */
+int ga_layer_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                      int64_t rows, int channels, float eps, int dtype, ga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,3 +228,27 @@ def test_geglu_matches_torch(shape, dtype):
     assert out.shape == ref.shape and out.dtype == dtype
     assert torch.allclose(out.float(), ref, rtol=rtol, atol=atol), float((out.float() - ref).abs().max())
     assert torch.allclose(dp.float(), dp_ref, rtol=rtol, atol=4 * atol), float((dp.float() - dp_ref).abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 4096, 320), (2, 1024, 640), (1, 256, 1280), (2, 64, 1280), (3, 5, 64), (1, 7, 2048)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_layer_norm_matches_torch(shape, dtype):
+    from guided_attention_b200 import ops
+    b, n, c = shape
+    g = torch.Generator(device=DEV).manual_seed(c)
+    x = (1.3 * torch.randn(b, n, c, device=DEV, generator=g) + 0.5).to(dtype)
+    wgt = (1.0 + 0.3 * torch.randn(c, device=DEV, generator=g)).to(dtype)
+    bias = (0.2 * torch.randn(c, device=DEV, generator=g)).to(dtype)
+    dy = torch.randn(b, n, c, device=DEV, generator=g).to(dtype)
+    assert ops.layer_norm_supported(x, wgt, bias)
+    xq = x.detach().requires_grad_(True)
+    y = ops.layer_norm(xq, wgt, bias, 1e-5)
+    (dx,) = torch.autograd.grad(y, xq, dy)
+    xr = x.float().detach().requires_grad_(True)
+    y_ref = F.layer_norm(xr, (c,), wgt.float(), bias.float(), 1e-5)
+    (dx_ref,) = torch.autograd.grad(y_ref, xr, dy.float())
+    rtol, atol = TOL[dtype]
+    assert torch.allclose(y.float(), y_ref, rtol=rtol, atol=atol), float((y.float() - y_ref).abs().max())
+    err = float((dx.float() - dx_ref).abs().max() / dx_ref.abs().max())
+    assert err < (4e-3 if dtype == torch.float16 else 3e-2), err
