@@ -21,7 +21,7 @@ GA_MAX_ACC_SLICES, GA_MAX_TOKENS, GA_MAX_BOXES, GA_MAX_CTX = 32, 24, 32, 128
  GA_STAT_UNSCALED, GA_STAT_HINGE_IN, GA_STAT_HINGE_OUT, GA_STAT_NINSIDE, GA_STAT_CENTER, GA_STAT_RAW_SUM,
  GA_STAT_RAW_COL, GA_STAT_RAW_ROW) = range(15)
 GA_STATS = 16
-GA_ABI_VERSION = 6
+GA_ABI_VERSION = 7
 GA_STEP_CTL_BYTES, GA_STEP_COUNTER_BASE = 256, 19
 (GA_STEP_N_EVAL, GA_STEP_N_UPDATE, GA_STEP_N_CFG, GA_STEP_N_REFINE, GA_STEP_N_ROUNDS, GA_STEP_N_RENOISE) = range(6)
 
@@ -92,8 +92,8 @@ PROTOTYPES = {
     "ga_box_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ga_box_loss_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ga_group_norm_ws_bytes": (_i64, [_i, _i, _i, _i]),
-    "ga_group_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
-    "ga_group_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ga_group_norm_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "ga_group_norm_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ga_add_bias_residual": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "ga_layer_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
     "ga_geglu_fwd": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

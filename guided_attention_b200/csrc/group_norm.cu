@@ -38,6 +38,7 @@ struct Params {
   const void* gamma;
   const void* beta;
   const void* shift;      // optional (n, c): the kernels normalise x + shift[n, c] (a conv bias + time embedding folded in)
+  int64_t shift_stride;   // elements between the shift rows of consecutive samples (>= c: a column slice of a wider matrix)
   void* out;              // y (forward) or dx (backward)
   float* stats;           // [n][groups][2] = mean, rstd
   float* ws;              // chunk partials [n][P][groups][2]: (mean, M2) forward, (sum dxh, sum dxh * xhat) backward
@@ -82,7 +83,7 @@ struct Coord {
 
 template <typename T> __device__ __forceinline__ void load_shift(const Params& p, const Coord& t, float* sh) {
   if (p.shift != nullptr) {
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.shift) + (int64_t)t.n * p.c + t.c0)), sh);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.shift) + (int64_t)t.n * p.shift_stride + t.c0)), sh);
   } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) sh[e] = 0.f;
@@ -501,24 +502,24 @@ static void launch_bwd(const Params& p, bool silu, cudaStream_t st) {
   }
 }
 
-int fwd(const void* x, const void* shift, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
+int fwd(const void* x, const void* shift, int64_t shift_stride, const void* gamma, const void* beta, void* y, float* stats, float* ws, int n,
         int hw, int c, int groups, float eps, int silu, int dtype, cudaStream_t st) {
   Params p;
   if (!plan(p, n, hw, c, groups))
     return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
-  p.x = x; p.shift = shift; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.out = y; p.stats = stats; p.ws = ws;
+  p.x = x; p.shift = shift; p.shift_stride = shift_stride; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.out = y; p.stats = stats; p.ws = ws;
   p.eps = eps;
   if (dtype == GA_F16) launch_fwd<__half>(p, silu != 0, st);
   else launch_fwd<__nv_bfloat16>(p, silu != 0, st);
   return check_launch("group_norm_fwd");
 }
 
-int bwd(const void* x, const void* shift, const void* dy, const void* gamma, const void* beta, const float* stats,
+int bwd(const void* x, const void* shift, int64_t shift_stride, const void* dy, const void* gamma, const void* beta, const float* stats,
         void* dx, float* ws, int n, int hw, int c, int groups, int silu, int dtype, cudaStream_t st) {
   Params p;
   if (!plan(p, n, hw, c, groups))
     return fail(GA_ERR_UNSUPPORTED, "group norm: shape n=%d hw=%d c=%d groups=%d is not supported", n, hw, c, groups);
-  p.x = x; p.shift = shift; p.dy = dy; p.gamma = gamma; p.beta = beta; p.out = dx; p.stats = const_cast<float*>(stats); p.ws = ws;
+  p.x = x; p.shift = shift; p.shift_stride = shift_stride; p.dy = dy; p.gamma = gamma; p.beta = beta; p.out = dx; p.stats = const_cast<float*>(stats); p.ws = ws;
   p.eps = 0.f;
   if (dtype == GA_F16) launch_bwd<__half>(p, silu != 0, st);
   else launch_bwd<__nv_bfloat16>(p, silu != 0, st);
@@ -772,24 +773,32 @@ static int check_gn_args(const void* x, const void* gamma, const void* beta, con
   return GA_OK;
 }
 
-extern "C" int ga_group_norm_fwd(const void* x, const void* shift, const void* gamma, const void* beta, void* y,
+extern "C" int ga_group_norm_fwd(const void* x, const void* shift, int64_t shift_stride, const void* gamma, const void* beta, void* y,
                                  float* stats, float* ws, int n, int hw, int channels, int groups, float eps, int silu,
                                  int dtype, ga_stream_t stream) {
   int rc = check_gn_args(x, gamma, beta, y, stats, ws, dtype);
   if (rc != GA_OK) return rc;
-  if (shift != nullptr) GA_CHECK_ALIGN(shift, 16, "shift");
-  return gn::fwd(x, shift, gamma, beta, y, stats, ws, n, hw, channels, groups, eps, silu, dtype,
+  if (shift != nullptr) {
+    GA_CHECK_ALIGN(shift, 16, "shift");
+    GA_CHECK_ARG(shift_stride >= channels && shift_stride % 8 == 0, "shift_stride %lld must be a multiple of 8 >= channels",
+                 (long long)shift_stride);
+  }
+  return gn::fwd(x, shift, shift_stride, gamma, beta, y, stats, ws, n, hw, channels, groups, eps, silu, dtype,
                  static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ga_group_norm_bwd(const void* x, const void* shift, const void* d_y, const void* gamma, const void* beta,
+extern "C" int ga_group_norm_bwd(const void* x, const void* shift, int64_t shift_stride, const void* d_y, const void* gamma, const void* beta,
                                  const float* stats, void* d_x, float* ws, int n, int hw, int channels, int groups,
                                  int silu, int dtype, ga_stream_t stream) {
   int rc = check_gn_args(x, gamma, beta, d_x, stats, ws, dtype);
   if (rc != GA_OK) return rc;
   GA_CHECK_ARG(d_y != nullptr, "NULL operand");
   GA_CHECK_ALIGN(d_y, 16, "d_y");
-  if (shift != nullptr) GA_CHECK_ALIGN(shift, 16, "shift");
-  return gn::bwd(x, shift, d_y, gamma, beta, stats, d_x, ws, n, hw, channels, groups, silu, dtype,
+  if (shift != nullptr) {
+    GA_CHECK_ALIGN(shift, 16, "shift");
+    GA_CHECK_ARG(shift_stride >= channels && shift_stride % 8 == 0, "shift_stride %lld must be a multiple of 8 >= channels",
+                 (long long)shift_stride);
+  }
+  return gn::bwd(x, shift, shift_stride, d_y, gamma, beta, stats, d_x, ws, n, hw, channels, groups, silu, dtype,
                  static_cast<cudaStream_t>(stream));
 }

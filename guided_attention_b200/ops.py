@@ -425,13 +425,17 @@ class _GroupNormFn(torch.autograd.Function):
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
         weight, bias = weight.contiguous(), bias.contiguous()
         if shift is not None:
-            shift = shift.to(x.dtype).reshape(n, c).contiguous()
+            # rows of c values, any row stride that keeps 16-byte alignment (a column slice of a wider matrix is fine)
+            shift = shift.to(x.dtype).reshape(n, c)
+            if shift.stride(1) != 1 or shift.stride(0) % 8 != 0 or shift.stride(0) < c or shift.data_ptr() % 16 != 0:
+                shift = shift.contiguous()
         y = torch.empty_like(x)                       # keeps the channels-last strides
         stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
         ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
         nbytes = 3 * x.numel() * x.element_size()     # x read twice (the second time from L2), y written
         with torch.cuda.device(x.device), _span("group_norm_fwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
-            abi.check(lib.ga_group_norm_fwd(_ptr(x), _ptr(shift), _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats),
+            abi.check(lib.ga_group_norm_fwd(_ptr(x), _ptr(shift), shift.stride(0) if shift is not None else 0,
+                                            _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats),
                                             _ptr(ws), n, h * w, c, groups, float(eps), int(silu), _DTYPES[x.dtype],
                                             _stream(x)), "ga_group_norm_fwd")
         _count("group_norm_fwd", 2)
@@ -450,7 +454,8 @@ class _GroupNormFn(torch.autograd.Function):
         ws = torch.empty(max(group_norm_ws_bytes(n, h * w, c, groups), 8) // 4, dtype=torch.float32, device=x.device)
         nbytes = 5 * x.numel() * x.element_size()
         with torch.cuda.device(x.device), _span("group_norm_bwd", (n, h * w, c, groups, int(silu)), nbytes, x.device):
-            abi.check(lib.ga_group_norm_bwd(_ptr(x), _ptr(shift), _ptr(d_y), _ptr(weight), _ptr(bias), _ptr(stats),
+            abi.check(lib.ga_group_norm_bwd(_ptr(x), _ptr(shift), shift.stride(0) if shift is not None else 0,
+                                            _ptr(d_y), _ptr(weight), _ptr(bias), _ptr(stats),
                                             _ptr(d_x), _ptr(ws), n, h * w, c, groups, int(silu), _DTYPES[x.dtype],
                                             _stream(x)), "ga_group_norm_bwd")
         _count("group_norm_bwd", 2)

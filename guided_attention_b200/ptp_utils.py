@@ -313,6 +313,10 @@ def _fused_silu_norm(norm, x):
     return F.silu(norm(x))
 
 
+def _frozen(p) -> bool:
+    return p is not None and not p.requires_grad
+
+
 def _plain_conv(conv) -> bool:
     return (conv.bias is not None and not conv.weight.requires_grad and not conv.bias.requires_grad and conv.groups == 1
             and tuple(conv.dilation) == (1, 1) and conv.padding_mode == "zeros" and not isinstance(conv.padding, str))
@@ -329,6 +333,43 @@ def _shift_bias(block):
     return hit[1]
 
 
+class _TembShifts:
+    """All ResNet blocks of one UNet read the same time embedding: their `time_emb_proj(silu(temb))` projections (22
+    launches of a one-row GEMM plus 22 SiLUs per UNet pass in the stock forward) are ONE GEMM against the concatenated
+    weights, computed by the first block that sees a new `temb` and cached on that tensor; conv1's bias is folded into
+    the concatenated bias, and every block's norm2 kernel reads its column slice as `shift`."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        self.key = None
+        self.weight = self.bias = None
+        self.offsets = {}
+
+    def _params(self):
+        return [p for b in self.blocks for p in (b.time_emb_proj.weight, b.time_emb_proj.bias, b.conv1.bias)]
+
+    def _build(self):
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in self._params())
+        if key != self.key:
+            with torch.no_grad():
+                self.weight = torch.cat([b.time_emb_proj.weight for b in self.blocks], dim=0).contiguous()
+                self.bias = torch.cat([b.time_emb_proj.bias + b.conv1.bias for b in self.blocks], dim=0).contiguous()
+            off = 0
+            for b in self.blocks:
+                self.offsets[id(b)] = (off, b.conv1.out_channels)
+                off += b.conv1.out_channels
+            self.key = key
+
+    def shift(self, block, temb):
+        cached = getattr(temb, "_ga_shifts", None)
+        if cached is None or cached[0] is not self:
+            self._build()
+            cached = (self, F.linear(F.silu(temb), self.weight, self.bias))
+            temb._ga_shifts = cached
+        off, c = self.offsets[id(block)]
+        return cached[1][:, off:off + c]
+
+
 def _fused_resnet_forward(block, x, temb):
     """ResnetBlock2D with its elementwise work folded away (same mathematics as the stock forward):
         h   = conv1_nobias(silu(norm1(x)))
@@ -343,7 +384,11 @@ def _fused_resnet_forward(block, x, temb):
                  c1.padding)
     if not ops.group_norm_supported(h, n2.weight, n2.bias, n2.num_groups):
         return None
-    shift = F.linear(F.silu(temb), block.time_emb_proj.weight, _shift_bias(block))
+    reg = getattr(block, "_ga_temb_shifts", None)
+    if reg is not None and temb.dtype == block.time_emb_proj.weight.dtype:
+        shift = reg.shift(block, temb)
+    else:
+        shift = F.linear(F.silu(temb), block.time_emb_proj.weight, _shift_bias(block))
     if shift.shape[0] != h.shape[0]:
         shift = shift.expand(h.shape[0], -1)
     h = F.conv2d(ops.group_norm(h, n2.weight, n2.bias, n2.num_groups, n2.eps, silu=True, shift=shift), c2.weight, None,
@@ -375,17 +420,18 @@ def register_fused_norms(unet) -> int:
     (fp32, CPU, trainable layers) keeps PyTorch's own ops:
       * every `nn.GroupNorm` (ResNet blocks, transformer wrappers, `conv_norm_out`) -> `ops.group_norm`;
       * blocks that expose the `fused_norm_act` / `fused_forward` hooks (the substrate's ResnetBlock2D) get SiLU, the
-        conv1 bias, the time-embedding add, the conv2 bias and the residual add folded in (`_fused_resnet_forward`);
+        conv1 bias, the time-embedding add, the conv2 bias and the residual add folded in (`_fused_resnet_forward`),
+        and all their time-embedding projections become one GEMM per UNet pass (`_TembShifts`);
       * every biased `nn.Conv2d`: 1x1 -> `F.linear` on the channels-last view (bias in the GEMM epilogue), others ->
         bias-free cuDNN convolution + one vectorised bias pass instead of PyTorch's broadcast `add_`;
       * every `GEGLU` feed-forward gate -> `ops.geglu` (one vectorised launch per direction);
       * every `nn.LayerNorm` over the channel dimension -> `ops.layer_norm` (warp-per-row forward).
     The guided loop runs the UNet forward and backward ~250 times per image and these ops were the largest non-GEMM
     items of its launch list (csrc/group_norm.cu, profiles/r02c_profile_ops.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
-    the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu,layernorm` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
+    the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu,layernorm,temb` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
     if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
         return 0
-    off = set(filter(None, os.environ.get("GA_FUSED_DISABLE", "").split(",")))   # A/B: any of conv, resnet, geglu, layernorm
+    off = set(filter(None, os.environ.get("GA_FUSED_DISABLE", "").split(",")))   # A/B: any of conv, resnet, geglu, layernorm, temb
     n = 0
     for m in unet.modules():
         if isinstance(m, torch.nn.GroupNorm):
@@ -432,6 +478,14 @@ def register_fused_norms(unet) -> int:
                 m.fused_norm_act = _fused_silu_norm
             if hasattr(m, "fused_forward") and "resnet" not in off:
                 m.fused_forward = _fused_resnet_forward
+    if "temb" not in off:
+        blocks = [m for m in unet.modules() if getattr(m, "fused_forward", None) is _fused_resnet_forward
+                  and all(hasattr(m, a) for a in ("time_emb_proj", "conv1"))
+                  and all(_frozen(q) for q in (m.time_emb_proj.weight, m.time_emb_proj.bias, m.conv1.bias))]
+        if len(blocks) > 1 and len({b.time_emb_proj.in_features for b in blocks}) == 1:
+            reg = _TembShifts(blocks)
+            for b in blocks:
+                b._ga_temb_shifts = reg
     return n
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GA_ABI_VERSION 6
+#define GA_ABI_VERSION 7
 
 typedef void* ga_stream_t; /* cudaStream_t */
 
@@ -306,15 +306,16 @@ int ga_box_loss_bwd(const float* p, const uint8_t* mask, const float* weights, i
  * ga_group_norm_ws_bytes returns -1 when the shape is not supported (channels % 8, channels % groups, a group
  * narrower than the kernels' 8-channel vectors allow). */
 int64_t ga_group_norm_ws_bytes(int n, int hw, int channels, int groups);
-/* `shift` (n, channels), same dtype, or NULL: the kernels normalise x + shift[n, c] -- the bias of the convolution that
- * produced x and the block's time-embedding projection (ResnetBlock2D: `conv1(..) + time_emb_proj(..)[:, :, None, None]`)
- * folded into the norm instead of two broadcast-add launches. */
-int ga_group_norm_fwd(const void* x, const void* shift, const void* gamma, const void* beta, void* y, float* stats,
-                      float* ws, int n, int hw, int channels, int groups, float eps, int silu, int dtype,
-                      ga_stream_t stream);
-int ga_group_norm_bwd(const void* x, const void* shift, const void* d_y, const void* gamma, const void* beta,
-                      const float* stats, void* d_x, float* ws, int n, int hw, int channels, int groups, int silu,
+/* `shift` (n rows of `channels` values, `shift_stride` elements apart), same dtype, or NULL: the kernels normalise
+ * x + shift[n, c] -- the bias of the convolution that produced x and the block's time-embedding projection
+ * (ResnetBlock2D: `conv1(..) + time_emb_proj(..)[:, :, None, None]`) folded into the norm instead of two broadcast-add
+ * launches; the stride lets the rows be a column slice of ONE projection computed for all blocks of the UNet. */
+int ga_group_norm_fwd(const void* x, const void* shift, int64_t shift_stride, const void* gamma, const void* beta,
+                      void* y, float* stats, float* ws, int n, int hw, int channels, int groups, float eps, int silu,
                       int dtype, ga_stream_t stream);
+int ga_group_norm_bwd(const void* x, const void* shift, int64_t shift_stride, const void* d_y, const void* gamma,
+                      const void* beta, const float* stats, void* d_x, float* ws, int n, int hw, int channels, int groups,
+                      int silu, int dtype, ga_stream_t stream);
 /* out = a + bias[c] (+ b when b != NULL) on channels-last (n_pixels, channels) 16-bit tensors: a convolution's bias and
  * the block's residual connection (`x + conv2(..)`) in one vectorised pass.  `out` may alias `a`. */
 int ga_add_bias_residual(const void* a, const void* b, const void* bias, void* out, int64_t n_pixels, int channels,
