@@ -715,11 +715,14 @@ struct FwdStreamParams {
   PipeParams b;
   int ring_stages;   // (Q block, K block) stages, 2 .. kMaxStages
   int v_slots;       // 2 .. 4
+  int stage_out;     // leading 64-channel blocks of O that leave through per-warp TMA-store staging tiles (0, 1 or 2)
 };
+constexpr uint32_t kOutStageBytes = 4u * 4096u;   // one staged block: 4 epilogue warps x (32 rows x 128 bytes)
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
 cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                                const __grid_constant__ CUtensorMap map_v, const FwdStreamParams sp) {
+                                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                                const FwdStreamParams sp) {
   const PipeParams& p = sp.b;
   extern __shared__ uint8_t smem_raw[];
   // ring_full[6], ring_free[6], v_full[4], v_free[4], s_ready[4], p_ready[4], p_free[4], o_ready[4], tmem_free[4]
@@ -734,7 +737,10 @@ cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
   const int R = sp.ring_stages, NV = sp.v_slots;
   const uint32_t v_slot_bytes = (uint32_t)p.nblk * kKVBlockBytes;
   const uint32_t v_base = base + (uint32_t)R * ring_stage_bytes;
-  float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)R * ring_stage_bytes + (size_t)NV * v_slot_bytes);
+  const uint32_t out_stage = v_base + (uint32_t)NV * v_slot_bytes;                     // 1024-byte aligned
+  const uint32_t out_stage_bytes = (uint32_t)sp.stage_out * kOutStageBytes;
+  float* sAcc = reinterpret_cast<float*>(base_ptr + (size_t)R * ring_stage_bytes + (size_t)NV * v_slot_bytes +
+                                         out_stage_bytes);
   auto RING_FULL = [&](int s) { return smem_u32(&bars[s]); };
   auto RING_FREE = [&](int s) { return smem_u32(&bars[kMaxStages + s]); };
   auto V_FULL = [&](int s) { return smem_u32(&bars[2 * kMaxStages + s]); };
@@ -757,6 +763,7 @@ cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
 
   if (tid == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    if (sp.stage_out) prefetch_tmap(&map_o);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(RING_FULL(s), 1); mbar_init(RING_FREE(s), 1); }
     for (int s = 0; s < 4; ++s) {
       mbar_init(V_FULL(s), 1);
@@ -870,7 +877,51 @@ cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
       const float inv = s_inv[k & 7][r];
       const int row = it.tile * kM + r;
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (((int64_t)it.b * p.N + row) * p.H + it.h) * (int64_t)p.d * 2;
-      for (int c0 = 0; c0 < p.npv / 16; c0 += 2) {
+      int c_first = 0;
+      if (sp.stage_out) {
+        // The leading 64-channel blocks leave through the TMA: registers -> this warp's 4 KB staging tile per block (the
+        // TMA's 128-byte swizzle, conflict-free) -> one cp.async.bulk.tensor store of 32 rows per block.  The per-thread
+        // 16-byte stores they replace have their lanes a row apart: 32 LSU wavefronts per instruction, and the epilogue
+        // warpgroup was the busiest role of this kernel (profiles/: 79 % of its samples outside the O_READY wait, the
+        // second MMA issuer waiting 35 % of its time for it to free an O buffer).  Lane 0 issues every store of its warp
+        // and is the one that waits for the previous item's stores to have READ the tiles before they are overwritten
+        // (bulk groups are per thread).  Columns past head_dim in a block's tile are never written and never stored (the
+        // TMA clips the box at the tensor's extent).
+        const int chunks = p.npv / 16;
+        for (int blk = 0; blk < sp.stage_out; ++blk) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {        // 32 columns per TMEM round trip (88 registers per thread here)
+            const int cb = blk * 4 + half * 2;
+            if (cb >= chunks) break;
+            float ov[32];
+            tmem_ld16(lane_base + colO(k) + cb * 16, ov);
+            if (cb + 1 < chunks) tmem_ld16(lane_base + colO(k) + (cb + 1) * 16, ov + 16);
+            tmem_ld_wait();
+            if (blk == 0 && half == 0 && k > 0) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (cb + u >= chunks) break;
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = pack16(ov[u * 16 + 2 * i] * inv, ov[u * 16 + 2 * i + 1] * inv, bf16);
+              st_swizzled_32B(out_stage + (uint32_t)blk * kOutStageBytes, r, (half * 2 + u) * 2, w);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          for (int blk = 0; blk < sp.stage_out && blk * 4 < chunks; ++blk)
+            tma_store_4d(&map_o, out_stage + (uint32_t)blk * kOutStageBytes + (uint32_t)warp * 4096u, blk * kBlockCols, it.h,
+                         it.tile * kM + warp * 32, it.b);
+          bulk_commit_group();
+        }
+        c_first = 4 * sp.stage_out;
+      }
+      for (int c0 = c_first; c0 < p.npv / 16; c0 += 2) {
         float ov[32];
         tmem_ld16(lane_base + colO(k) + c0 * 16, ov);
         if (c0 + 1 < p.npv / 16) tmem_ld16(lane_base + colO(k) + (c0 + 1) * 16, ov + 16);
@@ -892,6 +943,8 @@ cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
       mbar_arrive(TMEM_FREE(ob));
       it.next(p);
     }
+    if (sp.stage_out && lane == 0) bulk_wait_all0();      // the last stores have left before the CTA exits
+    __syncwarp();
   } else {
     reg_alloc<184>();
     // ------------------------------------------------------------------------------------ softmax groups
@@ -1851,15 +1904,53 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     const size_t acc_bytes = (size_t)kM * kAccStride * sizeof(float), ring = (size_t)kQBlockBytes + kKVBlockBytes;
     const size_t vslot = (size_t)p.nblk * kKVBlockBytes;
     sp.v_slots = 3;
-    sp.ring_stages = 0;
-    for (int n = kMaxStages; n >= 2; --n)
-      if (1024 + acc_bytes + sp.v_slots * vslot + n * ring <= 226 * 1024) { sp.ring_stages = n; break; }
+    // O staging tiles (TMA stores instead of row-strided 16-byte stores, see the epilogue) are paid for with the third
+    // V slot where needed, never with a ring stage.  Measured on B200 (profiles/r02d_k1_stage_ab.txt): d = 80
+    // 210 -> 167-171 us with one staged block, d = 160 191 -> 170 us with one staged block and two V slots, 158 us with two.
+    // GA_K1_STAGE_OUT=<blocks> / GA_K1_V_SLOTS=<n> override the choice (A/B measurements).
+    static int stage_mode = -2, slot_mode = -2;
+    if (stage_mode == -2) {
+      const char* eo = getenv("GA_K1_STAGE_OUT");
+      stage_mode = eo == nullptr ? -1 : atoi(eo);
+      const char* ev = getenv("GA_K1_V_SLOTS");
+      slot_mode = ev == nullptr ? -1 : atoi(ev);
+    }
+    // dynamic + static shared memory (barriers, s_inv: 4.4 KB) must stay within the 227 KB a CTA can opt in to
+    auto stages_for = [&](int blocks, int v_slots) {
+      for (int n = kMaxStages; n >= 2; --n)
+        if (1024 + acc_bytes + (size_t)blocks * kOutStageBytes + v_slots * vslot + n * ring <= 222 * 1024) return n;
+      return 0;
+    };
+    const int without = stages_for(0, 3);
+    sp.stage_out = 0;
+    sp.v_slots = 3;
+    if (stage_mode < 0) {
+      // first fit that keeps the ring depth: two staged blocks only when two FULL 64-channel blocks exist (staging the
+      // 16-channel tail of d = 80 at the price of a V slot measured slower: 176 vs 171 us)
+      const int full_blocks = p.d / kBlockCols;
+      const int cand[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}};
+      for (int i = 0; i < 4; ++i) {
+        if (cand[i][0] == 2 && full_blocks < 2) continue;
+        if (stages_for(cand[i][0], cand[i][1]) == without) {
+          sp.stage_out = cand[i][0];
+          sp.v_slots = cand[i][1];
+          break;
+        }
+      }
+    } else {
+      sp.stage_out = stage_mode > 2 ? 2 : stage_mode;
+    }
+    if (slot_mode == 2 || slot_mode == 3) sp.v_slots = slot_mode;
+    sp.ring_stages = stages_for(sp.stage_out, sp.v_slots);
     if (sp.ring_stages >= p.nblk) {
-      const size_t smem_s = 1024 + acc_bytes + sp.v_slots * vslot + sp.ring_stages * ring;
+      const size_t smem_s = 1024 + acc_bytes + (size_t)sp.stage_out * kOutStageBytes + sp.v_slots * vslot + sp.ring_stages * ring;
       cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_stream_kernel), 6, smem_s);
       if (es2 != cudaSuccess) return fail(GA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(es2));
+      CUtensorMap mo_s;
+      int rc_s;
+      if ((rc_s = make_map(&mo_s, f.o, dtype, f.B, f.N, f.H, f.d, 32)) != GA_OK) return rc_s;   // one store per epilogue warp
       const int grid_s = p.units < sm_count() ? p.units : sm_count();
-      cross_attn_fwd_tc_stream_kernel<<<grid_s, kPipeThreads, smem_s, st>>>(mq, mk, mv, sp);
+      cross_attn_fwd_tc_stream_kernel<<<grid_s, kPipeThreads, smem_s, st>>>(mq, mk, mv, mo_s, sp);
       return check_launch("cross_attn_fwd_tc_stream");
     }
   }

@@ -271,6 +271,12 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--single-self":
         a = sys.argv[2:]
         print(json.dumps(time_self_attn(int(a[1]), 8, int(a[2]), int(a[3]), torch.float16, a[0])))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--single-group-norm":      # direction n c r  (for ncu)
+        a = sys.argv[2:]
+        print(json.dumps(time_group_norm(int(a[1]), int(a[2]), int(a[3]), int(a[3]), 32, True, a[0], "fused")))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--single-geglu":           # direction rows inner  (for ncu)
+        a = sys.argv[2:]
+        print(json.dumps(time_geglu(int(a[1]), int(a[2]), a[0], "fused")))
     elif len(sys.argv) > 1 and sys.argv[1] == "--geglu":
         for rows, inner in ((4096, 1280), (1024, 2560), (256, 5120), (64, 5120), (8192, 1280)):
             for direction in ("fwd", "fwdbwd"):
