@@ -716,6 +716,7 @@ struct FwdStreamParams {
   int ring_stages;   // (Q block, K block) stages, 2 .. kMaxStages
   int v_slots;       // 2 .. 4
   int stage_out;     // leading 64-channel blocks of O that leave through per-warp TMA-store staging tiles (0, 1 or 2)
+  int acc_bulk;      // 1: a unit's 128 x T head-sum tile (contiguous in `acc`) leaves with one cp.async.bulk
 };
 constexpr uint32_t kOutStageBytes = 4u * 4096u;   // one staged block: 4 epilogue warps x (32 rows x 128 bytes)
 
@@ -988,30 +989,61 @@ cross_attn_fwd_tc_stream_kernel(const __grid_constant__ CUtensorMap map_q, const
         if (row < p.N)
           p.lse[((int64_t)b * p.H + h) * p.N + row] = (m * sc + lg2_approx(sum)) * 0.6931471805599453f;
       }
-      // ---- end of the (b, tile) unit: combine the two groups' head sums, write the accumulator rows coalesced
-      if (g == 1) {
+      // ---- end of the (b, tile) unit: combine the two groups' head sums and write the accumulator rows
+      if (sp.acc_bulk) {
+        // The unit's rows are CONTIGUOUS in `acc` (128 rows x T floats): the tile is assembled densely in shared memory
+        // (row stride T = 77: odd, conflict-free) and leaves with ONE bulk copy issued by one thread, instead of eight
+        // warps looping over dependent shared-load / global-store pairs (the loop and its barrier were ~15 % of the
+        // softmax groups' stall samples).  Group 1 does not wait for the copy: it only waits, at the NEXT unit, for the
+        // tile to have been read.
+        const bool t0 = tid == kGroupThreads;                  // first thread of group 0 owns the bulk group
+        if (u > 0 && t0) bulk_wait_read0();
+        named_bar_sync(1, 2 * kGroupThreads);
+        if (g == 1) {
 #pragma unroll
-        for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] = pacc[j];
-      }
-      named_bar_sync(1, 2 * kGroupThreads);
-      if (g == 0) {
+          for (int j = 0; j < kTpad; ++j)
+            if (j < p.T) sAcc[r * p.T + j] = pacc[j];
+          named_bar_arrive(2, 2 * kGroupThreads);
+        } else {
+          named_bar_sync(2, 2 * kGroupThreads);
 #pragma unroll
-        for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] += pacc[j];
-      }
-      named_bar_sync(2, 2 * kGroupThreads);
-      for (int i = warp - 4; i < kM; i += 8) {
-        const int gr = tile * kM + i;
-        if (gr >= p.N) break;
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          const int j = lane + 32 * kk;
-          if (j < p.T) p.acc[((int64_t)b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
+          for (int j = 0; j < kTpad; ++j)
+            if (j < p.T) sAcc[r * p.T + j] += pacc[j];
+          fence_proxy_async_smem();
+          named_bar_sync(3, kGroupThreads);
+          if (t0) {
+            const int rows = min(kM, p.N - tile * kM);
+            bulk_store_1d(p.acc + ((int64_t)b * p.N + (int64_t)tile * kM) * p.T, smem_u32(sAcc),
+                          (uint32_t)(rows * p.T * (int)sizeof(float)));
+            bulk_commit_group();
+          }
         }
+      } else {
+        if (g == 1) {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] = pacc[j];
+        }
+        named_bar_sync(1, 2 * kGroupThreads);
+        if (g == 0) {
+#pragma unroll
+          for (int j = 0; j < kTpad; ++j) sAcc[r * kAccStride + j] += pacc[j];
+        }
+        named_bar_sync(2, 2 * kGroupThreads);
+        for (int i = warp - 4; i < kM; i += 8) {
+          const int gr = tile * kM + i;
+          if (gr >= p.N) break;
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const int j = lane + 32 * kk;
+            if (j < p.T) p.acc[((int64_t)b * p.N + gr) * p.T + j] = sAcc[i * kAccStride + j];
+          }
+        }
+        named_bar_sync(3, 2 * kGroupThreads);
       }
-      named_bar_sync(3, 2 * kGroupThreads);
 #pragma unroll
       for (int j = 0; j < kTpad; ++j) pacc[j] = 0.f;
     }
+    if (sp.acc_bulk && tid == kGroupThreads) bulk_wait_all0();     // the last tile has left before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -1942,6 +1974,15 @@ static int fwd_pipe(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     }
     if (slot_mode == 2 || slot_mode == 3) sp.v_slots = slot_mode;
     sp.ring_stages = stages_for(sp.stage_out, sp.v_slots);
+    // one bulk copy per head-sum tile needs 16-byte aligned, 16-byte sized tiles: N % 4 == 0 and an aligned accumulator
+    static int bulk_mode = -2;
+    if (bulk_mode == -2) {
+      const char* eb = getenv("GA_K1_ACC_BULK");
+      bulk_mode = eb == nullptr ? -1 : atoi(eb);
+    }
+    // Measured SLOWER than the eight-warp write loop (d = 80: 184 vs 173 us, d = 160: 161 vs 159 us, B = 16: 17.8 vs 15.6 us;
+    // profiles/r02d_k1_stage_ab.txt): kept behind GA_K1_ACC_BULK=1 as a recorded negative result, off by default.
+    sp.acc_bulk = (bulk_mode == 1 && f.N % 4 == 0 && (reinterpret_cast<uintptr_t>(f.acc) & 15) == 0) ? 1 : 0;
     if (sp.ring_stages >= p.nblk) {
       const size_t smem_s = 1024 + acc_bytes + (size_t)sp.stage_out * kOutStageBytes + sp.v_slots * vslot + sp.ring_stages * ring;
       cudaError_t es2 = ensure_smem(reinterpret_cast<const void*>(cross_attn_fwd_tc_stream_kernel), 6, smem_s);
@@ -2034,7 +2075,9 @@ int fwd(const void* q, const void* k, const void* v, void* o, float* lse, float*
     // at d = 160 (streaming variant) however few units there are, while the single-shot cluster kernel costs ~9 us per
     // wave of ~8 units: the persistent kernel wins from ~24 units on (B = 3 at 32x32, B = 12 at 16x16) -- not from
     // sm_count / 2 = 74 as in round 1, which left the seed-batched launches (B = 8, 16) on the slow side.
-    const int min_units = acc != nullptr ? 24 : 2 * sm_count();
+    // (third pass, with the staged epilogue: 16 units already win when a batch element has more than one row tile --
+    // B = 2 at 32x32, the CFG pass: 14.6 vs 17.4 us -- profiles/r02d_crossover_sweep.jsonl)
+    const int min_units = acc != nullptr ? (tiles >= 2 ? 16 : 24) : 2 * sm_count();
     bool use_pipe = d <= 160 && units >= min_units;
     if (pipe_override() >= 0) use_pipe = pipe_override() == 1 && d <= 160;
     if (force_variant == 0) use_pipe = false;

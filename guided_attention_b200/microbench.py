@@ -271,6 +271,17 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--single-self":
         a = sys.argv[2:]
         print(json.dumps(time_self_attn(int(a[1]), 8, int(a[2]), int(a[3]), torch.float16, a[0])))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--saturated":       # bench.py's GPU-filling shapes, one JSON line each
+        dev_ = sys.argv[2] if len(sys.argv) > 2 else "cuda:0"
+        torch.cuda.set_device(torch.device(dev_))
+        for direction in ("fwd", "bwd"):
+            for (N, d, maps, B) in ((1024, 80, True, 256), (256, 160, True, 512), (4096, 40, False, 128)):
+                print(json.dumps(time_cross_attn(B, 8, N, 77, d, torch.float16, with_acc=maps, direction=direction,
+                                                 device=dev_)))
+            for res in (16, 32):
+                print(json.dumps(time_tail(res, 5, 2, n_samples=2048 if res == 16 else 512, direction=direction,
+                                           device=dev_)))
+            sys.stdout.flush()
     elif len(sys.argv) > 1 and sys.argv[1] == "--single-group-norm":      # direction n c r  (for ncu)
         a = sys.argv[2:]
         print(json.dumps(time_group_norm(int(a[1]), int(a[2]), int(a[3]), int(a[3]), 32, True, a[0], "fused")))
