@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(CSRC, "libguidedattn.so")
-SOURCES = ["c_api.cu", "cross_attn_simt.cu", "cross_attn_tc.cu", "self_attn_tc.cu", "guidance_tail.cu", "step_driver.cu", "group_norm.cu"]
+SOURCES = ["c_api.cu", "cross_attn_simt.cu", "cross_attn_tc.cu", "self_attn_tc.cu", "guidance_tail.cu", "step_driver.cu", "unet_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 

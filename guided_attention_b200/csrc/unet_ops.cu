@@ -1,4 +1,6 @@
-// Fused GroupNorm (+ SiLU) forward / backward for channels-last 16-bit activations (sm_100a).
+// UNet-side kernels of the guidance path (sm_100a): GroupNorm (+ SiLU, + shift) forward / backward, conv bias + residual,
+// the GEGLU gate forward / backward and the LayerNorm forward, all on channels-last / token-major 16-bit activations with
+// 128-bit accesses.  GroupNorm is described here; the three smaller kernels have their own headers further down.
 //
 // Why it is here: the guidance path differentiates the loss with respect to the LATENTS, so every guided step runs the
 // UNet forward AND backward (reference pipeline_guided_attention.py:455-470 `_update_latent`, :583-743 the UNet forward
@@ -23,7 +25,10 @@
 //                  dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)).
 // The second launch of each direction re-reads x (and dy) from L2 (the largest activation of an SD UNet is 7.9 MB).
 // Statistics are fp32; the affine parameters are read in the activation dtype.  d gamma / d beta are not produced (the
-// UNet is frozen on the guidance path: ptp_utils.register_attention_control).
+// UNet is frozen on the guidance path: ptp_utils.register_attention_control).  The optional `shift[n, c]` (the bias of
+// the convolution that produced x + the block's time-embedding projection) is added on load.  The second kernel of a
+// pair is launched with programmatic stream serialisation and starts with griddepcontrol.wait: its CTAs are scheduled
+// while the first kernel drains.
 #include "ga_common.cuh"
 #include <stdlib.h>
 

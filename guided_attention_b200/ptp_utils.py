@@ -416,7 +416,7 @@ def _patch_conv(m):
 
 def register_fused_norms(unet) -> int:
     """Routes the elementwise work of the UNet around the attention layers through the fused channels-last kernels of
-    `csrc/group_norm.cu` whenever the activation is a 16-bit CUDA tensor and the parameters are frozen; anything else
+    `csrc/unet_ops.cu` whenever the activation is a 16-bit CUDA tensor and the parameters are frozen; anything else
     (fp32, CPU, trainable layers) keeps PyTorch's own ops:
       * every `nn.GroupNorm` (ResNet blocks, transformer wrappers, `conv_norm_out`) -> `ops.group_norm`;
       * blocks that expose the `fused_norm_act` / `fused_forward` hooks (the substrate's ResnetBlock2D) get SiLU, the
@@ -427,7 +427,7 @@ def register_fused_norms(unet) -> int:
       * every `GEGLU` feed-forward gate -> `ops.geglu` (one vectorised launch per direction);
       * every `nn.LayerNorm` over the channel dimension -> `ops.layer_norm` (warp-per-row forward).
     The guided loop runs the UNet forward and backward ~250 times per image and these ops were the largest non-GEMM
-    items of its launch list (csrc/group_norm.cu, profiles/r02c_profile_ops.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
+    items of its launch list (csrc/unet_ops.cu, profiles/r02c_profile_ops_*.txt).  Idempotent; `GA_FUSED_NORM=0` leaves
     the UNet untouched, `GA_FUSED_DISABLE=conv,resnet,geglu,layernorm,temb` switches single items off (A/B measurements).  Returns the number of norm layers now routed."""
     if os.environ.get("GA_FUSED_NORM", "1") == "0" or not hasattr(unet, "modules"):
         return 0

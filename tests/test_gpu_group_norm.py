@@ -1,4 +1,4 @@
-"""GPU parity of the fused GroupNorm (+ SiLU) kernels (`csrc/group_norm.cu`, through the C ABI) against PyTorch's own
+"""GPU parity of the fused GroupNorm (+ SiLU) kernels (`csrc/unet_ops.cu`, through the C ABI) against PyTorch's own
 `F.group_norm` / `F.silu` evaluated in fp32 on the same 16-bit inputs -- the op pair the reference's UNet runs
 (`torch.nn.GroupNorm(32, C)` + SiLU inside diffusers' ResnetBlock2D / Transformer2DModel, driven by
 pipeline_guided_attention.py:583-743).  Floating point: the bound is the output dtype's rounding (stated per test).

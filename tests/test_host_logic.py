@@ -177,3 +177,25 @@ def test_ops_refuse_cpu_tensors():
 def test_missing_library_is_loud(tmp_path):
     with pytest.raises(_cabi.GuidedAttnLibraryError):
         _cabi.load(str(tmp_path / "nope.so"))
+
+
+def test_fused_unet_hooks_leave_cpu_and_fp32_untouched():
+    """`register_fused_norms` only reroutes 16-bit CUDA activations: on CPU / fp32 the patched UNet is bit-identical to
+    the stock one (the oracle and the fp32 goldens never see the fused kernels), and registration is idempotent."""
+    from guided_attention_b200 import ptp_utils
+    from guided_attention_b200.substrate import UNetConfig, build_unet
+    cfg = UNetConfig.tiny(sample_size=16)
+    stock = build_unet(cfg, seed=0).requires_grad_(False)
+    fused = build_unet(cfg, seed=0).requires_grad_(False)
+    assert ptp_utils.register_fused_norms(fused) == 61 and ptp_utils.register_fused_norms(fused) == 61
+    blocks = [m for m in fused.modules() if hasattr(m, "_ga_temb_shifts")]
+    assert len(blocks) == 22 and len({id(b._ga_temb_shifts) for b in blocks}) == 1
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    assert torch.equal(stock(x, 10, encoder_hidden_states=e).sample, fused(x, 10, encoder_hidden_states=e).sample)
+    # the one-GEMM time-embedding projection equals the per-block projection (+ conv1 bias) it replaces
+    reg, temb = blocks[0]._ga_temb_shifts, torch.randn(2, blocks[0].time_emb_proj.in_features, generator=g)
+    for b in (blocks[0], blocks[7], blocks[-1]):
+        ref = torch.nn.functional.linear(torch.nn.functional.silu(temb), b.time_emb_proj.weight,
+                                         b.time_emb_proj.bias + b.conv1.bias)
+        assert torch.allclose(reg.shift(b, temb), ref, rtol=0, atol=1e-6)
