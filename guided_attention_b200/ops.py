@@ -592,10 +592,6 @@ def layer_norm_supported(x, weight, bias) -> bool:
             and x.numel() > 0)
 
 
-def fused_unet_ops_supported(x: torch.Tensor) -> bool:
-    return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
-
-
 # ============================================================================================== K5 rasteriser
 def rasterize_boxes(boxes: Sequence[Sequence[float]], res: int, shrink: float, device) -> torch.Tensor:
     """(n, res, res) uint8 masks of `helpers.inside_box` for unit-square boxes (x, y, w, h); bit-exact vs the host."""
