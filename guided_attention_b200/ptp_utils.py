@@ -328,7 +328,11 @@ def _shift_bias(block):
     key = (tb.data_ptr(), tb._version, cb.data_ptr(), cb._version, tb.dtype)
     hit = getattr(block, "_ga_shift_bias", None)
     if hit is None or hit[0] != key:
-        hit = (key, (tb.detach() + cb.detach()))
+        fresh = tb.detach() + cb.detach()
+        if hit is not None and hit[1].shape == fresh.shape and hit[1].dtype == fresh.dtype and hit[1].device == fresh.device:
+            hit[1].copy_(fresh)          # in place: captured CUDA graphs hold this buffer's address
+            fresh = hit[1]
+        hit = (key, fresh)
         block._ga_shift_bias = hit
     return hit[1]
 
@@ -352,8 +356,15 @@ class _TembShifts:
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in self._params())
         if key != self.key:
             with torch.no_grad():
-                self.weight = torch.cat([b.time_emb_proj.weight for b in self.blocks], dim=0).contiguous()
-                self.bias = torch.cat([b.time_emb_proj.bias + b.conv1.bias for b in self.blocks], dim=0).contiguous()
+                weight = torch.cat([b.time_emb_proj.weight for b in self.blocks], dim=0).contiguous()
+                bias = torch.cat([b.time_emb_proj.bias + b.conv1.bias for b in self.blocks], dim=0).contiguous()
+                # captured CUDA graphs hold the ADDRESSES of these buffers: refresh them in place whenever possible
+                if (self.weight is not None and self.weight.shape == weight.shape and self.weight.dtype == weight.dtype
+                        and self.weight.device == weight.device):
+                    self.weight.copy_(weight)
+                    self.bias.copy_(bias)
+                else:
+                    self.weight, self.bias = weight, bias
             off = 0
             for b in self.blocks:
                 self.offsets[id(b)] = (off, b.conv1.out_channels)
@@ -483,7 +494,13 @@ def register_fused_norms(unet) -> int:
                   and all(hasattr(m, a) for a in ("time_emb_proj", "conv1"))
                   and all(_frozen(q) for q in (m.time_emb_proj.weight, m.time_emb_proj.bias, m.conv1.bias))]
         if len(blocks) > 1 and len({b.time_emb_proj.in_features for b in blocks}) == 1:
-            reg = _TembShifts(blocks)
+            # ONE registry per UNet for its whole life: `register_attention_control` runs again for every prompt / seed
+            # (run.py:44-67) while the pipeline's captured CUDA graphs, which hold the addresses of the registry's
+            # buffers, are reused -- a fresh registry per call would free the buffers under them
+            reg = getattr(unet, "_ga_temb_registry", None)
+            if reg is None or [id(b) for b in reg.blocks] != [id(b) for b in blocks]:
+                reg = _TembShifts(blocks)
+                unet._ga_temb_registry = reg
             for b in blocks:
                 b._ga_temb_shifts = reg
     return n

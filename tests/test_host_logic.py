@@ -190,6 +190,21 @@ def test_fused_unet_hooks_leave_cpu_and_fp32_untouched():
     assert ptp_utils.register_fused_norms(fused) == 61 and ptp_utils.register_fused_norms(fused) == 61
     blocks = [m for m in fused.modules() if hasattr(m, "_ga_temb_shifts")]
     assert len(blocks) == 22 and len({id(b._ga_temb_shifts) for b in blocks}) == 1
+    # registering again (run.py does it for every seed) keeps the SAME registry and the SAME buffers: captured CUDA
+    # graphs hold their addresses; an in-place weight change refreshes them in place
+    reg0 = blocks[0]._ga_temb_shifts
+    probe = torch.randn(1, blocks[0].time_emb_proj.in_features)
+    reg0.shift(blocks[0], probe)
+    w_ptr, b_ptr = reg0.weight.data_ptr(), reg0.bias.data_ptr()
+    ptp_utils.register_fused_norms(fused)
+    assert blocks[0]._ga_temb_shifts is reg0
+    saved = blocks[3].conv1.bias.detach().clone()
+    with torch.no_grad():
+        blocks[3].conv1.bias.add_(1.0)
+    reg0.shift(blocks[3], torch.randn(1, blocks[0].time_emb_proj.in_features))
+    assert (reg0.weight.data_ptr(), reg0.bias.data_ptr()) == (w_ptr, b_ptr)
+    with torch.no_grad():
+        blocks[3].conv1.bias.copy_(saved)
     g = torch.Generator().manual_seed(0)
     x, e = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
     assert torch.equal(stock(x, 10, encoder_hidden_states=e).sample, fused(x, 10, encoder_hidden_states=e).sample)
