@@ -214,3 +214,22 @@ def test_fused_unet_hooks_leave_cpu_and_fp32_untouched():
         ref = torch.nn.functional.linear(torch.nn.functional.silu(temb), b.time_emb_proj.weight,
                                          b.time_emb_proj.bias + b.conv1.bias)
         assert torch.allclose(reg.shift(b, temb), ref, rtol=0, atol=1e-6)
+
+
+def test_group_norm_plan_without_a_gpu():
+    """`ga_group_norm_ws_bytes` runs the kernels' host-side decomposition (pixel chunks x channel slices) and needs no
+    device: chunk counts for the UNet's shapes and the declined shapes."""
+    lib = _cabi.load()
+    ws = lib.ga_group_norm_ws_bytes
+    per = 32 * 2 * 4                                     # groups x (mean, M2) x fp32 per chunk and sample
+    assert ws(1, 4096, 320, 32) == 128 * per            # 40 vectors, 6 pixel lanes -> 32-pixel chunks
+    assert ws(8, 4096, 640, 32) == 8 * 128 * per
+    assert ws(1, 64, 2560, 32) == 64 * per              # 320 vectors -> two channel slices of 16 groups, one pixel per CTA
+    assert ws(1, 64, 1280, 32) == 64 * per
+    assert ws(1, 9216, 320, 32) == 128 * per            # SD-2.x 96x96 latent: 72-pixel chunks
+    assert ws(1, 35, 64, 8) == 2 * 8 * 2 * 4            # ragged: 32-pixel chunk + 3-pixel chunk
+    assert ws(3, 1, 128, 8) == 3 * 1 * 8 * 2 * 4
+    assert ws(1, 64, 36, 6) == -1                       # channels not a multiple of 8
+    assert ws(1, 64, 40, 8) == -1                       # 5-channel groups: a 128-bit vector would touch three groups
+    assert ws(1, 64, 320, 3) == -1                      # channels not divisible by the group count
+    assert ws(0, 64, 320, 32) == -1
