@@ -233,3 +233,31 @@ def test_group_norm_plan_without_a_gpu():
     assert ws(1, 64, 40, 8) == -1                       # 5-channel groups: a 128-bit vector would touch three groups
     assert ws(1, 64, 320, 3) == -1                      # channels not divisible by the group count
     assert ws(0, 64, 320, 32) == -1
+
+
+def test_unet_side_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the UNet-side entry points happen before any CUDA call: status code + thread-local message."""
+    lib = _cabi.load()
+    buf = (ctypes.c_char * 4096)()
+    base = ctypes.addressof(buf)
+    a16 = (base + 15) // 16 * 16                         # 16-byte aligned address inside the buffer
+    F16, F32 = _cabi.GA_F16, _cabi.GA_F32
+    BAD_ARG, ALIGN = -1, -3
+    p = ctypes.c_void_p
+    # NULL operands / wrong dtype / misaligned pointers
+    assert lib.ga_group_norm_fwd(None, None, 0, p(a16), p(a16), p(a16), p(a16), p(a16), 1, 64, 320, 32, 1e-5, 1, F16, None) == BAD_ARG
+    assert lib.ga_group_norm_fwd(p(a16), None, 0, p(a16), p(a16), p(a16), p(a16), p(a16), 1, 64, 320, 32, 1e-5, 1, F32, None) == BAD_ARG
+    assert b"16-bit" in lib.ga_last_error()
+    assert lib.ga_group_norm_fwd(p(a16 + 2), None, 0, p(a16), p(a16), p(a16), p(a16), p(a16), 1, 64, 320, 32, 1e-5, 1, F16, None) == ALIGN
+    # a shift row stride that is not a multiple of 8 elements (or shorter than a row) is refused
+    assert lib.ga_group_norm_fwd(p(a16), p(a16), 324, p(a16), p(a16), p(a16), p(a16), p(a16), 1, 64, 320, 32, 1e-5, 1, F16, None) == BAD_ARG
+    assert lib.ga_group_norm_bwd(p(a16), p(a16), 312, p(a16), p(a16), p(a16), p(a16), p(a16), p(a16), 1, 64, 320, 32, 1, F16, None) == BAD_ARG
+    assert lib.ga_add_bias_residual(p(a16), None, p(a16), p(a16), 64, 36, F16, None) == BAD_ARG       # channels % 8
+    assert lib.ga_add_bias_residual(p(a16), p(a16 + 4), p(a16), p(a16), 64, 320, F16, None) == ALIGN
+    assert lib.ga_geglu_fwd(p(a16), p(a16), 64, 12, F16, None) == BAD_ARG                              # inner % 8
+    assert lib.ga_geglu_bwd(p(a16), None, p(a16), 64, 1280, F16, None) == BAD_ARG
+    assert lib.ga_layer_norm_fwd(p(a16), p(a16), p(a16), p(a16), p(a16), p(a16), 64, 4096, 1e-5, F16, None) == BAD_ARG
+    assert b"2048" in lib.ga_last_error()
+    # zero rows: nothing to launch, no error
+    assert lib.ga_geglu_fwd(p(a16), p(a16), 0, 1280, F16, None) == 0
+    assert lib.ga_layer_norm_fwd(p(a16), p(a16), p(a16), p(a16), p(a16), p(a16), 0, 320, 1e-5, F16, None) == 0
